@@ -1,0 +1,105 @@
+"""Loader + build recipe of the C-ABI library libb200np.so (include/b200np.h).
+
+The library is hand-written sm_100a CUDA behind a plain C ABI; this module only
+dlopens it.  There is no CPU fallback: if the library is missing or no CUDA
+device is usable the product path raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_PKG)
+CSRC = os.path.join(_PKG, "csrc")
+LIBDIR = os.path.join(_PKG, "lib")
+SO = os.path.join(LIBDIR, "libb200np.so")
+SOURCES = ["b200np.cu"]
+HEADERS = ["np_level.h", "np_kernels.cuh", os.path.join(ROOT, "include", "b200np.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> incflo_b200/lib/libb200np.so"""
+    if not force and not _stale():
+        return SO
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)
+    subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"], env=env)
+    return SO
+
+
+class Geom(C.Structure):
+    _fields_ = [("n_cell", C.c_int * 3), ("dx", C.c_double * 3), ("bc_lo", C.c_int * 3), ("bc_hi", C.c_int * 3)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("verbose", C.c_int), ("bottom_verbose", C.c_int), ("maxiter", C.c_int), ("bottom_maxiter", C.c_int),
+                ("bottom_rtol", C.c_double), ("bottom_atol", C.c_double), ("mg_max_coarsening_level", C.c_int),
+                ("num_pre_smooth", C.c_int), ("num_post_smooth", C.c_int), ("smooth_num_sweeps", C.c_int),
+                ("bottom_solver", C.c_int), ("tile", C.c_int * 3), ("use_graph", C.c_int)]
+
+
+class FabBox(C.Structure):
+    _fields_ = [("lo", C.c_int * 3), ("hi", C.c_int * 3), ("ncomp", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("iters", C.c_int), ("nlevels", C.c_int), ("bottom_iters", C.c_int), ("status", C.c_int),
+                ("rhsnorm", C.c_double), ("resnorm0", C.c_double), ("resnorm", C.c_double),
+                ("resnorm_hist", C.c_double * 128), ("ms_total", C.c_double), ("ms_solve", C.c_double),
+                ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("h2d_bytes", C.c_longlong),
+                ("d2h_bytes", C.c_longlong), ("launches", C.c_longlong)]
+
+
+# every symbol include/b200np.h declares
+EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np_destroy", "b200np_project",
+           "b200np_apply_nodal_projection", "b200np_strerror", "b200np_version", "b200np_nlevels",
+           "b200np_level_dims", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
+           "b200np_time_op"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise RuntimeError("libb200np.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(SO)
+    vp, dp, ip = C.c_void_p, C.c_void_p, C.POINTER(C.c_int * 3)
+    fb = C.POINTER(FabBox)
+    L.b200np_default_opts.argtypes = [C.POINTER(Opts)]
+    L.b200np_default_opts.restype = None
+    L.b200np_create.argtypes = [C.POINTER(vp), C.POINTER(Geom), C.POINTER(Opts), C.c_int]
+    L.b200np_create_dist.argtypes = [C.POINTER(vp), C.POINTER(Geom), C.POINTER(Opts), C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.b200np_destroy.argtypes = [vp]
+    L.b200np_destroy.restype = None
+    L.b200np_project.argtypes = [vp, dp, fb, dp, fb, C.c_double, dp, fb, dp, fb, C.c_double, C.c_double, C.POINTER(Stats)]
+    L.b200np_apply_nodal_projection.argtypes = [vp, dp, fb, dp, dp, fb, C.c_double, dp, fb, dp, fb, dp, C.c_double,
+                                                C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
+    L.b200np_strerror.argtypes = [C.c_int]
+    L.b200np_strerror.restype = C.c_char_p
+    L.b200np_version.restype = C.c_int
+    L.b200np_nlevels.argtypes = [vp]
+    L.b200np_level_dims.argtypes = [vp, C.c_int, ip, ip]
+    L.b200np_set_sigma.argtypes = [vp, dp, fb, C.c_double]
+    L.b200np_level_set.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.b200np_level_get.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.b200np_level_op.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.b200np_time_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    _lib = L
+    return L

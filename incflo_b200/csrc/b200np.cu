@@ -1,0 +1,757 @@
+// b200np.cu -- host side of the B200-native nodal projection: multigrid hierarchy, MLMG
+// driver, C ABI (include/b200np.h).  Host code is C++ and only launches the sm_100a kernels
+// in np_kernels.cuh / np_smooth.cuh; there is no CPU compute path.
+//
+// Reference functions restated here (see include/b200np.h and DESIGN.md for the map):
+//   incflo::ApplyNodalProjection      src/projection/incflo_apply_nodal_projection.cpp:29-267
+//   Hydro::NodalProjector::project    [U] SURVEY.md A.1
+//   MLMG::solve / mgVcycle            [U] SURVEY.md A.9
+//   MLNodeLinOp::defineGrids          [U] SURVEY.md A.8 (hierarchy)
+#include "../../include/b200np.h"
+#include "np_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace b200np_dev;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            fprintf(stderr, "b200np: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw int(B200NP_ERR_CUDA);                                                                  \
+        }                                                                                                \
+    } while (0)
+
+namespace {
+
+struct LevelData {
+    Lev g{};
+    double* sigma = nullptr;  // plane 0 of owned cells (allocation starts one plane earlier)
+    double* sigma_alloc = nullptr;
+    double *sol = nullptr, *rhs = nullptr, *res = nullptr, *cor = nullptr, *cor2 = nullptr, *rescor = nullptr;
+    std::vector<double*> allocs;
+    dim3 gn, gc;     // grids of 64x4-thread blocks over owned nodes / cells
+    dim3 gsm;        // smoother grid
+    long long nblk_n = 0;
+};
+
+}  // namespace
+
+struct b200np {
+    b200np_geom geom{};
+    b200np_opts opts{};
+    int device = 0;
+    int rank = 0, nranks = 1;
+    int singular = 1;
+    bool var_sigma = false;
+    bool sigma_valid = false;
+    std::vector<LevelData> lv;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6]{};
+    double* partial = nullptr;  // reduction partials
+    double* dscal = nullptr;    // device scalars: [0..1] sums, [2] norm
+    double* hscal = nullptr;    // pinned host mirror
+    int* dinfo = nullptr;       // bottom solver info (iters, ret)
+    int* hinfo = nullptr;
+    double* bottom_work = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool graph_var = false;
+    double graph_csig = 0.0;  // kernel parameters (Lev by value) are baked into the captured graph
+    long long launches = 0, launches_per_vcycle = 0;
+    // staging buffers for host-pointer callers
+    struct Stage { double* d = nullptr; size_t bytes = 0; };
+    Stage stage[8];
+    int TZ = 16;
+};
+
+namespace {
+
+
+#define LAUNCH(h, kern, grid, block, ...)                        \
+    do {                                                         \
+        kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__);      \
+        (h)->launches++;                                         \
+    } while (0)
+
+double* dev_alloc(size_t n_doubles)
+{
+    double* p = nullptr;
+    CK(cudaMalloc(&p, n_doubles * sizeof(double)));
+    CK(cudaMemset(p, 0, n_doubles * sizeof(double)));
+    return p;
+}
+
+// allocate a nodal array with ghost plane slots; returns pointer to owned plane 0
+double* alloc_nodal(LevelData& L)
+{
+    double* base = dev_alloc((size_t)L.g.ps * (L.g.nzl + 2));
+    L.allocs.push_back(base);
+    return base + L.g.ps;
+}
+
+void build_hierarchy(b200np* h)
+{
+    const b200np_geom& G = h->geom;
+    int n[3] = {G.n_cell[0], G.n_cell[1], G.n_cell[2]};
+    double dx[3] = {G.dx[0], G.dx[1], G.dx[2]};
+    h->singular = 1;
+    for (int d = 0; d < 3; ++d)
+        if (G.bc_lo[d] == B200NP_BC_DIRICHLET || G.bc_hi[d] == B200NP_BC_DIRICHLET) h->singular = 0;
+    int lev = 0;
+    for (;;) {
+        LevelData L;
+        Lev& g = L.g;
+        for (int d = 0; d < 3; ++d) {
+            g.n[d] = n[d];
+            g.per[d] = (G.bc_lo[d] == B200NP_BC_PERIODIC);
+            g.nn[d] = n[d] + (g.per[d] ? 0 : 1);
+            g.rlo[d] = G.bc_lo[d] == B200NP_BC_NEUMANN ? 1 : (G.bc_lo[d] == B200NP_BC_INFLOW ? 2 : 0);
+            g.rhi[d] = G.bc_hi[d] == B200NP_BC_NEUMANN ? 1 : (G.bc_hi[d] == B200NP_BC_INFLOW ? 2 : 0);
+            g.dlo[d] = G.bc_lo[d] == B200NP_BC_DIRICHLET;
+            g.dhi[d] = G.bc_hi[d] == B200NP_BC_DIRICHLET;
+            g.dxinv[d] = 1.0 / dx[d];
+        }
+        g.px = (g.nn[0] + 7) / 8 * 8;
+        g.ps = (long long)g.px * g.nn[1];
+        g.cpx = (g.n[0] + 7) / 8 * 8;
+        g.cps = (long long)g.cpx * g.n[1];
+        g.k0 = 0; g.nzl = g.nn[2];
+        g.ck0 = 0; g.cnzl = g.n[2];
+        g.dist = 0;
+        const double fx = g.dxinv[0] * g.dxinv[0] / 36.0, fy = g.dxinv[1] * g.dxinv[1] / 36.0, fz = g.dxinv[2] * g.dxinv[2] / 36.0;
+        g.fxyz = fx + fy + fz;
+        g.fmx2y2z = -fx + 2 * fy + 2 * fz; g.f2xmy2z = 2 * fx - fy + 2 * fz; g.f2x2ymz = 2 * fx + 2 * fy - fz;
+        g.f4xm2ym2z = 4 * fx - 2 * fy - 2 * fz; g.fm2x4ym2z = -2 * fx + 4 * fy - 2 * fz; g.fm2xm2y4z = -2 * fx - 2 * fy + 4 * fz;
+        g.csig = 1.0; g.sigma = nullptr;
+        L.gn = dim3((g.nn[0] + 63) / 64, (g.nn[1] + 3) / 4, g.nzl);
+        L.gc = dim3((g.n[0] + 63) / 64, (g.n[1] + 3) / 4, g.cnzl);
+        L.gsm = dim3((g.nn[0] + NP_TX - 1) / NP_TX, (g.nn[1] + NP_TY - 1) / NP_TY, (g.nzl + h->TZ - 1) / h->TZ);
+        L.nblk_n = (long long)L.gn.x * L.gn.y * L.gn.z;
+        // arrays
+        L.sigma_alloc = dev_alloc((size_t)g.cps * (g.cnzl + 2));
+        L.sigma = L.sigma_alloc + g.cps;
+        L.res = alloc_nodal(L); L.cor = alloc_nodal(L); L.cor2 = alloc_nodal(L); L.rescor = alloc_nodal(L);
+        if (lev == 0) { L.sol = alloc_nodal(L); L.rhs = alloc_nodal(L); }
+        h->lv.push_back(L);
+        ++lev;
+        // coarsen by 2 while every direction stays even and >= 2 cells wide (A.8)
+        bool ok = lev <= h->opts.mg_max_coarsening_level && lev < 30;
+        for (int d = 0; d < 3; ++d) if (n[d] % 2 != 0 || n[d] / 2 < 2) ok = false;
+        if (!ok) break;
+        for (int d = 0; d < 3; ++d) { n[d] /= 2; dx[d] *= 2; }
+    }
+    long long maxblk = 0;
+    for (auto& L : h->lv) maxblk = std::max(maxblk, L.nblk_n);
+    h->partial = dev_alloc((size_t)2 * maxblk + 16);
+    h->dscal = dev_alloc(16);
+    CK(cudaMallocHost(&h->hscal, 16 * sizeof(double)));
+    CK(cudaMalloc(&h->dinfo, 4 * sizeof(int)));
+    CK(cudaMemset(h->dinfo, 0, 4 * sizeof(int)));
+    CK(cudaMallocHost(&h->hinfo, 4 * sizeof(int)));
+    const Lev& B = h->lv.back().g;
+    h->bottom_work = dev_alloc((size_t)B.ps * B.nzl * 8);
+}
+
+void set_level_sigma_ptrs(b200np* h, bool var, double csig)
+{
+    h->var_sigma = var;
+    for (auto& L : h->lv) { L.g.sigma = var ? L.sigma : nullptr; L.g.csig = csig; }
+}
+
+void coarsen_sigma(b200np* h)
+{
+    if (!h->var_sigma) return;
+    for (size_t l = 0; l + 1 < h->lv.size(); ++l) {
+        LevelData &F = h->lv[l], &C = h->lv[l + 1];
+        LAUNCH(h, k_coarsen_sigma, C.gc, 256, F.g, C.g, F.sigma, C.sigma);
+    }
+}
+
+// one Gauss-Seidel sweep (ping-pong cor -> cor2, then swap)
+void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double* rhs, int nsweeps)
+{
+    for (int s = 0; s < nsweeps; ++s) {
+        if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, h->TZ);
+        else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, h->TZ);
+        std::swap(x, y);
+    }
+}
+
+void residual(b200np* h, LevelData& L, const double* phi, const double* rhs, double* res, double* norm_partial)
+{
+    if (h->var_sigma) LAUNCH(h, k_residual<true>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
+    else              LAUNCH(h, k_residual<false>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
+}
+
+void bottom_solve(b200np* h)
+{
+    LevelData& B = h->lv.back();
+    if (h->var_sigma)
+        LAUNCH(h, k_bottom_bicgstab<true>, 1, 512, B.g, B.cor, B.res, h->bottom_work, h->opts.bottom_maxiter,
+               h->opts.bottom_rtol, h->opts.bottom_atol, h->singular, h->opts.smooth_num_sweeps, h->opts.bottom_solver, h->dinfo);
+    else
+        LAUNCH(h, k_bottom_bicgstab<false>, 1, 512, B.g, B.cor, B.res, h->bottom_work, h->opts.bottom_maxiter,
+               h->opts.bottom_rtol, h->opts.bottom_atol, h->singular, h->opts.smooth_num_sweeps, h->opts.bottom_solver, h->dinfo);
+}
+
+void restrict_to(b200np* h, int l)
+{
+    LevelData &F = h->lv[l], &C = h->lv[l + 1];
+    LAUNCH(h, k_restrict, C.gn, 256, F.g, C.g, F.rescor, C.res);
+}
+void interp_add(b200np* h, int l)
+{
+    LevelData &F = h->lv[l], &C = h->lv[l + 1];
+    if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
+    else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
+}
+
+// MLMG::mgVcycle (A.9) on (cor, res), all launches on h->stream, no host synchronisation
+void vcycle_launch(b200np* h, int lev0)
+{
+    const int nl = (int)h->lv.size();
+    const int nsw = h->opts.smooth_num_sweeps;
+    for (int l = lev0; l < nl - 1; ++l) {
+        LevelData& L = h->lv[l];
+        CK(cudaMemsetAsync(L.cor - L.g.ps, 0, (size_t)L.g.ps * (L.g.nzl + 2) * sizeof(double), h->stream));
+        double *x = L.cor, *y = L.cor2;
+        smooth_sweeps(h, L, x, y, L.res, h->opts.num_pre_smooth * nsw);
+        if (x != L.cor) { CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); }
+        residual(h, L, L.cor, L.res, L.rescor, nullptr);
+        restrict_to(h, l);
+    }
+    bottom_solve(h);
+    for (int l = nl - 2; l >= lev0; --l) {
+        LevelData& L = h->lv[l];
+        interp_add(h, l);
+        double *x = L.cor, *y = L.cor2;
+        smooth_sweeps(h, L, x, y, L.res, h->opts.num_post_smooth * nsw);
+        if (x != L.cor) { CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); }
+    }
+}
+
+void vcycle(b200np* h)
+{
+    if (!h->opts.use_graph) { vcycle_launch(h, 0); return; }
+    if (h->graph_exec && (h->graph_var != h->var_sigma || h->graph_csig != h->lv[0].g.csig)) {
+        cudaGraphExecDestroy(h->graph_exec); cudaGraphDestroy(h->graph);
+        h->graph_exec = nullptr; h->graph = nullptr;
+    }
+    if (!h->graph_exec) {
+        long long before = h->launches;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        vcycle_launch(h, 0);
+        CK(cudaStreamEndCapture(h->stream, &h->graph));
+        CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+        h->launches_per_vcycle = h->launches - before;
+        h->launches = before;
+        h->graph_var = h->var_sigma;
+        h->graph_csig = h->lv[0].g.csig;
+    }
+    CK(cudaGraphLaunch(h->graph_exec, h->stream));
+    h->launches += h->launches_per_vcycle;
+}
+
+double norm_from_partials(b200np* h, long long nb)
+{
+    LAUNCH(h, k_max_final, 1, 1024, h->partial, nb, h->dscal + 2);
+    CK(cudaMemcpyAsync(h->hscal + 2, h->dscal + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return h->hscal[2];
+}
+
+double norminf(b200np* h, LevelData& L, const double* x)
+{
+    LAUNCH(h, k_norminf_partial, L.gn, 256, L.g, x, h->partial);
+    return norm_from_partials(h, L.nblk_n);
+}
+
+// MLMG::solve (A.9) on level-0 arrays sol (initial guess, in/out) and rhs
+int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
+{
+    LevelData& L0 = h->lv[0];
+    st->iters = 0; st->bottom_iters = 0; st->status = B200NP_OK; st->nlevels = (int)h->lv.size();
+    CK(cudaMemsetAsync(h->dinfo, 0, 4 * sizeof(int), h->stream));
+    if (!h->singular) {
+        LAUNCH(h, k_zero_masked, L0.gn, 256, L0.g, L0.sol);
+        LAUNCH(h, k_zero_masked, L0.gn, 256, L0.g, L0.rhs);
+    } else {  // makeSolvable: subtract the weighted mean of rhs (A.8)
+        LAUNCH(h, k_wsum_partial, L0.gn, 256, L0.g, L0.rhs, h->partial);
+        LAUNCH(h, k_sum2_final, 1, 1024, h->partial, L0.nblk_n, h->dscal);
+        LAUNCH(h, k_sub_mean, L0.gn, 256, L0.g, L0.rhs, h->dscal);
+    }
+    st->rhsnorm = norminf(h, L0, L0.rhs);
+    residual(h, L0, L0.sol, L0.rhs, L0.res, h->partial);
+    st->resnorm0 = norm_from_partials(h, L0.nblk_n);
+    const double maxnorm = std::max(st->rhsnorm, st->resnorm0);
+    const double target = std::max(atol, std::max(rtol, 1e-16) * maxnorm);
+    st->resnorm = st->resnorm0;
+    st->resnorm_hist[0] = st->resnorm0;
+    if (h->opts.verbose >= 1) printf("MLMG: Initial rhs               = %.12g\nMLMG: Initial residual (resid0) = %.12g\n", st->rhsnorm, st->resnorm0);
+    if (st->resnorm0 <= target) return B200NP_OK;
+    bool converged = false;
+    for (int it = 0; it < h->opts.maxiter; ++it) {
+        vcycle(h);
+        LAUNCH(h, k_axpy, L0.gn, 256, L0.g, L0.sol, L0.cor, 1.0);
+        residual(h, L0, L0.sol, L0.rhs, L0.res, h->partial);
+        st->resnorm = norm_from_partials(h, L0.nblk_n);
+        st->iters = it + 1;
+        if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
+        if (h->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
+        if (st->resnorm <= target) { converged = true; break; }
+        if (!(st->resnorm <= 1e20 * maxnorm)) { st->status = B200NP_ERR_DIVERGED; break; }
+    }
+    if (!converged && st->status == B200NP_OK) st->status = B200NP_ERR_NOT_CONVERGED;
+    CK(cudaMemcpyAsync(h->hinfo, h->dinfo, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    st->bottom_iters = h->hinfo[0];
+    if (h->opts.verbose >= 1)
+        printf("MLMG: Final Iter. %d resid, resid/bnorm = %.12g, %.12g\n", st->iters, st->resnorm, st->resnorm / maxnorm);
+    return st->status;
+}
+
+// ---- caller arrays ------------------------------------------------------------------------
+Fab make_fab(double* p, const b200np_fab* b)
+{
+    Fab f{};
+    f.p = p;
+    if (!b) return f;
+    for (int d = 0; d < 3; ++d) f.lo[d] = b->lo[d];
+    f.nx = b->hi[0] - b->lo[0] + 1; f.ny = b->hi[1] - b->lo[1] + 1; f.nz = b->hi[2] - b->lo[2] + 1;
+    f.cstride = (long long)f.nx * f.ny * f.nz;
+    return f;
+}
+size_t fab_bytes(const b200np_fab* b)
+{
+    return (size_t)(b->hi[0] - b->lo[0] + 1) * (b->hi[1] - b->lo[1] + 1) * (b->hi[2] - b->lo[2] + 1) * b->ncomp * sizeof(double);
+}
+bool is_device_ptr(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes a{};
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+// returns a device pointer for `p` (staging host memory when needed)
+double* stage_in(b200np* h, int slot, const double* p, const b200np_fab* box, bool copy, bool* staged, b200np_stats* st)
+{
+    *staged = false;
+    if (!p) return nullptr;
+    if (is_device_ptr(p)) return const_cast<double*>(p);
+    size_t bytes = fab_bytes(box);
+    auto& S = h->stage[slot];
+    if (S.bytes < bytes) {
+        if (S.d) CK(cudaFree(S.d));
+        CK(cudaMalloc(&S.d, bytes));
+        S.bytes = bytes;
+    }
+    if (copy) {
+        CK(cudaMemcpyAsync(S.d, p, bytes, cudaMemcpyHostToDevice, h->stream));
+        st->h2d_bytes += (long long)bytes;
+    }
+    *staged = true;
+    return S.d;
+}
+void stage_out(b200np* h, int slot, double* p, const b200np_fab* box, bool staged, b200np_stats* st)
+{
+    if (!staged || !p) return;
+    size_t bytes = fab_bytes(box);
+    CK(cudaMemcpyAsync(p, h->stage[slot].d, bytes, cudaMemcpyDeviceToHost, h->stream));
+    st->d2h_bytes += (long long)bytes;
+}
+
+bool box_covers(const b200np_fab* b, const int lo[3], const int hi[3], int ncomp)
+{
+    if (!b || b->ncomp < ncomp) return false;
+    for (int d = 0; d < 3; ++d) if (b->lo[d] > lo[d] || b->hi[d] < hi[d]) return false;
+    return true;
+}
+
+// the common core: rhs = D vel; solve; vel -= sigma G phi; gphi, phi copy-out.
+int project_core(b200np* h, Fab vel, Fab velo, int add_old, Fab gphi, int acc_g, Fab pout, int acc_p, double rtol,
+                 double atol, b200np_stats* st)
+{
+    LevelData& L0 = h->lv[0];
+    coarsen_sigma(h);
+    LAUNCH(h, k_divu, L0.gn, 256, L0.g, vel, L0.rhs);
+    CK(cudaMemsetAsync(L0.sol - L0.g.ps, 0, (size_t)L0.g.ps * (L0.g.nzl + 2) * sizeof(double), h->stream));
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    int status = mlmg_solve(h, rtol, atol, st);
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    LAUNCH(h, k_mknewu, L0.gc, 256, L0.g, L0.sol, vel, velo, add_old, gphi, acc_g);
+    if (pout.p) {
+        dim3 g((pout.nx + 63) / 64, (pout.ny + 3) / 4, pout.nz);
+        LAUNCH(h, k_copy_phi, g, 256, L0.g, L0.sol, pout, acc_p);
+    }
+    return status;
+}
+
+void finish_stats(b200np* h, b200np_stats* st)
+{
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    CK(cudaEventSynchronize(h->ev[1]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); st->ms_total = ms;
+    CK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); st->ms_solve = ms;
+    st->launches = h->launches;
+}
+
+int check_geom(const b200np_geom* g)
+{
+    for (int d = 0; d < 3; ++d) {
+        if (g->n_cell[d] < 2 || !(g->dx[d] > 0)) return B200NP_ERR_BAD_ARG;
+        if (g->bc_lo[d] < 0 || g->bc_lo[d] > 3 || g->bc_hi[d] < 0 || g->bc_hi[d] > 3) return B200NP_ERR_BAD_BC;
+        if ((g->bc_lo[d] == B200NP_BC_PERIODIC) != (g->bc_hi[d] == B200NP_BC_PERIODIC)) return B200NP_ERR_BAD_BC;
+    }
+    return B200NP_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" {
+
+void b200np_default_opts(b200np_opts* o)
+{
+    memset(o, 0, sizeof(*o));
+    o->verbose = 0; o->bottom_verbose = 0;
+    o->maxiter = 100; o->bottom_maxiter = 100;
+    o->bottom_rtol = 1e-4; o->bottom_atol = -1.0;
+    o->mg_max_coarsening_level = 100;  // src/incflo.H:458
+    o->num_pre_smooth = 2; o->num_post_smooth = 2; o->smooth_num_sweeps = 4;
+    o->bottom_solver = 0;
+    o->tile[0] = NP_TX; o->tile[1] = NP_TY; o->tile[2] = 16;
+    o->use_graph = 1;
+}
+
+int b200np_version(void) { return B200NP_VERSION; }
+
+const char* b200np_strerror(int s)
+{
+    switch (s) {
+    case B200NP_OK: return "ok";
+    case B200NP_ERR_NOT_CONVERGED: return "MLMG failed to converge within maxiter";
+    case B200NP_ERR_DIVERGED: return "MLMG is diverging";
+    case B200NP_ERR_BAD_BC: return "get_projection_bc: undefined BC type";
+    case B200NP_ERR_BAD_ARG: return "bad argument";
+    case B200NP_ERR_CUDA: return "CUDA error / no usable sm_100 device (there is no CPU fallback)";
+    case B200NP_ERR_NCCL: return "NCCL error";
+    case B200NP_ERR_UNSUPPORTED: return "not supported by this build";
+    default: return "unknown status";
+    }
+}
+
+int b200np_create(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device)
+{
+    if (!out || !geom) return B200NP_ERR_BAD_ARG;
+    *out = nullptr;
+    int rc = check_geom(geom);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return B200NP_ERR_CUDA;
+    }
+    b200np* h = new b200np();
+    try {
+        CK(cudaSetDevice(device));
+        h->device = device;
+        h->geom = *geom;
+        if (opts) h->opts = *opts; else b200np_default_opts(&h->opts);
+        if (h->opts.tile[0] != NP_TX || h->opts.tile[1] != NP_TY || h->opts.tile[2] < 1) { delete h; return B200NP_ERR_BAD_ARG; }
+        h->TZ = h->opts.tile[2];
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (auto& e : h->ev) CK(cudaEventCreate(&e));
+        build_hierarchy(h);
+        CK(cudaDeviceSynchronize());
+    } catch (int e) {
+        b200np_destroy(h);
+        return e;
+    }
+    *out = h;
+    return B200NP_OK;
+}
+
+int b200np_create_dist(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device, int rank,
+                       int nranks, const void* nccl_unique_id)
+{
+    if (nranks == 1) return b200np_create(out, geom, opts, device);
+    (void)rank; (void)nccl_unique_id;
+    if (out) *out = nullptr;
+    return B200NP_ERR_UNSUPPORTED;
+}
+
+void b200np_destroy(b200np_t* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    for (auto& L : h->lv) {
+        for (double* p : L.allocs) cudaFree(p);
+        cudaFree(L.sigma_alloc);
+    }
+    cudaFree(h->partial); cudaFree(h->dscal); cudaFree(h->dinfo); cudaFree(h->bottom_work);
+    if (h->hscal) cudaFreeHost(h->hscal);
+    if (h->hinfo) cudaFreeHost(h->hinfo);
+    for (auto& s : h->stage) if (s.d) cudaFree(s.d);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int b200np_nlevels(const b200np_t* h) { return h ? (int)h->lv.size() : 0; }
+
+int b200np_level_dims(const b200np_t* h, int lev, int n_cell[3], int n_node[3])
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size()) return B200NP_ERR_BAD_ARG;
+    for (int d = 0; d < 3; ++d) { n_cell[d] = h->lv[lev].g.n[d]; n_node[d] = h->lv[lev].g.nn[d]; }
+    return B200NP_OK;
+}
+
+int b200np_set_sigma(b200np_t* h, const double* sigma, const b200np_fab* sigma_box, double const_sigma)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        LevelData& L0 = h->lv[0];
+        if (sigma) {
+            const int lo[3] = {0, 0, L0.g.ck0}, hi[3] = {L0.g.n[0] - 1, L0.g.n[1] - 1, L0.g.ck0 + L0.g.cnzl - 1};
+            if (!box_covers(sigma_box, lo, hi, 1)) return B200NP_ERR_BAD_ARG;
+            b200np_stats st{};
+            bool staged;
+            double* d = stage_in(h, 3, sigma, sigma_box, true, &staged, &st);
+            set_level_sigma_ptrs(h, true, 1.0);
+            LAUNCH(h, k_copy_sigma, L0.gc, 256, L0.g, make_fab(d, sigma_box), L0.sigma);
+        } else {
+            set_level_sigma_ptrs(h, false, const_sigma);
+        }
+        coarsen_sigma(h);
+        CK(cudaStreamSynchronize(h->stream));
+    } catch (int e) { return e; }
+    return B200NP_OK;
+}
+
+int b200np_project(b200np_t* h, double* vel, const b200np_fab* vel_box, const double* sigma, const b200np_fab* sigma_box,
+                   double const_sigma, double* phi, const b200np_fab* phi_box, double* gphi, const b200np_fab* gphi_box,
+                   double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h || !vel || !vel_box) return st->status = B200NP_ERR_BAD_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        LevelData& L0 = h->lv[0];
+        const Lev& g = L0.g;
+        const int clo[3] = {0, 0, g.ck0}, chi[3] = {g.n[0] - 1, g.n[1] - 1, g.ck0 + g.cnzl - 1};
+        if (!box_covers(vel_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
+        for (int d = 0; d < 3; ++d)  // a ghost layer is an input at non-periodic faces
+            if (!g.per[d] && (vel_box->lo[d] > -1 || vel_box->hi[d] < g.n[d])) return st->status = B200NP_ERR_BAD_ARG;
+        if (sigma && !box_covers(sigma_box, clo, chi, 1)) return st->status = B200NP_ERR_BAD_ARG;
+        if (gphi && !box_covers(gphi_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
+        if (phi && (!phi_box || phi_box->ncomp < 1)) return st->status = B200NP_ERR_BAD_ARG;
+        h->launches = 0;
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        bool s_vel, s_sig, s_phi = false, s_g = false;
+        double* dvel = stage_in(h, 0, vel, vel_box, true, &s_vel, st);
+        const double* dsig = stage_in(h, 3, sigma, sigma_box, true, &s_sig, st);
+        double* dphi = phi ? stage_in(h, 5, phi, phi_box, false, &s_phi, st) : nullptr;
+        double* dg = gphi ? stage_in(h, 4, gphi, gphi_box, false, &s_g, st) : nullptr;
+        CK(cudaEventRecord(h->ev[4], h->stream));
+        if (sigma) {
+            set_level_sigma_ptrs(h, true, 1.0);
+            LAUNCH(h, k_copy_sigma, L0.gc, 256, L0.g, make_fab(const_cast<double*>(dsig), sigma_box), L0.sigma);
+        } else {
+            set_level_sigma_ptrs(h, false, const_sigma);
+        }
+        int status = project_core(h, make_fab(dvel, vel_box), Fab{}, 0, make_fab(dg, gphi_box), 0,
+                                  make_fab(dphi, phi_box), 0, rtol, atol, st);
+        CK(cudaEventRecord(h->ev[5], h->stream));
+        stage_out(h, 0, vel, vel_box, s_vel, st);
+        stage_out(h, 5, phi, phi_box, s_phi, st);
+        stage_out(h, 4, gphi, gphi_box, s_g, st);
+        finish_stats(h, st);
+        float ms;
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); st->ms_h2d = ms;
+        CK(cudaEventElapsedTime(&ms, h->ev[5], h->ev[1])); st->ms_d2h = ms;
+        return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fab* vel_box, const double* velocity_o,
+                                  const double* density, const b200np_fab* rho_box, double ro_0, double* gp,
+                                  const b200np_fab* gp_box, double* p_nd, const b200np_fab* p_box, const double* inflow_vel,
+                                  double scaling_factor, int incremental, int proj_for_small_dt, double rtol, double atol,
+                                  b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h || !velocity || !vel_box || !gp || !gp_box || !p_nd || !p_box) return st->status = B200NP_ERR_BAD_ARG;
+    const int use_old = (incremental || proj_for_small_dt);
+    if (use_old && !velocity_o) return st->status = B200NP_ERR_BAD_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        LevelData& L0 = h->lv[0];
+        const Lev& g = L0.g;
+        const int clo[3] = {0, 0, g.ck0}, chi[3] = {g.n[0] - 1, g.n[1] - 1, g.ck0 + g.cnzl - 1};
+        if (!box_covers(vel_box, clo, chi, 3) || !box_covers(gp_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
+        if (density && !box_covers(rho_box, clo, chi, 1)) return st->status = B200NP_ERR_BAD_ARG;
+        for (int d = 0; d < 3; ++d)
+            if (!g.per[d] && (vel_box->lo[d] > -1 || vel_box->hi[d] < g.n[d])) return st->status = B200NP_ERR_BAD_ARG;
+        h->launches = 0;
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        bool s_vel, s_velo, s_rho, s_gp, s_p, s_in;
+        double* dvel = stage_in(h, 0, velocity, vel_box, true, &s_vel, st);
+        double* dvelo = stage_in(h, 1, use_old ? velocity_o : nullptr, vel_box, true, &s_velo, st);
+        double* drho = stage_in(h, 2, density, rho_box, true, &s_rho, st);
+        double* dgp = stage_in(h, 4, gp, gp_box, true, &s_gp, st);   // gp is an input in both modes
+        double* dp = stage_in(h, 5, p_nd, p_box, incremental != 0, &s_p, st);
+        const int set_inflow = (!proj_for_small_dt && !incremental);   // :81
+        double* din = stage_in(h, 6, set_inflow ? inflow_vel : nullptr, vel_box, true, &s_in, st);
+        CK(cudaEventRecord(h->ev[4], h->stream));
+        Fab fvel = make_fab(dvel, vel_box), fvelo = make_fab(dvelo, vel_box), frho = make_fab(drho, rho_box),
+            fgp = make_fab(dgp, gp_box), fp = make_fab(dp, p_box), fin = make_fab(din, vel_box);
+        // :39-71, :101-121 fused
+        set_level_sigma_ptrs(h, density != nullptr, scaling_factor / ro_0);
+        if (!incremental || use_old || density)
+            LAUNCH(h, k_pre_add_sigma, L0.gc, 256, L0.g, fvel, fgp, frho, fvelo, scaling_factor, ro_0, incremental ? 0 : 1,
+                   use_old, density ? L0.sigma : nullptr);
+        // :137-163
+        {
+            long long total = (long long)fvel.nx * fvel.ny * fvel.nz;
+            int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+            LAUNCH(h, k_set_vel_ghosts, blocks, 256, L0.g, fvel, fin, set_inflow);
+        }
+        // :181-256
+        int status = project_core(h, fvel, fvelo, use_old, fgp, incremental, fp, incremental, rtol, atol, st);
+        CK(cudaEventRecord(h->ev[5], h->stream));
+        stage_out(h, 0, velocity, vel_box, s_vel, st);
+        stage_out(h, 4, gp, gp_box, s_gp, st);
+        stage_out(h, 5, p_nd, p_box, s_p, st);
+        finish_stats(h, st);
+        float ms;
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); st->ms_h2d = ms;
+        CK(cudaEventElapsedTime(&ms, h->ev[5], h->ev[1])); st->ms_d2h = ms;
+        return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+// ---- test hooks ---------------------------------------------------------------------------
+static double* level_array(b200np* h, int lev, int which)
+{
+    LevelData& L = h->lv[lev];
+    switch (which) {
+    case B200NP_A_SOL: return L.sol;
+    case B200NP_A_RHS: return L.rhs;
+    case B200NP_A_RES: return L.res;
+    case B200NP_A_COR: return L.cor;
+    case B200NP_A_RESCOR: return L.rescor;
+    case B200NP_A_SIGMA: return L.sigma;
+    default: return nullptr;
+    }
+}
+
+int b200np_level_set(b200np_t* h, int lev, int which, const double* host)
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size() || !host) return B200NP_ERR_BAD_ARG;
+    double* d = level_array(h, lev, which);
+    if (!d) return B200NP_ERR_BAD_ARG;
+    const Lev& g = h->lv[lev].g;
+    try {
+        CK(cudaSetDevice(h->device));
+        if (which == B200NP_A_SIGMA)
+            CK(cudaMemcpy2D(d, g.cpx * sizeof(double), host, g.n[0] * sizeof(double), g.n[0] * sizeof(double),
+                            (size_t)g.n[1] * g.cnzl, cudaMemcpyHostToDevice));
+        else
+            CK(cudaMemcpy2D(d, g.px * sizeof(double), host, g.nn[0] * sizeof(double), g.nn[0] * sizeof(double),
+                            (size_t)g.nn[1] * g.nzl, cudaMemcpyHostToDevice));
+    } catch (int e) { return e; }
+    return B200NP_OK;
+}
+
+int b200np_level_get(b200np_t* h, int lev, int which, double* host)
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size() || !host) return B200NP_ERR_BAD_ARG;
+    double* d = level_array(h, lev, which);
+    if (!d) return B200NP_ERR_BAD_ARG;
+    const Lev& g = h->lv[lev].g;
+    try {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        if (which == B200NP_A_SIGMA)
+            CK(cudaMemcpy2D(host, g.n[0] * sizeof(double), d, g.cpx * sizeof(double), g.n[0] * sizeof(double),
+                            (size_t)g.n[1] * g.cnzl, cudaMemcpyDeviceToHost));
+        else
+            CK(cudaMemcpy2D(host, g.nn[0] * sizeof(double), d, g.px * sizeof(double), g.nn[0] * sizeof(double),
+                            (size_t)g.nn[1] * g.nzl, cudaMemcpyDeviceToHost));
+    } catch (int e) { return e; }
+    return B200NP_OK;
+}
+
+static int run_op(b200np* h, int lev, int op, int arg)
+{
+    const int nl = (int)h->lv.size();
+    LevelData& L = h->lv[lev];
+    switch (op) {
+    case B200NP_OP_SMOOTH: {
+        double *x = L.cor, *y = L.cor2;
+        smooth_sweeps(h, L, x, y, L.res, arg);
+        if (x != L.cor) CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        break;
+    }
+    case B200NP_OP_RESIDUAL: residual(h, L, L.cor, L.res, L.rescor, nullptr); break;
+    case B200NP_OP_RESTRICT: if (lev + 1 >= nl) return B200NP_ERR_BAD_ARG; restrict_to(h, lev); break;
+    case B200NP_OP_INTERP: if (lev + 1 >= nl) return B200NP_ERR_BAD_ARG; interp_add(h, lev); break;
+    case B200NP_OP_BOTTOM: bottom_solve(h); break;
+    case B200NP_OP_VCYCLE: vcycle_launch(h, 0); break;
+    case B200NP_OP_COARSEN_SIGMA: coarsen_sigma(h); break;
+    default: return B200NP_ERR_BAD_ARG;
+    }
+    return B200NP_OK;
+}
+
+int b200np_level_op(b200np_t* h, int lev, int op, int arg)
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size()) return B200NP_ERR_BAD_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        int rc = run_op(h, lev, op, arg);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        return rc;
+    } catch (int e) { return e; }
+}
+
+int b200np_time_op(b200np_t* h, int lev, int op, int arg, int reps, double* ms)
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size() || reps < 1 || !ms) return B200NP_ERR_BAD_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        int rc = run_op(h, lev, op, arg);  // warm-up
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaEventRecord(h->ev[0], h->stream));
+        for (int r = 0; r < reps; ++r) run_op(h, lev, op, arg);
+        CK(cudaEventRecord(h->ev[1], h->stream));
+        CK(cudaEventSynchronize(h->ev[1]));
+        float t;
+        CK(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+        *ms = t / reps;
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+}  // extern "C"

@@ -1,0 +1,801 @@
+// np_kernels.cuh -- sm_100a kernels of the nodal projection (one GPU's slab of one level each).
+//
+// Kernel inventory (reference function replaced -> kernel), SURVEY.md 2.4 / DESIGN.md section 4:
+//   K1  incflo_apply_nodal_projection.cpp:53-59,:68,:115-118      -> k_pre_add_sigma
+//   K2  mlndlap_divu + mlndlap_impose_neumann_bc (A.2)            -> k_divu
+//   K3  mlndlap_adotx_{aa,c} / solutionResidual (A.3)             -> k_residual
+//   K4  mlndlap_gauss_seidel_{aa,c} / mlndlap_gscolor (A.4)       -> k_smooth_tile
+//   K5  mlndlap_restriction (A.5)                                 -> k_restrict
+//   K6  mlndlap_interpadd_{aa,c} (A.6)                            -> k_interp_add
+//   K7  mlndlap_mknewu{,_c} + copy-out :221-256 (A.7)             -> k_mknewu, k_copy_phi
+//   K8  MLCGSolver BiCGStab / CG (A.10)                           -> k_bottom_bicgstab (one CTA)
+//   K9  average_down of sigma (A.8)                               -> k_coarsen_sigma
+#pragma once
+#include "np_level.h"
+
+namespace b200np_dev {
+
+#define NP_TX 64
+#define NP_TY 16
+
+// ------------------------------------------------------------------------------------------
+// generic gathers from global memory (used by the small / non-critical kernels)
+// ------------------------------------------------------------------------------------------
+template <bool VAR>
+__device__ __forceinline__ void gather_sigma_g(const Lev& L, int i, int j, int kl, double (&S)[2][2][2])
+{
+    if (!VAR) return;
+    int ci[2] = {cmap(i - 1, L.n[0], L.per[0]), cmap(i, L.n[0], L.per[0])};
+    int cj[2] = {cmap(j - 1, L.n[1], L.per[1]), cmap(j, L.n[1], L.per[1])};
+    int ck[2] = {czplane(L, kl - 1), czplane(L, kl)};
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) S[c][b][a] = __ldg(L.sigma + ck[c] * L.cps + (long long)cj[b] * L.cpx + ci[a]);
+}
+
+__device__ __forceinline__ void gather_phi_g(const Lev& L, const double* __restrict__ phi, int i, int j, int kl,
+                                             double (&P)[3][3][3])
+{
+    int ix[3], jy[3], kz[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        ix[a] = nmap(i - 1 + a, L.n[0], L.per[0]);
+        jy[a] = nmap(j - 1 + a, L.n[1], L.per[1]);
+        kz[a] = zplane(L, kl - 1 + a);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) P[c][b][a] = phi[kz[c] * L.ps + (long long)jy[b] * L.px + ix[a]];
+}
+
+template <bool VAR>
+__device__ __forceinline__ double node_Lphi_g(const Lev& L, const double* __restrict__ phi, int i, int j, int kl, double& s0)
+{
+    double P[3][3][3];
+    gather_phi_g(L, phi, i, j, kl, P);
+    if (VAR) {
+        double S[2][2][2];
+        gather_sigma_g<true>(L, i, j, kl, S);
+        return stencil27(L, S, P, s0);
+    }
+    return stencil27_c(L, L.csig, P, s0);
+}
+
+// ------------------------------------------------------------------------------------------
+// block reductions (warp shuffles + one smem hop)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// all threads of the block must call; result valid in every thread
+template <bool MAX>
+__device__ __forceinline__ double block_reduce(double v, double* sh /* >= 33 doubles */)
+{
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = MAX ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double x = lane < nw ? sh[lane] : (MAX ? 0.0 : 0.0);
+        x = MAX ? warp_max(x) : warp_sum(x);
+        if (lane == 0) sh[32] = x;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: tile-resident Gauss-Seidel sweep.
+// One CTA owns a tile of NP_TX x NP_TY node columns and marches through TZ planes.  Inside the
+// tile the update order is: planes in ascending k, and inside a plane the 4 colours
+// c = (i&1) + 2(j&1) in order 0..3 (nodes of one colour in a plane are not coupled).  Values
+// outside the tile (x/y halo ring, the plane below the chunk and the plane above it) are taken
+// from the previous sweep (pin); results go to pout (ping-pong), so the sweep is deterministic
+// and independent of CTA scheduling and of the number of GPUs as long as chunk boundaries are
+// aligned with slab boundaries.  This is AMReX's multi-box Gauss-Seidel semantics (A.4: no halo
+// refresh inside a box sweep) with box == tile and one sweep per refresh.
+// Algorithmic traffic: 8 R + 8 W (phi) + 8 R (rhs) + 8 R (sigma) = 32 B/node (24 B const sigma).
+// ------------------------------------------------------------------------------------------
+template <bool VAR>
+__global__ void __launch_bounds__(256) k_smooth_tile(const Lev L, const double* __restrict__ pin,
+                                                     double* __restrict__ pout, const double* __restrict__ rhs, int TZ)
+{
+    constexpr int SX = NP_TX + 2, SY = NP_TY + 2, CX = NP_TX + 1, CY = NP_TY + 1;
+    __shared__ double sphi[3][SY][SX];
+    __shared__ double ssig[VAR ? 2 : 1][VAR ? CY : 1][VAR ? CX : 1];
+
+    const int tid = threadIdx.x;
+    const int i0 = blockIdx.x * NP_TX, j0 = blockIdx.y * NP_TY;
+    const int kc0 = blockIdx.z * TZ;
+    const int kc1 = min(kc0 + TZ, L.nzl);
+
+    // per-thread column offsets for the staged loads (fixed for the whole march)
+    int poff[5], coff[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        int idx = tid + s * 256;
+        poff[s] = -1; coff[s] = -1;
+        if (idx < SX * SY) {
+            int lx = idx % SX, ly = idx / SX;
+            int gi = i0 - 1 + lx, gj = j0 - 1 + ly;
+            if (gi <= L.n[0] + 1 && gj <= L.n[1] + 1 && (L.per[0] ? gi <= L.n[0] : true) && (L.per[1] ? gj <= L.n[1] : true))
+                poff[s] = nmap(gj, L.n[1], L.per[1]) * L.px + nmap(gi, L.n[0], L.per[0]);
+        }
+        if (VAR && idx < CX * CY) {
+            int lx = idx % CX, ly = idx / CX;
+            int gi = i0 - 1 + lx, gj = j0 - 1 + ly;
+            if (gi <= L.n[0] && gj <= L.n[1])
+                coff[s] = cmap(gj, L.n[1], L.per[1]) * L.cpx + cmap(gi, L.n[0], L.per[0]);
+        }
+    }
+    auto load_phi = [&](int kl) {  // kl in [-1, nzl]
+        const double* src = pin + zplane(L, kl) * L.ps;
+        double* dst = &sphi[(kl + 1) % 3][0][0];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            int idx = tid + s * 256;
+            if (idx < SX * SY) dst[idx] = poff[s] >= 0 ? src[poff[s]] : 0.0;
+        }
+    };
+    auto load_sig = [&](int cl) {  // cell layer cl in [-1, cnzl]
+        if (!VAR) return;
+        const double* src = L.sigma + czplane(L, cl) * L.cps;
+        double* dst = &ssig[(cl + 1) & 1][0][0];
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            int idx = tid + s * 256;
+            if (idx < CX * CY) dst[idx] = coff[s] >= 0 ? __ldg(src + coff[s]) : 0.0;
+        }
+    };
+
+    load_phi(kc0 - 1);
+    load_phi(kc0);
+    load_sig(kc0 - 1);
+
+    const int tx = tid & 31, ty = tid >> 5;
+    for (int kl = kc0; kl < kc1; ++kl) {
+        load_phi(kl + 1);
+        load_sig(kl);
+        __syncthreads();
+        const int kg = kl + L.k0;
+        const double(*pm)[SX] = sphi[(kl) % 3];      // plane kl-1
+        double(*p0)[SX] = sphi[(kl + 1) % 3];        // plane kl
+        const double(*pp)[SX] = sphi[(kl + 2) % 3];  // plane kl+1
+#pragma unroll 1
+        for (int color = 0; color < 4; ++color) {
+            const int li = 2 * tx + (color & 1), lj = 2 * ty + (color >> 1);
+            const int gi = i0 + li, gj = j0 + lj;
+            if (gi < L.nn[0] && gj < L.nn[1]) {
+                double P[3][3][3];
+#pragma unroll
+                for (int b = 0; b < 3; ++b)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        P[0][b][a] = pm[lj + b][li + a];
+                        P[1][b][a] = p0[lj + b][li + a];
+                        P[2][b][a] = pp[lj + b][li + a];
+                    }
+                double s0, Ax;
+                if (VAR) {
+                    double S[2][2][2];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int b = 0; b < 2; ++b)
+#pragma unroll
+                            for (int a = 0; a < 2; ++a) S[c][b][a] = ssig[(kl + c) & 1][lj + b][li + a];
+                    Ax = stencil27(L, S, P, s0);
+                } else {
+                    Ax = stencil27_c(L, L.csig, P, s0);
+                }
+                double r = rhs[kl * L.ps + (long long)gj * L.px + gi];
+                double v = node_masked(L, gi, gj, kg) ? 0.0 : P[1][1][1] + (r - Ax) / s0;
+                p0[lj + 1][li + 1] = v;
+            }
+            __syncthreads();
+        }
+        // write the finished plane (interior of the tile) to the output array
+        double* dst = pout + kl * L.ps;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            int idx = tid + s * 256;
+            int lx = idx % NP_TX, ly = idx / NP_TX;
+            int gi = i0 + lx, gj = j0 + ly;
+            if (gi < L.nn[0] && gj < L.nn[1]) dst[(long long)gj * L.px + gi] = p0[ly + 1][lx + 1];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: res = rhs - L phi (masked nodes -> 0); optional fused inf-norm partials.
+// Algorithmic traffic 32 B/node (24 B const sigma).
+// ------------------------------------------------------------------------------------------
+template <bool VAR>
+__global__ void __launch_bounds__(256) k_residual(const Lev L, const double* __restrict__ phi,
+                                                  const double* __restrict__ rhs, double* __restrict__ res,
+                                                  double* __restrict__ norm_partial)
+{
+    __shared__ double sh[34];
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int kl = blockIdx.z;
+    double a = 0.0;
+    if (i < L.nn[0] && j < L.nn[1]) {
+        long long id = kl * L.ps + (long long)j * L.px + i;
+        double r = 0.0;
+        if (!node_masked(L, i, j, kl + L.k0)) {
+            double s0;
+            r = rhs[id] - node_Lphi_g<VAR>(L, phi, i, j, kl, s0);
+        }
+        res[id] = r;
+        a = fabs(r);
+    }
+    if (norm_partial) {
+        a = block_reduce<true>(a, sh);
+        if (threadIdx.x == 0) norm_partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: full-weighting restriction (A.5).  One thread per coarse node.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_restrict(const Lev F, const Lev C, const double* __restrict__ fine,
+                                                  double* __restrict__ crse)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int kl = blockIdx.z;  // coarse local plane
+    if (i >= C.nn[0] || j >= C.nn[1]) return;
+    long long id = kl * C.ps + (long long)j * C.px + i;
+    if (node_masked(C, i, j, kl + C.k0)) { crse[id] = 0.0; return; }
+    const int fk = 2 * (kl + C.k0) - F.k0;  // fine local plane
+    double s = 0.0;
+#pragma unroll
+    for (int c = -1; c <= 1; ++c) {
+        const double* pl = fine + zplane(F, fk + c) * F.ps;
+#pragma unroll
+        for (int b = -1; b <= 1; ++b) {
+            const double* row = pl + (long long)nmap(2 * j + b, F.n[1], F.per[1]) * F.px;
+#pragma unroll
+            for (int a = -1; a <= 1; ++a) {
+                double w = (a ? 1.0 : 2.0) * (b ? 1.0 : 2.0) * (c ? 1.0 : 2.0);
+                s += w * row[nmap(2 * i + a, F.n[0], F.per[0])];
+            }
+        }
+    }
+    crse[id] = s * (1.0 / 64.0);
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: sigma-weighted trilinear prolongation, added to the fine correction (A.6).
+// ------------------------------------------------------------------------------------------
+template <bool VAR>
+struct Interp {
+    const Lev& F;
+    const Lev& C;
+    const double* crse;
+    int fk0;  // F.k0
+    __device__ __forceinline__ double sg(int i, int j, int kl) const
+    {
+        if (!VAR) return 1.0;
+        return __ldg(F.sigma + czplane(F, kl) * F.cps + (long long)cmap(j, F.n[1], F.per[1]) * F.cpx + cmap(i, F.n[0], F.per[0]));
+    }
+    // coarse value at coarse global index (ic, jc, kcg)
+    __device__ __forceinline__ double cr(int ic, int jc, int kcg) const
+    {
+        return crse[zplane(C, kcg - C.k0) * C.ps + (long long)nmap(jc, C.n[1], C.per[1]) * C.px + nmap(ic, C.n[0], C.per[0])];
+    }
+    __device__ __forceinline__ double qx(int i, int j, int k, int side) const
+    {
+        int ii = i - 1 + side;
+        return sg(ii, j - 1, k - 1) + sg(ii, j, k - 1) + sg(ii, j - 1, k) + sg(ii, j, k);
+    }
+    __device__ __forceinline__ double qy(int i, int j, int k, int side) const
+    {
+        int jj = j - 1 + side;
+        return sg(i - 1, jj, k - 1) + sg(i, jj, k - 1) + sg(i - 1, jj, k) + sg(i, jj, k);
+    }
+    __device__ __forceinline__ double qz(int i, int j, int k, int side) const
+    {
+        int kk = k - 1 + side;
+        return sg(i - 1, j - 1, kk) + sg(i, j - 1, kk) + sg(i - 1, j, kk) + sg(i, j, kk);
+    }
+    // (i,j,k): fine node, k local; (ic,jc,kc): coarse node below it, kc global
+    __device__ __forceinline__ double line_x(int i, int j, int k, int ic, int jc, int kc) const
+    {
+        double w1 = qx(i, j, k, 0), w2 = qx(i, j, k, 1);
+        return (w1 * cr(ic, jc, kc) + w2 * cr(ic + 1, jc, kc)) / (w1 + w2);
+    }
+    __device__ __forceinline__ double line_y(int i, int j, int k, int ic, int jc, int kc) const
+    {
+        double w1 = qy(i, j, k, 0), w2 = qy(i, j, k, 1);
+        return (w1 * cr(ic, jc, kc) + w2 * cr(ic, jc + 1, kc)) / (w1 + w2);
+    }
+    __device__ __forceinline__ double line_z(int i, int j, int k, int ic, int jc, int kc) const
+    {
+        double w1 = qz(i, j, k, 0), w2 = qz(i, j, k, 1);
+        return (w1 * cr(ic, jc, kc) + w2 * cr(ic, jc, kc + 1)) / (w1 + w2);
+    }
+    __device__ double face_xy(int i, int j, int k, int ic, int jc, int kc) const
+    {
+        double w1 = qx(i, j, k, 0), w2 = qx(i, j, k, 1), w3 = qy(i, j, k, 0), w4 = qy(i, j, k, 1);
+        return (w1 * line_y(i - 1, j, k, ic, jc, kc) + w2 * line_y(i + 1, j, k, ic + 1, jc, kc) +
+                w3 * line_x(i, j - 1, k, ic, jc, kc) + w4 * line_x(i, j + 1, k, ic, jc + 1, kc)) / (w1 + w2 + w3 + w4);
+    }
+    __device__ double face_xz(int i, int j, int k, int ic, int jc, int kc) const
+    {
+        double w1 = qx(i, j, k, 0), w2 = qx(i, j, k, 1), w3 = qz(i, j, k, 0), w4 = qz(i, j, k, 1);
+        return (w1 * line_z(i - 1, j, k, ic, jc, kc) + w2 * line_z(i + 1, j, k, ic + 1, jc, kc) +
+                w3 * line_x(i, j, k - 1, ic, jc, kc) + w4 * line_x(i, j, k + 1, ic, jc, kc + 1)) / (w1 + w2 + w3 + w4);
+    }
+    __device__ double face_yz(int i, int j, int k, int ic, int jc, int kc) const
+    {
+        double w1 = qy(i, j, k, 0), w2 = qy(i, j, k, 1), w3 = qz(i, j, k, 0), w4 = qz(i, j, k, 1);
+        return (w1 * line_z(i, j - 1, k, ic, jc, kc) + w2 * line_z(i, j + 1, k, ic, jc + 1, kc) +
+                w3 * line_y(i, j, k - 1, ic, jc, kc) + w4 * line_y(i, j, k + 1, ic, jc, kc + 1)) / (w1 + w2 + w3 + w4);
+    }
+};
+
+template <bool VAR>
+__global__ void __launch_bounds__(256) k_interp_add(const Lev F, const Lev C, double* __restrict__ fine,
+                                                    const double* __restrict__ crse)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int k = blockIdx.z;  // fine local plane
+    if (i >= F.nn[0] || j >= F.nn[1]) return;
+    const int kg = k + F.k0;
+    if (node_masked(F, i, j, kg)) return;
+    Interp<VAR> x{F, C, crse, F.k0};
+    const int ic = i >> 1, jc = j >> 1, kc = kg >> 1;
+    const int io = i & 1, jo = j & 1, ko = kg & 1;
+    double v;
+    if (io && jo && ko) {
+        double w1 = x.qx(i, j, k, 0), w2 = x.qx(i, j, k, 1), w3 = x.qy(i, j, k, 0), w4 = x.qy(i, j, k, 1),
+               w5 = x.qz(i, j, k, 0), w6 = x.qz(i, j, k, 1);
+        v = (w1 * x.face_yz(i - 1, j, k, ic, jc, kc) + w2 * x.face_yz(i + 1, j, k, ic + 1, jc, kc) +
+             w3 * x.face_xz(i, j - 1, k, ic, jc, kc) + w4 * x.face_xz(i, j + 1, k, ic, jc + 1, kc) +
+             w5 * x.face_xy(i, j, k - 1, ic, jc, kc) + w6 * x.face_xy(i, j, k + 1, ic, jc, kc + 1)) /
+            (w1 + w2 + w3 + w4 + w5 + w6);
+    } else if (jo && ko) v = x.face_yz(i, j, k, ic, jc, kc);
+    else if (io && ko)   v = x.face_xz(i, j, k, ic, jc, kc);
+    else if (io && jo)   v = x.face_xy(i, j, k, ic, jc, kc);
+    else if (io)         v = x.line_x(i, j, k, ic, jc, kc);
+    else if (jo)         v = x.line_y(i, j, k, ic, jc, kc);
+    else if (ko)         v = x.line_z(i, j, k, ic, jc, kc);
+    else                 v = x.cr(ic, jc, kc);
+    fine[k * F.ps + (long long)j * F.px + i] += v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K9: sigma on the next-coarser level = arithmetic mean of the 8 children (A.8)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_coarsen_sigma(const Lev F, const Lev C, const double* __restrict__ fs,
+                                                       double* __restrict__ cs)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int k = blockIdx.z;  // coarse local cell plane
+    if (i >= C.n[0] || j >= C.n[1]) return;
+    const int fk = 2 * (k + C.ck0) - F.ck0;
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double2 v = *reinterpret_cast<const double2*>(fs + (fk + c) * F.cps + (long long)(2 * j + b) * F.cpx + 2 * i);
+            s += v.x + v.y;
+        }
+    cs[k * C.cps + (long long)j * C.cpx + i] = 0.125 * s;
+}
+
+// ------------------------------------------------------------------------------------------
+// caller-side arrays (amrex::Array4 layout)
+// ------------------------------------------------------------------------------------------
+struct Fab {
+    double* p;
+    int lo[3];
+    int nx, ny, nz;   // extents of the grown box
+    long long cstride;
+    __host__ __device__ __forceinline__ long long idx(int i, int j, int k, int c) const
+    {
+        return (i - lo[0]) + (long long)nx * ((j - lo[1]) + (long long)ny * (k - lo[2])) + c * cstride;
+    }
+    __host__ __device__ __forceinline__ bool has(int i, int j, int k) const
+    {
+        return i >= lo[0] && i < lo[0] + nx && j >= lo[1] && j < lo[1] + ny && k >= lo[2] && k < lo[2] + nz;
+    }
+};
+
+// K1: u += s*gp/rho (when !incremental), u -= u_old (when sub_old), sigma = s/rho.
+// Also zeroes nothing: ghost handling is done by k_set_vel_ghosts.  One thread per valid cell.
+// Traffic: 24 R + 24 R + 8 R + 24 W + 8 W = 88 B/cell (variable density, non-incremental).
+__global__ void __launch_bounds__(256) k_pre_add_sigma(const Lev L, Fab vel, Fab gp, Fab rho, Fab velo, double s,
+                                                       double ro_0, int add_gp, int sub_old, double* __restrict__ sigma)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int kl = blockIdx.z;
+    if (i >= L.n[0] || j >= L.n[1]) return;
+    const int kg = kl + L.ck0;
+    double r = rho.p ? rho.p[rho.idx(i, j, kg, 0)] : ro_0;
+    double soverrho = s / r;
+    if (sigma) sigma[kl * L.cps + (long long)j * L.cpx + i] = soverrho;
+    if (add_gp || sub_old) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            long long vi = vel.idx(i, j, kg, c);
+            double u = vel.p[vi];
+            if (add_gp) u += gp.p[gp.idx(i, j, kg, c)] * soverrho;
+            if (sub_old) u -= velo.p[velo.idx(i, j, kg, c)];
+            vel.p[vi] = u;
+        }
+    }
+}
+
+// copies sigma from the caller's box into the level array
+__global__ void __launch_bounds__(256) k_copy_sigma(const Lev L, Fab sig, double* __restrict__ sigma)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int kl = blockIdx.z;
+    if (i >= L.n[0] || j >= L.n[1]) return;
+    sigma[kl * L.cps + (long long)j * L.cpx + i] = sig.p[sig.idx(i, j, kl + L.ck0, 0)];
+}
+
+// vel.setBndry(0.0) (:137) followed by the inflow fill of the first ghost layer (:138-163).
+// One thread per cell of the grown box; only ghost cells are touched.
+__global__ void __launch_bounds__(256) k_set_vel_ghosts(const Lev L, Fab vel, Fab inflow, int set_inflow)
+{
+    const long long total = (long long)vel.nx * vel.ny * vel.nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int i = (int)(t % vel.nx) + vel.lo[0];
+        int j = (int)((t / vel.nx) % vel.ny) + vel.lo[1];
+        int k = (int)(t / ((long long)vel.nx * vel.ny)) + vel.lo[2];
+        bool out = i < 0 || i >= L.n[0] || j < 0 || j >= L.n[1] || k < 0 || k >= L.n[2];
+        if (!out) continue;
+        bool infl = false;
+        if (set_inflow && inflow.p && i >= -1 && i <= L.n[0] && j >= -1 && j <= L.n[1] && k >= -1 && k <= L.n[2]) {
+            infl = (i < 0 && L.rlo[0] == 2) || (i >= L.n[0] && L.rhi[0] == 2) || (j < 0 && L.rlo[1] == 2) ||
+                   (j >= L.n[1] && L.rhi[1] == 2) || (k < 0 && L.rlo[2] == 2) || (k >= L.n[2] && L.rhi[2] == 2);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vel.p[vel.idx(i, j, k, c)] = infl ? inflow.p[inflow.idx(i, j, k, c)] : 0.0;
+    }
+}
+
+// K2: rhs = D u with the Neumann/inflow treatment of A.2.  One thread per owned node.
+// Traffic 24 B/cell R + 8 B/node W.
+__global__ void __launch_bounds__(256) k_divu(const Lev L, Fab vel, double* __restrict__ rhs)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int kl = blockIdx.z;
+    if (i >= L.nn[0] || j >= L.nn[1]) return;
+    const int kg = kl + L.k0;
+    long long id = kl * L.ps + (long long)j * L.px + i;
+    if (node_masked(L, i, j, kg)) { rhs[id] = 0.0; return; }
+    double zx[2] = {1.0, 1.0}, zy[2] = {1.0, 1.0}, zz[2] = {1.0, 1.0}, scale = 1.0;
+    if (!L.per[0]) { if (i == 0 && L.rlo[0]) { zx[0] = 0; scale *= 2; } if (i == L.n[0] && L.rhi[0]) { zx[1] = 0; scale *= 2; } }
+    if (!L.per[1]) { if (j == 0 && L.rlo[1]) { zy[0] = 0; scale *= 2; } if (j == L.n[1] && L.rhi[1]) { zy[1] = 0; scale *= 2; } }
+    if (!L.per[2]) { if (kg == 0 && L.rlo[2]) { zz[0] = 0; scale *= 2; } if (kg == L.n[2] && L.rhi[2]) { zz[1] = 0; scale *= 2; } }
+    // cell coordinates of the 2x2x2 block around the node; periodic ghosts wrap (FillBoundary)
+    int ci[2] = {i - 1, i}, cj[2] = {j - 1, j}, ck[2] = {kg - 1, kg};
+    if (L.per[0]) { ci[0] = cmap(ci[0], L.n[0], 1); ci[1] = cmap(ci[1], L.n[0], 1); }
+    if (L.per[1]) { cj[0] = cmap(cj[0], L.n[1], 1); cj[1] = cmap(cj[1], L.n[1], 1); }
+    if (L.per[2] && !L.dist) { ck[0] = cmap(ck[0], L.n[2], 1); ck[1] = cmap(ck[1], L.n[2], 1); }
+    double u[2][2][2], v[2][2][2], w[2][2][2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                bool ok = vel.has(ci[a], cj[b], ck[c]);
+                long long q = ok ? vel.idx(ci[a], cj[b], ck[c], 0) : 0;
+                u[c][b][a] = ok ? vel.p[q] : 0.0;
+                v[c][b][a] = ok ? vel.p[q + vel.cstride] : 0.0;
+                w[c][b][a] = ok ? vel.p[q + 2 * vel.cstride] : 0.0;
+            }
+    double dux = 0, dvy = 0, dwz = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            dux += (u[c][b][1] - u[c][b][0]) * zy[b] * zz[c];
+            dvy += (v[c][1][b] - v[c][0][b]) * zx[b] * zz[c];
+            dwz += (w[1][c][b] - w[0][c][b]) * zx[b] * zy[c];
+        }
+    rhs[id] = scale * 0.25 * (L.dxinv[0] * dux + L.dxinv[1] * dvy + L.dxinv[2] * dwz);
+}
+
+// K7: fused final update, one thread per valid cell:
+//   g = G phi;  vel -= sigma g;  (vel += vel_old);  gphi (=|+=) g
+// Traffic: 8 R phi + 8 R sigma + 24 R + 24 W vel + 24 W gp = 88 B/cell (+24 R when accumulating).
+__global__ void __launch_bounds__(256) k_mknewu(const Lev L, const double* __restrict__ phi, Fab vel, Fab velo, int add_old,
+                                                Fab gphi, int accumulate)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int kl = blockIdx.z;  // local cell plane
+    if (i >= L.n[0] || j >= L.n[1]) return;
+    const int kg = kl + L.ck0;
+    const int nl = kg - L.k0;  // local node plane of the cell's lower face
+    int ix[2] = {i, nmap(i + 1, L.n[0], L.per[0])}, jy[2] = {j, nmap(j + 1, L.n[1], L.per[1])};
+    int kz[2] = {nl, zplane(L, nl + 1)};
+    double P[2][2][2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) P[c][b][a] = phi[kz[c] * L.ps + (long long)jy[b] * L.px + ix[a]];
+    double g[3];
+    g[0] = 0.25 * L.dxinv[0] * ((P[0][0][1] - P[0][0][0]) + (P[0][1][1] - P[0][1][0]) + (P[1][0][1] - P[1][0][0]) + (P[1][1][1] - P[1][1][0]));
+    g[1] = 0.25 * L.dxinv[1] * ((P[0][1][0] - P[0][0][0]) + (P[0][1][1] - P[0][0][1]) + (P[1][1][0] - P[1][0][0]) + (P[1][1][1] - P[1][0][1]));
+    g[2] = 0.25 * L.dxinv[2] * ((P[1][0][0] - P[0][0][0]) + (P[1][0][1] - P[0][0][1]) + (P[1][1][0] - P[0][1][0]) + (P[1][1][1] - P[0][1][1]));
+    double sg = L.sigma ? L.sigma[kl * L.cps + (long long)j * L.cpx + i] : L.csig;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (vel.p) {
+            long long vi = vel.idx(i, j, kg, c);
+            double u = vel.p[vi] - sg * g[c];
+            if (add_old) u += velo.p[velo.idx(i, j, kg, c)];
+            vel.p[vi] = u;
+        }
+        if (gphi.p) {
+            long long gi = gphi.idx(i, j, kg, c);
+            gphi.p[gi] = accumulate ? gphi.p[gi] + g[c] : g[c];
+        }
+    }
+}
+
+// copy-out of phi into the caller's nodal box (p_nd (=|+=) phi, :235-253); duplicates the
+// periodic image nodes that the unique-node storage does not hold.
+__global__ void __launch_bounds__(256) k_copy_phi(const Lev L, const double* __restrict__ phi, Fab out, int accumulate)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63) + out.lo[0];
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6) + out.lo[1];
+    const int k = blockIdx.z + out.lo[2];
+    if (i >= out.lo[0] + out.nx || j >= out.lo[1] + out.ny) return;
+    if (i < 0 || i > L.n[0] || j < 0 || j > L.n[1] || k < 0 || k > L.n[2]) return;
+    int kl = zplane(L, k - L.k0);
+    double v = phi[kl * L.ps + (long long)nmap(j, L.n[1], L.per[1]) * L.px + nmap(i, L.n[0], L.per[0])];
+    long long o = out.idx(i, j, k, 0);
+    out.p[o] = accumulate ? out.p[o] + v : v;
+}
+
+// ------------------------------------------------------------------------------------------
+// small vector kernels over the owned nodes of a level
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_axpy(const Lev L, double* __restrict__ y, const double* __restrict__ x, double a)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= L.nn[0] || j >= L.nn[1]) return;
+    long long id = blockIdx.z * L.ps + (long long)j * L.px + i;
+    y[id] += a * x[id];
+}
+
+// partial[block] = sum w*x  and  sum w   (weighted mean for the solvability offset, A.8)
+__global__ void __launch_bounds__(256) k_wsum_partial(const Lev L, const double* __restrict__ x, double* __restrict__ partial)
+{
+    __shared__ double sh[34];
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int kl = blockIdx.z;
+    double w = 0.0, v = 0.0;
+    if (i < L.nn[0] && j < L.nn[1]) {
+        w = node_weight(L, i, j, kl + L.k0);
+        v = w * x[kl * L.ps + (long long)j * L.px + i];
+    }
+    v = block_reduce<false>(v, sh);
+    w = block_reduce<false>(w, sh);
+    if (threadIdx.x == 0) {
+        long long b = (blockIdx.z * gridDim.y + blockIdx.y) * (long long)gridDim.x + blockIdx.x;
+        partial[2 * b] = v; partial[2 * b + 1] = w;
+    }
+}
+// out[0] = sum partial[2b], out[1] = sum partial[2b+1] in a fixed order (deterministic)
+__global__ void __launch_bounds__(1024) k_sum2_final(const double* __restrict__ partial, long long nb, double* __restrict__ out)
+{
+    __shared__ double sh[34];
+    double a = 0, b = 0;
+    for (long long t = threadIdx.x; t < nb; t += blockDim.x) { a += partial[2 * t]; b += partial[2 * t + 1]; }
+    a = block_reduce<false>(a, sh);
+    b = block_reduce<false>(b, sh);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+__global__ void __launch_bounds__(1024) k_max_final(const double* __restrict__ partial, long long nb, double* __restrict__ out)
+{
+    __shared__ double sh[34];
+    double a = 0;
+    for (long long t = threadIdx.x; t < nb; t += blockDim.x) a = fmax(a, partial[t]);
+    a = block_reduce<true>(a, sh);
+    if (threadIdx.x == 0) out[0] = a;
+}
+// x -= sums[0]/sums[1] on unmasked owned nodes
+__global__ void __launch_bounds__(256) k_sub_mean(const Lev L, double* __restrict__ x, const double* __restrict__ sums)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= L.nn[0] || j >= L.nn[1]) return;
+    x[blockIdx.z * L.ps + (long long)j * L.px + i] -= sums[0] / sums[1];
+}
+__global__ void __launch_bounds__(256) k_norminf_partial(const Lev L, const double* __restrict__ x, double* __restrict__ partial)
+{
+    __shared__ double sh[34];
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    double a = 0.0;
+    if (i < L.nn[0] && j < L.nn[1]) a = fabs(x[blockIdx.z * L.ps + (long long)j * L.px + i]);
+    a = block_reduce<true>(a, sh);
+    if (threadIdx.x == 0) partial[(blockIdx.z * gridDim.y + blockIdx.y) * (long long)gridDim.x + blockIdx.x] = a;
+}
+// zero masked (Dirichlet) nodes of x
+__global__ void __launch_bounds__(256) k_zero_masked(const Lev L, double* __restrict__ x)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (i >= L.nn[0] || j >= L.nn[1]) return;
+    if (node_masked(L, i, j, blockIdx.z + L.k0)) x[blockIdx.z * L.ps + (long long)j * L.px + i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K8: bottom solve on the coarsest level in ONE CTA: BiCGStab (A.10) with a CG retry
+// (bottom_solver = bicgcg), all dot products / norms by warp-shuffle block reductions, no host
+// round trips.  The coarsest level lives on a single GPU (after agglomeration in the
+// multi-GPU case), so there is no collective either.
+//   work: 8 vectors of L.ps*nzl doubles (r, rh, p, v, s, t, b, tmp)
+//   info[0] = iterations, info[1] = return code (0 ok)
+// ------------------------------------------------------------------------------------------
+template <bool VAR>
+__device__ void bottom_apply(const Lev& L, const double* __restrict__ x, double* __restrict__ y)
+{
+    const int nxy = L.nn[0] * L.nn[1], ntot = nxy * L.nzl;
+    for (int t = threadIdx.x; t < ntot; t += blockDim.x) {
+        int kl = t / nxy, r = t - kl * nxy, j = r / L.nn[0], i = r - j * L.nn[0];
+        double s0, v = 0.0;
+        if (!node_masked(L, i, j, kl + L.k0)) v = node_Lphi_g<VAR>(L, x, i, j, kl, s0);
+        y[kl * L.ps + (long long)j * L.px + i] = v;
+    }
+    __syncthreads();
+}
+
+#define BOT_FOR_NODES(body)                                                        \
+    for (int t = threadIdx.x; t < ntot; t += blockDim.x) {                         \
+        int kl = t / nxy, rr = t - kl * nxy, j = rr / L.nn[0], i = rr - j * L.nn[0]; \
+        long long id = kl * L.ps + (long long)j * L.px + i;                        \
+        (void)i; (void)j; (void)kl;                                                \
+        body                                                                       \
+    }
+
+template <bool VAR>
+__global__ void __launch_bounds__(512) k_bottom_bicgstab(const Lev L, double* __restrict__ x, const double* __restrict__ b,
+                                                         double* __restrict__ work, int maxiter, double rtol, double atol,
+                                                         int singular, int nsweeps, int bottom_solver, int* __restrict__ info)
+{
+    __shared__ double sh[34];
+    const int nxy = L.nn[0] * L.nn[1], ntot = nxy * L.nzl;
+    const long long vs = L.ps * L.nzl;
+    double *r = work, *rh = work + vs, *p = work + 2 * vs, *v = work + 3 * vs, *s = work + 4 * vs, *t_ = work + 5 * vs,
+           *bb = work + 6 * vs;
+    // make the rhs solvable: subtract the weighted mean (A.8)
+    {
+        double sw = 0, sv = 0;
+        BOT_FOR_NODES({ double w = node_weight(L, i, j, kl + L.k0); sw += w; sv += w * b[id]; })
+        sv = block_reduce<false>(sv, sh);
+        sw = block_reduce<false>(sw, sh);
+        double off = singular ? sv / sw : 0.0;
+        BOT_FOR_NODES({ bb[id] = node_masked(L, i, j, kl + L.k0) ? 0.0 : b[id] - off; })
+        __syncthreads();
+    }
+    int total_iters = 0, ret = 0;
+    if (bottom_solver == 1) ret = 9;  // nodal_proj.bottom_solver = smoother
+    for (int attempt = 0; attempt < 2 && bottom_solver != 1; ++attempt) {
+        // attempt 0: BiCGStab, attempt 1: CG (bicgcg fallback)
+        double rn = 0;
+        BOT_FOR_NODES({ x[id] = 0.0; r[id] = bb[id]; rh[id] = bb[id]; rn = fmax(rn, fabs(bb[id])); })
+        const double rnorm0 = block_reduce<true>(rn, sh);
+        ret = 0;
+        if (rnorm0 == 0.0 || rnorm0 < atol) break;
+        double rho1 = 0, alpha = 0, omega = 0;
+        int it = 1;
+        bool done = false;
+        for (; it <= maxiter && !done; ++it) {
+            if (attempt == 0) {
+                double d = 0;
+                BOT_FOR_NODES({ d += node_weight(L, i, j, kl + L.k0) * rh[id] * r[id]; })
+                const double rho = block_reduce<false>(d, sh);
+                if (rho == 0.0) { ret = 1; break; }
+                if (it == 1) { BOT_FOR_NODES({ p[id] = r[id]; }) }
+                else {
+                    const double beta = (rho / rho1) * (alpha / omega);
+                    BOT_FOR_NODES({ p[id] = r[id] + beta * (p[id] - omega * v[id]); })
+                }
+                __syncthreads();
+                bottom_apply<VAR>(L, p, v);
+                d = 0;
+                BOT_FOR_NODES({ d += node_weight(L, i, j, kl + L.k0) * rh[id] * v[id]; })
+                const double rhTv = block_reduce<false>(d, sh);
+                if (rhTv == 0.0) { ret = 3; break; }
+                alpha = rho / rhTv;
+                double m = 0;
+                BOT_FOR_NODES({ x[id] += alpha * p[id]; double sv_ = r[id] - alpha * v[id]; s[id] = sv_; m = fmax(m, fabs(sv_)); })
+                double rnorm = block_reduce<true>(m, sh);
+                if (rnorm < rtol * rnorm0 || rnorm < atol) { done = true; break; }
+                bottom_apply<VAR>(L, s, t_);
+                double d1 = 0, d2 = 0;
+                BOT_FOR_NODES({ double w = node_weight(L, i, j, kl + L.k0); d1 += w * t_[id] * t_[id]; d2 += w * t_[id] * s[id]; })
+                const double tt = block_reduce<false>(d1, sh);
+                const double ts = block_reduce<false>(d2, sh);
+                if (tt == 0.0) { ret = 4; break; }
+                omega = ts / tt;
+                m = 0;
+                BOT_FOR_NODES({ x[id] += omega * s[id]; double rv = s[id] - omega * t_[id]; r[id] = rv; m = fmax(m, fabs(rv)); })
+                rnorm = block_reduce<true>(m, sh);
+                if (rnorm < rtol * rnorm0 || rnorm < atol) { done = true; break; }
+                if (omega == 0.0) { ret = 4; break; }
+                rho1 = rho;
+            } else {
+                double d = 0;
+                BOT_FOR_NODES({ d += node_weight(L, i, j, kl + L.k0) * r[id] * r[id]; })
+                const double rho = block_reduce<false>(d, sh);
+                if (rho == 0.0) { ret = 1; break; }
+                if (it == 1) { BOT_FOR_NODES({ p[id] = r[id]; }) }
+                else { const double beta = rho / rho1; BOT_FOR_NODES({ p[id] = r[id] + beta * p[id]; }) }
+                __syncthreads();
+                bottom_apply<VAR>(L, p, v);
+                d = 0;
+                BOT_FOR_NODES({ d += node_weight(L, i, j, kl + L.k0) * p[id] * v[id]; })
+                const double pq = block_reduce<false>(d, sh);
+                if (pq == 0.0) { ret = 1; break; }
+                alpha = rho / pq;
+                double m = 0;
+                BOT_FOR_NODES({ x[id] += alpha * p[id]; double rv = r[id] - alpha * v[id]; r[id] = rv; m = fmax(m, fabs(rv)); })
+                const double rnorm = block_reduce<true>(m, sh);
+                if (rnorm < rtol * rnorm0 || rnorm < atol) { done = true; break; }
+                rho1 = rho;
+            }
+        }
+        total_iters += (it > maxiter ? maxiter : it);
+        if (!done && ret == 0) ret = 8;
+        __syncthreads();
+        if (ret == 0) break;
+    }
+    if (ret != 0) {
+        // MLMG::actualBottomSolve fallback: cor = 0 then 8 smooth calls (A.9), here 8-colour GS in the CTA
+        BOT_FOR_NODES({ x[id] = 0.0; })
+        __syncthreads();
+        for (int sw = 0; sw < 8 * nsweeps; ++sw)
+            for (int color = 0; color < 8; ++color) {
+                BOT_FOR_NODES({
+                    if (((i & 1) + 2 * (j & 1) + 4 * ((kl + L.k0) & 1)) == color) {
+                        if (node_masked(L, i, j, kl + L.k0)) x[id] = 0.0;
+                        else { double s0; double Ax = node_Lphi_g<VAR>(L, x, i, j, kl, s0); x[id] += (bb[id] - Ax) / s0; }
+                    }
+                })
+                __syncthreads();
+            }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { atomicAdd(&info[0], total_iters); info[1] = ret; }
+}
+
+}  // namespace b200np_dev

@@ -1,0 +1,134 @@
+// np_level.h -- device-visible description of one multigrid level and the index maps
+// shared by every kernel.
+//
+// Data layout in HBM:
+//   * nodal fields are stored once per UNIQUE node: nn[d] = n[d] in a periodic direction,
+//     n[d]+1 otherwise; i fastest with pitch px (multiple of 8 doubles = 64 B), then j, then
+//     the locally owned z planes [k0, k0+nzl) plus one ghost plane slot on either side
+//     (slot -1 and slot nzl).  Ghost slots are only used by the slab-decomposed multi-GPU
+//     path; on one GPU the z neighbours are found by wrap / reflection like x and y.
+//   * cell fields (sigma): n[d] cells, pitch cpx, same ghost-plane-slot convention.
+// Boundary conditions follow MLNodeLinOp::applyBC: periodic wrap, Neumann /
+// inflow reflection phi(-1) = phi(1), Dirichlet nodes masked to 0; sigma ghost cells copy the
+// adjacent interior cell.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200np_dev {
+
+struct Lev {
+    int n[3];    // global cells
+    int nn[3];   // global unique nodes
+    int per[3];  // periodic
+    int rlo[3], rhi[3];  // Neumann / inflow (reflecting) face
+    int dlo[3], dhi[3];  // Dirichlet face
+    int px;              // node pitch in x (doubles)
+    long long ps;        // node plane stride
+    int cpx;             // cell pitch in x
+    long long cps;       // cell plane stride
+    int k0, nzl;         // owned node planes: global [k0, k0+nzl)
+    int ck0, cnzl;       // owned cell planes
+    int dist;            // 1: z neighbours live in ghost plane slots (multi-GPU slab)
+    double dxinv[3];
+    // stencil factors of mlndlap_adotx_aa
+    double fxyz, fmx2y2z, f2xmy2z, f2x2ymz, f4xm2ym2z, fm2x4ym2z, fm2xm2y4z;
+    double csig;          // constant sigma (used when sigma == nullptr)
+    const double* sigma;  // cell array, plane 0 of the owned range (ghost slot at -1)
+};
+
+// node index in [-1, n+1] -> unique storage index
+__host__ __device__ __forceinline__ int nmap(int i, int n, int per)
+{
+    if (per) { if (i < 0) i += n; else if (i >= n) i -= n; }
+    else     { if (i < 0) i = -i; else if (i > n) i = 2 * n - i; }
+    return i;
+}
+// cell index in [-1, n] -> storage index
+__host__ __device__ __forceinline__ int cmap(int i, int n, int per)
+{
+    if (per) { if (i < 0) i += n; else if (i >= n) i -= n; }
+    else     { if (i < 0) i = 0; else if (i >= n) i = n - 1; }
+    return i;
+}
+// local node plane index (may be -1 or nzl) -> local storage plane
+__host__ __device__ __forceinline__ int zplane(const Lev& L, int kl)
+{
+    return L.dist ? kl : nmap(kl, L.n[2], L.per[2]);
+}
+__host__ __device__ __forceinline__ int czplane(const Lev& L, int kl)
+{
+    return L.dist ? kl : cmap(kl, L.n[2], L.per[2]);
+}
+__host__ __device__ __forceinline__ bool node_masked(const Lev& L, int i, int j, int kg)
+{
+    return (L.dlo[0] && i == 0) || (L.dhi[0] && i == L.n[0]) || (L.dlo[1] && j == 0) || (L.dhi[1] && j == L.n[1]) ||
+           (L.dlo[2] && kg == 0) || (L.dhi[2] && kg == L.n[2]);
+}
+// dot-product / solvability weight: 1/2 per reflecting boundary direction
+__host__ __device__ __forceinline__ double node_weight(const Lev& L, int i, int j, int kg)
+{
+    if (node_masked(L, i, j, kg)) return 0.0;
+    double w = 1.0;
+    if (!L.per[0]) { if (L.rlo[0] && i == 0) w *= 0.5; if (L.rhi[0] && i == L.n[0]) w *= 0.5; }
+    if (!L.per[1]) { if (L.rlo[1] && j == 0) w *= 0.5; if (L.rhi[1] && j == L.n[1]) w *= 0.5; }
+    if (!L.per[2]) { if (L.rlo[2] && kg == 0) w *= 0.5; if (L.rhi[2] && kg == L.n[2]) w *= 0.5; }
+    return w;
+}
+
+// y = L phi at one node from the 8 surrounding sigma and the 27 phi values; returns the
+// diagonal in s0.  S[c][b][a] = sigma(i-1+a, j-1+b, k-1+c); P[c][b][a] = phi(i-1+a, j-1+b, k-1+c).
+// Restates mlndlap_adotx_aa; verified == Q1 finite-element stiffness by the
+// oracle tests.
+__device__ __forceinline__ double stencil27(const Lev& L, const double (&S)[2][2][2], const double (&P)[3][3][3],
+                                            double& s0)
+{
+    double sumS = 0, corner = 0, ex = 0, ey = 0, ez = 0, fxs = 0, fys = 0, fzs = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                sumS += S[c][b][a];
+                corner += S[c][b][a] * P[2 * c][2 * b][2 * a];
+            }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            ex += (S[c][b][0] + S[c][b][1]) * P[2 * c][2 * b][1];   // neighbours (0, +-1, +-1)
+            ey += (S[c][0][b] + S[c][1][b]) * P[2 * c][1][2 * b];   // (+-1, 0, +-1)
+            ez += (S[0][c][b] + S[1][c][b]) * P[1][2 * c][2 * b];   // (+-1, +-1, 0)
+        }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        fxs += (S[0][0][a] + S[0][1][a] + S[1][0][a] + S[1][1][a]) * P[1][1][2 * a];  // (+-1,0,0)
+        fys += (S[0][a][0] + S[0][a][1] + S[1][a][0] + S[1][a][1]) * P[1][2 * a][1];  // (0,+-1,0)
+        fzs += (S[a][0][0] + S[a][0][1] + S[a][1][0] + S[a][1][1]) * P[2 * a][1][1];  // (0,0,+-1)
+    }
+    s0 = -4.0 * L.fxyz * sumS;
+    return s0 * P[1][1][1] + L.fxyz * corner + L.fmx2y2z * ex + L.f2xmy2z * ey + L.f2x2ymz * ez + L.f4xm2ym2z * fxs +
+           L.fm2x4ym2z * fys + L.fm2xm2y4z * fzs;
+}
+
+// constant-sigma variant (mlndlap_adotx_c): S == sig everywhere
+__device__ __forceinline__ double stencil27_c(const Lev& L, double sig, const double (&P)[3][3][3], double& s0)
+{
+    double corner = 0, ex = 0, ey = 0, ez = 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            corner += P[2 * c][2 * b][0] + P[2 * c][2 * b][2];
+            ex += P[2 * c][2 * b][1];
+            ey += P[2 * c][1][2 * b];
+            ez += P[1][2 * c][2 * b];
+        }
+    double fxs = P[1][1][0] + P[1][1][2], fys = P[1][0][1] + P[1][2][1], fzs = P[0][1][1] + P[2][1][1];
+    s0 = -32.0 * L.fxyz * sig;
+    return s0 * P[1][1][1] +
+           sig * (L.fxyz * corner + 2.0 * (L.fmx2y2z * ex + L.f2xmy2z * ey + L.f2x2ymz * ez) +
+                  4.0 * (L.f4xm2ym2z * fxs + L.fm2x4ym2z * fys + L.fm2xm2y4z * fzs));
+}
+
+}  // namespace b200np_dev

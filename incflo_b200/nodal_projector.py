@@ -1,0 +1,271 @@
+"""Host-side mirror of the reference interface for the nodal-projection path.
+
+Same names / argument meaning / error behaviour as the reference:
+  * ``NodalProjector``  <->  Hydro::NodalProjector as used by incflo
+    (src/projection/incflo_apply_nodal_projection.cpp:181-219): ctor(vel, sigma |
+    const_sigma, geom, LPInfo), setDomainBC(lo, hi), project(rtol, atol), getPhi(),
+    getGradPhi().
+  * ``apply_nodal_projection``  <->  incflo::ApplyNodalProjection (:29-267).
+  * ``get_projection_bc``  <->  incflo::get_projection_bc
+    (src/projection/incflo_projection_bc.cpp:5-41).
+Everything numerical happens in libb200np.so (sm_100a CUDA) through the C ABI of
+include/b200np.h.  Arrays are numpy (host, staged inside the call) or torch CUDA
+tensors (zero copy), shape (ncomp, nz, ny, nx) / (nz, ny, nx), C-contiguous float64,
+which is amrex::Array4 order (i fastest, component outermost).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FabBox, Geom, Opts, Stats
+
+BC_PERIODIC, BC_NEUMANN, BC_DIRICHLET, BC_INFLOW = 0, 1, 2, 3
+A_SOL, A_RHS, A_RES, A_COR, A_RESCOR, A_SIGMA = range(6)
+OP_SMOOTH, OP_RESIDUAL, OP_RESTRICT, OP_INTERP, OP_BOTTOM, OP_VCYCLE, OP_COARSEN_SIGMA = range(7)
+
+# incflo BC names (src/boundary_conditions/boundary_conditions.cpp:30-222) -> LinOpBCType
+_INCFLO_BC = {"pi": BC_DIRICHLET, "pressure_inflow": BC_DIRICHLET, "po": BC_DIRICHLET, "pressure_outflow": BC_DIRICHLET,
+              "mi": BC_INFLOW, "mass_inflow": BC_INFLOW, "dd": BC_INFLOW, "direction_dependent": BC_INFLOW,
+              "mixed": BC_INFLOW, "sw": BC_NEUMANN, "slip_wall": BC_NEUMANN, "nsw": BC_NEUMANN,
+              "no_slip_wall": BC_NEUMANN}
+
+
+class ProjectionError(RuntimeError):
+    """The reference calls amrex::Abort in these situations."""
+
+    def __init__(self, status):
+        self.status = status
+        super().__init__(_lib.lib().b200np_strerror(status).decode())
+
+
+def get_projection_bc(is_periodic, bc_types):
+    """incflo::get_projection_bc for one side: list of 3 incflo BC names -> LinOpBCType codes."""
+    r = []
+    for d in range(3):
+        if is_periodic[d]:
+            r.append(BC_PERIODIC)
+        else:
+            if bc_types[d] not in _INCFLO_BC:
+                raise ProjectionError(3)  # "get_projection_bc: undefined BC type"
+            r.append(_INCFLO_BC[bc_types[d]])
+    return tuple(r)
+
+
+def nodal_proj_opts(**keys):
+    """nodal_proj.* ParmParse keys -> b200np_opts (defaults: src/incflo.H:449-458, InputsMultigrid.rst)."""
+    o = Opts()
+    _lib.lib().b200np_default_opts(C.byref(o))
+    alias = {"mg_max_coarsening_level": "mg_max_coarsening_level"}
+    for k, v in keys.items():
+        k = alias.get(k, k)
+        if k == "tile":
+            for d in range(3):
+                o.tile[d] = int(v[d])
+        elif k == "bottom_solver" and isinstance(v, str):
+            o.bottom_solver = {"bicgcg": 0, "bicgstab": 0, "cg": 0, "cgbicg": 0, "smoother": 1}[v]
+        elif k in ("mg_rtol", "mg_atol"):
+            continue  # passed to project()
+        else:
+            if not hasattr(o, k):
+                raise KeyError("unknown nodal_proj key: " + k)
+            setattr(o, k, v)
+    return o
+
+
+def _ptr_box(a, lo, ncomp):
+    """(pointer, FabBox) of a numpy array or torch tensor laid out (ncomp?, nz, ny, nx)."""
+    if a is None:
+        return None, None, None
+    shape = tuple(a.shape)
+    if len(shape) == 4:
+        assert shape[0] == ncomp, (shape, ncomp)
+        nz, ny, nx = shape[1:]
+    else:
+        assert ncomp == 1
+        nz, ny, nx = shape
+    b = FabBox()
+    for d, (l, n) in enumerate(zip(lo, (nx, ny, nz))):
+        b.lo[d] = int(l); b.hi[d] = int(l) + n - 1
+    b.ncomp = ncomp
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data, b, a
+    # torch tensor
+    import torch
+    assert a.dtype == torch.float64 and a.is_contiguous()
+    return a.data_ptr(), b, a
+
+
+class NodalProjector:
+    """Hydro::NodalProjector, single level, backed by libb200np.so.
+
+    vel: (3, nz+2ng, ny+2ng, nx+2ng); sigma: (nz, ny, nx) or None with const_sigma.
+    geom: dict(n_cell=(nx,ny,nz), dx=(..), is_periodic=(..)) -- amrex::Geometry.
+    """
+
+    def __init__(self, vel, sigma=None, const_sigma=None, geom=None, ng=None, opts=None, device=0):
+        self._L = _lib.lib()
+        self.vel, self.sigma, self.const_sigma = vel, sigma, (1.0 if const_sigma is None else float(const_sigma))
+        self.n = tuple(int(x) for x in geom["n_cell"])
+        self.dx = tuple(float(x) for x in geom["dx"])
+        self.per = tuple(bool(x) for x in geom.get("is_periodic", (1, 1, 1)))
+        self.ng = int(ng) if ng is not None else (vel.shape[-1] - self.n[0]) // 2
+        self.opts = opts if opts is not None else nodal_proj_opts()
+        self.device = device
+        self.bclo = tuple(BC_PERIODIC if p else BC_NEUMANN for p in self.per)
+        self.bchi = self.bclo
+        self._h = None
+        self._phi = None
+        self._gphi = None
+        self.stats = Stats()
+
+    # -- reference API ----------------------------------------------------------------
+    def setDomainBC(self, lo, hi):
+        self.bclo, self.bchi = tuple(int(x) for x in lo), tuple(int(x) for x in hi)
+        self._destroy()
+
+    def project(self, rtol, atol):
+        h = self._handle()
+        like = self.vel
+        self._phi = _empty_like(like, (self.n[2] + 1, self.n[1] + 1, self.n[0] + 1))
+        self._gphi = _empty_like(like, (3, self.n[2], self.n[1], self.n[0]))
+        pv, bv, _ = _ptr_box(self.vel, (-self.ng,) * 3, 3)
+        ps, bs, _ = _ptr_box(self.sigma, (0, 0, 0), 1)
+        pp, bp, _ = _ptr_box(self._phi, (0, 0, 0), 1)
+        pg, bg, _ = _ptr_box(self._gphi, (0, 0, 0), 3)
+        rc = self._L.b200np_project(h, pv, C.byref(bv), ps, C.byref(bs) if bs is not None else None, self.const_sigma,
+                                    pp, C.byref(bp), pg, C.byref(bg), float(rtol), float(atol), C.byref(self.stats))
+        if rc != 0:
+            raise ProjectionError(rc)
+        return self.stats
+
+    def getPhi(self):
+        return self._phi
+
+    def getGradPhi(self):
+        return self._gphi
+
+    # -- plumbing ---------------------------------------------------------------------
+    def _handle(self):
+        if self._h is None:
+            g = Geom()
+            for d in range(3):
+                g.n_cell[d] = self.n[d]; g.dx[d] = self.dx[d]; g.bc_lo[d] = self.bclo[d]; g.bc_hi[d] = self.bchi[d]
+            h = C.c_void_p()
+            rc = self._L.b200np_create(C.byref(h), C.byref(g), C.byref(self.opts), self.device)
+            if rc != 0:
+                raise ProjectionError(rc)
+            self._h = h
+        return self._h
+
+    def _destroy(self):
+        if self._h is not None:
+            self._L.b200np_destroy(self._h)
+            self._h = None
+
+    def close(self):
+        self._destroy()
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    # -- per-kernel hooks used by the parity tests ---------------------------------------
+    def nlevels(self):
+        return self._L.b200np_nlevels(self._handle())
+
+    def level_dims(self, lev):
+        n = (C.c_int * 3)(); nn = (C.c_int * 3)()
+        self._L.b200np_level_dims(self._handle(), lev, C.byref(n), C.byref(nn))
+        return tuple(n), tuple(nn)
+
+    def set_sigma(self, sigma=None, const_sigma=1.0):
+        ps, bs, _ = _ptr_box(sigma, (0, 0, 0), 1)
+        rc = self._L.b200np_set_sigma(self._handle(), ps, C.byref(bs) if bs is not None else None, float(const_sigma))
+        if rc:
+            raise ProjectionError(rc)
+
+    def level_set(self, lev, which, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64)
+        rc = self._L.b200np_level_set(self._handle(), lev, which, arr.ctypes.data)
+        if rc:
+            raise ProjectionError(rc)
+
+    def level_get(self, lev, which):
+        n, nn = self.level_dims(lev)
+        shape = (n[2], n[1], n[0]) if which == A_SIGMA else (nn[2], nn[1], nn[0])
+        out = np.empty(shape)
+        rc = self._L.b200np_level_get(self._handle(), lev, which, out.ctypes.data)
+        if rc:
+            raise ProjectionError(rc)
+        return out
+
+    def level_op(self, lev, op, arg=0):
+        rc = self._L.b200np_level_op(self._handle(), lev, op, arg)
+        if rc:
+            raise ProjectionError(rc)
+
+    def time_op(self, lev, op, arg=1, reps=10):
+        ms = C.c_double()
+        rc = self._L.b200np_time_op(self._handle(), lev, op, arg, reps, C.byref(ms))
+        if rc:
+            raise ProjectionError(rc)
+        return ms.value
+
+
+def _empty_like(like, shape):
+    if isinstance(like, np.ndarray):
+        return np.zeros(shape)
+    import torch
+    return torch.zeros(shape, dtype=torch.float64, device=like.device)
+
+
+class IncfloProjection:
+    """Keeps one b200np handle alive across time steps (the reference rebuilds the
+    projector every call, :181-193; caching the hierarchy gives identical results)."""
+
+    def __init__(self, n_cell, dx, bclo, bchi, opts=None, device=0):
+        self._L = _lib.lib()
+        self.n = tuple(int(x) for x in n_cell)
+        g = Geom()
+        for d in range(3):
+            g.n_cell[d] = self.n[d]; g.dx[d] = float(dx[d]); g.bc_lo[d] = int(bclo[d]); g.bc_hi[d] = int(bchi[d])
+        self.opts = opts if opts is not None else nodal_proj_opts()
+        h = C.c_void_p()
+        rc = self._L.b200np_create(C.byref(h), C.byref(g), C.byref(self.opts), device)
+        if rc != 0:
+            raise ProjectionError(rc)
+        self._h = h
+        self.stats = Stats()
+
+    def apply_nodal_projection(self, velocity, ng, gp, p_nd, density=None, ngd=0, ro_0=1.0, velocity_o=None,
+                               inflow_vel=None, scaling_factor=1.0, incremental=False, proj_for_small_dt=False,
+                               mg_rtol=1e-11, mg_atol=1e-14):
+        """incflo::ApplyNodalProjection(density, time, scaling_factor, incremental)."""
+        pv, bv, _ = _ptr_box(velocity, (-ng,) * 3, 3)
+        po, _, _ = _ptr_box(velocity_o, (-ng,) * 3, 3)
+        pr, br, _ = _ptr_box(density, (-ngd,) * 3, 1)
+        pg, bg, _ = _ptr_box(gp, (0, 0, 0), 3)
+        pp, bp, _ = _ptr_box(p_nd, (0, 0, 0), 1)
+        pi, _, _ = _ptr_box(inflow_vel, (-ng,) * 3, 3)
+        rc = self._L.b200np_apply_nodal_projection(self._h, pv, C.byref(bv), po, pr, C.byref(br) if br is not None else None,
+                                                   float(ro_0), pg, C.byref(bg), pp, C.byref(bp), pi,
+                                                   float(scaling_factor), int(incremental), int(proj_for_small_dt),
+                                                   float(mg_rtol), float(mg_atol), C.byref(self.stats))
+        if rc != 0:
+            raise ProjectionError(rc)
+        return self.stats
+
+    def close(self):
+        if self._h is not None:
+            self._L.b200np_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,178 @@
+/*
+ * b200np.h -- C ABI of the B200-native approximate nodal projection.
+ *
+ * Drop-in boundary for ONE hot path of AMReX-Fluids/incflo:
+ *   incflo::ApplyNodalProjection            src/projection/incflo_apply_nodal_projection.cpp:29-267
+ *     -> Hydro::NodalProjector (ctor, setDomainBC, project, getPhi, getGradPhi)   call sites :181-219
+ *        -> amrex::MLMG / amrex::MLNodeLaplacian (un-vendored)
+ *
+ * Plain C: pointers + sizes only, no torch / AMReX types.  All field memory is
+ * owned by the caller (AMReX arenas); every array comes with its own box
+ * descriptor because ghost widths differ per MultiFab (src/incflo.H:714-724,
+ * src/setup/incflo_arrays.cpp:9-26).  Array layout is amrex::Array4:
+ *   idx = (i-lo.x) + nx*((j-lo.y) + ny*((k-lo.z) + nz*comp)),   nx = hi.x-lo.x+1 ...
+ * Pointers may be device pointers (zero copy) or host pointers (staged H2D/D2H
+ * inside the call); the kind is detected with cudaPointerGetAttributes.
+ *
+ * The solver runs ONLY as sm_100a CUDA kernels.  There is no CPU fallback: if
+ * no CUDA device is usable every entry point returns B200NP_ERR_CUDA.
+ */
+#ifndef B200NP_H
+#define B200NP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NP_VERSION 1
+
+/* amrex::LinOpBCType as produced by incflo::get_projection_bc
+ * (src/projection/incflo_projection_bc.cpp:5-41):
+ *   periodic -> PERIODIC; pi,po -> DIRICHLET; mi,dd,mixed -> INFLOW; sw,nsw -> NEUMANN */
+enum b200np_bc { B200NP_BC_PERIODIC = 0, B200NP_BC_NEUMANN = 1, B200NP_BC_DIRICHLET = 2, B200NP_BC_INFLOW = 3 };
+
+enum b200np_status {
+    B200NP_OK = 0,
+    B200NP_ERR_NOT_CONVERGED = 1, /* MLMG: failed to converge in maxiter (AMReX aborts)        */
+    B200NP_ERR_DIVERGED = 2,      /* residual > 1e20 * max(rhsnorm,resnorm0) (AMReX aborts)    */
+    B200NP_ERR_BAD_BC = 3,        /* get_projection_bc: undefined BC type (:36 aborts)         */
+    B200NP_ERR_BAD_ARG = 4,
+    B200NP_ERR_CUDA = 5,          /* no device / CUDA runtime error                            */
+    B200NP_ERR_NCCL = 6,
+    B200NP_ERR_UNSUPPORTED = 7    /* multi-level AMR, EB, overset mask: not built yet          */
+};
+
+/* amrex::Geometry + domain BCs of one level (NodalProjector ctor + setDomainBC, :187-194) */
+typedef struct {
+    int    n_cell[3];  /* amr.n_cell: domain is cells [0,n_cell) (domain box lo = 0)   */
+    double dx[3];      /* geom.CellSize()                                               */
+    int    bc_lo[3];   /* enum b200np_bc                                                */
+    int    bc_hi[3];
+} b200np_geom;
+
+/* nodal_proj.* keys.  Read by incflo: src/setup/init.cpp:172-177 (defaults
+ * src/incflo.H:449-458); read by Hydro::NodalProjector::setOptions: documented
+ * at src/incflo.H:436-445 and Docs/.../InputsMultigrid.rst:10-36. */
+typedef struct {
+    int    verbose;                 /* nodal_proj.verbose            0      */
+    int    bottom_verbose;          /* nodal_proj.bottom_verbose     0      */
+    int    maxiter;                 /* nodal_proj.maxiter            100    */
+    int    bottom_maxiter;          /* nodal_proj.bottom_maxiter     100    */
+    double bottom_rtol;             /* nodal_proj.bottom_rtol        1e-4   */
+    double bottom_atol;             /* nodal_proj.bottom_atol        -1     */
+    int    mg_max_coarsening_level; /* nodal_proj.mg_max_coarsening_level 100 */
+    int    num_pre_smooth;          /* nodal_proj.num_pre_smooth     2      */
+    int    num_post_smooth;         /* nodal_proj.num_post_smooth    2      */
+    int    smooth_num_sweeps;       /* MLNodeLinOp m_smooth_num_sweeps 4    */
+    int    bottom_solver;           /* 0 = bicgcg (default): BiCGStab, CG retry; 1 = smoother  */
+    /* B200-specific knobs (not reference keys) */
+    int    tile[3];                 /* smoother tile in nodes, default {64,16,16}: Gauss-Seidel
+                                       inside a tile, previous-sweep values outside           */
+    int    use_graph;               /* capture each V-cycle in a CUDA graph, default 1        */
+} b200np_opts;
+
+/* amrex::FArrayBox shape: the allocated (grown) box and component count */
+typedef struct {
+    int lo[3];
+    int hi[3];
+    int ncomp;
+} b200np_fab;
+
+/* what MLMG prints with nodal_proj.verbose >= 1, plus timers */
+typedef struct {
+    int    iters;            /* V-cycles                                    */
+    int    nlevels;          /* MG levels                                   */
+    int    bottom_iters;     /* BiCGStab iterations, summed                 */
+    int    status;           /* enum b200np_status                          */
+    double rhsnorm;          /* ||rhs||_inf                                 */
+    double resnorm0;         /* initial ||rhs - L phi||_inf                 */
+    double resnorm;          /* final                                       */
+    double resnorm_hist[128];
+    double ms_total;         /* device time of the whole call (CUDA events) */
+    double ms_solve;         /* MLMG::solve part                            */
+    double ms_h2d, ms_d2h;   /* staging when host pointers were passed      */
+    long long h2d_bytes, d2h_bytes;
+    long long launches;      /* kernels launched by this call               */
+} b200np_stats;
+
+typedef struct b200np b200np_t;
+
+void b200np_default_opts(b200np_opts* o);
+
+/* Hydro::NodalProjector::NodalProjector(vel, sigma, geom, LPInfo) + setOptions()
+ * + setDomainBC(lo,hi)  (call sites :181-194).  The multigrid hierarchy is built
+ * once and cached in the handle; incflo rebuilds it every projection (:181-193),
+ * so re-using a handle across calls is a pure saving.
+ * Single process / single GPU: device = CUDA ordinal. */
+int b200np_create(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device);
+
+/* Slab-decomposed multi-GPU variant (one process per GPU): this rank
+ * owns cell planes [zlo, zhi) of the domain.  nccl_unique_id: the 128 bytes of an
+ * ncclUniqueId created by rank 0 and broadcast by the host program. */
+int b200np_create_dist(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device,
+                       int rank, int nranks, const void* nccl_unique_id);
+
+void b200np_destroy(b200np_t* h);
+
+/* Hydro::NodalProjector::project(rtol, atol)   (:215) followed by getPhi() /
+ * getGradPhi() (:218-219).
+ *   vel   in/out: cell-centred, 3 comps, box grown by >= 1 ghost cell.  Valid
+ *         cells are overwritten with u - sigma*grad(phi).  One ghost layer is an
+ *         INPUT at non-periodic faces (0 at walls, inflow value at inflow faces,
+ *         :137-163); periodic ghosts need not be filled (FillBoundary is internal).
+ *   sigma cell-centred 1 comp (any ghost width; ghosts unused) or NULL => const_sigma
+ *   phi   out, nodal box [0,n_cell] in every direction (may be NULL)
+ *   gphi  out, cell-centred 3 comps, +grad(phi) (may be NULL)
+ * In the slab-decomposed case every box is the rank's local box (cells
+ * [zlo,zhi) in z, nodes [zlo,zhi] in z). */
+int b200np_project(b200np_t* h, double* vel, const b200np_fab* vel_box, const double* sigma,
+                   const b200np_fab* sigma_box, double const_sigma, double* phi, const b200np_fab* phi_box,
+                   double* gphi, const b200np_fab* gphi_box, double rtol, double atol, b200np_stats* stats);
+
+/* incflo::ApplyNodalProjection(density, time, scaling_factor, incremental)
+ * (:29-93 and :95-267 fused; single level).
+ *   velocity  in/out  ld.velocity  (3 comps, ng = nghost_state())
+ *   velocity_o in     ld.velocity_o (used iff incremental || proj_for_small_dt, else may be NULL)
+ *   density   in      density[lev] or NULL => incflo.constant_density with ro_0
+ *   gp        in/out  ld.gp   (3 comps, 0 ghosts)
+ *   p_nd      in/out  ld.p_nd (nodal)
+ *   inflow_vel in     optional: same box as velocity; its first ghost layer at
+ *                     INFLOW faces holds the IncfloVelFill values (src/prob/prob_bc.H:8-351)
+ *                     to impose when set_inflow_bc = !proj_for_small_dt && !incremental (:81)
+ * All velocity ghost cells are zeroed first, as vel.setBndry(0.0) does (:137). */
+int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fab* vel_box,
+                                  const double* velocity_o, const double* density, const b200np_fab* rho_box,
+                                  double ro_0, double* gp, const b200np_fab* gp_box, double* p_nd,
+                                  const b200np_fab* p_box, const double* inflow_vel, double scaling_factor,
+                                  int incremental, int proj_for_small_dt, double rtol, double atol,
+                                  b200np_stats* stats);
+
+const char* b200np_strerror(int status);
+int b200np_version(void);
+
+/* ---- test / profiling hooks: run one multigrid building block on device-resident
+ * level arrays so that each kernel can be compared with the oracle.  Host arrays
+ * are in the unique-node layout (nn = n in periodic directions, n+1 otherwise;
+ * i fastest; no ghosts) or plain cell layout. ---- */
+enum b200np_array { B200NP_A_SOL = 0, B200NP_A_RHS = 1, B200NP_A_RES = 2, B200NP_A_COR = 3, B200NP_A_RESCOR = 4,
+                    B200NP_A_SIGMA = 5 };
+enum b200np_op { B200NP_OP_SMOOTH = 0,   /* cor <- nsweeps sweeps on (cor, res)         */
+                 B200NP_OP_RESIDUAL = 1, /* rescor <- res - L cor                       */
+                 B200NP_OP_RESTRICT = 2, /* res[lev+1] <- R rescor[lev]                 */
+                 B200NP_OP_INTERP = 3,   /* cor[lev] += P cor[lev+1]                    */
+                 B200NP_OP_BOTTOM = 4,   /* cor[bottom] <- bottom solve of res[bottom]  */
+                 B200NP_OP_VCYCLE = 5,   /* one V-cycle on (cor, res) from level 0      */
+                 B200NP_OP_COARSEN_SIGMA = 6 };
+int b200np_nlevels(const b200np_t* h);
+int b200np_level_dims(const b200np_t* h, int lev, int n_cell[3], int n_node[3]);
+int b200np_set_sigma(b200np_t* h, const double* sigma, const b200np_fab* sigma_box, double const_sigma);
+int b200np_level_set(b200np_t* h, int lev, int which, const double* host);
+int b200np_level_get(b200np_t* h, int lev, int which, double* host);
+int b200np_level_op(b200np_t* h, int lev, int op, int arg);
+/* time `reps` back-to-back launches of one op with CUDA events; returns ms per launch in *ms */
+int b200np_time_op(b200np_t* h, int lev, int op, int arg, int reps, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

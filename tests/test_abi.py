@@ -1,0 +1,87 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/b200np.h declares, mirrors the reference's defaults and error behaviour, and fails
+loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, has_gpu
+
+
+def _lib():
+    from incflo_b200 import _lib
+    return _lib, _lib.lib()
+
+
+def test_library_exports_every_declared_symbol():
+    mod, L = _lib()
+    header = open(os.path.join(ROOT, "include", "b200np.h")).read()
+    declared = set(re.findall(r"\b(b200np_[a-z_]+)\s*\(", header))
+    assert declared == set(mod.EXPORTS), declared ^ set(mod.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.b200np_version() == 1
+
+
+def test_default_opts_match_reference_defaults():
+    mod, L = _lib()
+    o = mod.Opts()
+    L.b200np_default_opts(C.byref(o))
+    # src/incflo.H:449-458 and Docs/sphinx_documentation/source/InputsMultigrid.rst:10-36
+    assert (o.verbose, o.bottom_verbose, o.maxiter, o.bottom_maxiter) == (0, 0, 100, 100)
+    assert o.bottom_rtol == 1e-4 and o.bottom_atol == -1.0
+    assert o.mg_max_coarsening_level == 100
+    assert (o.num_pre_smooth, o.num_post_smooth, o.smooth_num_sweeps) == (2, 2, 4)
+
+
+def test_projection_bc_mapping():
+    """incflo::get_projection_bc (src/projection/incflo_projection_bc.cpp:5-41)"""
+    from incflo_b200 import nodal_projector as npj
+    assert npj.get_projection_bc((1, 0, 0), ("x", "po", "mi")) == (npj.BC_PERIODIC, npj.BC_DIRICHLET, npj.BC_INFLOW)
+    assert npj.get_projection_bc((0, 0, 0), ("pi", "sw", "nsw")) == (npj.BC_DIRICHLET, npj.BC_NEUMANN, npj.BC_NEUMANN)
+    assert npj.get_projection_bc((0, 0, 0), ("dd", "mixed", "mass_inflow")) == (npj.BC_INFLOW,) * 3
+    with pytest.raises(npj.ProjectionError):  # "get_projection_bc: undefined BC type" aborts in the reference
+        npj.get_projection_bc((0, 0, 0), ("bogus", "sw", "sw"))
+
+
+def test_bad_arguments_are_rejected():
+    mod, L = _lib()
+    g = mod.Geom()
+    h = C.c_void_p()
+    for d in range(3):
+        g.n_cell[d] = 8; g.dx[d] = 0.1
+    g.bc_lo[0] = 7
+    assert L.b200np_create(C.byref(h), C.byref(g), None, 0) == 3  # B200NP_ERR_BAD_BC
+    g.bc_lo[0] = 0; g.bc_hi[0] = 1  # periodic on one side only
+    assert L.b200np_create(C.byref(h), C.byref(g), None, 0) == 3
+    g.bc_hi[0] = 0; g.n_cell[1] = 0
+    assert L.b200np_create(C.byref(h), C.byref(g), None, 0) == 4  # B200NP_ERR_BAD_ARG
+    assert b"undefined BC type" in L.b200np_strerror(3)
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_gpu():
+    mod, L = _lib()
+    g = mod.Geom()
+    for d in range(3):
+        g.n_cell[d] = 8; g.dx[d] = 0.1
+    h = C.c_void_p()
+    rc = L.b200np_create(C.byref(h), C.byref(g), None, 0)
+    assert rc == 5 and not h.value  # B200NP_ERR_CUDA: fails loudly, nothing computed on the CPU
+    from incflo_b200 import nodal_projector as npj
+    import numpy as np
+    proj = npj.NodalProjector(np.zeros((3, 10, 10, 10)), None, 1.0, dict(n_cell=(8, 8, 8), dx=(0.1,) * 3), ng=1)
+    with pytest.raises(npj.ProjectionError):
+        proj.project(1e-11, 1e-14)
+
+
+def test_product_never_imports_oracle():
+    """the oracle is test infrastructure: nothing under incflo_b200/ may reference it"""
+    pkg = os.path.join(ROOT, "incflo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in src and "nodal_oracle" not in src and "liboracle" not in src, f
