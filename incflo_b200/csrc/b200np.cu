@@ -9,6 +9,7 @@
 //   MLNodeLinOp::defineGrids          [U] SURVEY.md A.8 (hierarchy)
 #include "../../include/b200np.h"
 #include "np_kernels.cuh"
+#include "np_smooth.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -38,6 +39,8 @@ struct LevelData {
     std::vector<double*> allocs;
     dim3 gn, gc;     // grids of 64x4-thread blocks over owned nodes / cells
     dim3 gsm;        // smoother grid
+    dim3 git;        // interpolation grid (fine tiles)
+    int tz = 16;     // smoother z-chunk of this level
     long long nblk_n = 0;
 };
 
@@ -69,6 +72,7 @@ struct b200np {
     struct Stage { double* d = nullptr; size_t bytes = 0; };
     Stage stage[8];
     int TZ = 16;
+    int smoother_version = 2, interp_version = 2;  // B200NP_SMOOTHER / B200NP_INTERP env override (1 = simple kernels)
 };
 
 namespace {
@@ -132,7 +136,10 @@ void build_hierarchy(b200np* h)
         g.csig = 1.0; g.sigma = nullptr;
         L.gn = dim3((g.nn[0] + 63) / 64, (g.nn[1] + 3) / 4, g.nzl);
         L.gc = dim3((g.n[0] + 63) / 64, (g.n[1] + 3) / 4, g.cnzl);
-        L.gsm = dim3((g.nn[0] + NP_TX - 1) / NP_TX, (g.nn[1] + NP_TY - 1) / NP_TY, (g.nzl + h->TZ - 1) / h->TZ);
+        // z-chunk rule (mirrored by the oracle): at least 8 chunks per level where possible
+        L.tz = std::max(2, std::min(h->TZ, g.nn[2] / 8));
+        L.gsm = dim3((g.nn[0] + NP_TX - 1) / NP_TX, (g.nn[1] + NP_TY - 1) / NP_TY, (g.nzl + L.tz - 1) / L.tz);
+        L.git = dim3((g.nn[0] + IT_X - 1) / IT_X, (g.nn[1] + IT_Y - 1) / IT_Y, (g.nzl + IT_Z - 1) / IT_Z);
         L.nblk_n = (long long)L.gn.x * L.gn.y * L.gn.z;
         // arrays
         L.sigma_alloc = dev_alloc((size_t)g.cps * (g.cnzl + 2));
@@ -178,8 +185,14 @@ void coarsen_sigma(b200np* h)
 void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double* rhs, int nsweeps)
 {
     for (int s = 0; s < nsweeps; ++s) {
-        if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, h->TZ);
-        else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, h->TZ);
+        if (h->smoother_version == 1) {
+            if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, L.tz);
+            else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, L.tz);
+        } else {
+            if (h->var_sigma) k_smooth_v2<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
+            else              k_smooth_v2<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
+            h->launches++;
+        }
         std::swap(x, y);
     }
 }
@@ -209,8 +222,13 @@ void restrict_to(b200np* h, int l)
 void interp_add(b200np* h, int l)
 {
     LevelData &F = h->lv[l], &C = h->lv[l + 1];
-    if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
-    else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
+    if (h->interp_version == 1) {
+        if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
+        else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
+    } else {
+        if (h->var_sigma) LAUNCH(h, k_interp_tile<true>, F.git, 256, F.g, C.g, F.cor, C.cor);
+        else              LAUNCH(h, k_interp_tile<false>, F.git, 256, F.g, C.g, F.cor, C.cor);
+    }
 }
 
 // MLMG::mgVcycle (A.9) on (cor, res), all launches on h->stream, no host synchronisation
@@ -470,6 +488,10 @@ int b200np_create(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (opts) h->opts = *opts; else b200np_default_opts(&h->opts);
         if (h->opts.tile[0] != NP_TX || h->opts.tile[1] != NP_TY || h->opts.tile[2] < 1) { delete h; return B200NP_ERR_BAD_ARG; }
         h->TZ = h->opts.tile[2];
+        if (const char* e = getenv("B200NP_SMOOTHER")) h->smoother_version = atoi(e);
+        if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
+        CK(cudaFuncSetAttribute(k_smooth_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         for (auto& e : h->ev) CK(cudaEventCreate(&e));
         build_hierarchy(h);
@@ -673,11 +695,14 @@ int b200np_level_set(b200np_t* h, int lev, int which, const double* host)
     try {
         CK(cudaSetDevice(h->device));
         if (which == B200NP_A_SIGMA)
-            CK(cudaMemcpy2D(d, g.cpx * sizeof(double), host, g.n[0] * sizeof(double), g.n[0] * sizeof(double),
-                            (size_t)g.n[1] * g.cnzl, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy2DAsync(d, g.cpx * sizeof(double), host, g.n[0] * sizeof(double), g.n[0] * sizeof(double),
+                                 (size_t)g.n[1] * g.cnzl, cudaMemcpyHostToDevice, h->stream));
         else
-            CK(cudaMemcpy2D(d, g.px * sizeof(double), host, g.nn[0] * sizeof(double), g.nn[0] * sizeof(double),
-                            (size_t)g.nn[1] * g.nzl, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy2DAsync(d, g.px * sizeof(double), host, g.nn[0] * sizeof(double), g.nn[0] * sizeof(double),
+                                 (size_t)g.nn[1] * g.nzl, cudaMemcpyHostToDevice, h->stream));
+        // the solver stream is non-blocking: order the copy on it (a pageable cudaMemcpy on the
+        // legacy stream may still be in flight when the next kernel starts)
+        CK(cudaStreamSynchronize(h->stream));
     } catch (int e) { return e; }
     return B200NP_OK;
 }

@@ -340,19 +340,22 @@ static void smooth_level(const orc_mg* mg, level* L, double* phi, const double* 
         return;
     }
     if (p->smoother == ORC_SM_BOX) {
+        /* z-chunk rule shared with the CUDA smoother: at least 8 chunks per level where possible */
+        int bsz[3] = {p->box[0], p->box[1], p->box[2]};
+        { int c = L->nn[2] / 8; if (c < bsz[2]) bsz[2] = c; if (bsz[2] < 2) bsz[2] = 2; }
         int nb[3];
-        for (int d = 0; d < 3; ++d) nb[d] = (L->nn[d] + p->box[d] - 1) / p->box[d];
+        for (int d = 0; d < 3; ++d) nb[d] = (L->nn[d] + bsz[d] - 1) / bsz[d];
         int outer = p->box_stale_per_call ? 1 : nsweeps, inner = p->box_stale_per_call ? nsweeps : 1;
         for (int so = 0; so < outer; ++so) {
             memcpy(L->old, phi, sizeof(double) * L->nnodes);
 #pragma omp parallel for collapse(3) schedule(dynamic)
             for (int bk = 0; bk < nb[2]; ++bk) for (int bj = 0; bj < nb[1]; ++bj) for (int bi = 0; bi < nb[0]; ++bi) {
-                int lo0 = bi * p->box[0], lo1 = bj * p->box[1], lo2 = bk * p->box[2];
-                int hi0 = lo0 + p->box[0] < L->nn[0] ? lo0 + p->box[0] : L->nn[0];
-                int hi1 = lo1 + p->box[1] < L->nn[1] ? lo1 + p->box[1] : L->nn[1];
-                int hi2 = lo2 + p->box[2] < L->nn[2] ? lo2 + p->box[2] : L->nn[2];
+                int lo0 = bi * bsz[0], lo1 = bj * bsz[1], lo2 = bk * bsz[2];
+                int hi0 = lo0 + bsz[0] < L->nn[0] ? lo0 + bsz[0] : L->nn[0];
+                int hi1 = lo1 + bsz[1] < L->nn[1] ? lo1 + bsz[1] : L->nn[1];
+                int hi2 = lo2 + bsz[2] < L->nn[2] ? lo2 + bsz[2] : L->nn[2];
                 for (int si = 0; si < inner; ++si)
-                    sweep_ordered(mg, L, phi, L->old, p->box, rhs, p->box_order, lo0, hi0, lo1, hi1, lo2, hi2, 0);
+                    sweep_ordered(mg, L, phi, L->old, bsz, rhs, p->box_order, lo0, hi0, lo1, hi1, lo2, hi2, 0);
             }
         }
         return;
