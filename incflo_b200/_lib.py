@@ -14,7 +14,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIBDIR = os.path.join(_PKG, "lib")
 SO = os.path.join(LIBDIR, "libb200np.so")
 SOURCES = ["b200np.cu"]
-HEADERS = ["np_level.h", "np_kernels.cuh", os.path.join(ROOT, "include", "b200np.h")]
+HEADERS = ["np_level.h", "np_kernels.cuh", "np_smooth.cuh", os.path.join(ROOT, "include", "b200np.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -65,7 +65,7 @@ class Stats(C.Structure):
 
 
 # every symbol include/b200np.h declares
-EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np_destroy", "b200np_project",
+EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np_destroy", "b200np_set_stream", "b200np_project",
            "b200np_apply_nodal_projection", "b200np_strerror", "b200np_version", "b200np_nlevels",
            "b200np_level_dims", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
            "b200np_time_op"]
@@ -88,6 +88,7 @@ def lib():
     L.b200np_create_dist.argtypes = [C.POINTER(vp), C.POINTER(Geom), C.POINTER(Opts), C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.b200np_destroy.argtypes = [vp]
     L.b200np_destroy.restype = None
+    L.b200np_set_stream.argtypes = [vp, C.c_void_p]
     L.b200np_project.argtypes = [vp, dp, fb, dp, fb, C.c_double, dp, fb, dp, fb, C.c_double, C.c_double, C.POINTER(Stats)]
     L.b200np_apply_nodal_projection.argtypes = [vp, dp, fb, dp, dp, fb, C.c_double, dp, fb, dp, fb, dp, C.c_double,
                                                 C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]

@@ -56,6 +56,7 @@ struct b200np {
     bool sigma_valid = false;
     std::vector<LevelData> lv;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[6]{};
     double* partial = nullptr;  // reduction partials
     double* dscal = nullptr;    // device scalars: [0..1] sums, [2] norm
@@ -492,7 +493,8 @@ int b200np_create(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
         CK(cudaFuncSetAttribute(k_smooth_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
-        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
         for (auto& e : h->ev) CK(cudaEventCreate(&e));
         build_hierarchy(h);
         CK(cudaDeviceSynchronize());
@@ -529,8 +531,17 @@ void b200np_destroy(b200np_t* h)
     if (h->hinfo) cudaFreeHost(h->hinfo);
     for (auto& s : h->stage) if (s.d) cudaFree(s.d);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+}
+
+int b200np_set_stream(b200np_t* h, void* stream)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return B200NP_OK;
 }
 
 int b200np_nlevels(const b200np_t* h) { return h ? (int)h->lv.size() : 0; }

@@ -259,6 +259,22 @@ class IncfloProjection:
             raise ProjectionError(rc)
         return self.stats
 
+    def set_stream(self, cuda_stream):
+        """run on the caller's stream (int handle of a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)"""
+        self._L.b200np_set_stream(self._h, C.c_void_p(cuda_stream))
+
+    def time_op(self, lev, op, arg=1, reps=10):
+        ms = C.c_double()
+        rc = self._L.b200np_time_op(self._h, lev, op, arg, reps, C.byref(ms))
+        if rc:
+            raise ProjectionError(rc)
+        return ms.value
+
+    def level_dims(self, lev):
+        n = (C.c_int * 3)(); nn = (C.c_int * 3)()
+        self._L.b200np_level_dims(self._h, lev, C.byref(n), C.byref(nn))
+        return tuple(n), tuple(nn)
+
     def close(self):
         if self._h is not None:
             self._L.b200np_destroy(self._h)

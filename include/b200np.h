@@ -114,6 +114,11 @@ int b200np_create_dist(b200np_t** out, const b200np_geom* geom, const b200np_opt
 
 void b200np_destroy(b200np_t* h);
 
+/* Run on the caller's CUDA stream (e.g. amrex::Gpu::gpuStream()) instead of the handle's own
+ * non-blocking stream.  stream = a cudaStream_t cast to void*; NULL restores the own stream
+ * (the legacy default stream cannot be captured into a graph, so it is never used). */
+int b200np_set_stream(b200np_t* h, void* stream);
+
 /* Hydro::NodalProjector::project(rtol, atol)   (:215) followed by getPhi() /
  * getGradPhi() (:218-219).
  *   vel   in/out: cell-centred, 3 comps, box grown by >= 1 ghost cell.  Valid
