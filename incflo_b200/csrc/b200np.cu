@@ -73,7 +73,7 @@ struct b200np {
     struct Stage { double* d = nullptr; size_t bytes = 0; };
     Stage stage[8];
     int TZ = 16;
-    int smoother_version = 2, interp_version = 2;  // B200NP_SMOOTHER / B200NP_INTERP env override (1 = simple kernels)
+    int smoother_version = 2, interp_version = 2, resid_version = 2;  // B200NP_SMOOTHER / B200NP_INTERP env override (1 = simple kernels)
 };
 
 namespace {
@@ -200,8 +200,19 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
 
 void residual(b200np* h, LevelData& L, const double* phi, const double* rhs, double* res, double* norm_partial)
 {
-    if (h->var_sigma) LAUNCH(h, k_residual<true>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
-    else              LAUNCH(h, k_residual<false>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
+    if (h->resid_version == 1) {
+        if (h->var_sigma) LAUNCH(h, k_residual<true>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
+        else              LAUNCH(h, k_residual<false>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
+    } else {
+        if (h->var_sigma) k_residual_v2<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
+        else              k_residual_v2<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
+        h->launches++;
+    }
+}
+// number of per-CTA norm partials the residual kernel writes
+long long resid_nblk(b200np* h, LevelData& L)
+{
+    return h->resid_version == 1 ? L.nblk_n : (long long)L.gsm.x * L.gsm.y * L.gsm.z;
 }
 
 void bottom_solve(b200np* h)
@@ -308,7 +319,7 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
     }
     st->rhsnorm = norminf(h, L0, L0.rhs);
     residual(h, L0, L0.sol, L0.rhs, L0.res, h->partial);
-    st->resnorm0 = norm_from_partials(h, L0.nblk_n);
+    st->resnorm0 = norm_from_partials(h, resid_nblk(h, L0));
     const double maxnorm = std::max(st->rhsnorm, st->resnorm0);
     const double target = std::max(atol, std::max(rtol, 1e-16) * maxnorm);
     st->resnorm = st->resnorm0;
@@ -320,7 +331,7 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
         vcycle(h);
         LAUNCH(h, k_axpy, L0.gn, 256, L0.g, L0.sol, L0.cor, 1.0);
         residual(h, L0, L0.sol, L0.rhs, L0.res, h->partial);
-        st->resnorm = norm_from_partials(h, L0.nblk_n);
+        st->resnorm = norm_from_partials(h, resid_nblk(h, L0));
         st->iters = it + 1;
         if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
         if (h->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
@@ -491,6 +502,9 @@ int b200np_create(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         h->TZ = h->opts.tile[2];
         if (const char* e = getenv("B200NP_SMOOTHER")) h->smoother_version = atoi(e);
         if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
+        if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
+        CK(cudaFuncSetAttribute(k_residual_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_residual_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
