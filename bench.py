@@ -126,7 +126,7 @@ def cpu_port_run(N, steps, warmup):
     vel0 = problems.rayleigh_taylor_velocity(n, ng, "cpu", "b").numpy()
     rho = problems.rayleigh_taylor_density(n, ng, "cpu").numpy()
     gp0 = np.zeros((3, N, N, N)); gp0[2] = -0.05
-    prm = po.make_params(n, (1.0 / N,) * 3, (0, 0, 1), (0, 0, 1), smoother=po.SM_BOX, box=(64, 16, 16),
+    prm = po.make_params(n, (1.0 / N,) * 3, (0, 0, 1), (0, 0, 1), smoother=po.SM_BOX, box=(64, 16, 64),
                          box_order=po.SM_PLANE4, box_stale_per_call=0)
     times, iters = [], 0
     for s in range(warmup + steps):

@@ -1,15 +1,20 @@
 // b200np.cu -- host side of the B200-native nodal projection: multigrid hierarchy, MLMG
-// driver, C ABI (include/b200np.h).  Host code is C++ and only launches the sm_100a kernels
-// in np_kernels.cuh / np_smooth.cuh; there is no CPU compute path.
+// driver, slab decomposition over the GPUs of one node (NCCL), C ABI (include/b200np.h).
+// Host code is C++ and only launches the sm_100a kernels in np_kernels.cuh / np_smooth.cuh;
+// there is no CPU compute path.
 //
 // Reference functions restated here (see include/b200np.h and DESIGN.md for the map):
 //   incflo::ApplyNodalProjection      src/projection/incflo_apply_nodal_projection.cpp:29-267
 //   Hydro::NodalProjector::project    [U] SURVEY.md A.1
 //   MLMG::solve / mgVcycle            [U] SURVEY.md A.9
-//   MLNodeLinOp::defineGrids          [U] SURVEY.md A.8 (hierarchy)
+//   MLNodeLinOp::defineGrids, applyBC [U] SURVEY.md A.8 (hierarchy, FillBoundary)
+//   FabArray::FillBoundary / ParallelAllReduce [U] -> NCCL send/recv of z planes, ncclAllReduce
 #include "../../include/b200np.h"
 #include "np_kernels.cuh"
 #include "np_smooth.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -31,17 +36,58 @@ using namespace b200np_dev;
 
 namespace {
 
+// NCCL is loaded lazily (dlopen) so that single-GPU users never depend on it.
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        if (lib) return true;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+#define NP_SYM(name) *(void**)(&name) = dlsym(lib, "nccl" #name); if (!name) return false;
+        NP_SYM(GetUniqueId) NP_SYM(CommInitRank) NP_SYM(CommDestroy) NP_SYM(Send) NP_SYM(Recv) NP_SYM(AllReduce)
+        NP_SYM(GroupStart) NP_SYM(GroupEnd) NP_SYM(GetErrorString)
+#undef NP_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+#define NK(call)                                                                                       \
+    do {                                                                                               \
+        ncclResult_t r_ = (call);                                                                      \
+        if (r_ != ncclSuccess) {                                                                       \
+            fprintf(stderr, "b200np: NCCL error %s at %s:%d\n", g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+            throw int(B200NP_ERR_NCCL);                                                                \
+        }                                                                                              \
+    } while (0)
+
 struct LevelData {
     Lev g{};
+    bool dist = false;        // slab-distributed level (ghost plane slots are exchanged)
     double* sigma = nullptr;  // plane 0 of owned cells (allocation starts one plane earlier)
     double* sigma_alloc = nullptr;
     double *sol = nullptr, *rhs = nullptr, *res = nullptr, *cor = nullptr, *cor2 = nullptr, *rescor = nullptr;
     std::vector<double*> allocs;
     dim3 gn, gc;     // grids of 64x4-thread blocks over owned nodes / cells
-    dim3 gsm;        // smoother grid
+    dim3 gsm;        // smoother / residual grid (tiles x z-chunks)
     dim3 git;        // interpolation grid (fine tiles)
     int tz = 16;     // smoother z-chunk of this level
     long long nblk_n = 0;
+    // first replicated level only: this rank's share as produced by restriction / sigma coarsening
+    Lev gpart{};
+    dim3 gn_part, gc_part;
+    double *part_nodal = nullptr, *part_sigma = nullptr;
 };
 
 }  // namespace
@@ -51,9 +97,10 @@ struct b200np {
     b200np_opts opts{};
     int device = 0;
     int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    int nlev_dist = 0;       // levels [0, nlev_dist) are slab-distributed, the rest replicated on every rank
     int singular = 1;
     bool var_sigma = false;
-    bool sigma_valid = false;
     std::vector<LevelData> lv;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
@@ -68,16 +115,14 @@ struct b200np {
     cudaGraphExec_t graph_exec = nullptr;
     bool graph_var = false;
     double graph_csig = 0.0;  // kernel parameters (Lev by value) are baked into the captured graph
-    long long launches = 0, launches_per_vcycle = 0;
-    // staging buffers for host-pointer callers
+    long long launches = 0, launches_per_vcycle = 0, exchanges = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; };
-    Stage stage[8];
-    int TZ = 16;
-    int smoother_version = 2, interp_version = 2, resid_version = 2;  // B200NP_SMOOTHER / B200NP_INTERP env override (1 = simple kernels)
+    Stage stage[8];  // staging buffers for host-pointer callers
+    int TZ = 64;
+    int smoother_version = 2, interp_version = 2, resid_version = 2;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
 };
 
 namespace {
-
 
 #define LAUNCH(h, kern, grid, block, ...)                        \
     do {                                                         \
@@ -101,48 +146,89 @@ double* alloc_nodal(LevelData& L)
     return base + L.g.ps;
 }
 
+inline bool zper(const b200np* h) { return h->geom.bc_lo[2] == B200NP_BC_PERIODIC; }
+
+// fills the level-independent part of a descriptor for global cell counts n and spacing dx
+void fill_lev(const b200np_geom& G, const int n[3], const double dx[3], Lev& g)
+{
+    for (int d = 0; d < 3; ++d) {
+        g.n[d] = n[d];
+        g.per[d] = (G.bc_lo[d] == B200NP_BC_PERIODIC);
+        g.nn[d] = n[d] + (g.per[d] ? 0 : 1);
+        g.rlo[d] = G.bc_lo[d] == B200NP_BC_NEUMANN ? 1 : (G.bc_lo[d] == B200NP_BC_INFLOW ? 2 : 0);
+        g.rhi[d] = G.bc_hi[d] == B200NP_BC_NEUMANN ? 1 : (G.bc_hi[d] == B200NP_BC_INFLOW ? 2 : 0);
+        g.dlo[d] = G.bc_lo[d] == B200NP_BC_DIRICHLET;
+        g.dhi[d] = G.bc_hi[d] == B200NP_BC_DIRICHLET;
+        g.dxinv[d] = 1.0 / dx[d];
+    }
+    g.px = (g.nn[0] + 7) / 8 * 8;
+    g.ps = (long long)g.px * g.nn[1];
+    g.cpx = (g.n[0] + 7) / 8 * 8;
+    g.cps = (long long)g.cpx * g.n[1];
+    g.k0 = 0; g.nzl = g.nn[2];
+    g.ck0 = 0; g.cnzl = g.n[2];
+    g.dist = 0;
+    const double fx = g.dxinv[0] * g.dxinv[0] / 36.0, fy = g.dxinv[1] * g.dxinv[1] / 36.0, fz = g.dxinv[2] * g.dxinv[2] / 36.0;
+    g.fxyz = fx + fy + fz;
+    g.fmx2y2z = -fx + 2 * fy + 2 * fz; g.f2xmy2z = 2 * fx - fy + 2 * fz; g.f2x2ymz = 2 * fx + 2 * fy - fz;
+    g.f4xm2ym2z = 4 * fx - 2 * fy - 2 * fz; g.fm2x4ym2z = -2 * fx + 4 * fy - 2 * fz; g.fm2xm2y4z = -2 * fx - 2 * fy + 4 * fz;
+    g.csig = 1.0; g.sigma = nullptr;
+}
+
+// this rank's slab of a level with n2 cell planes split over P ranks
+void set_slab(Lev& g, int rank, int P, bool periodic_z)
+{
+    const int m = g.n[2] / P;
+    g.ck0 = rank * m; g.cnzl = m;
+    g.k0 = rank * m; g.nzl = m + ((!periodic_z && rank == P - 1) ? 1 : 0);
+    g.dist = 1;
+}
+
 void build_hierarchy(b200np* h)
 {
     const b200np_geom& G = h->geom;
+    const int P = h->nranks;
     int n[3] = {G.n_cell[0], G.n_cell[1], G.n_cell[2]};
     double dx[3] = {G.dx[0], G.dx[1], G.dx[2]};
     h->singular = 1;
     for (int d = 0; d < 3; ++d)
         if (G.bc_lo[d] == B200NP_BC_DIRICHLET || G.bc_hi[d] == B200NP_BC_DIRICHLET) h->singular = 0;
     int lev = 0;
+    bool still_dist = P > 1;
+    h->nlev_dist = 0;
     for (;;) {
         LevelData L;
         Lev& g = L.g;
-        for (int d = 0; d < 3; ++d) {
-            g.n[d] = n[d];
-            g.per[d] = (G.bc_lo[d] == B200NP_BC_PERIODIC);
-            g.nn[d] = n[d] + (g.per[d] ? 0 : 1);
-            g.rlo[d] = G.bc_lo[d] == B200NP_BC_NEUMANN ? 1 : (G.bc_lo[d] == B200NP_BC_INFLOW ? 2 : 0);
-            g.rhi[d] = G.bc_hi[d] == B200NP_BC_NEUMANN ? 1 : (G.bc_hi[d] == B200NP_BC_INFLOW ? 2 : 0);
-            g.dlo[d] = G.bc_lo[d] == B200NP_BC_DIRICHLET;
-            g.dhi[d] = G.bc_hi[d] == B200NP_BC_DIRICHLET;
-            g.dxinv[d] = 1.0 / dx[d];
+        fill_lev(G, n, dx, g);
+        // a level stays distributed while every rank keeps an even number (>= 8) of cell planes
+        if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && n[2] / P >= 8) {
+            set_slab(g, h->rank, P, zper(h));
+            L.dist = true;
+            h->nlev_dist = lev + 1;
+        } else {
+            if (still_dist && lev == 0) throw int(B200NP_ERR_BAD_ARG);  // level 0 must be distributable
+            if (still_dist) {  // first replicated level: remember this rank's share
+                L.gpart = g;
+                set_slab(L.gpart, h->rank, P, zper(h));
+                L.gn_part = dim3((g.nn[0] + 63) / 64, (g.nn[1] + 3) / 4, L.gpart.nzl);
+                L.gc_part = dim3((g.n[0] + 63) / 64, (g.n[1] + 3) / 4, L.gpart.cnzl);
+                L.part_nodal = dev_alloc((size_t)g.ps * (L.gpart.nzl + 2));
+                L.part_sigma = dev_alloc((size_t)g.cps * (L.gpart.cnzl + 2));
+            }
+            still_dist = false;
         }
-        g.px = (g.nn[0] + 7) / 8 * 8;
-        g.ps = (long long)g.px * g.nn[1];
-        g.cpx = (g.n[0] + 7) / 8 * 8;
-        g.cps = (long long)g.cpx * g.n[1];
-        g.k0 = 0; g.nzl = g.nn[2];
-        g.ck0 = 0; g.cnzl = g.n[2];
-        g.dist = 0;
-        const double fx = g.dxinv[0] * g.dxinv[0] / 36.0, fy = g.dxinv[1] * g.dxinv[1] / 36.0, fz = g.dxinv[2] * g.dxinv[2] / 36.0;
-        g.fxyz = fx + fy + fz;
-        g.fmx2y2z = -fx + 2 * fy + 2 * fz; g.f2xmy2z = 2 * fx - fy + 2 * fz; g.f2x2ymz = 2 * fx + 2 * fy - fz;
-        g.f4xm2ym2z = 4 * fx - 2 * fy - 2 * fz; g.fm2x4ym2z = -2 * fx + 4 * fy - 2 * fz; g.fm2xm2y4z = -2 * fx - 2 * fy + 4 * fz;
-        g.csig = 1.0; g.sigma = nullptr;
         L.gn = dim3((g.nn[0] + 63) / 64, (g.nn[1] + 3) / 4, g.nzl);
         L.gc = dim3((g.n[0] + 63) / 64, (g.n[1] + 3) / 4, g.cnzl);
-        // z-chunk rule (mirrored by the oracle): at least 8 chunks per level where possible
-        L.tz = std::max(2, std::min(h->TZ, g.nn[2] / 8));
+        // z-chunk rule (mirrored by the oracle): aim at 592 CTAs per sweep = 148 SMs x 2 resident
+        // CTAs x 2 waves, chunk height between 8 and the cap opts.tile[2] (< 8 costs a V-cycle)
+        {
+            const int ntiles = ((g.nn[0] + NP_TX - 1) / NP_TX) * ((g.nn[1] + NP_TY - 1) / NP_TY);
+            const int nch = std::max(1, 592 / ntiles);
+            L.tz = std::max(8, std::min(h->TZ, (g.nn[2] + nch - 1) / nch));
+        }
         L.gsm = dim3((g.nn[0] + NP_TX - 1) / NP_TX, (g.nn[1] + NP_TY - 1) / NP_TY, (g.nzl + L.tz - 1) / L.tz);
         L.git = dim3((g.nn[0] + IT_X - 1) / IT_X, (g.nn[1] + IT_Y - 1) / IT_Y, (g.nzl + IT_Z - 1) / IT_Z);
         L.nblk_n = (long long)L.gn.x * L.gn.y * L.gn.z;
-        // arrays
         L.sigma_alloc = dev_alloc((size_t)g.cps * (g.cnzl + 2));
         L.sigma = L.sigma_alloc + g.cps;
         L.res = alloc_nodal(L); L.cor = alloc_nodal(L); L.cor2 = alloc_nodal(L); L.rescor = alloc_nodal(L);
@@ -155,6 +241,7 @@ void build_hierarchy(b200np* h)
         if (!ok) break;
         for (int d = 0; d < 3; ++d) { n[d] /= 2; dx[d] *= 2; }
     }
+    if (P > 1 && h->nlev_dist >= (int)h->lv.size()) throw int(B200NP_ERR_BAD_ARG);  // needs a replicated coarse level
     long long maxblk = 0;
     for (auto& L : h->lv) maxblk = std::max(maxblk, L.nblk_n);
     h->partial = dev_alloc((size_t)2 * maxblk + 16);
@@ -167,25 +254,117 @@ void build_hierarchy(b200np* h)
     h->bottom_work = dev_alloc((size_t)B.ps * B.nzl * 8);
 }
 
+// ---- slab communication (MLNodeLinOp::applyBC's FillBoundary) ------------------------
+// Exchanges one plane with each z neighbour: plane `first` -> lower neighbour's upper ghost slot,
+// plane `last` -> upper neighbour's lower ghost slot.  Physical (non-periodic) ends are filled
+// locally by `end_lo` / `end_hi` (reflection for nodes, clamp for cells).
+void exchange_planes(b200np* h, double* base, long long plane, int nown, bool nodal)
+{
+    const int P = h->nranks, r = h->rank;
+    const bool per = zper(h);
+    const bool has_lo = per || r > 0, has_hi = per || r < P - 1;
+    const int lo = (r - 1 + P) % P, hi = (r + 1) % P;
+    double* ghost_lo = base - plane;
+    double* ghost_hi = base + (long long)nown * plane;
+    NK(g_nccl.GroupStart());
+    if (has_lo) NK(g_nccl.Send(base, plane, ncclDouble, lo, h->comm, h->stream));
+    if (has_hi) NK(g_nccl.Send(base + (long long)(nown - 1) * plane, plane, ncclDouble, hi, h->comm, h->stream));
+    if (has_hi) NK(g_nccl.Recv(ghost_hi, plane, ncclDouble, hi, h->comm, h->stream));
+    if (has_lo) NK(g_nccl.Recv(ghost_lo, plane, ncclDouble, lo, h->comm, h->stream));
+    NK(g_nccl.GroupEnd());
+    if (!has_lo)  // nodes: phi(-1) = phi(1); cells: copy of the adjacent interior cell
+        CK(cudaMemcpyAsync(ghost_lo, base + (nodal ? plane : 0), plane * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (!has_hi)
+        CK(cudaMemcpyAsync(ghost_hi, base + (long long)(nown - (nodal ? 2 : 1)) * plane, plane * sizeof(double),
+                           cudaMemcpyDeviceToDevice, h->stream));
+    h->exchanges++;
+}
+inline void halo_nodes(b200np* h, LevelData& L, double* x)
+{
+    if (L.dist) exchange_planes(h, x, L.g.ps, L.g.nzl, true);
+}
+inline void halo_cells(b200np* h, LevelData& L, double* s)
+{
+    if (L.dist) exchange_planes(h, s, L.g.cps, L.g.cnzl, false);
+}
+// vel.FillBoundary(1 ghost) across slabs, written into the caller's ghost cell planes (compRHS, A.2)
+void halo_vel(b200np* h, Fab vel)
+{
+    if (h->nranks == 1) return;
+    const Lev& g = h->lv[0].g;
+    const int P = h->nranks, r = h->rank;
+    const bool per = zper(h);
+    const bool has_lo = per || r > 0, has_hi = per || r < P - 1;
+    const int lo = (r - 1 + P) % P, hi = (r + 1) % P;
+    const long long pl = (long long)vel.nx * vel.ny;
+    const int zfirst = g.ck0 - vel.lo[2], zlast = g.ck0 + g.cnzl - 1 - vel.lo[2];
+    NK(g_nccl.GroupStart());
+    for (int c = 0; c < 3; ++c) {
+        double* b = vel.p + c * vel.cstride;
+        if (has_lo) NK(g_nccl.Send(b + zfirst * pl, pl, ncclDouble, lo, h->comm, h->stream));
+        if (has_hi) NK(g_nccl.Send(b + zlast * pl, pl, ncclDouble, hi, h->comm, h->stream));
+        if (has_hi) NK(g_nccl.Recv(b + (zlast + 1) * pl, pl, ncclDouble, hi, h->comm, h->stream));
+        if (has_lo) NK(g_nccl.Recv(b + (zfirst - 1) * pl, pl, ncclDouble, lo, h->comm, h->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    h->exchanges++;
+}
+// assemble a replicated array from every rank's share (agglomeration onto all ranks):
+// rank q's planes [q*m, q*m + cnt_q) of `full` come from q's `part`.
+void allgather_parts(b200np* h, const Lev& gfull, const double* part, double* full, bool nodal)
+{
+    const int P = h->nranks, r = h->rank;
+    const long long plane = nodal ? gfull.ps : gfull.cps;
+    const int m = gfull.n[2] / P;
+    auto cnt = [&](int q) { return m + ((nodal && !zper(h) && q == P - 1) ? 1 : 0); };
+    NK(g_nccl.GroupStart());
+    for (int q = 0; q < P; ++q) {
+        if (q == r) continue;
+        NK(g_nccl.Send(part, (size_t)cnt(r) * plane, ncclDouble, q, h->comm, h->stream));
+        NK(g_nccl.Recv(full + (long long)q * m * plane, (size_t)cnt(q) * plane, ncclDouble, q, h->comm, h->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    CK(cudaMemcpyAsync(full + (long long)r * m * plane, part, (size_t)cnt(r) * plane * sizeof(double),
+                       cudaMemcpyDeviceToDevice, h->stream));
+    h->exchanges++;
+}
+inline void allreduce(b200np* h, double* d, int n, ncclRedOp_t op)
+{
+    if (h->nranks > 1) NK(g_nccl.AllReduce(d, d, n, ncclDouble, op, h->comm, h->stream));
+}
+
+// ---- multigrid building blocks --------------------------------------------------------------------
 void set_level_sigma_ptrs(b200np* h, bool var, double csig)
 {
     h->var_sigma = var;
-    for (auto& L : h->lv) { L.g.sigma = var ? L.sigma : nullptr; L.g.csig = csig; }
-}
-
-void coarsen_sigma(b200np* h)
-{
-    if (!h->var_sigma) return;
-    for (size_t l = 0; l + 1 < h->lv.size(); ++l) {
-        LevelData &F = h->lv[l], &C = h->lv[l + 1];
-        LAUNCH(h, k_coarsen_sigma, C.gc, 256, F.g, C.g, F.sigma, C.sigma);
+    for (auto& L : h->lv) {
+        L.g.sigma = var ? L.sigma : nullptr; L.g.csig = csig;
+        L.gpart.sigma = nullptr; L.gpart.csig = csig;
     }
 }
 
-// one Gauss-Seidel sweep (ping-pong cor -> cor2, then swap)
+// average_down of sigma to every level (A.8) + ghost layers across slabs
+void coarsen_sigma(b200np* h)
+{
+    if (!h->var_sigma) return;
+    halo_cells(h, h->lv[0], h->lv[0].sigma);
+    for (size_t l = 0; l + 1 < h->lv.size(); ++l) {
+        LevelData &F = h->lv[l], &C = h->lv[l + 1];
+        if (F.dist && !C.dist) {  // first replicated level: coarsen my share, then gather everybody's
+            LAUNCH(h, k_coarsen_sigma, C.gc_part, 256, F.g, C.gpart, F.sigma, C.part_sigma + C.g.cps);
+            allgather_parts(h, C.g, C.part_sigma + C.g.cps, C.sigma, false);
+        } else {
+            LAUNCH(h, k_coarsen_sigma, C.gc, 256, F.g, C.g, F.sigma, C.sigma);
+            halo_cells(h, C, C.sigma);
+        }
+    }
+}
+
+// Gauss-Seidel sweeps (ping-pong x -> y, then swap); halo refresh before every sweep on slab levels
 void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double* rhs, int nsweeps)
 {
     for (int s = 0; s < nsweeps; ++s) {
+        halo_nodes(h, L, x);
         if (h->smoother_version == 1) {
             if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, L.tz);
             else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, L.tz);
@@ -198,8 +377,10 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
     }
 }
 
-void residual(b200np* h, LevelData& L, const double* phi, const double* rhs, double* res, double* norm_partial)
+// res = rhs - L phi (phi's ghost planes are refreshed first on slab levels)
+void residual(b200np* h, LevelData& L, double* phi, const double* rhs, double* res, double* norm_partial)
 {
+    halo_nodes(h, L, phi);
     if (h->resid_version == 1) {
         if (h->var_sigma) LAUNCH(h, k_residual<true>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
         else              LAUNCH(h, k_residual<false>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
@@ -229,11 +410,18 @@ void bottom_solve(b200np* h)
 void restrict_to(b200np* h, int l)
 {
     LevelData &F = h->lv[l], &C = h->lv[l + 1];
-    LAUNCH(h, k_restrict, C.gn, 256, F.g, C.g, F.rescor, C.res);
+    halo_nodes(h, F, F.rescor);
+    if (F.dist && !C.dist) {  // agglomeration: my share of the coarse rhs, then gather onto every rank
+        LAUNCH(h, k_restrict, C.gn_part, 256, F.g, C.gpart, F.rescor, C.part_nodal + C.g.ps);
+        allgather_parts(h, C.g, C.part_nodal + C.g.ps, C.res, true);
+    } else {
+        LAUNCH(h, k_restrict, C.gn, 256, F.g, C.g, F.rescor, C.res);
+    }
 }
 void interp_add(b200np* h, int l)
 {
     LevelData &F = h->lv[l], &C = h->lv[l + 1];
+    halo_nodes(h, C, C.cor);
     if (h->interp_version == 1) {
         if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
         else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
@@ -269,7 +457,7 @@ void vcycle_launch(b200np* h, int lev0)
 
 void vcycle(b200np* h)
 {
-    if (!h->opts.use_graph) { vcycle_launch(h, 0); return; }
+    if (!h->opts.use_graph || h->nranks > 1) { vcycle_launch(h, 0); return; }
     if (h->graph_exec && (h->graph_var != h->var_sigma || h->graph_csig != h->lv[0].g.csig)) {
         cudaGraphExecDestroy(h->graph_exec); cudaGraphDestroy(h->graph);
         h->graph_exec = nullptr; h->graph = nullptr;
@@ -289,9 +477,11 @@ void vcycle(b200np* h)
     h->launches += h->launches_per_vcycle;
 }
 
+// global inf-norm from per-CTA partials: device max, ncclAllReduce(max) over slabs, one host read
 double norm_from_partials(b200np* h, long long nb)
 {
     LAUNCH(h, k_max_final, 1, 1024, h->partial, nb, h->dscal + 2);
+    allreduce(h, h->dscal + 2, 1, ncclMax);
     CK(cudaMemcpyAsync(h->hscal + 2, h->dscal + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return h->hscal[2];
@@ -315,6 +505,7 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
     } else {  // makeSolvable: subtract the weighted mean of rhs (A.8)
         LAUNCH(h, k_wsum_partial, L0.gn, 256, L0.g, L0.rhs, h->partial);
         LAUNCH(h, k_sum2_final, 1, 1024, h->partial, L0.nblk_n, h->dscal);
+        allreduce(h, h->dscal, 2, ncclSum);
         LAUNCH(h, k_sub_mean, L0.gn, 256, L0.g, L0.rhs, h->dscal);
     }
     st->rhsnorm = norminf(h, L0, L0.rhs);
@@ -324,7 +515,8 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
     const double target = std::max(atol, std::max(rtol, 1e-16) * maxnorm);
     st->resnorm = st->resnorm0;
     st->resnorm_hist[0] = st->resnorm0;
-    if (h->opts.verbose >= 1) printf("MLMG: Initial rhs               = %.12g\nMLMG: Initial residual (resid0) = %.12g\n", st->rhsnorm, st->resnorm0);
+    const bool talk = h->rank == 0;
+    if (talk && h->opts.verbose >= 1) printf("MLMG: Initial rhs               = %.12g\nMLMG: Initial residual (resid0) = %.12g\n", st->rhsnorm, st->resnorm0);
     if (st->resnorm0 <= target) return B200NP_OK;
     bool converged = false;
     for (int it = 0; it < h->opts.maxiter; ++it) {
@@ -334,7 +526,7 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
         st->resnorm = norm_from_partials(h, resid_nblk(h, L0));
         st->iters = it + 1;
         if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
-        if (h->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
+        if (talk && h->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
         if (st->resnorm <= target) { converged = true; break; }
         if (!(st->resnorm <= 1e20 * maxnorm)) { st->status = B200NP_ERR_DIVERGED; break; }
     }
@@ -342,7 +534,7 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
     CK(cudaMemcpyAsync(h->hinfo, h->dinfo, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     st->bottom_iters = h->hinfo[0];
-    if (h->opts.verbose >= 1)
+    if (talk && h->opts.verbose >= 1)
         printf("MLMG: Final Iter. %d resid, resid/bnorm = %.12g, %.12g\n", st->iters, st->resnorm, st->resnorm / maxnorm);
     return st->status;
 }
@@ -404,6 +596,19 @@ bool box_covers(const b200np_fab* b, const int lo[3], const int hi[3], int ncomp
     for (int d = 0; d < 3; ++d) if (b->lo[d] > lo[d] || b->hi[d] < hi[d]) return false;
     return true;
 }
+// the caller's velocity box must hold one ghost layer wherever the divergence reads it:
+// at non-periodic faces and, on a slab, towards the z neighbours
+bool vel_box_ok(const b200np* h, const b200np_fab* vb)
+{
+    const Lev& g = h->lv[0].g;
+    const int clo[3] = {0, 0, g.ck0}, chi[3] = {g.n[0] - 1, g.n[1] - 1, g.ck0 + g.cnzl - 1};
+    if (!box_covers(vb, clo, chi, 3)) return false;
+    for (int d = 0; d < 3; ++d) {
+        const bool need = !g.per[d] || (d == 2 && h->nranks > 1);
+        if (need && (vb->lo[d] > clo[d] - 1 || vb->hi[d] < chi[d] + 1)) return false;
+    }
+    return true;
+}
 
 // the common core: rhs = D vel; solve; vel -= sigma G phi; gphi, phi copy-out.
 int project_core(b200np* h, Fab vel, Fab velo, int add_old, Fab gphi, int acc_g, Fab pout, int acc_p, double rtol,
@@ -411,11 +616,13 @@ int project_core(b200np* h, Fab vel, Fab velo, int add_old, Fab gphi, int acc_g,
 {
     LevelData& L0 = h->lv[0];
     coarsen_sigma(h);
+    halo_vel(h, vel);
     LAUNCH(h, k_divu, L0.gn, 256, L0.g, vel, L0.rhs);
     CK(cudaMemsetAsync(L0.sol - L0.g.ps, 0, (size_t)L0.g.ps * (L0.g.nzl + 2) * sizeof(double), h->stream));
     CK(cudaEventRecord(h->ev[2], h->stream));
     int status = mlmg_solve(h, rtol, atol, st);
     CK(cudaEventRecord(h->ev[3], h->stream));
+    halo_nodes(h, L0, L0.sol);  // the gradient and the copy-out read the node plane above the slab
     LAUNCH(h, k_mknewu, L0.gc, 256, L0.g, L0.sol, vel, velo, add_old, gphi, acc_g);
     if (pout.p) {
         dim3 g((pout.nx + 63) / 64, (pout.ny + 3) / 4, pout.nz);
@@ -444,6 +651,54 @@ int check_geom(const b200np_geom* g)
     return B200NP_OK;
 }
 
+int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device, int rank, int nranks,
+                  const void* nccl_unique_id)
+{
+    if (!out || !geom) return B200NP_ERR_BAD_ARG;
+    *out = nullptr;
+    int rc = check_geom(geom);
+    if (rc) return rc;
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !nccl_unique_id)) return B200NP_ERR_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return B200NP_ERR_CUDA;
+    }
+    if (nranks > 1 && !g_nccl.load()) return B200NP_ERR_NCCL;
+    b200np* h = new b200np();
+    try {
+        CK(cudaSetDevice(device));
+        h->device = device;
+        h->rank = rank; h->nranks = nranks;
+        h->geom = *geom;
+        if (opts) h->opts = *opts; else b200np_default_opts(&h->opts);
+        if (h->opts.tile[0] != NP_TX || h->opts.tile[1] != NP_TY || h->opts.tile[2] < 1) { delete h; return B200NP_ERR_BAD_ARG; }
+        h->TZ = h->opts.tile[2];
+        if (const char* e = getenv("B200NP_SMOOTHER")) h->smoother_version = atoi(e);
+        if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
+        if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
+        CK(cudaFuncSetAttribute(k_residual_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_residual_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
+        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        for (auto& e : h->ev) CK(cudaEventCreate(&e));
+        if (nranks > 1) {
+            ncclUniqueId id;
+            memcpy(&id, nccl_unique_id, sizeof(id));
+            NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+        }
+        build_hierarchy(h);
+        CK(cudaDeviceSynchronize());
+    } catch (int e) {
+        b200np_destroy(h);
+        return e;
+    }
+    *out = h;
+    return B200NP_OK;
+}
+
 }  // namespace
 
 // ============================================================================================
@@ -460,7 +715,7 @@ void b200np_default_opts(b200np_opts* o)
     o->mg_max_coarsening_level = 100;  // src/incflo.H:458
     o->num_pre_smooth = 2; o->num_post_smooth = 2; o->smooth_num_sweeps = 4;
     o->bottom_solver = 0;
-    o->tile[0] = NP_TX; o->tile[1] = NP_TY; o->tile[2] = 16;
+    o->tile[0] = NP_TX; o->tile[1] = NP_TY; o->tile[2] = 64;
     o->use_graph = 1;
 }
 
@@ -483,50 +738,35 @@ const char* b200np_strerror(int s)
 
 int b200np_create(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device)
 {
-    if (!out || !geom) return B200NP_ERR_BAD_ARG;
-    *out = nullptr;
-    int rc = check_geom(geom);
-    if (rc) return rc;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
-        cudaGetLastError();
-        return B200NP_ERR_CUDA;
-    }
-    b200np* h = new b200np();
-    try {
-        CK(cudaSetDevice(device));
-        h->device = device;
-        h->geom = *geom;
-        if (opts) h->opts = *opts; else b200np_default_opts(&h->opts);
-        if (h->opts.tile[0] != NP_TX || h->opts.tile[1] != NP_TY || h->opts.tile[2] < 1) { delete h; return B200NP_ERR_BAD_ARG; }
-        h->TZ = h->opts.tile[2];
-        if (const char* e = getenv("B200NP_SMOOTHER")) h->smoother_version = atoi(e);
-        if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
-        if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
-        CK(cudaFuncSetAttribute(k_residual_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
-        CK(cudaFuncSetAttribute(k_residual_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
-        CK(cudaFuncSetAttribute(k_smooth_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
-        CK(cudaFuncSetAttribute(k_smooth_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
-        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-        h->stream = h->own_stream;
-        for (auto& e : h->ev) CK(cudaEventCreate(&e));
-        build_hierarchy(h);
-        CK(cudaDeviceSynchronize());
-    } catch (int e) {
-        b200np_destroy(h);
-        return e;
-    }
-    *out = h;
-    return B200NP_OK;
+    return create_common(out, geom, opts, device, 0, 1, nullptr);
 }
 
 int b200np_create_dist(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device, int rank,
                        int nranks, const void* nccl_unique_id)
 {
-    if (nranks == 1) return b200np_create(out, geom, opts, device);
-    (void)rank; (void)nccl_unique_id;
-    if (out) *out = nullptr;
-    return B200NP_ERR_UNSUPPORTED;
+    return create_common(out, geom, opts, device, rank, nranks, nccl_unique_id);
+}
+
+int b200np_nccl_unique_id(void* out128)
+{
+    if (!out128) return B200NP_ERR_BAD_ARG;
+    if (!g_nccl.load()) return B200NP_ERR_NCCL;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return B200NP_ERR_NCCL;
+    memcpy(out128, &id, sizeof(id));
+    return B200NP_OK;
+}
+
+int b200np_slab_range(const b200np_geom* geom, int rank, int nranks, int* cell_lo, int* cell_hi, int* node_lo, int* node_hi)
+{
+    if (!geom || nranks < 1 || rank < 0 || rank >= nranks || geom->n_cell[2] % nranks != 0) return B200NP_ERR_BAD_ARG;
+    const int m = geom->n_cell[2] / nranks;
+    const bool per = geom->bc_lo[2] == B200NP_BC_PERIODIC;
+    if (cell_lo) *cell_lo = rank * m;
+    if (cell_hi) *cell_hi = (rank + 1) * m - 1;
+    if (node_lo) *node_lo = rank * m;
+    if (node_hi) *node_hi = (rank + 1) * m - 1 + ((!per && rank == nranks - 1) ? 1 : 0);  // owned (unique) node planes
+    return B200NP_OK;
 }
 
 void b200np_destroy(b200np_t* h)
@@ -536,9 +776,12 @@ void b200np_destroy(b200np_t* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
     for (auto& L : h->lv) {
         for (double* p : L.allocs) cudaFree(p);
         cudaFree(L.sigma_alloc);
+        if (L.part_nodal) cudaFree(L.part_nodal);
+        if (L.part_sigma) cudaFree(L.part_sigma);
     }
     cudaFree(h->partial); cudaFree(h->dscal); cudaFree(h->dinfo); cudaFree(h->bottom_work);
     if (h->hscal) cudaFreeHost(h->hscal);
@@ -564,6 +807,7 @@ int b200np_level_dims(const b200np_t* h, int lev, int n_cell[3], int n_node[3])
 {
     if (!h || lev < 0 || lev >= (int)h->lv.size()) return B200NP_ERR_BAD_ARG;
     for (int d = 0; d < 3; ++d) { n_cell[d] = h->lv[lev].g.n[d]; n_node[d] = h->lv[lev].g.nn[d]; }
+    n_cell[2] = h->lv[lev].g.cnzl; n_node[2] = h->lv[lev].g.nzl;  // locally owned planes
     return B200NP_OK;
 }
 
@@ -603,13 +847,11 @@ int b200np_project(b200np_t* h, double* vel, const b200np_fab* vel_box, const do
         LevelData& L0 = h->lv[0];
         const Lev& g = L0.g;
         const int clo[3] = {0, 0, g.ck0}, chi[3] = {g.n[0] - 1, g.n[1] - 1, g.ck0 + g.cnzl - 1};
-        if (!box_covers(vel_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
-        for (int d = 0; d < 3; ++d)  // a ghost layer is an input at non-periodic faces
-            if (!g.per[d] && (vel_box->lo[d] > -1 || vel_box->hi[d] < g.n[d])) return st->status = B200NP_ERR_BAD_ARG;
+        if (!vel_box_ok(h, vel_box)) return st->status = B200NP_ERR_BAD_ARG;
         if (sigma && !box_covers(sigma_box, clo, chi, 1)) return st->status = B200NP_ERR_BAD_ARG;
         if (gphi && !box_covers(gphi_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
         if (phi && (!phi_box || phi_box->ncomp < 1)) return st->status = B200NP_ERR_BAD_ARG;
-        h->launches = 0;
+        h->launches = 0; h->exchanges = 0;
         CK(cudaEventRecord(h->ev[0], h->stream));
         bool s_vel, s_sig, s_phi = false, s_g = false;
         double* dvel = stage_in(h, 0, vel, vel_box, true, &s_vel, st);
@@ -654,11 +896,9 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
         LevelData& L0 = h->lv[0];
         const Lev& g = L0.g;
         const int clo[3] = {0, 0, g.ck0}, chi[3] = {g.n[0] - 1, g.n[1] - 1, g.ck0 + g.cnzl - 1};
-        if (!box_covers(vel_box, clo, chi, 3) || !box_covers(gp_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
+        if (!vel_box_ok(h, vel_box) || !box_covers(gp_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
         if (density && !box_covers(rho_box, clo, chi, 1)) return st->status = B200NP_ERR_BAD_ARG;
-        for (int d = 0; d < 3; ++d)
-            if (!g.per[d] && (vel_box->lo[d] > -1 || vel_box->hi[d] < g.n[d])) return st->status = B200NP_ERR_BAD_ARG;
-        h->launches = 0;
+        h->launches = 0; h->exchanges = 0;
         CK(cudaEventRecord(h->ev[0], h->stream));
         bool s_vel, s_velo, s_rho, s_gp, s_p, s_in;
         double* dvel = stage_in(h, 0, velocity, vel_box, true, &s_vel, st);

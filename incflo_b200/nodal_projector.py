@@ -223,19 +223,48 @@ def _empty_like(like, shape):
     return torch.zeros(shape, dtype=torch.float64, device=like.device)
 
 
+def nccl_unique_id():
+    """the 128 bytes of an ncclUniqueId (call on rank 0, broadcast to the other ranks)"""
+    buf = C.create_string_buffer(128)
+    rc = _lib.lib().b200np_nccl_unique_id(buf)
+    if rc != 0:
+        raise ProjectionError(rc)
+    return buf.raw
+
+
+def slab_range(n_cell, bclo, rank, nranks):
+    """(cell_lo, cell_hi, node_lo, node_hi) in z of `rank` (b200np_slab_range; needs no GPU)"""
+    g = Geom()
+    for d in range(3):
+        g.n_cell[d] = int(n_cell[d]); g.dx[d] = 1.0; g.bc_lo[d] = int(bclo[d]); g.bc_hi[d] = int(bclo[d])
+    v = [C.c_int() for _ in range(4)]
+    rc = _lib.lib().b200np_slab_range(C.byref(g), rank, nranks, *[C.byref(x) for x in v])
+    if rc != 0:
+        raise ProjectionError(rc)
+    return tuple(x.value for x in v)
+
+
 class IncfloProjection:
     """Keeps one b200np handle alive across time steps (the reference rebuilds the
     projector every call, :181-193; caching the hierarchy gives identical results)."""
 
-    def __init__(self, n_cell, dx, bclo, bchi, opts=None, device=0):
+    def __init__(self, n_cell, dx, bclo, bchi, opts=None, device=0, rank=0, nranks=1, nccl_id=None):
+        """n_cell is the GLOBAL domain; with nranks > 1 this rank owns the z slab slab_range(...)
+        and every array passed to apply_nodal_projection is the rank's local box."""
         self._L = _lib.lib()
         self.n = tuple(int(x) for x in n_cell)
         g = Geom()
         for d in range(3):
             g.n_cell[d] = self.n[d]; g.dx[d] = float(dx[d]); g.bc_lo[d] = int(bclo[d]); g.bc_hi[d] = int(bchi[d])
         self.opts = opts if opts is not None else nodal_proj_opts()
+        self.rank, self.nranks = int(rank), int(nranks)
+        self.zlo = slab_range(self.n, bclo, rank, nranks)[0] if nranks > 1 else 0
         h = C.c_void_p()
-        rc = self._L.b200np_create(C.byref(h), C.byref(g), C.byref(self.opts), device)
+        if nranks > 1:
+            buf = C.create_string_buffer(bytes(nccl_id), 128)
+            rc = self._L.b200np_create_dist(C.byref(h), C.byref(g), C.byref(self.opts), device, rank, nranks, buf)
+        else:
+            rc = self._L.b200np_create(C.byref(h), C.byref(g), C.byref(self.opts), device)
         if rc != 0:
             raise ProjectionError(rc)
         self._h = h
@@ -245,12 +274,13 @@ class IncfloProjection:
                                inflow_vel=None, scaling_factor=1.0, incremental=False, proj_for_small_dt=False,
                                mg_rtol=1e-11, mg_atol=1e-14):
         """incflo::ApplyNodalProjection(density, time, scaling_factor, incremental)."""
-        pv, bv, _ = _ptr_box(velocity, (-ng,) * 3, 3)
-        po, _, _ = _ptr_box(velocity_o, (-ng,) * 3, 3)
-        pr, br, _ = _ptr_box(density, (-ngd,) * 3, 1)
-        pg, bg, _ = _ptr_box(gp, (0, 0, 0), 3)
-        pp, bp, _ = _ptr_box(p_nd, (0, 0, 0), 1)
-        pi, _, _ = _ptr_box(inflow_vel, (-ng,) * 3, 3)
+        z = self.zlo
+        pv, bv, _ = _ptr_box(velocity, (-ng, -ng, z - ng), 3)
+        po, _, _ = _ptr_box(velocity_o, (-ng, -ng, z - ng), 3)
+        pr, br, _ = _ptr_box(density, (-ngd, -ngd, z - ngd), 1)
+        pg, bg, _ = _ptr_box(gp, (0, 0, z), 3)
+        pp, bp, _ = _ptr_box(p_nd, (0, 0, z), 1)
+        pi, _, _ = _ptr_box(inflow_vel, (-ng, -ng, z - ng), 3)
         rc = self._L.b200np_apply_nodal_projection(self._h, pv, C.byref(bv), po, pr, C.byref(br) if br is not None else None,
                                                    float(ro_0), pg, C.byref(bg), pp, C.byref(bp), pi,
                                                    float(scaling_factor), int(incremental), int(proj_for_small_dt),

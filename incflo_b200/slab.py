@@ -1,0 +1,50 @@
+"""Host-side description of the z-slab decomposition used by libb200np.so.
+
+Mirrors, in Python, the partition (b200np_slab_range) and the neighbour exchange plan
+(exchange_planes in csrc/b200np.cu) so that the multi-process logic can be exercised on CPU with
+torch.distributed's gloo backend and so that bench.py / tests can cut global fields into slabs.
+"""
+from . import nodal_projector as npj
+
+
+def halo_plan(rank, nranks, periodic_z):
+    """Order of the grouped point-to-point operations of one plane exchange.
+
+    Returns (sends, recvs): sends = [(peer, 'first'|'last')], recvs = [(peer, 'hi'|'lo')] -- the
+    first owned plane goes to the lower neighbour's upper ghost slot, the last owned plane to the
+    upper neighbour's lower ghost slot.  Ends of a non-periodic domain have no partner (the ghost
+    slot is filled locally: reflection for nodes, clamp for cells)."""
+    has_lo = periodic_z or rank > 0
+    has_hi = periodic_z or rank < nranks - 1
+    lo, hi = (rank - 1) % nranks, (rank + 1) % nranks
+    sends, recvs = [], []
+    if has_lo:
+        sends.append((lo, "first"))
+    if has_hi:
+        sends.append((hi, "last"))
+    if has_hi:
+        recvs.append((hi, "hi"))
+    if has_lo:
+        recvs.append((lo, "lo"))
+    return sends, recvs
+
+
+def distributed_levels(n_cell_z, nranks, max_levels=30):
+    """number of multigrid levels that stay slab-distributed: every rank keeps an even number
+    (>= 8) of cell planes; coarser levels are replicated on every rank (agglomeration)."""
+    n, lev = n_cell_z, 0
+    while lev < max_levels and n % nranks == 0 and (n // nranks) % 2 == 0 and n // nranks >= 8:
+        lev += 1
+        n //= 2
+    return lev
+
+
+def cut(global_arr, zlo, zhi, ng, node=False):
+    """local box [zlo-ng, zhi+ng] (cells) or [zlo, zhi+1] (nodes, ng must be 0) of a global array whose
+    z axis is axis -3 and already carries ng ghost planes."""
+    if node:
+        return global_arr[..., zlo:zhi + 2, :, :].copy()
+    return global_arr[..., zlo:zhi + 1 + 2 * ng, :, :].copy()
+
+
+slab_range = npj.slab_range

@@ -66,7 +66,7 @@ typedef struct {
     int    smooth_num_sweeps;       /* MLNodeLinOp m_smooth_num_sweeps 4    */
     int    bottom_solver;           /* 0 = bicgcg (default): BiCGStab, CG retry; 1 = smoother  */
     /* B200-specific knobs (not reference keys) */
-    int    tile[3];                 /* smoother tile in nodes, default {64,16,16}: Gauss-Seidel
+    int    tile[3];                 /* smoother tile in nodes, default {64,16,64}: Gauss-Seidel
                                        inside a tile, previous-sweep values outside           */
     int    use_graph;               /* capture each V-cycle in a CUDA graph, default 1        */
 } b200np_opts;
@@ -111,6 +111,17 @@ int b200np_create(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
  * ncclUniqueId created by rank 0 and broadcast by the host program. */
 int b200np_create_dist(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device,
                        int rank, int nranks, const void* nccl_unique_id);
+
+/* Helpers for the slab-decomposed variant.
+ * b200np_nccl_unique_id: rank 0 creates the 128-byte ncclUniqueId the host program broadcasts
+ *   (incflo would use MPI_Bcast / ParallelDescriptor::Bcast; bench.py uses torch.distributed).
+ * b200np_slab_range: the z range of cells [cell_lo, cell_hi] and of uniquely owned node planes
+ *   [node_lo, node_hi] of `rank` (the node plane shared with the upper neighbour belongs to the
+ *   upper neighbour; the last rank of a non-periodic domain also owns the top boundary plane).
+ *   Needs no GPU. */
+int b200np_nccl_unique_id(void* out128);
+int b200np_slab_range(const b200np_geom* geom, int rank, int nranks, int* cell_lo, int* cell_hi, int* node_lo,
+                      int* node_hi);
 
 void b200np_destroy(b200np_t* h);
 

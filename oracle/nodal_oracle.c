@@ -340,9 +340,16 @@ static void smooth_level(const orc_mg* mg, level* L, double* phi, const double* 
         return;
     }
     if (p->smoother == ORC_SM_BOX) {
-        /* z-chunk rule shared with the CUDA smoother: at least 8 chunks per level where possible */
+        /* z-chunk rule shared with the CUDA smoother: aim at 592 tile-chunks per sweep (148 SMs x 2
+         * resident CTAs x 2 waves), chunk height between 4 and the cap box[2] */
         int bsz[3] = {p->box[0], p->box[1], p->box[2]};
-        { int c = L->nn[2] / 8; if (c < bsz[2]) bsz[2] = c; if (bsz[2] < 2) bsz[2] = 2; }
+        {
+            int ntiles = ((L->nn[0] + bsz[0] - 1) / bsz[0]) * ((L->nn[1] + bsz[1] - 1) / bsz[1]);
+            int nch = 592 / ntiles; if (nch < 1) nch = 1;
+            int c = (L->nn[2] + nch - 1) / nch;
+            if (c < bsz[2]) bsz[2] = c;
+            if (bsz[2] < 8) bsz[2] = 8; /* shorter chunks cost a V-cycle (measured: 4 -> 8 cycles, 8 -> 7) */
+        }
         int nb[3];
         for (int d = 0; d < 3; ++d) nb[d] = (L->nn[d] + bsz[d] - 1) / bsz[d];
         int outer = p->box_stale_per_call ? 1 : nsweeps, inner = p->box_stale_per_call ? nsweeps : 1;
