@@ -13,12 +13,36 @@ import math
 import torch
 
 
+_SLAB = None  # (zlo, nzl): generate only the cell planes [zlo, zlo+nzl) of the global domain n
+
+
+class slab:
+    """with problems.slab(zlo, nzl): ...  -> the generators return that z slab of the global fields"""
+
+    def __init__(self, zlo, nzl):
+        self.s = (int(zlo), int(nzl))
+
+    def __enter__(self):
+        global _SLAB
+        self.prev, _SLAB = _SLAB, self.s
+
+    def __exit__(self, *a):
+        global _SLAB
+        _SLAB = self.prev
+
+
+def _local(n):
+    """shape of the generated block: the global n with the slab's plane count in z"""
+    return (n[0], n[1], _SLAB[1] if _SLAB else n[2])
+
+
 def _centres(n, device):
     nx, ny, nz = n
     h = 1.0 / nx
+    zlo, nzl = _SLAB if _SLAB else (0, nz)
     x = (torch.arange(nx, dtype=torch.float64, device=device) + 0.5) * h
     y = (torch.arange(ny, dtype=torch.float64, device=device) + 0.5) * h
-    z = (torch.arange(nz, dtype=torch.float64, device=device) + 0.5) * h
+    z = (torch.arange(zlo, zlo + nzl, dtype=torch.float64, device=device) + 0.5) * h
     return x[None, None, :], y[None, :, None], z[:, None, None], h
 
 
@@ -33,7 +57,7 @@ def grad_psi(n, device, neumann_z=False):
     gx = a * tp * torch.cos(tp * x) * torch.sin(2 * tp * y) * torch.cos(kz * z)
     gy = a * 2 * tp * torch.sin(tp * x) * torch.cos(2 * tp * y) * torch.cos(kz * z)
     gz = -a * kz * torch.sin(tp * x) * torch.sin(2 * tp * y) * torch.sin(kz * z)
-    return torch.stack([gx.expand(n[2], n[1], n[0]), gy.expand(n[2], n[1], n[0]), gz.expand(n[2], n[1], n[0])])
+    return torch.stack([gx.expand(*_local(n)[::-1]), gy.expand(*_local(n)[::-1]), gz.expand(*_local(n)[::-1])])
 
 
 def _with_ghosts(v, ng):
@@ -48,9 +72,9 @@ def _with_ghosts(v, ng):
 def taylor_green(n, ng=1, device="cpu", perturb=True):
     x, y, z, h = _centres(n, device)
     tp = 2.0 * math.pi
-    u = (torch.sin(tp * x) * torch.cos(tp * y)).expand(n[2], n[1], n[0])
-    v = (-torch.cos(tp * x) * torch.sin(tp * y)).expand(n[2], n[1], n[0])
-    w = torch.zeros((n[2], n[1], n[0]), dtype=torch.float64, device=device)
+    u = (torch.sin(tp * x) * torch.cos(tp * y)).expand(*_local(n)[::-1])
+    v = (-torch.cos(tp * x) * torch.sin(tp * y)).expand(*_local(n)[::-1])
+    w = torch.zeros(_local(n)[::-1], dtype=torch.float64, device=device)
     vel = torch.stack([u, v, w])
     if perturb:
         vel = vel + grad_psi(n, device)
@@ -60,9 +84,9 @@ def taylor_green(n, ng=1, device="cpu", perturb=True):
 def double_shear_layer(n, ng=1, device="cpu", perturb=True):
     x, y, z, h = _centres(n, device)
     tp = 2.0 * math.pi
-    u = torch.tanh(30.0 * (0.25 - torch.abs(y - 0.5))).expand(n[2], n[1], n[0])
-    v = (0.05 * torch.sin(tp * x)).expand(n[2], n[1], n[0])
-    w = torch.zeros((n[2], n[1], n[0]), dtype=torch.float64, device=device)
+    u = torch.tanh(30.0 * (0.25 - torch.abs(y - 0.5))).expand(*_local(n)[::-1])
+    v = (0.05 * torch.sin(tp * x)).expand(*_local(n)[::-1])
+    w = torch.zeros(_local(n)[::-1], dtype=torch.float64, device=device)
     vel = torch.stack([u, v, w])
     if perturb:
         vel = vel + grad_psi(n, device)
@@ -77,11 +101,12 @@ def rayleigh_taylor_density(n, ngd=0, device="cpu"):
     r2d = torch.clamp(torch.hypot(x - 0.5 * lx, y - 0.5 * ly), max=0.5 * lx)
     pert = 0.5 * lz - 0.01 * torch.cos(2.0 * math.pi * r2d / lx)
     rho = rho_1 + 0.5 * (rho_2 - rho_1) * (1.0 + torch.tanh((z - pert) / width))
-    rho = rho.expand(n[2], n[1], n[0]).contiguous()
+    rho = rho.expand(*_local(n)[::-1]).contiguous()
     if ngd == 0:
         return rho
-    out = torch.ones((n[2] + 2 * ngd, n[1] + 2 * ngd, n[0] + 2 * ngd), dtype=torch.float64, device=device)
-    out[ngd:ngd + n[2], ngd:ngd + n[1], ngd:ngd + n[0]] = rho
+    nl = _local(n)
+    out = torch.ones((nl[2] + 2 * ngd, nl[1] + 2 * ngd, nl[0] + 2 * ngd), dtype=torch.float64, device=device)
+    out[ngd:ngd + nl[2], ngd:ngd + nl[1], ngd:ngd + nl[0]] = rho
     return out
 
 
@@ -89,15 +114,16 @@ def rayleigh_taylor_velocity(n, ng=1, device="cpu", case="b"):
     """case 'a': the InitialPressureProjection input u = g = (0,0,-0.1) in valid cells and one
     ghost layer (src/setup/init.cpp:533-560); case 'b': Taylor-Green + grad(psi) (walls in z)."""
     if case == "a":
+        assert _SLAB is None
         vel = torch.zeros((3, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng), dtype=torch.float64, device=device)
         lo = ng - 1
         vel[2, lo:ng + n[2] + 1, lo:ng + n[1] + 1, lo:ng + n[0] + 1] = -0.1
         return vel
     x, y, z, h = _centres(n, device)
     tp = 2.0 * math.pi
-    u = (torch.sin(tp * x) * torch.cos(tp * y)).expand(n[2], n[1], n[0])
-    v = (-torch.cos(tp * x) * torch.sin(tp * y)).expand(n[2], n[1], n[0])
-    w = torch.zeros((n[2], n[1], n[0]), dtype=torch.float64, device=device)
+    u = (torch.sin(tp * x) * torch.cos(tp * y)).expand(*_local(n)[::-1])
+    v = (-torch.cos(tp * x) * torch.sin(tp * y)).expand(*_local(n)[::-1])
+    w = torch.zeros(_local(n)[::-1], dtype=torch.float64, device=device)
     vel = torch.stack([u, v, w]) + grad_psi(n, device, neumann_z=True)
     return _with_ghosts(vel, ng)
 

@@ -19,11 +19,14 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
-    if rank == 0:
-        idt.copy_(torch.tensor(list(npj.nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    nccl_id = bytes(idt.cpu().tolist())
+
+    def fresh_id():   # an ncclUniqueId serves exactly one communicator
+        idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            idt.copy_(torch.tensor(list(npj.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return bytes(idt.cpu().tolist())
+
     ok = True
     for cfgname, N, ng in (("tgv", 64, 2), ("rt", 64, 3)):
         n = (N, N, N)
@@ -52,7 +55,7 @@ def main():
         lr = torch.from_numpy(slab.cut(rho, clo, chi, ng)).cuda() if var else None
         lg = torch.from_numpy(gp[:, clo:chi + 1].copy()).cuda()
         lp = torch.from_numpy(p[clo:chi + 2].copy()).cuda()
-        ip = npj.IncfloProjection(n, dx, bclo, bchi, device=local, rank=rank, nranks=world, nccl_id=nccl_id)
+        ip = npj.IncfloProjection(n, dx, bclo, bchi, device=local, rank=rank, nranks=world, nccl_id=fresh_id())
         st = ip.apply_nodal_projection(lv, ng, lg, lp, density=lr, ngd=ng, ro_0=1.0, scaling_factor=dt)
         torch.cuda.synchronize()
         gv, gg, gpn = lv.cpu().numpy(), lg.cpu().numpy(), lp.cpu().numpy()
