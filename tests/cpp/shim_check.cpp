@@ -1,0 +1,115 @@
+// shim_check.cpp -- exercises include/B200NodalProjector.H (the C++ mirror of Hydro::NodalProjector /
+// incflo::ApplyNodalProjection) the way incflo_apply_nodal_projection.cpp:181-219 uses the reference.
+//   shim_check host                         : host-logic checks, no GPU needed (BC map, options, abort behaviour)
+//   shim_check project in.bin out.bin nx ny nz dx bclo(3) bchi(3) var
+//       in.bin : vel (3,(nz+2),(ny+2),(nx+2)) [+ sigma (nz,ny,nx) if var]; out.bin: vel, phi, gphi, iters
+#include "../../include/B200NodalProjector.H"
+
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+using namespace b200;
+
+static void throwing_abort(const char* msg) { throw std::runtime_error(msg); }
+
+#define EXPECT(cond)                                                              \
+    do {                                                                          \
+        if (!(cond)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); return 1; } \
+    } while (0)
+
+static int host_checks()
+{
+    abort_handler() = throwing_abort;
+    // incflo_projection_bc.cpp:5-41
+    std::array<bool, 3> per{true, false, false};
+    auto r = get_projection_bc(per, {BC::undefined, BC::pressure_outflow, BC::no_slip_wall});
+    EXPECT(r[0] == LinOpBCType::Periodic && r[1] == LinOpBCType::Dirichlet && r[2] == LinOpBCType::Neumann);
+    r = get_projection_bc({false, false, false}, {BC::mass_inflow, BC::direction_dependent, BC::mixed});
+    EXPECT(r[0] == LinOpBCType::inflow && r[1] == LinOpBCType::inflow && r[2] == LinOpBCType::inflow);
+    r = get_projection_bc({false, false, false}, {BC::pressure_inflow, BC::slip_wall, BC::slip_wall});
+    EXPECT(r[0] == LinOpBCType::Dirichlet && r[1] == LinOpBCType::Neumann);
+    bool threw = false;
+    try { get_projection_bc({false, true, true}, {BC::undefined, BC::undefined, BC::undefined}); }
+    catch (const std::runtime_error& e) { threw = std::string(e.what()) == "get_projection_bc: undefined BC type"; }
+    EXPECT(threw);
+    // nodal_proj.* keys and defaults (src/incflo.H:436-458)
+    b200np_opts o = nodal_proj_options();
+    EXPECT(o.maxiter == 100 && o.bottom_maxiter == 100 && o.bottom_rtol == 1e-4 && o.mg_max_coarsening_level == 100);
+    EXPECT(o.num_pre_smooth == 2 && o.num_post_smooth == 2 && o.verbose == 0);
+    o = nodal_proj_options({{"verbose", "2"}, {"maxiter", "7"}, {"bottom_solver", "smoother"}, {"mg_rtol", "1e-9"}});
+    EXPECT(o.verbose == 2 && o.maxiter == 7 && o.bottom_solver == 1);
+    threw = false;
+    try { nodal_proj_options({{"no_such_key", "1"}}); } catch (const std::runtime_error&) { threw = true; }
+    EXPECT(threw);
+    threw = false;
+    try { nodal_proj_options({{"bottom_solver", "hypre"}}); } catch (const std::runtime_error&) { threw = true; }
+    EXPECT(threw);
+    // project() before setDomainBC aborts; multi-level aborts
+    const int n[3] = {8, 8, 8};
+    std::vector<double> v((size_t)3 * 10 * 10 * 10, 0.0);
+    Geometry g{{8, 8, 8}, {0.125, 0.125, 0.125}, {true, true, true}};
+    {
+        NodalProjector np({Fab::make(v.data(), n, 1, 3)}, 1.0, {g}, LPInfo().setMaxCoarseningLevel(100));
+        threw = false;
+        try { np.project(1e-11, 1e-14); } catch (const std::runtime_error&) { threw = true; }
+        EXPECT(threw);
+    }
+    threw = false;
+    try { NodalProjector np2({Fab::make(v.data(), n, 1, 3), Fab::make(v.data(), n, 1, 3)}, 1.0, {g, g}); }
+    catch (const std::runtime_error&) { threw = true; }
+    EXPECT(threw);
+    // Fab geometry: ld.velocity (ng=3), ld.p_nd (nodal, ng=0)   src/setup/incflo_arrays.cpp:9-26
+    Fab f = Fab::make(nullptr, n, 3, 3);
+    EXPECT(f.box.lo[0] == -3 && f.box.hi[2] == 10 && f.size() == (size_t)3 * 14 * 14 * 14);
+    Fab pn = Fab::make(nullptr, n, 0, 1, true);
+    EXPECT(pn.box.lo[1] == 0 && pn.box.hi[1] == 8 && pn.size() == (size_t)9 * 9 * 9);
+    std::printf("shim host checks OK\n");
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc >= 2 && !std::strcmp(argv[1], "host")) return host_checks();
+    if (argc < 15 || std::strcmp(argv[1], "project")) { std::printf("usage: see header comment\n"); return 2; }
+    abort_handler() = throwing_abort;
+    const int n[3] = {std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6])};
+    const double dx = std::atof(argv[7]);
+    std::array<LinOpBCType, 3> lo, hi;
+    Geometry g;
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = (LinOpBCType)std::atoi(argv[8 + d]); hi[d] = (LinOpBCType)std::atoi(argv[11 + d]);
+        g.n_cell[d] = n[d]; g.dx[d] = dx; g.is_periodic[d] = lo[d] == LinOpBCType::Periodic;
+    }
+    const bool var = std::atoi(argv[14]) != 0;
+    const size_t nv = (size_t)3 * (n[0] + 2) * (n[1] + 2) * (n[2] + 2), nc = (size_t)n[0] * n[1] * n[2];
+    std::vector<double> vel(nv), sig(var ? nc : 0);
+    std::ifstream in(argv[2], std::ios::binary);
+    in.read((char*)vel.data(), nv * 8);
+    if (var) in.read((char*)sig.data(), nc * 8);
+    if (!in) { std::printf("short input\n"); return 3; }
+    try {
+        // the call sequence of incflo_apply_nodal_projection.cpp:181-219
+        LPInfo info;
+        info.setMaxCoarseningLevel(100);
+        std::unique_ptr<NodalProjector> nodal_projector;
+        std::vector<Fab> velv{Fab::make(vel.data(), n, 1, 3)};
+        if (!var) nodal_projector = std::make_unique<NodalProjector>(velv, 0.37, std::vector<Geometry>{g}, info);
+        else nodal_projector = std::make_unique<NodalProjector>(velv, std::vector<Fab>{Fab::make(sig.data(), n, 0, 1)}, std::vector<Geometry>{g}, info);
+        nodal_projector->setDomainBC(lo, hi);
+        nodal_projector->project(1e-11, 1e-14);
+        auto phi = nodal_projector->getPhi();
+        auto gradphi = nodal_projector->getGradPhi();
+        std::ofstream out(argv[3], std::ios::binary);
+        out.write((const char*)vel.data(), nv * 8);
+        out.write((const char*)phi[0]->p, phi[0]->size() * 8);
+        out.write((const char*)gradphi[0]->p, gradphi[0]->size() * 8);
+        double it = nodal_projector->stats().iters;
+        out.write((const char*)&it, 8);
+        std::printf("shim project OK: %d V-cycles\n", nodal_projector->stats().iters);
+    } catch (const std::runtime_error& e) {
+        std::printf("amrex::Abort::%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
