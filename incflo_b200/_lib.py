@@ -14,7 +14,7 @@ CSRC = os.path.join(_PKG, "csrc")
 LIBDIR = os.path.join(_PKG, "lib")
 SO = os.path.join(LIBDIR, "libb200np.so")
 SOURCES = ["b200np.cu"]
-HEADERS = ["np_level.h", "np_kernels.cuh", "np_smooth.cuh", os.path.join(ROOT, "include", "b200np.h")]
+HEADERS = ["np_level.h", "np_kernels.cuh", "np_smooth.cuh", "np_smooth3.cuh", os.path.join(ROOT, "include", "b200np.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -12,6 +12,7 @@
 #include "../../include/b200np.h"
 #include "np_kernels.cuh"
 #include "np_smooth.cuh"
+#include "np_smooth3.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -75,6 +76,7 @@ NcclApi g_nccl;
 struct LevelData {
     Lev g{};
     bool dist = false;        // slab-distributed level (ghost plane slots are exchanged)
+    bool iso = false;         // dx == dy == dz: face coefficients of the stencil vanish (np_smooth3.cuh)
     double* sigma = nullptr;  // plane 0 of owned cells (allocation starts one plane earlier)
     double* sigma_alloc = nullptr;
     double *sol = nullptr, *rhs = nullptr, *res = nullptr, *cor = nullptr, *cor2 = nullptr, *rescor = nullptr;
@@ -119,7 +121,7 @@ struct b200np {
     struct Stage { double* d = nullptr; size_t bytes = 0; };
     Stage stage[8];  // staging buffers for host-pointer callers
     int TZ = 64;
-    int smoother_version = 2, interp_version = 2, resid_version = 2;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
+    int smoother_version = 3, interp_version = 2, resid_version = 2;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
 };
 
 namespace {
@@ -200,6 +202,7 @@ void build_hierarchy(b200np* h)
         LevelData L;
         Lev& g = L.g;
         fill_lev(G, n, dx, g);
+        L.iso = (dx[0] == dx[1] && dx[1] == dx[2]);
         // a level stays distributed while every rank keeps an even number (>= 8) of cell planes
         if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && n[2] / P >= 8) {
             set_slab(g, h->rank, P, zper(h));
@@ -368,9 +371,13 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
         if (h->smoother_version == 1) {
             if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, L.tz);
             else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, L.tz);
-        } else {
+        } else if (h->smoother_version == 2 || !L.iso) {
             if (h->var_sigma) k_smooth_v2<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
             else              k_smooth_v2<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
+            h->launches++;
+        } else {  // isotropic level: 2-barrier / register-carried variant, same semantics
+            if (h->var_sigma) k_smooth_iso<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
+            else              k_smooth_iso<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
             h->launches++;
         }
         std::swap(x, y);
@@ -681,6 +688,8 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         CK(cudaFuncSetAttribute(k_residual_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_iso<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
         for (auto& e : h->ev) CK(cudaEventCreate(&e));

@@ -1,0 +1,349 @@
+// np_smooth3.cuh -- K4, isotropic specialisation (dx == dy == dz on the level, which holds for every
+// level of every benchmark configuration): the tile-resident Gauss-Seidel sweep of np_smooth.cuh
+// with the same semantics (tile 64 x 16 x TZ, planes ascending, 4 colours c = (i&1) + 2(j&1) per
+// plane, previous-sweep values outside the tile), restructured around three facts:
+//
+//  (1) With fx == fy == fz = f the six face coefficients of mlndlap_adotx_aa are
+//      exactly 0.0 and the other twenty are all F = 3f.  In a plane, colour 1 couples to colour 0
+//      and colour 3 to colour 2 only through face neighbours, so {0,1} and {2,3} can be relaxed
+//      together: 2 block barriers per plane instead of 5, bit-identical to the 4-step order.
+//  (2) L phi = s0 phi + F T with s0 = -4 F G (G = sum of the 8 sigma cells, T = sigma-weighted sum
+//      of the 20 neighbours), so the update phi + (rhs - L phi)/s0 is (T - rhs/F) / (4 G): the
+//      centre value cancels and the diagonal needs one reciprocal of 4G (MUFU.RCP64H + 5 DFMA).
+//  (3) The window of plane k+1 read for the "upper" contribution of plane k is, one iteration later,
+//      the previous-sweep window of the plane being relaxed; the sigma layer and the thread's own
+//      new values are carried in registers too: 43 shared-memory loads per thread-plane instead of 74.
+//
+// Staging (cp.async ring of de-interleaved rows), tile shape, thread mapping (2x2 patch per thread)
+// and HBM traffic (32 B/node variable sigma, 24 B constant) are those of k_smooth_v2.
+#pragma once
+#include "np_smooth.cuh"
+
+namespace b200np_dev {
+
+// 1/x for normal positive x: MUFU.RCP64H seed (~20 bits), cubic step, Newton step (the sequence
+// nvcc emits for __drcp_rn minus its special-case branch); relative error <= ~1 ulp
+__device__ __forceinline__ double rcp_fast(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+template <bool VAR, bool FULL>
+__device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __restrict__ pin, double* __restrict__ pout,
+                                                const double* __restrict__ rhs, const int TZ, double* smem)
+{
+    double* sphi = smem;
+    double* ssig = smem + 4 * SM_PHI_SLOT;
+    const unsigned sphi_a = (unsigned)__cvta_generic_to_shared(sphi);
+    const unsigned ssig_a = (unsigned)__cvta_generic_to_shared(ssig);
+
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
+    const int kc0 = blockIdx.z * TZ, kc1 = min(kc0 + TZ, L.nzl);
+    const bool anyD = L.dlo[0] | L.dhi[0] | L.dlo[1] | L.dhi[1] | L.dlo[2] | L.dhi[2];
+
+    // ---- staging tables (fixed for the whole march): source offset (elements), smem byte offset ----
+    int psrc[5], csrc[5];
+    unsigned pdst[5], cdst[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int idx = tid + s * 256;
+        psrc[s] = -1; csrc[s] = -1; pdst[s] = 0; cdst[s] = 0;
+        if (idx < 66 * 18) {
+            const int li = idx % 66 - 1, lj = idx / 66 - 1;
+            const int gi = i0 + li, gj = j0 + lj;
+            pdst[s] = ((lj + 1) * SM_ROW + sm_col(li)) * 8u;
+            const bool ok = FULL || ((L.per[0] ? gi <= L.n[0] : gi <= L.n[0] + 1) && (L.per[1] ? gj <= L.n[1] : gj <= L.n[1] + 1));
+            if (ok) psrc[s] = nmap(gj, L.n[1], L.per[1]) * L.px + nmap(gi, L.n[0], L.per[0]);
+            else for (int q = 0; q < 4; ++q) sphi[q * SM_PHI_SLOT + (lj + 1) * SM_ROW + sm_col(li)] = 0.0;
+        }
+        if (VAR && idx < 65 * 17) {
+            const int ci = idx % 65 - 1, cj = idx / 65 - 1;
+            const int gi = i0 + ci, gj = j0 + cj;
+            cdst[s] = ((cj + 1) * SM_ROW + sm_ccol(ci)) * 8u;
+            if (FULL || (gi <= L.n[0] && gj <= L.n[1])) csrc[s] = cmap(gj, L.n[1], L.per[1]) * L.cpx + cmap(gi, L.n[0], L.per[0]);
+            else for (int q = 0; q < 3; ++q) ssig[q * SM_SIG_SLOT + (cj + 1) * SM_ROW + sm_ccol(ci)] = 1.0;
+        }
+    }
+    auto issue_phi = [&](int kl) {  // kl in [-1, nzl]
+        const double* src = pin + zplane(L, kl) * L.ps;
+        unsigned dst = sphi_a + ((kl + 1) & 3) * (SM_PHI_SLOT * 8);
+        asm volatile("" : "+l"(src), "+r"(dst));  // keep the plane base materialised (no per-copy 64-bit multiply)
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+            if (psrc[s] >= 0) cp_async8(dst + pdst[s], src + psrc[s]);
+    };
+    auto issue_sig = [&](int cl) {  // cell layer in [-1, cnzl]
+        if (!VAR) return;
+        const double* src = L.sigma + czplane(L, cl) * L.cps;
+        unsigned dst = ssig_a + ((cl + 1) % 3) * (SM_SIG_SLOT * 8);
+        asm volatile("" : "+l"(src), "+r"(dst));
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+            if (csrc[s] >= 0) cp_async8(dst + cdst[s], src + csrc[s]);
+    };
+
+    // ---- the thread's 2x2 patch ----
+    const int gi0 = i0 + 2 * tx, gj0 = j0 + 2 * ty;
+    const bool colok[2] = {FULL || gi0 < L.nn[0], FULL || gi0 + 1 < L.nn[0]};
+    const bool rowok[2] = {FULL || gj0 < L.nn[1], FULL || gj0 + 1 < L.nn[1]};
+    const int roff = gj0 * L.px + gi0;
+    auto load_rhs = [&](int kl, double (&r)[2][2]) {
+        const double* q0 = rhs + kl * L.ps + roff;
+        asm volatile("" : "+l"(q0));
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double* q = q0 + b * L.px;
+            if (FULL) { const double2 v = *reinterpret_cast<const double2*>(q); r[b][0] = v.x; r[b][1] = v.y; }
+            else {
+                r[b][0] = r[b][1] = 0.0;
+                if (rowok[b]) {
+                    if (colok[1]) { const double2 v = *reinterpret_cast<const double2*>(q); r[b][0] = v.x; r[b][1] = v.y; }
+                    else if (colok[0]) r[b][0] = q[0];
+                }
+            }
+        }
+    };
+
+    const double Finv = 1.0 / L.fxyz;                       // F = 3 dxinv^2 / 36
+    const double kr = VAR ? 0.0 : Finv / (32.0 * L.csig);   // constant sigma: phi = (C + 2E)/32 - rhs/(32 F sigma)
+
+    // window columns of this thread in a de-interleaved row: li = 2tx-1, 2tx, 2tx+1, 2tx+2
+    const int wc[4] = {33 + tx, tx, 34 + tx, tx + 1};
+    const int cc[3] = {32 + tx, tx, 33 + tx};  // cells 2tx-1, 2tx, 2tx+1
+    const int rbase = (2 * ty) * SM_ROW;       // window row 0 of this thread
+
+    // prologue: planes kc0-1, kc0 (+ sigma layer kc0-1), then plane kc0+1 (+ sigma layer kc0)
+    issue_phi(kc0 - 1); issue_phi(kc0); issue_sig(kc0 - 1);
+    cp_async_commit();
+    issue_phi(kc0 + 1); issue_sig(kc0);
+    cp_async_commit();
+    double rcur[2][2], rnext[2][2];
+    load_rhs(kc0, rcur);
+    cp_async_wait<1>();
+    __syncthreads();
+
+    // state carried from plane to plane
+    double SL[3][3];     // sigma layer kl-1
+    double ownp[2][2];   // this sweep's values of the patch on plane kl-1 (previous sweep's for kl = kc0)
+    double Wn[2][4];     // previous-sweep values of plane kl, window rows 0 and 2
+    {
+        const double* Pm = sphi + ((kc0) & 3) * SM_PHI_SLOT + rbase;
+        const double* P0 = sphi + ((kc0 + 1) & 3) * SM_PHI_SLOT + rbase;
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) ownp[b][a] = Pm[(b + 1) * SM_ROW + wc[a + 1]];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { Wn[0][c] = P0[wc[c]]; Wn[1][c] = P0[2 * SM_ROW + wc[c]]; }
+        if (VAR) {
+            const double* S = ssig + ((kc0) % 3) * SM_SIG_SLOT + rbase;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) SL[r][c] = S[r * SM_ROW + cc[c]];
+        }
+    }
+
+#pragma unroll 1
+    for (int kl = kc0; kl < kc1; ++kl) {
+        if (kl + 2 <= kc1) { issue_phi(kl + 2); issue_sig(kl + 1); }
+        cp_async_commit();
+        load_rhs(kl + 1 < kc1 ? kl + 1 : kl, rnext);
+        cp_async_wait<1>();   // plane kl+1 / sigma layer kl have landed (this thread's copies)
+        __syncthreads();      // ... everybody else's, and plane kl-1's colours 2,3 are published
+        const int kg = kl + L.k0;
+        const double* Pm = sphi + ((kl) & 3) * SM_PHI_SLOT + rbase;       // plane kl-1 (this sweep)
+        double* P0 = sphi + ((kl + 1) & 3) * SM_PHI_SLOT + rbase;         // plane kl
+        const double* Pp = sphi + ((kl + 2) & 3) * SM_PHI_SLOT + rbase;   // plane kl+1 (previous sweep)
+
+        double T[2][2];      // sigma-weighted neighbour sums
+        double Sz[3][3];     // SL + SU: weights of the in-plane diagonal neighbours
+        double rinv[2][2];   // 1 / (4 G)
+        double Wp02[2][4];   // rows 0 and 2 of plane kl+1 (next iteration's Wn)
+        if (VAR) {
+            // ---- lower side: plane kl-1, sigma layer kl-1 ----
+            {
+                double W[4][4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { W[0][c] = Pm[wc[c]]; W[3][c] = Pm[3 * SM_ROW + wc[c]]; }
+#pragma unroll
+                for (int r = 1; r < 3; ++r) {
+                    W[r][0] = Pm[r * SM_ROW + wc[0]]; W[r][3] = Pm[r * SM_ROW + wc[3]];
+                    W[r][1] = ownp[r - 1][0]; W[r][2] = ownp[r - 1][1];
+                }
+                double hx[3][2], hy[2][3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { hx[r][0] = SL[r][0] + SL[r][1]; hx[r][1] = SL[r][1] + SL[r][2]; }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { hy[0][c] = SL[0][c] + SL[1][c]; hy[1][c] = SL[1][c] + SL[2][c]; }
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        double t = SL[b][a] * W[b][a];
+                        t = fma(SL[b][a + 1], W[b][a + 2], t);
+                        t = fma(SL[b + 1][a], W[b + 2][a], t);
+                        t = fma(SL[b + 1][a + 1], W[b + 2][a + 2], t);
+                        double u = hx[b][a] * W[b][a + 1];
+                        u = fma(hx[b + 1][a], W[b + 2][a + 1], u);
+                        u = fma(hy[b][a], W[b + 1][a], u);
+                        u = fma(hy[b][a + 1], W[b + 1][a + 2], u);
+                        T[b][a] = t + u;
+                    }
+            }
+            // ---- upper side: plane kl+1, sigma layer kl ----
+            {
+                const double* S = ssig + ((kl + 1) % 3) * SM_SIG_SLOT + rbase;
+                double SU[3][3], W[4][4];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) SU[r][c] = S[r * SM_ROW + cc[c]];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) W[r][c] = Pp[r * SM_ROW + wc[c]];
+                double hx[3][2], hy[2][3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { hx[r][0] = SU[r][0] + SU[r][1]; hx[r][1] = SU[r][1] + SU[r][2]; }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { hy[0][c] = SU[0][c] + SU[1][c]; hy[1][c] = SU[1][c] + SU[2][c]; }
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        double t = SU[b][a] * W[b][a];
+                        t = fma(SU[b][a + 1], W[b][a + 2], t);
+                        t = fma(SU[b + 1][a], W[b + 2][a], t);
+                        t = fma(SU[b + 1][a + 1], W[b + 2][a + 2], t);
+                        double u = hx[b][a] * W[b][a + 1];
+                        u = fma(hx[b + 1][a], W[b + 2][a + 1], u);
+                        u = fma(hy[b][a], W[b + 1][a], u);
+                        u = fma(hy[b][a + 1], W[b + 1][a + 2], u);
+                        T[b][a] += t + u;
+                    }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { Sz[r][c] = SL[r][c] + SU[r][c]; SL[r][c] = SU[r][c]; }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { Wp02[0][c] = W[0][c]; Wp02[1][c] = W[2][c]; }
+            }
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+                    rinv[b][a] = rcp_fast(4.0 * ((Sz[b][a] + Sz[b][a + 1]) + (Sz[b + 1][a] + Sz[b + 1][a + 1])));
+        } else {
+            // constant sigma: T = C + 2E over the summed window of planes kl-1 and kl+1
+            double W[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double up = Pp[r * SM_ROW + wc[c]];
+                    const bool mine = (r == 1 || r == 2) && (c == 1 || c == 2);
+                    const double lo = mine ? ownp[(r - 1) & 1][(c - 1) & 1] : Pm[r * SM_ROW + wc[c]];
+                    W[r][c] = lo + up;
+                    if (r == 0) Wp02[0][c] = up;
+                    if (r == 2) Wp02[1][c] = up;
+                }
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const double C = (W[b][a] + W[b][a + 2]) + (W[b + 2][a] + W[b + 2][a + 2]);
+                    const double E = (W[b][a + 1] + W[b + 2][a + 1]) + (W[b + 1][a] + W[b + 1][a + 2]);
+                    T[b][a] = fma(2.0, E, C);
+                }
+        }
+
+        double v[2][2];
+        // ---- step 1: colours 0 and 1 (patch row 0); their in-plane diagonal neighbours (window rows 0
+        //      and 2 of plane kl) are colours 2/3 = previous-sweep values, already in registers ----
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            double t;
+            if (VAR) {
+                t = fma(Sz[0][a], Wn[0][a], T[0][a]);
+                t = fma(Sz[0][a + 1], Wn[0][a + 2], t);
+                t = fma(Sz[1][a], Wn[1][a], t);
+                t = fma(Sz[1][a + 1], Wn[1][a + 2], t);
+                v[0][a] = fma(-rcur[0][a], Finv, t) * rinv[0][a];
+            } else {
+                t = fma(2.0, (Wn[0][a] + Wn[0][a + 2]) + (Wn[1][a] + Wn[1][a + 2]), T[0][a]);
+                v[0][a] = fma(-rcur[0][a], kr, t * 0.03125);
+            }
+            if (anyD && node_masked(L, gi0 + a, gj0, kg)) v[0][a] = 0.0;
+            // a patch node outside the domain holds the staged wrap / reflection image of a real
+            // node (previous-sweep value, like any other halo entry): it must not be relaxed
+            if (FULL || (colok[a] && rowok[0])) P0[SM_ROW + wc[a + 1]] = v[0][a];
+            else v[0][a] = P0[SM_ROW + wc[a + 1]];
+        }
+        __syncthreads();
+        // ---- step 2: colours 2 and 3 (patch row 1); diagonal neighbours are colours 1/0 of window rows
+        //      1 and 3, relaxed in step 1 (by this thread, its neighbours, or halo = previous sweep) ----
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const double n00 = a ? v[0][0] : P0[SM_ROW + wc[0]];         // (1, a)
+            const double n01 = a ? P0[SM_ROW + wc[3]] : v[0][1];         // (1, a+2)
+            const double n10 = P0[3 * SM_ROW + wc[a]];                   // (3, a)
+            const double n11 = P0[3 * SM_ROW + wc[a + 2]];               // (3, a+2)
+            double t;
+            if (VAR) {
+                t = fma(Sz[1][a], n00, T[1][a]);
+                t = fma(Sz[1][a + 1], n01, t);
+                t = fma(Sz[2][a], n10, t);
+                t = fma(Sz[2][a + 1], n11, t);
+                v[1][a] = fma(-rcur[1][a], Finv, t) * rinv[1][a];
+            } else {
+                t = fma(2.0, (n00 + n01) + (n10 + n11), T[1][a]);
+                v[1][a] = fma(-rcur[1][a], kr, t * 0.03125);
+            }
+            if (anyD && node_masked(L, gi0 + a, gj0 + 1, kg)) v[1][a] = 0.0;
+            if (FULL || (colok[a] && rowok[1])) P0[2 * SM_ROW + wc[a + 1]] = v[1][a];
+            else v[1][a] = P0[2 * SM_ROW + wc[a + 1]];
+        }
+        // ---- store the finished plane ----
+        {
+            double* q0 = pout + kl * L.ps + roff;
+            asm volatile("" : "+l"(q0));
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                double* q = q0 + b * L.px;
+                if (FULL) *reinterpret_cast<double2*>(q) = make_double2(v[b][0], v[b][1]);
+                else if (rowok[b]) {
+                    if (colok[1]) *reinterpret_cast<double2*>(q) = make_double2(v[b][0], v[b][1]);
+                    else if (colok[0]) q[0] = v[b][0];
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) { rcur[b][a] = rnext[b][a]; ownp[b][a] = v[b][a]; }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { Wn[0][c] = Wp02[0][c]; Wn[1][c] = Wp02[1][c]; }
+    }
+    cp_async_wait<0>();
+}
+
+template <bool VAR>
+__global__ void __launch_bounds__(256, 2) k_smooth_iso(const Lev L, const double* __restrict__ pin,
+                                                       double* __restrict__ pout, const double* __restrict__ rhs, int TZ)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
+    const bool full = (i0 + SM_TX <= L.nn[0]) && (j0 + SM_TY <= L.nn[1]);
+    if (full) smooth_iso_body<VAR, true>(L, pin, pout, rhs, TZ, smem);
+    else      smooth_iso_body<VAR, false>(L, pin, pout, rhs, TZ, smem);
+}
+
+}  // namespace b200np_dev
