@@ -273,13 +273,14 @@ def run_ours(args):
                                     "frac": alg_bytes / (ms_res * 1e-3) / 1e9 / peak}}
 
     # ---------------- e2e arm: host (pinned) buffers through the same C-ABI call ----------------
-    Ke = min(K, 3)
+    Ke = 0 if args.no_e2e else min(K, 3)
     hv = [wl["vel"].cpu().pin_memory() for _ in range(Ke)]
     hg = [wl["gp"].cpu().pin_memory() for _ in range(Ke)]
     hp = [wl["p"].cpu().pin_memory() for _ in range(Ke)]
     hr = wl["rho"].cpu().pin_memory()
-    step(hv[0].numpy(), hg[0].numpy(), hp[0].numpy(), hr.numpy())          # warm-up (allocates staging buffers)
-    hv[0].copy_(wl["vel"].cpu()); hg[0].copy_(wl["gp"].cpu())
+    if Ke:
+        step(hv[0].numpy(), hg[0].numpy(), hp[0].numpy(), hr.numpy())          # warm-up (allocates staging buffers)
+        hv[0].copy_(wl["vel"].cpu()); hg[0].copy_(wl["gp"].cpu())
     torch.cuda.synchronize()
     if nranks > 1:
         dist.barrier()
@@ -294,7 +295,7 @@ def run_ours(args):
         tt = torch.tensor([te], dtype=torch.float64, device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
-    e2e_val = ncell * nranks / (te / Ke) / 1e6
+    e2e_val = ncell * nranks / (te / Ke) / 1e6 if Ke else None
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
@@ -308,7 +309,7 @@ def run_ours(args):
                                                                                  f"domain {N}x{N}x{N * nranks}",
                            "solves_per_s": 1e3 / ms_per_step * nranks},
                 "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                                          "d2h_bytes_per_step": int(d2h), "steps": Ke, "ms_per_step": te / Ke * 1e3},
+                                          "d2h_bytes_per_step": int(d2h), "steps": Ke, "ms_per_step": te / Ke * 1e3 if Ke else None},
                 "gpu_launches": int(launches), "roofline": roofline, "wall_s_timed_region": wall}
         if nranks == 1 and not args.no_cpu:
             cores = os.cpu_count()
@@ -325,6 +326,15 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """Native libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the run and keep the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,11 +343,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer arm (the line is then not a valid bench line)")
     args = ap.parse_args()
+    real_stdout = _json_only_stdout()
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":

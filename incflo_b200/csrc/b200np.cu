@@ -121,7 +121,10 @@ struct b200np {
     struct Stage { double* d = nullptr; size_t bytes = 0; };
     Stage stage[8];  // staging buffers for host-pointer callers
     int TZ = 64;
-    int smoother_version = 3, interp_version = 2, resid_version = 2;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
+    int dist_graph = 1;       // capture the slab-decomposed V-cycle (NCCL send/recv included) into a CUDA graph (B200NP_DIST_GRAPH)
+    int dist_min_planes = 8;  // a level stays slab-distributed while every rank keeps at least this many cell planes (B200NP_DIST_MIN_PLANES)
+    int res_max_ctas = 148;   // levels with at most this many smoother CTAs use the resident-chunk kernel (B200NP_RES_CTAS)
+    int smoother_version = 3, interp_version = 2, resid_version = 3;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
 };
 
 namespace {
@@ -204,7 +207,7 @@ void build_hierarchy(b200np* h)
         fill_lev(G, n, dx, g);
         L.iso = (dx[0] == dx[1] && dx[1] == dx[2]);
         // a level stays distributed while every rank keeps an even number (>= 8) of cell planes
-        if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && n[2] / P >= 8) {
+        if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && n[2] / P >= h->dist_min_planes) {
             set_slab(g, h->rank, P, zper(h));
             L.dist = true;
             h->nlev_dist = lev + 1;
@@ -375,6 +378,11 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
             if (h->var_sigma) k_smooth_v2<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
             else              k_smooth_v2<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
             h->launches++;
+        } else if (L.tz <= SM_RES_TZ && (int)(L.gsm.x * L.gsm.y * L.gsm.z) <= h->res_max_ctas) {
+            // small isotropic level: whole chunk resident in shared memory, one CTA per SM
+            if (h->var_sigma) k_smooth_iso_res<true><<<L.gsm, 256, SM_RES_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
+            else              k_smooth_iso_res<false><<<L.gsm, 256, (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
+            h->launches++;
         } else {  // isotropic level: 2-barrier / register-carried variant, same semantics
             if (h->var_sigma) k_smooth_iso<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
             else              k_smooth_iso<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
@@ -391,9 +399,13 @@ void residual(b200np* h, LevelData& L, double* phi, const double* rhs, double* r
     if (h->resid_version == 1) {
         if (h->var_sigma) LAUNCH(h, k_residual<true>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
         else              LAUNCH(h, k_residual<false>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
-    } else {
+    } else if (h->resid_version == 2 || !L.iso) {
         if (h->var_sigma) k_residual_v2<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
         else              k_residual_v2<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
+        h->launches++;
+    } else {
+        if (h->var_sigma) k_residual_iso<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
+        else              k_residual_iso<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
         h->launches++;
     }
 }
@@ -464,7 +476,7 @@ void vcycle_launch(b200np* h, int lev0)
 
 void vcycle(b200np* h)
 {
-    if (!h->opts.use_graph || h->nranks > 1) { vcycle_launch(h, 0); return; }
+    if (!h->opts.use_graph || (h->nranks > 1 && !h->dist_graph)) { vcycle_launch(h, 0); return; }
     if (h->graph_exec && (h->graph_var != h->var_sigma || h->graph_csig != h->lv[0].g.csig)) {
         cudaGraphExecDestroy(h->graph_exec); cudaGraphDestroy(h->graph);
         h->graph_exec = nullptr; h->graph = nullptr;
@@ -682,6 +694,9 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (h->opts.tile[0] != NP_TX || h->opts.tile[1] != NP_TY || h->opts.tile[2] < 1) { delete h; return B200NP_ERR_BAD_ARG; }
         h->TZ = h->opts.tile[2];
         if (const char* e = getenv("B200NP_SMOOTHER")) h->smoother_version = atoi(e);
+        if (const char* e = getenv("B200NP_RES_CTAS")) h->res_max_ctas = atoi(e);
+        if (const char* e = getenv("B200NP_DIST_GRAPH")) h->dist_graph = atoi(e);
+        if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) h->dist_min_planes = std::max(8, atoi(e));
         if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
         if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
         CK(cudaFuncSetAttribute(k_residual_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
@@ -690,6 +705,10 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         CK(cudaFuncSetAttribute(k_smooth_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_residual_iso<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_residual_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_iso_res<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_RES_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_iso_res<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double))));
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
         for (auto& e : h->ev) CK(cudaEventCreate(&e));

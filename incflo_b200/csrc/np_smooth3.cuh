@@ -21,25 +21,19 @@
 
 namespace b200np_dev {
 
-// 1/x for normal positive x: MUFU.RCP64H seed (~20 bits), cubic step, Newton step (the sequence
-// nvcc emits for __drcp_rn minus its special-case branch); relative error <= ~1 ulp
-__device__ __forceinline__ double rcp_fast(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    e = fma(e, e, e);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-}
+// RES: "resident chunk" variant for small levels (few CTAs, TZ <= SM_RES_TZ): every plane and sigma
+// layer of the chunk gets its own shared-memory slot and is requested up front, so the march never
+// waits on memory (a 4-slot ring leaves a lone CTA per SM exposed to one DRAM/L2 latency per plane).
+constexpr int SM_RES_TZ = 8;
+constexpr int SM_RES_DOUBLES = (SM_RES_TZ + 2) * SM_PHI_SLOT + (SM_RES_TZ + 1) * SM_SIG_SLOT;
 
-template <bool VAR, bool FULL>
+template <bool VAR, bool FULL, bool RES>
 __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __restrict__ pin, double* __restrict__ pout,
                                                 const double* __restrict__ rhs, const int TZ, double* smem)
 {
     double* sphi = smem;
-    double* ssig = smem + 4 * SM_PHI_SLOT;
+    constexpr int NPS = RES ? SM_RES_TZ + 2 : 4, NSS = RES ? SM_RES_TZ + 1 : 3;
+    double* ssig = smem + NPS * SM_PHI_SLOT;
     const unsigned sphi_a = (unsigned)__cvta_generic_to_shared(sphi);
     const unsigned ssig_a = (unsigned)__cvta_generic_to_shared(ssig);
 
@@ -47,6 +41,9 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
     const int kc0 = blockIdx.z * TZ, kc1 = min(kc0 + TZ, L.nzl);
     const bool anyD = L.dlo[0] | L.dhi[0] | L.dlo[1] | L.dhi[1] | L.dlo[2] | L.dhi[2];
+    // shared-memory slot of node plane p / sigma layer c
+    auto pslot = [&](int p) { return RES ? p - kc0 + 1 : (p + 1) & 3; };
+    auto sslot = [&](int c) { return RES ? c - kc0 + 1 : (c + 1) % 3; };
 
     // ---- staging tables (fixed for the whole march): source offset (elements), smem byte offset ----
     int psrc[5], csrc[5];
@@ -61,19 +58,19 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
             pdst[s] = ((lj + 1) * SM_ROW + sm_col(li)) * 8u;
             const bool ok = FULL || ((L.per[0] ? gi <= L.n[0] : gi <= L.n[0] + 1) && (L.per[1] ? gj <= L.n[1] : gj <= L.n[1] + 1));
             if (ok) psrc[s] = nmap(gj, L.n[1], L.per[1]) * L.px + nmap(gi, L.n[0], L.per[0]);
-            else for (int q = 0; q < 4; ++q) sphi[q * SM_PHI_SLOT + (lj + 1) * SM_ROW + sm_col(li)] = 0.0;
+            else for (int q = 0; q < NPS; ++q) sphi[q * SM_PHI_SLOT + (lj + 1) * SM_ROW + sm_col(li)] = 0.0;
         }
         if (VAR && idx < 65 * 17) {
             const int ci = idx % 65 - 1, cj = idx / 65 - 1;
             const int gi = i0 + ci, gj = j0 + cj;
             cdst[s] = ((cj + 1) * SM_ROW + sm_ccol(ci)) * 8u;
             if (FULL || (gi <= L.n[0] && gj <= L.n[1])) csrc[s] = cmap(gj, L.n[1], L.per[1]) * L.cpx + cmap(gi, L.n[0], L.per[0]);
-            else for (int q = 0; q < 3; ++q) ssig[q * SM_SIG_SLOT + (cj + 1) * SM_ROW + sm_ccol(ci)] = 1.0;
+            else for (int q = 0; q < NSS; ++q) ssig[q * SM_SIG_SLOT + (cj + 1) * SM_ROW + sm_ccol(ci)] = 1.0;
         }
     }
     auto issue_phi = [&](int kl) {  // kl in [-1, nzl]
         const double* src = pin + zplane(L, kl) * L.ps;
-        unsigned dst = sphi_a + ((kl + 1) & 3) * (SM_PHI_SLOT * 8);
+        unsigned dst = sphi_a + pslot(kl) * (SM_PHI_SLOT * 8);
         asm volatile("" : "+l"(src), "+r"(dst));  // keep the plane base materialised (no per-copy 64-bit multiply)
 #pragma unroll
         for (int s = 0; s < 5; ++s)
@@ -82,7 +79,7 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     auto issue_sig = [&](int cl) {  // cell layer in [-1, cnzl]
         if (!VAR) return;
         const double* src = L.sigma + czplane(L, cl) * L.cps;
-        unsigned dst = ssig_a + ((cl + 1) % 3) * (SM_SIG_SLOT * 8);
+        unsigned dst = ssig_a + sslot(cl) * (SM_SIG_SLOT * 8);
         asm volatile("" : "+l"(src), "+r"(dst));
 #pragma unroll
         for (int s = 0; s < 5; ++s)
@@ -119,14 +116,23 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     const int cc[3] = {32 + tx, tx, 33 + tx};  // cells 2tx-1, 2tx, 2tx+1
     const int rbase = (2 * ty) * SM_ROW;       // window row 0 of this thread
 
-    // prologue: planes kc0-1, kc0 (+ sigma layer kc0-1), then plane kc0+1 (+ sigma layer kc0)
-    issue_phi(kc0 - 1); issue_phi(kc0); issue_sig(kc0 - 1);
-    cp_async_commit();
-    issue_phi(kc0 + 1); issue_sig(kc0);
-    cp_async_commit();
     double rcur[2][2], rnext[2][2];
-    load_rhs(kc0, rcur);
-    cp_async_wait<1>();
+    if (RES) {
+        // the whole chunk: planes kc0-1 .. kc1, sigma layers kc0-1 .. kc1-1
+        for (int p = kc0 - 1; p <= kc1; ++p) issue_phi(p);
+        for (int c = kc0 - 1; c < kc1; ++c) issue_sig(c);
+        cp_async_commit();
+        load_rhs(kc0, rcur);
+        cp_async_wait<0>();
+    } else {
+        // prologue: planes kc0-1, kc0 (+ sigma layer kc0-1), then plane kc0+1 (+ sigma layer kc0)
+        issue_phi(kc0 - 1); issue_phi(kc0); issue_sig(kc0 - 1);
+        cp_async_commit();
+        issue_phi(kc0 + 1); issue_sig(kc0);
+        cp_async_commit();
+        load_rhs(kc0, rcur);
+        cp_async_wait<1>();
+    }
     __syncthreads();
 
     // state carried from plane to plane
@@ -134,8 +140,8 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     double ownp[2][2];   // this sweep's values of the patch on plane kl-1 (previous sweep's for kl = kc0)
     double Wn[2][4];     // previous-sweep values of plane kl, window rows 0 and 2
     {
-        const double* Pm = sphi + ((kc0) & 3) * SM_PHI_SLOT + rbase;
-        const double* P0 = sphi + ((kc0 + 1) & 3) * SM_PHI_SLOT + rbase;
+        const double* Pm = sphi + pslot(kc0 - 1) * SM_PHI_SLOT + rbase;
+        const double* P0 = sphi + pslot(kc0) * SM_PHI_SLOT + rbase;
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
@@ -143,7 +149,7 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
 #pragma unroll
         for (int c = 0; c < 4; ++c) { Wn[0][c] = P0[wc[c]]; Wn[1][c] = P0[2 * SM_ROW + wc[c]]; }
         if (VAR) {
-            const double* S = ssig + ((kc0) % 3) * SM_SIG_SLOT + rbase;
+            const double* S = ssig + sslot(kc0 - 1) * SM_SIG_SLOT + rbase;
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -153,15 +159,17 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
 
 #pragma unroll 1
     for (int kl = kc0; kl < kc1; ++kl) {
-        if (kl + 2 <= kc1) { issue_phi(kl + 2); issue_sig(kl + 1); }
-        cp_async_commit();
+        if (!RES) {
+            if (kl + 2 <= kc1) { issue_phi(kl + 2); issue_sig(kl + 1); }
+            cp_async_commit();
+        }
         load_rhs(kl + 1 < kc1 ? kl + 1 : kl, rnext);
-        cp_async_wait<1>();   // plane kl+1 / sigma layer kl have landed (this thread's copies)
+        if (!RES) cp_async_wait<1>();   // plane kl+1 / sigma layer kl have landed (this thread's copies)
         __syncthreads();      // ... everybody else's, and plane kl-1's colours 2,3 are published
         const int kg = kl + L.k0;
-        const double* Pm = sphi + ((kl) & 3) * SM_PHI_SLOT + rbase;       // plane kl-1 (this sweep)
-        double* P0 = sphi + ((kl + 1) & 3) * SM_PHI_SLOT + rbase;         // plane kl
-        const double* Pp = sphi + ((kl + 2) & 3) * SM_PHI_SLOT + rbase;   // plane kl+1 (previous sweep)
+        const double* Pm = sphi + pslot(kl - 1) * SM_PHI_SLOT + rbase;   // plane kl-1 (this sweep)
+        double* P0 = sphi + pslot(kl) * SM_PHI_SLOT + rbase;             // plane kl
+        const double* Pp = sphi + pslot(kl + 1) * SM_PHI_SLOT + rbase;   // plane kl+1 (previous sweep)
 
         double T[2][2];      // sigma-weighted neighbour sums
         double Sz[3][3];     // SL + SU: weights of the in-plane diagonal neighbours
@@ -200,7 +208,7 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
             }
             // ---- upper side: plane kl+1, sigma layer kl ----
             {
-                const double* S = ssig + ((kl + 1) % 3) * SM_SIG_SLOT + rbase;
+                const double* S = ssig + sslot(kl) * SM_SIG_SLOT + rbase;
                 double SU[3][3], W[4][4];
 #pragma unroll
                 for (int r = 0; r < 3; ++r)
@@ -342,8 +350,298 @@ __global__ void __launch_bounds__(256, 2) k_smooth_iso(const Lev L, const double
     extern __shared__ __align__(16) double smem[];
     const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
     const bool full = (i0 + SM_TX <= L.nn[0]) && (j0 + SM_TY <= L.nn[1]);
-    if (full) smooth_iso_body<VAR, true>(L, pin, pout, rhs, TZ, smem);
-    else      smooth_iso_body<VAR, false>(L, pin, pout, rhs, TZ, smem);
+    if (full) smooth_iso_body<VAR, true, false>(L, pin, pout, rhs, TZ, smem);
+    else      smooth_iso_body<VAR, false, false>(L, pin, pout, rhs, TZ, smem);
+}
+
+// small levels: one CTA per SM, whole chunk resident (TZ <= SM_RES_TZ)
+template <bool VAR>
+__global__ void __launch_bounds__(256, 1) k_smooth_iso_res(const Lev L, const double* __restrict__ pin,
+                                                           double* __restrict__ pout, const double* __restrict__ rhs, int TZ)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
+    const bool full = (i0 + SM_TX <= L.nn[0]) && (j0 + SM_TY <= L.nn[1]);
+    if (full) smooth_iso_body<VAR, true, true>(L, pin, pout, rhs, TZ, smem);
+    else      smooth_iso_body<VAR, false, true>(L, pin, pout, rhs, TZ, smem);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3, isotropic specialisation: res = rhs - L phi with the same cancelled-coefficient form
+// (L phi = F (T - 4 G phi)); the window of the plane itself is carried in registers from the
+// previous iteration's "upper" window.  One barrier per plane.  Optional per-CTA inf-norm partial.
+// ------------------------------------------------------------------------------------------
+template <bool VAR, bool FULL>
+__device__ __forceinline__ double resid_iso_body(const Lev& L, const double* __restrict__ phi, const double* __restrict__ rhs,
+                                                 double* __restrict__ res, const int TZ, double* smem)
+{
+    double* sphi = smem;
+    double* ssig = smem + 4 * SM_PHI_SLOT;
+    const unsigned sphi_a = (unsigned)__cvta_generic_to_shared(sphi);
+    const unsigned ssig_a = (unsigned)__cvta_generic_to_shared(ssig);
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
+    const int kc0 = blockIdx.z * TZ, kc1 = min(kc0 + TZ, L.nzl);
+    const bool anyD = L.dlo[0] | L.dhi[0] | L.dlo[1] | L.dhi[1] | L.dlo[2] | L.dhi[2];
+
+    int psrc[5], csrc[5];
+    unsigned pdst[5], cdst[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int idx = tid + s * 256;
+        psrc[s] = -1; csrc[s] = -1; pdst[s] = 0; cdst[s] = 0;
+        if (idx < 66 * 18) {
+            const int li = idx % 66 - 1, lj = idx / 66 - 1;
+            const int gi = i0 + li, gj = j0 + lj;
+            pdst[s] = ((lj + 1) * SM_ROW + sm_col(li)) * 8u;
+            const bool ok = FULL || ((L.per[0] ? gi <= L.n[0] : gi <= L.n[0] + 1) && (L.per[1] ? gj <= L.n[1] : gj <= L.n[1] + 1));
+            if (ok) psrc[s] = nmap(gj, L.n[1], L.per[1]) * L.px + nmap(gi, L.n[0], L.per[0]);
+            else for (int q = 0; q < 4; ++q) sphi[q * SM_PHI_SLOT + (lj + 1) * SM_ROW + sm_col(li)] = 0.0;
+        }
+        if (VAR && idx < 65 * 17) {
+            const int ci = idx % 65 - 1, cj = idx / 65 - 1;
+            const int gi = i0 + ci, gj = j0 + cj;
+            cdst[s] = ((cj + 1) * SM_ROW + sm_ccol(ci)) * 8u;
+            if (FULL || (gi <= L.n[0] && gj <= L.n[1])) csrc[s] = cmap(gj, L.n[1], L.per[1]) * L.cpx + cmap(gi, L.n[0], L.per[0]);
+            else for (int q = 0; q < 3; ++q) ssig[q * SM_SIG_SLOT + (cj + 1) * SM_ROW + sm_ccol(ci)] = 1.0;
+        }
+    }
+    auto issue_phi = [&](int kl) {
+        const double* src = phi + zplane(L, kl) * L.ps;
+        unsigned dst = sphi_a + ((kl + 1) & 3) * (SM_PHI_SLOT * 8);
+        asm volatile("" : "+l"(src), "+r"(dst));
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+            if (psrc[s] >= 0) cp_async8(dst + pdst[s], src + psrc[s]);
+    };
+    auto issue_sig = [&](int cl) {
+        if (!VAR) return;
+        const double* src = L.sigma + czplane(L, cl) * L.cps;
+        unsigned dst = ssig_a + ((cl + 1) % 3) * (SM_SIG_SLOT * 8);
+        asm volatile("" : "+l"(src), "+r"(dst));
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+            if (csrc[s] >= 0) cp_async8(dst + cdst[s], src + csrc[s]);
+    };
+    const int gi0 = i0 + 2 * tx, gj0 = j0 + 2 * ty;
+    const bool colok[2] = {FULL || gi0 < L.nn[0], FULL || gi0 + 1 < L.nn[0]};
+    const bool rowok[2] = {FULL || gj0 < L.nn[1], FULL || gj0 + 1 < L.nn[1]};
+    const int roff = gj0 * L.px + gi0;
+    auto load_rhs = [&](int kl, double (&r)[2][2]) {
+        const double* q0 = rhs + kl * L.ps + roff;
+        asm volatile("" : "+l"(q0));
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double* q = q0 + b * L.px;
+            if (FULL) { const double2 v = *reinterpret_cast<const double2*>(q); r[b][0] = v.x; r[b][1] = v.y; }
+            else {
+                r[b][0] = r[b][1] = 0.0;
+                if (rowok[b]) {
+                    if (colok[1]) { const double2 v = *reinterpret_cast<const double2*>(q); r[b][0] = v.x; r[b][1] = v.y; }
+                    else if (colok[0]) r[b][0] = q[0];
+                }
+            }
+        }
+    };
+    const double F = L.fxyz;
+    const double sF = L.csig * F;
+    const int wc[4] = {33 + tx, tx, 34 + tx, tx + 1};
+    const int cc[3] = {32 + tx, tx, 33 + tx};
+    const int rbase = (2 * ty) * SM_ROW;
+
+    issue_phi(kc0 - 1); issue_phi(kc0); issue_phi(kc0 + 1); issue_sig(kc0 - 1); issue_sig(kc0);
+    cp_async_commit();
+    double rcur[2][2], rnext[2][2];
+    load_rhs(kc0, rcur);
+    cp_async_wait<0>();
+    __syncthreads();
+    double W0[4][4];   // window of plane kl
+    double SL[3][3];   // sigma layer kl-1
+    {
+        const double* P0 = sphi + ((kc0 + 1) & 3) * SM_PHI_SLOT + rbase;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) W0[r][c] = P0[r * SM_ROW + wc[c]];
+        if (VAR) {
+            const double* S = ssig + ((kc0) % 3) * SM_SIG_SLOT + rbase;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) SL[r][c] = S[r * SM_ROW + cc[c]];
+        }
+    }
+    double amax = 0.0;
+
+#pragma unroll 1
+    for (int kl = kc0; kl < kc1; ++kl) {
+        if (kl > kc0) {
+            cp_async_wait<0>();
+            __syncthreads();   // planes kl-1, kl+1 visible; everybody is done with plane kl-2's slot
+        }
+        if (kl + 2 <= kc1) { issue_phi(kl + 2); issue_sig(kl + 1); }
+        cp_async_commit();
+        load_rhs(kl + 1 < kc1 ? kl + 1 : kl, rnext);
+        const int kg = kl + L.k0;
+        const double* Pm = sphi + ((kl) & 3) * SM_PHI_SLOT + rbase;
+        const double* Pp = sphi + ((kl + 2) & 3) * SM_PHI_SLOT + rbase;
+        double out[2][2];
+        double Wp[4][4];
+        if (VAR) {
+            // acc = 4 G phi - T, built in three stages ordered to keep few registers live:
+            // in-plane diagonals (retires W0), lower side (retires SL), upper side (its window is the next W0)
+            double acc[2][2];
+            double SU[3][3];
+            {
+                const double* S = ssig + ((kl + 1) % 3) * SM_SIG_SLOT + rbase;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) SU[r][c] = S[r * SM_ROW + cc[c]];
+                double Sz[3][3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Sz[r][c] = SL[r][c] + SU[r][c];
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        double t = Sz[b][a] * W0[b][a];
+                        t = fma(Sz[b][a + 1], W0[b][a + 2], t);
+                        t = fma(Sz[b + 1][a], W0[b + 2][a], t);
+                        t = fma(Sz[b + 1][a + 1], W0[b + 2][a + 2], t);
+                        const double G4 = 4.0 * ((Sz[b][a] + Sz[b][a + 1]) + (Sz[b + 1][a] + Sz[b + 1][a + 1]));
+                        acc[b][a] = fma(G4, W0[b + 1][a + 1], -t);
+                    }
+            }
+            {
+                double W[4][4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) W[r][c] = Pm[r * SM_ROW + wc[c]];
+                double hx[3][2], hy[2][3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { hx[r][0] = SL[r][0] + SL[r][1]; hx[r][1] = SL[r][1] + SL[r][2]; }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { hy[0][c] = SL[0][c] + SL[1][c]; hy[1][c] = SL[1][c] + SL[2][c]; }
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        double t = SL[b][a] * W[b][a];
+                        t = fma(SL[b][a + 1], W[b][a + 2], t);
+                        t = fma(SL[b + 1][a], W[b + 2][a], t);
+                        t = fma(SL[b + 1][a + 1], W[b + 2][a + 2], t);
+                        double u = hx[b][a] * W[b][a + 1];
+                        u = fma(hx[b + 1][a], W[b + 2][a + 1], u);
+                        u = fma(hy[b][a], W[b + 1][a], u);
+                        u = fma(hy[b][a + 1], W[b + 1][a + 2], u);
+                        acc[b][a] -= t + u;
+                    }
+            }
+            {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) Wp[r][c] = Pp[r * SM_ROW + wc[c]];
+                double hx[3][2], hy[2][3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { hx[r][0] = SU[r][0] + SU[r][1]; hx[r][1] = SU[r][1] + SU[r][2]; }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { hy[0][c] = SU[0][c] + SU[1][c]; hy[1][c] = SU[1][c] + SU[2][c]; }
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        double t = SU[b][a] * Wp[b][a];
+                        t = fma(SU[b][a + 1], Wp[b][a + 2], t);
+                        t = fma(SU[b + 1][a], Wp[b + 2][a], t);
+                        t = fma(SU[b + 1][a + 1], Wp[b + 2][a + 2], t);
+                        double u = hx[b][a] * Wp[b][a + 1];
+                        u = fma(hx[b + 1][a], Wp[b + 2][a + 1], u);
+                        u = fma(hy[b][a], Wp[b + 1][a], u);
+                        u = fma(hy[b][a + 1], Wp[b + 1][a + 2], u);
+                        out[b][a] = fma(F, acc[b][a] - (t + u), rcur[b][a]);   // rhs - F (T - 4 G phi)
+                    }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) SL[r][c] = SU[r][c];
+            }
+        } else {
+            double W[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { Wp[r][c] = Pp[r * SM_ROW + wc[c]]; W[r][c] = Pm[r * SM_ROW + wc[c]] + Wp[r][c]; }
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const double C = (W[b][a] + W[b][a + 2]) + (W[b + 2][a] + W[b + 2][a + 2]);
+                    const double E = ((W[b][a + 1] + W[b + 2][a + 1]) + (W[b + 1][a] + W[b + 1][a + 2])) +
+                                     ((W0[b][a] + W0[b][a + 2]) + (W0[b + 2][a] + W0[b + 2][a + 2]));
+                    const double t = fma(2.0, E, C);
+                    out[b][a] = fma(sF, fma(32.0, W0[b + 1][a + 1], -t), rcur[b][a]);     // rhs - sigma F (C + 2E - 32 phi)
+                }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                if (anyD && node_masked(L, gi0 + a, gj0 + b, kg)) out[b][a] = 0.0;
+                if (FULL || (colok[a] && rowok[b])) amax = fmax(amax, fabs(out[b][a]));
+            }
+        {
+            double* q0 = res + kl * L.ps + roff;
+            asm volatile("" : "+l"(q0));
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                double* q = q0 + b * L.px;
+                if (FULL) *reinterpret_cast<double2*>(q) = make_double2(out[b][0], out[b][1]);
+                else if (rowok[b]) {
+                    if (colok[1]) *reinterpret_cast<double2*>(q) = make_double2(out[b][0], out[b][1]);
+                    else if (colok[0]) q[0] = out[b][0];
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) rcur[b][a] = rnext[b][a];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) W0[r][c] = Wp[r][c];
+    }
+    cp_async_wait<0>();
+    return amax;
+}
+
+template <bool VAR>
+__global__ void __launch_bounds__(256, 2) k_residual_iso(const Lev L, const double* __restrict__ phi,
+                                                         const double* __restrict__ rhs, double* __restrict__ res, int TZ,
+                                                         double* __restrict__ norm_partial)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
+    const bool full = (i0 + SM_TX <= L.nn[0]) && (j0 + SM_TY <= L.nn[1]);
+    double amax = full ? resid_iso_body<VAR, true>(L, phi, rhs, res, TZ, smem) : resid_iso_body<VAR, false>(L, phi, rhs, res, TZ, smem);
+    if (norm_partial) {
+        __syncthreads();
+        double* sh = smem;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = amax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = 0.0;
+            for (int w = 0; w < 8; ++w) m = fmax(m, sh[w]);
+            norm_partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = m;
+        }
+    }
 }
 
 }  // namespace b200np_dev

@@ -24,7 +24,7 @@ proj.set_sigma(cfg["sigma"], cfg["const_sigma"])
 st = proj.project(1e-11, 1e-14)
 print(f"N={N} cfg={cfgname} var={var} iters={st.iters} ms_total={st.ms_total:.2f} ms_solve={st.ms_solve:.2f} "
       f"launches={st.launches} Mcells/s={N**3 / st.ms_total / 1e3:.1f}")
-for lev in range(min(3, proj.nlevels())):
+for lev in range(proj.nlevels() if os.environ.get('KB_ALL') else min(3, proj.nlevels())):
     n, nn = proj.level_dims(lev)
     nodes = nn[0] * nn[1] * nn[2]
     bytes_per = {"smooth": 32 if var else 24, "residual": 32 if var else 24, "restrict": 9, "interp": 25 if var else 17}
