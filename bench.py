@@ -14,8 +14,10 @@ value  : Mcell-updates/s = cells * K / t with every input already resident in HB
          pointers through the C ABI), timed with CUDA events on the launching stream.
 e2e    : same metric through the same C-ABI call with HOST (pinned) buffers: H2D of
          velocity/density/gp and D2H of velocity/gp/p_nd inside the timed region.
-roofline: the dominant kernel (tile-resident Gauss-Seidel sweep, level 0): algorithmic bytes
-         (32 B/node variable sigma) / CUDA-event time per launch vs MEASURED_PEAKS.json hbm_gbs.
+roofline: the dominant kernel (tile-resident Gauss-Seidel sweep k_smooth_iso, level 0): algorithmic
+         bytes (32 B/node variable sigma) / CUDA-event time per launch vs MEASURED_PEAKS.json hbm_gbs
+         (burst copy figure; the kernel is timed alone, back to back); traffic = dram bytes of one
+         launch from the committed ncu --set full capture (profiles/ncu_traffic.json).
 cpu_baseline: the CPU oracle (a port of the reference algorithm, NOT incflo/AMReX itself, which
          cannot be built offline) on the box's host cores, on a bounded sample (128^3 of the same
          workload).
@@ -261,11 +263,11 @@ def run_ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(f"k_smooth_v2_var_{N}")
+            traffic = json.load(f).get(f"k_smooth_iso_var_{N}")
     except Exception:
         pass
     sweeps_per_step = iters * 16
-    roofline = {"bound": "hbm", "kernel": "k_smooth_v2<variable sigma> level 0 (one Gauss-Seidel sweep)",
+    roofline = {"bound": "hbm", "kernel": "k_smooth_iso<variable sigma> level 0 (one Gauss-Seidel sweep)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms_sm * 1e3,
                 "launches_per_step": sweeps_per_step, "share_of_step": sweeps_per_step * ms_sm / ms_per_step,

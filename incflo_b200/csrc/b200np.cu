@@ -123,6 +123,7 @@ struct b200np {
     int TZ = 64;
     int dist_graph = 1;       // capture the slab-decomposed V-cycle (NCCL send/recv included) into a CUDA graph (B200NP_DIST_GRAPH)
     int dist_min_planes = 8;  // a level stays slab-distributed while every rank keeps at least this many cell planes (B200NP_DIST_MIN_PLANES)
+    int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200NP_PDL)
     int res_max_ctas = 148;   // levels with at most this many smoother CTAs use the resident-chunk kernel (B200NP_RES_CTAS)
     int smoother_version = 3, interp_version = 2, resid_version = 3;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
 };
@@ -134,6 +135,22 @@ namespace {
         kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__);      \
         (h)->launches++;                                         \
     } while (0)
+
+// Launch with programmatic dependent launch (PDL): the kernel may become resident while its
+// predecessor drains; every kernel launched this way calls pdl_wait() before its first access to
+// data the predecessor produced (np_level.h).  Captured into the V-cycle graph as programmatic edges.
+template <typename... KArgs, typename... Args>
+void launch_pdl(b200np* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->use_pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+    h->launches++;
+}
 
 double* dev_alloc(size_t n_doubles)
 {
@@ -230,7 +247,10 @@ void build_hierarchy(b200np* h)
         {
             const int ntiles = ((g.nn[0] + NP_TX - 1) / NP_TX) * ((g.nn[1] + NP_TY - 1) / NP_TY);
             const int nch = std::max(1, 592 / ntiles);
-            L.tz = std::max(8, std::min(h->TZ, (g.nn[2] + nch - 1) / nch));
+            // lower bound: 8 planes on levels with more than 33 node planes (shorter chunks cost a V-cycle);
+            // coarse levels are insensitive and use 4 / 2 / 1 so that more chunks run in parallel
+            const int mn = g.nn[2] > 33 ? 8 : g.nn[2] > 17 ? 4 : g.nn[2] > 9 ? 2 : 1;
+            L.tz = std::max(mn, std::min(h->TZ, (g.nn[2] + nch - 1) / nch));
         }
         L.gsm = dim3((g.nn[0] + NP_TX - 1) / NP_TX, (g.nn[1] + NP_TY - 1) / NP_TY, (g.nzl + L.tz - 1) / L.tz);
         L.git = dim3((g.nn[0] + IT_X - 1) / IT_X, (g.nn[1] + IT_Y - 1) / IT_Y, (g.nzl + IT_Z - 1) / IT_Z);
@@ -375,18 +395,15 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
             if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, L.tz);
             else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, L.tz);
         } else if (h->smoother_version == 2 || !L.iso) {
-            if (h->var_sigma) k_smooth_v2<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
-            else              k_smooth_v2<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
-            h->launches++;
+            if (h->var_sigma) launch_pdl(h, k_smooth_v2<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, x, y, rhs, L.tz);
+            else              launch_pdl(h, k_smooth_v2<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
         } else if (L.tz <= SM_RES_TZ && (int)(L.gsm.x * L.gsm.y * L.gsm.z) <= h->res_max_ctas) {
             // small isotropic level: whole chunk resident in shared memory, one CTA per SM
-            if (h->var_sigma) k_smooth_iso_res<true><<<L.gsm, 256, SM_RES_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
-            else              k_smooth_iso_res<false><<<L.gsm, 256, (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
-            h->launches++;
+            if (h->var_sigma) launch_pdl(h, k_smooth_iso_res<true>, L.gsm, dim3(256), SM_RES_DOUBLES * sizeof(double), L.g, x, y, rhs, L.tz);
+            else              launch_pdl(h, k_smooth_iso_res<false>, L.gsm, dim3(256), (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
         } else {  // isotropic level: 2-barrier / register-carried variant, same semantics
-            if (h->var_sigma) k_smooth_iso<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
-            else              k_smooth_iso<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, x, y, rhs, L.tz);
-            h->launches++;
+            if (h->var_sigma) launch_pdl(h, k_smooth_iso<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, x, y, rhs, L.tz);
+            else              launch_pdl(h, k_smooth_iso<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
         }
         std::swap(x, y);
     }
@@ -400,13 +417,11 @@ void residual(b200np* h, LevelData& L, double* phi, const double* rhs, double* r
         if (h->var_sigma) LAUNCH(h, k_residual<true>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
         else              LAUNCH(h, k_residual<false>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
     } else if (h->resid_version == 2 || !L.iso) {
-        if (h->var_sigma) k_residual_v2<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
-        else              k_residual_v2<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
-        h->launches++;
+        if (h->var_sigma) launch_pdl(h, k_residual_v2<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, phi, rhs, res, L.tz, norm_partial);
+        else              launch_pdl(h, k_residual_v2<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, phi, rhs, res, L.tz, norm_partial);
     } else {
-        if (h->var_sigma) k_residual_iso<true><<<L.gsm, 256, SM_SMOOTH_DOUBLES * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
-        else              k_residual_iso<false><<<L.gsm, 256, 4 * SM_PHI_SLOT * sizeof(double), h->stream>>>(L.g, phi, rhs, res, L.tz, norm_partial);
-        h->launches++;
+        if (h->var_sigma) launch_pdl(h, k_residual_iso<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, phi, rhs, res, L.tz, norm_partial);
+        else              launch_pdl(h, k_residual_iso<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, phi, rhs, res, L.tz, norm_partial);
     }
 }
 // number of per-CTA norm partials the residual kernel writes
@@ -419,10 +434,10 @@ void bottom_solve(b200np* h)
 {
     LevelData& B = h->lv.back();
     if (h->var_sigma)
-        LAUNCH(h, k_bottom_bicgstab<true>, 1, 512, B.g, B.cor, B.res, h->bottom_work, h->opts.bottom_maxiter,
+        launch_pdl(h, k_bottom_bicgstab<true>, dim3(1), dim3(512), 0, B.g, B.cor, B.res, h->bottom_work, h->opts.bottom_maxiter,
                h->opts.bottom_rtol, h->opts.bottom_atol, h->singular, h->opts.smooth_num_sweeps, h->opts.bottom_solver, h->dinfo);
     else
-        LAUNCH(h, k_bottom_bicgstab<false>, 1, 512, B.g, B.cor, B.res, h->bottom_work, h->opts.bottom_maxiter,
+        launch_pdl(h, k_bottom_bicgstab<false>, dim3(1), dim3(512), 0, B.g, B.cor, B.res, h->bottom_work, h->opts.bottom_maxiter,
                h->opts.bottom_rtol, h->opts.bottom_atol, h->singular, h->opts.smooth_num_sweeps, h->opts.bottom_solver, h->dinfo);
 }
 
@@ -431,10 +446,10 @@ void restrict_to(b200np* h, int l)
     LevelData &F = h->lv[l], &C = h->lv[l + 1];
     halo_nodes(h, F, F.rescor);
     if (F.dist && !C.dist) {  // agglomeration: my share of the coarse rhs, then gather onto every rank
-        LAUNCH(h, k_restrict, C.gn_part, 256, F.g, C.gpart, F.rescor, C.part_nodal + C.g.ps);
+        launch_pdl(h, k_restrict, C.gn_part, dim3(256), 0, F.g, C.gpart, (const double*)F.rescor, C.part_nodal + C.g.ps);
         allgather_parts(h, C.g, C.part_nodal + C.g.ps, C.res, true);
     } else {
-        LAUNCH(h, k_restrict, C.gn, 256, F.g, C.g, F.rescor, C.res);
+        launch_pdl(h, k_restrict, C.gn, dim3(256), 0, F.g, C.g, (const double*)F.rescor, C.res);
     }
 }
 void interp_add(b200np* h, int l)
@@ -445,8 +460,8 @@ void interp_add(b200np* h, int l)
         if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
         else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
     } else {
-        if (h->var_sigma) LAUNCH(h, k_interp_tile<true>, F.git, 256, F.g, C.g, F.cor, C.cor);
-        else              LAUNCH(h, k_interp_tile<false>, F.git, 256, F.g, C.g, F.cor, C.cor);
+        if (h->var_sigma) launch_pdl(h, k_interp_tile<true>, F.git, dim3(256), 0, F.g, C.g, F.cor, (const double*)C.cor);
+        else              launch_pdl(h, k_interp_tile<false>, F.git, dim3(256), 0, F.g, C.g, F.cor, (const double*)C.cor);
     }
 }
 
@@ -696,6 +711,7 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (const char* e = getenv("B200NP_SMOOTHER")) h->smoother_version = atoi(e);
         if (const char* e = getenv("B200NP_RES_CTAS")) h->res_max_ctas = atoi(e);
         if (const char* e = getenv("B200NP_DIST_GRAPH")) h->dist_graph = atoi(e);
+        if (const char* e = getenv("B200NP_PDL")) h->use_pdl = atoi(e);
         if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) h->dist_min_planes = std::max(8, atoi(e));
         if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
         if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);

@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(256) k_restrict(const Lev F, const Lev C, cons
     const int i = blockIdx.x * 64 + (threadIdx.x & 63);
     const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
     const int kl = blockIdx.z;  // coarse local plane
+    pdl_trigger();
+    pdl_wait();
     if (i >= C.nn[0] || j >= C.nn[1]) return;
     long long id = kl * C.ps + (long long)j * C.px + i;
     if (node_masked(C, i, j, kl + C.k0)) { crse[id] = 0.0; return; }
@@ -692,6 +694,8 @@ __global__ void __launch_bounds__(512) k_bottom_bicgstab(const Lev L, double* __
                                                          int singular, int nsweeps, int bottom_solver, int* __restrict__ info)
 {
     __shared__ double sh[34];
+    pdl_trigger();
+    pdl_wait();
     const int nxy = L.nn[0] * L.nn[1], ntot = nxy * L.nzl;
     const long long vs = L.ps * L.nzl;
     double *r = work, *rh = work + vs, *p = work + 2 * vs, *v = work + 3 * vs, *s = work + 4 * vs, *t_ = work + 5 * vs,

@@ -36,6 +36,15 @@ struct Lev {
     const double* sigma;  // cell array, plane 0 of the owned range (ghost slot at -1)
 };
 
+// Programmatic dependent launch (PDL).  pdl_wait(): block until the predecessor kernel has completed
+// and its writes are visible -- must precede the first access to data it produced.
+// pdl_trigger(): allow the successor to become resident (it still waits in its own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// small grids (a single wave) let the successor in right away; multi-wave grids only at their tail,
+// so that waiting successor CTAs do not take SM slots from this grid's later waves
+__device__ __forceinline__ bool pdl_small_grid() { return gridDim.x * gridDim.y * gridDim.z <= 296u; }
+
 // node index in [-1, n+1] -> unique storage index
 __host__ __device__ __forceinline__ int nmap(int i, int n, int per)
 {

@@ -116,6 +116,8 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     const int cc[3] = {32 + tx, tx, 33 + tx};  // cells 2tx-1, 2tx, 2tx+1
     const int rbase = (2 * ty) * SM_ROW;       // window row 0 of this thread
 
+    if (pdl_small_grid()) pdl_trigger();
+    pdl_wait();   // everything above only touched kernel parameters and shared memory
     double rcur[2][2], rnext[2][2];
     if (RES) {
         // the whole chunk: planes kc0-1 .. kc1, sigma layers kc0-1 .. kc1-1
@@ -339,7 +341,9 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
             for (int a = 0; a < 2; ++a) { rcur[b][a] = rnext[b][a]; ownp[b][a] = v[b][a]; }
 #pragma unroll
         for (int c = 0; c < 4; ++c) { Wn[0][c] = Wp02[0][c]; Wn[1][c] = Wp02[1][c]; }
+        if (kl + 2 == kc1) pdl_trigger();   // tail of the march (no-op if already triggered)
     }
+    pdl_trigger();
     cp_async_wait<0>();
 }
 
@@ -449,6 +453,8 @@ __device__ __forceinline__ double resid_iso_body(const Lev& L, const double* __r
     const int cc[3] = {32 + tx, tx, 33 + tx};
     const int rbase = (2 * ty) * SM_ROW;
 
+    if (pdl_small_grid()) pdl_trigger();
+    pdl_wait();
     issue_phi(kc0 - 1); issue_phi(kc0); issue_phi(kc0 + 1); issue_sig(kc0 - 1); issue_sig(kc0);
     cp_async_commit();
     double rcur[2][2], rnext[2][2];
@@ -616,6 +622,7 @@ __device__ __forceinline__ double resid_iso_body(const Lev& L, const double* __r
 #pragma unroll
             for (int c = 0; c < 4; ++c) W0[r][c] = Wp[r][c];
     }
+    pdl_trigger();
     cp_async_wait<0>();
     return amax;
 }

@@ -348,7 +348,11 @@ static void smooth_level(const orc_mg* mg, level* L, double* phi, const double* 
             int nch = 592 / ntiles; if (nch < 1) nch = 1;
             int c = (L->nn[2] + nch - 1) / nch;
             if (c < bsz[2]) bsz[2] = c;
-            if (bsz[2] < 8) bsz[2] = 8; /* shorter chunks cost a V-cycle (measured: 4 -> 8 cycles, 8 -> 7) */
+            /* lower bound of the chunk height: 8 planes on levels with more than 33 node planes (shorter
+             * chunks cost a V-cycle there: measured 4 -> 8 cycles, 8 -> 7); coarse levels are insensitive
+             * (same residual history to 2 digits), so they use 4 / 2 / 1 to expose more parallel chunks */
+            { int mn = L->nn[2] > 33 ? 8 : L->nn[2] > 17 ? 4 : L->nn[2] > 9 ? 2 : 1;
+              if (bsz[2] < mn) bsz[2] = mn; }
         }
         int nb[3];
         for (int d = 0; d < 3; ++d) nb[d] = (L->nn[d] + bsz[d] - 1) / bsz[d];
