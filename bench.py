@@ -100,18 +100,20 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(N, nranks, rank, device, ng=3):
-    """per-rank slab of the rayleigh_taylor workload (weak scaling: N x N x N cells per rank)."""
+def workload(N, nranks, rank, device, ng=3, strong=False):
+    """per-rank slab of the rayleigh_taylor workload.  weak scaling: N x N x N cells per rank
+    (domain N x N x N*nranks); strong scaling: the N^3 domain cut into nranks z slabs."""
     import torch
     from incflo_b200 import problems
-    n_glob = (N, N, N * nranks)
+    n_glob = (N, N, N) if strong else (N, N, N * nranks)
+    nz = N // nranks if strong else N
     dt = 0.45 / N
-    with problems.slab(rank * N, N):   # this rank's cell planes [rank*N, (rank+1)*N) of the global closed forms
+    with problems.slab(rank * nz, nz):   # this rank's cell planes [rank*nz, (rank+1)*nz) of the global closed forms
         vel = problems.rayleigh_taylor_velocity(n_glob, ng, device, "b")
         rho = problems.rayleigh_taylor_density(n_glob, ng, device)
-    gp = torch.zeros((3, N, N, N), dtype=torch.float64, device=device)
+    gp = torch.zeros((3, nz, N, N), dtype=torch.float64, device=device)
     gp[2] = -0.05  # a hydrostatic-like old pressure gradient so the pre-add does work
-    p = torch.zeros((N + 1, N + 1, N + 1), dtype=torch.float64, device=device)
+    p = torch.zeros((nz + 1, N + 1, N + 1), dtype=torch.float64, device=device)
     return dict(n=n_glob, dx=(1.0 / N,) * 3, dt=dt, vel=vel, rho=rho, gp=gp, p=p, ng=ng,
                 bclo=(0, 0, 1), bchi=(0, 0, 1))
 
@@ -180,7 +182,8 @@ def run_ours(args):
     if nranks > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
     N, K, W = args.n, args.steps, args.warmup
-    wl = workload(N, nranks, rank, device)   # weak scaling: every rank owns an N^3 slab of an N x N x (N*nranks) domain
+    strong = args.scaling == "strong" and nranks > 1
+    wl = workload(N, nranks, rank, device, strong=strong)   # weak (default): every rank owns an N^3 slab of an N x N x (N*nranks) domain
     nccl_id = None
     if nranks > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device=device)
@@ -193,7 +196,7 @@ def run_ours(args):
                                 nccl_id=nccl_id)
     stream = torch.cuda.Stream()           # the launching stream: the handle runs on it, the events are recorded on it
     proj.set_stream(stream.cuda_stream)
-    ncell = N ** 3
+    ncell = N ** 3 // nranks if strong else N ** 3   # cells per rank
 
     def step(vel, gp, p, rho):
         return proj.apply_nodal_projection(vel, ng, gp, p, density=rho, ngd=ng, scaling_factor=wl["dt"],
@@ -301,14 +304,14 @@ def run_ours(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"rayleigh_taylor variable-density (sigma=dt/rho, 4:1) {N}^3 per GPU, periodic x/y + "
+                "config": {"workload": f"rayleigh_taylor variable-density (sigma=dt/rho, 4:1) {N}^3 {'in total' if strong else 'per GPU'}, periodic x/y + "
                                        f"walls z, nodal projection to rtol 1e-11 (BASELINE configs[1])",
                            "rtol": RTOL, "atol": ATOL, "vcycles": iters, "resid_over_bnorm": resid_ratio,
                            "cycle": "V(2,2) x 4 sweeps (reference defaults)", "inputs_vs_l2": "working set >> 126 MB L2",
                            "parallelism": "1 GPU" if nranks == 1 else f"z-slab decomposition over {nranks} GPUs (NCCL halo planes + allreduce), "
-                                                                                 f"domain {N}x{N}x{N * nranks}",
+                                                                                 f"domain {N}x{N}x{N if strong else N * nranks}",
                            "solves_per_s": 1e3 / ms_per_step * nranks},
                 "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                                           "d2h_bytes_per_step": int(d2h), "steps": Ke, "ms_per_step": te / Ke * 1e3 if Ke else None},
@@ -343,7 +346,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--n", "--size", dest="n", type=int, default=256,
+                    help="cells per side (--size: spelling that torchrun's own option parser does not claim)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = n^3 cells per GPU (default, the driver's scaling run); strong = n^3 in total")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer arm (the line is then not a valid bench line)")
     args = ap.parse_args()

@@ -22,6 +22,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 using namespace b200np_dev;
@@ -46,6 +48,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -56,7 +59,7 @@ struct NcclApi {
         if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!lib) return false;
 #define NP_SYM(name) *(void**)(&name) = dlsym(lib, "nccl" #name); if (!name) return false;
-        NP_SYM(GetUniqueId) NP_SYM(CommInitRank) NP_SYM(CommDestroy) NP_SYM(Send) NP_SYM(Recv) NP_SYM(AllReduce)
+        NP_SYM(GetUniqueId) NP_SYM(CommInitRank) NP_SYM(CommDestroy) NP_SYM(Send) NP_SYM(Recv) NP_SYM(AllReduce) NP_SYM(AllGather)
         NP_SYM(GroupStart) NP_SYM(GroupEnd) NP_SYM(GetErrorString)
 #undef NP_SYM
         return true;
@@ -73,14 +76,30 @@ NcclApi g_nccl;
         }                                                                                              \
     } while (0)
 
+// Every device array of a handle lives in ONE allocation.  Sizes are rank-independent, so an array
+// sits at the same offset on every rank and a neighbour's copy is (peer base + my offset) once the
+// neighbour's arena is mapped with CUDA IPC (slab-decomposed path).  Pass 1 measures, pass 2 places.
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0, off = 0;
+    bool measure = true;
+    double* take(size_t n_doubles)
+    {
+        const size_t b = (n_doubles * sizeof(double) + 1023) & ~size_t(1023);
+        double* p = measure ? nullptr : reinterpret_cast<double*>(base + off);
+        off += b;
+        return p;
+    }
+};
+
 struct LevelData {
     Lev g{};
     bool dist = false;        // slab-distributed level (ghost plane slots are exchanged)
     bool iso = false;         // dx == dy == dz: face coefficients of the stencil vanish (np_smooth3.cuh)
     double* sigma = nullptr;  // plane 0 of owned cells (allocation starts one plane earlier)
     double* sigma_alloc = nullptr;
+    int nzl_alloc = 0;        // node planes allocated per array (rank-independent: the largest slab)
     double *sol = nullptr, *rhs = nullptr, *res = nullptr, *cor = nullptr, *cor2 = nullptr, *rescor = nullptr;
-    std::vector<double*> allocs;
     dim3 gn, gc;     // grids of 64x4-thread blocks over owned nodes / cells
     dim3 gsm;        // smoother / residual grid (tiles x z-chunks)
     dim3 git;        // interpolation grid (fine tiles)
@@ -100,6 +119,14 @@ struct b200np {
     int device = 0;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
+    Arena arena;
+    // NVLink peer-memory halos (CUDA IPC): the neighbours' arenas mapped into this process
+    int use_p2p = 1;          // B200NP_P2P=0: grouped ncclSend/ncclRecv per halo instead
+    int fuse_halo = 1;        // B200NP_FUSE_HALO=0: separate k_halo_pull before every sweep
+    bool p2p = false;         // active (every rank mapped its neighbours)
+    char *peer_lo = nullptr, *peer_hi = nullptr;
+    unsigned long long* flags = nullptr;  // HaloFlags::my
+    double* ipc_buf = nullptr;
     int nlev_dist = 0;       // levels [0, nlev_dist) are slab-distributed, the rest replicated on every rank
     int singular = 1;
     bool var_sigma = false;
@@ -122,10 +149,16 @@ struct b200np {
     Stage stage[8];  // staging buffers for host-pointer callers
     int TZ = 64;
     int dist_graph = 1;       // capture the slab-decomposed V-cycle (NCCL send/recv included) into a CUDA graph (B200NP_DIST_GRAPH)
-    int dist_min_planes = 8;  // a level stays slab-distributed while every rank keeps at least this many cell planes (B200NP_DIST_MIN_PLANES)
+    int dist_min_planes = 64; // a level stays slab-distributed while every rank keeps at least this many cell planes (B200NP_DIST_MIN_PLANES;
+                              // measured at 2 GPUs, 256^3 per GPU: 8 -> 33.1 ms, 64 -> 30.6 ms per solve)
     int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200NP_PDL)
     int res_max_ctas = 148;   // levels with at most this many smoother CTAs use the resident-chunk kernel (B200NP_RES_CTAS)
     int smoother_version = 3, interp_version = 2, resid_version = 3;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
+    // B200NP_PROFILE=1: per-phase device times (CUDA events between phases, graph capture off); printed per call
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<std::string> prof_tag;
+    size_t prof_n = 0;
 };
 
 namespace {
@@ -152,19 +185,40 @@ void launch_pdl(b200np* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
     h->launches++;
 }
 
-double* dev_alloc(size_t n_doubles)
+// profiling: the time between two marks is charged to the tag of the later one
+void prof_mark(b200np* h, const char* tag, int lev = -1)
 {
-    double* p = nullptr;
-    CK(cudaMalloc(&p, n_doubles * sizeof(double)));
-    CK(cudaMemset(p, 0, n_doubles * sizeof(double)));
-    return p;
+    if (!h->profile) return;
+    if (h->prof_n == h->prof_ev.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->prof_ev.push_back(e); h->prof_tag.emplace_back(); }
+    h->prof_tag[h->prof_n] = lev >= 0 ? std::string("L") + std::to_string(lev) + " " + tag : std::string(tag);
+    CK(cudaEventRecord(h->prof_ev[h->prof_n++], h->stream));
+}
+void prof_report(b200np* h)
+{
+    if (!h->profile || h->prof_n < 2) { h->prof_n = 0; return; }
+    CK(cudaEventSynchronize(h->prof_ev[h->prof_n - 1]));
+    std::map<std::string, std::pair<double, int>> acc;
+    double tot = 0;
+    for (size_t i = 1; i < h->prof_n; ++i) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->prof_ev[i - 1], h->prof_ev[i]));
+        auto& a = acc[h->prof_tag[i]];
+        a.first += ms; a.second++;
+        tot += ms;
+    }
+    fprintf(stderr, "b200np profile (rank %d): %.3f ms between first and last mark\n", h->rank, tot);
+    for (auto& kv : acc)
+        fprintf(stderr, "  %-22s n=%5d %9.3f ms %5.1f %%  avg %8.1f us\n", kv.first.c_str(), kv.second.second, kv.second.first,
+                100.0 * kv.second.first / tot, 1e3 * kv.second.first / kv.second.second);
+    h->prof_n = 0;
 }
 
+inline double* dev_alloc(b200np* h, size_t n_doubles) { return h->arena.take(n_doubles); }
+
 // allocate a nodal array with ghost plane slots; returns pointer to owned plane 0
-double* alloc_nodal(LevelData& L)
+double* alloc_nodal(b200np* h, LevelData& L)
 {
-    double* base = dev_alloc((size_t)L.g.ps * (L.g.nzl + 2));
-    L.allocs.push_back(base);
+    double* base = dev_alloc(h, (size_t)L.g.ps * (L.nzl_alloc + 2));
     return base + L.g.ps;
 }
 
@@ -206,9 +260,10 @@ void set_slab(Lev& g, int rank, int P, bool periodic_z)
     g.dist = 1;
 }
 
-void build_hierarchy(b200np* h)
+void build_levels(b200np* h)
 {
     const b200np_geom& G = h->geom;
+    h->lv.clear();
     const int P = h->nranks;
     int n[3] = {G.n_cell[0], G.n_cell[1], G.n_cell[2]};
     double dx[3] = {G.dx[0], G.dx[1], G.dx[2]};
@@ -223,8 +278,9 @@ void build_hierarchy(b200np* h)
         Lev& g = L.g;
         fill_lev(G, n, dx, g);
         L.iso = (dx[0] == dx[1] && dx[1] == dx[2]);
-        // a level stays distributed while every rank keeps an even number (>= 8) of cell planes
-        if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && n[2] / P >= h->dist_min_planes) {
+        // level 0 is always distributed; a coarser level stays distributed while every rank keeps an even
+        // number (>= dist_min_planes) of cell planes
+        if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && (lev == 0 || n[2] / P >= h->dist_min_planes)) {
             set_slab(g, h->rank, P, zper(h));
             L.dist = true;
             h->nlev_dist = lev + 1;
@@ -235,8 +291,8 @@ void build_hierarchy(b200np* h)
                 set_slab(L.gpart, h->rank, P, zper(h));
                 L.gn_part = dim3((g.nn[0] + 63) / 64, (g.nn[1] + 3) / 4, L.gpart.nzl);
                 L.gc_part = dim3((g.n[0] + 63) / 64, (g.n[1] + 3) / 4, L.gpart.cnzl);
-                L.part_nodal = dev_alloc((size_t)g.ps * (L.gpart.nzl + 2));
-                L.part_sigma = dev_alloc((size_t)g.cps * (L.gpart.cnzl + 2));
+                L.part_nodal = dev_alloc(h, (size_t)g.ps * (n[2] / P + 1 + 2));
+                L.part_sigma = dev_alloc(h, (size_t)g.cps * (L.gpart.cnzl + 2));
             }
             still_dist = false;
         }
@@ -250,15 +306,19 @@ void build_hierarchy(b200np* h)
             // lower bound: 8 planes on levels with more than 33 node planes (shorter chunks cost a V-cycle);
             // coarse levels are insensitive and use 4 / 2 / 1 so that more chunks run in parallel
             const int mn = g.nn[2] > 33 ? 8 : g.nn[2] > 17 ? 4 : g.nn[2] > 9 ? 2 : 1;
-            L.tz = std::max(mn, std::min(h->TZ, (g.nn[2] + nch - 1) / nch));
+            // slab-decomposed level: the chunks tile this rank's planes (rank-independent count), so that a
+            // sweep still fills the SMs twice; the converged answer does not depend on the chunking
+            const int nzp = L.dist ? n[2] / P + (g.per[2] ? 0 : 1) : g.nn[2];
+            L.tz = std::max(mn, std::min(h->TZ, (nzp + nch - 1) / nch));
         }
         L.gsm = dim3((g.nn[0] + NP_TX - 1) / NP_TX, (g.nn[1] + NP_TY - 1) / NP_TY, (g.nzl + L.tz - 1) / L.tz);
         L.git = dim3((g.nn[0] + IT_X - 1) / IT_X, (g.nn[1] + IT_Y - 1) / IT_Y, (g.nzl + IT_Z - 1) / IT_Z);
         L.nblk_n = (long long)L.gn.x * L.gn.y * L.gn.z;
-        L.sigma_alloc = dev_alloc((size_t)g.cps * (g.cnzl + 2));
+        L.nzl_alloc = L.dist ? n[2] / P + 1 : g.nzl;   // the last slab of a non-periodic domain owns one more plane
+        L.sigma_alloc = dev_alloc(h, (size_t)g.cps * (g.cnzl + 2));
         L.sigma = L.sigma_alloc + g.cps;
-        L.res = alloc_nodal(L); L.cor = alloc_nodal(L); L.cor2 = alloc_nodal(L); L.rescor = alloc_nodal(L);
-        if (lev == 0) { L.sol = alloc_nodal(L); L.rhs = alloc_nodal(L); }
+        L.res = alloc_nodal(h, L); L.cor = alloc_nodal(h, L); L.cor2 = alloc_nodal(h, L); L.rescor = alloc_nodal(h, L);
+        if (lev == 0) { L.sol = alloc_nodal(h, L); L.rhs = alloc_nodal(h, L); }
         h->lv.push_back(L);
         ++lev;
         // coarsen by 2 while every direction stays even and >= 2 cells wide (A.8)
@@ -268,23 +328,60 @@ void build_hierarchy(b200np* h)
         for (int d = 0; d < 3; ++d) { n[d] /= 2; dx[d] *= 2; }
     }
     if (P > 1 && h->nlev_dist >= (int)h->lv.size()) throw int(B200NP_ERR_BAD_ARG);  // needs a replicated coarse level
-    long long maxblk = 0;
-    for (auto& L : h->lv) maxblk = std::max(maxblk, L.nblk_n);
-    h->partial = dev_alloc((size_t)2 * maxblk + 16);
-    h->dscal = dev_alloc(16);
-    CK(cudaMallocHost(&h->hscal, 16 * sizeof(double)));
-    CK(cudaMalloc(&h->dinfo, 4 * sizeof(int)));
-    CK(cudaMemset(h->dinfo, 0, 4 * sizeof(int)));
-    CK(cudaMallocHost(&h->hinfo, 4 * sizeof(int)));
+    long long maxblk = 0;  // rank-independent bound on the per-block reduction partials
+    for (auto& L : h->lv) maxblk = std::max(maxblk, (long long)L.gn.x * L.gn.y * L.nzl_alloc);
+    h->partial = dev_alloc(h, (size_t)2 * maxblk + 16);
+    h->dscal = dev_alloc(h, 16);
+    h->flags = reinterpret_cast<unsigned long long*>(dev_alloc(h, 16));
+    h->ipc_buf = dev_alloc(h, (size_t)8 * std::max(P, 1) + 8);   // 64 bytes per rank
+    h->dinfo = reinterpret_cast<int*>(dev_alloc(h, 8));
     const Lev& B = h->lv.back().g;
-    h->bottom_work = dev_alloc((size_t)B.ps * B.nzl * 8);
+    h->bottom_work = dev_alloc(h, (size_t)B.ps * B.nzl * 8);
+}
+
+void build_hierarchy(b200np* h)
+{
+    h->arena = Arena{};
+    build_levels(h);                       // pass 1: sizes
+    h->arena.size = h->arena.off;
+    void* base = nullptr;
+    CK(cudaMalloc(&base, h->arena.size));
+    CK(cudaMemset(base, 0, h->arena.size));
+    h->arena.base = static_cast<char*>(base);
+    h->arena.off = 0; h->arena.measure = false;
+    build_levels(h);                       // pass 2: pointers
+    CK(cudaMallocHost(&h->hscal, 16 * sizeof(double)));
+    CK(cudaMallocHost(&h->hinfo, 4 * sizeof(int)));
 }
 
 // ---- slab communication (MLNodeLinOp::applyBC's FillBoundary) ------------------------
 // Exchanges one plane with each z neighbour: plane `first` -> lower neighbour's upper ghost slot,
 // plane `last` -> upper neighbour's lower ghost slot.  Physical (non-periodic) ends are filled
 // locally by `end_lo` / `end_hi` (reflection for nodes, clamp for cells).
-void exchange_planes(b200np* h, double* base, long long plane, int nown, bool nodal)
+// peer copy of one of my arena arrays
+template <typename T>
+inline T* peer_ptr(const b200np* h, const char* peer_base, T* mine)
+{
+    return reinterpret_cast<T*>(const_cast<char*>(peer_base) + (reinterpret_cast<const char*>(mine) - h->arena.base));
+}
+inline HaloFlags halo_flags(const b200np* h)
+{
+    const int P = h->nranks, r = h->rank;
+    const bool per = zper(h);
+    HaloFlags f{};
+    f.my = h->flags;
+    if (per || r > 0) f.lo_flag = peer_ptr(h, h->peer_lo, h->flags) + 1;      // I am my lower neighbour's upper neighbour
+    if (per || r < P - 1) f.hi_flag = peer_ptr(h, h->peer_hi, h->flags) + 0;
+    return f;
+}
+// handshake without data: everything both neighbours launched before it is complete when it returns
+void p2p_fence(b200np* h)
+{
+    if (!h->p2p) return;
+    launch_pdl(h, k_halo_pull, dim3(1), dim3(256), 0, halo_flags(h), (double2*)nullptr, (const double2*)nullptr, (double2*)nullptr,
+               (const double2*)nullptr, 0ll);
+}
+void exchange_planes(b200np* h, double* base, long long plane, int nown, int m, bool nodal)
 {
     const int P = h->nranks, r = h->rank;
     const bool per = zper(h);
@@ -292,26 +389,79 @@ void exchange_planes(b200np* h, double* base, long long plane, int nown, bool no
     const int lo = (r - 1 + P) % P, hi = (r + 1) % P;
     double* ghost_lo = base - plane;
     double* ghost_hi = base + (long long)nown * plane;
+    // physical (non-periodic) ends -- nodes: phi(-1) = phi(1); cells: copy of the adjacent interior cell
+    const double* end_lo = base + (nodal ? plane : 0);
+    const double* end_hi = base + (long long)(nown - (nodal ? 2 : 1)) * plane;
+    h->exchanges++;
+    if (h->p2p) {
+        // pull the lower neighbour's top owned plane (every rank but the last owns m planes; the lower
+        // neighbour is the last rank only through the periodic wrap) and the upper neighbour's plane 0.
+        // WAR safety (np_kernels.cuh K10): callers never overwrite an exchanged array before the next
+        // exchange -- sweeps ping-pong, residual / restriction / interpolation write other arrays.
+        const double* src_lo = has_lo ? peer_ptr(h, h->peer_lo, base) + (long long)(m - 1) * plane : end_lo;
+        const double* src_hi = has_hi ? peer_ptr(h, h->peer_hi, base) : end_hi;
+        const long long n2 = plane / 2;
+        const int nb = (int)std::max(1ll, std::min(64ll, (n2 + 511) / 512));
+        launch_pdl(h, k_halo_pull, dim3(nb), dim3(256), 0, halo_flags(h), (double2*)ghost_lo, (const double2*)src_lo, (double2*)ghost_hi,
+                   (const double2*)src_hi, n2);
+        return;
+    }
     NK(g_nccl.GroupStart());
     if (has_lo) NK(g_nccl.Send(base, plane, ncclDouble, lo, h->comm, h->stream));
     if (has_hi) NK(g_nccl.Send(base + (long long)(nown - 1) * plane, plane, ncclDouble, hi, h->comm, h->stream));
     if (has_hi) NK(g_nccl.Recv(ghost_hi, plane, ncclDouble, hi, h->comm, h->stream));
     if (has_lo) NK(g_nccl.Recv(ghost_lo, plane, ncclDouble, lo, h->comm, h->stream));
     NK(g_nccl.GroupEnd());
-    if (!has_lo)  // nodes: phi(-1) = phi(1); cells: copy of the adjacent interior cell
-        CK(cudaMemcpyAsync(ghost_lo, base + (nodal ? plane : 0), plane * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    if (!has_hi)
-        CK(cudaMemcpyAsync(ghost_hi, base + (long long)(nown - (nodal ? 2 : 1)) * plane, plane * sizeof(double),
-                           cudaMemcpyDeviceToDevice, h->stream));
-    h->exchanges++;
+    if (!has_lo) CK(cudaMemcpyAsync(ghost_lo, end_lo, plane * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (!has_hi) CK(cudaMemcpyAsync(ghost_hi, end_hi, plane * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+}
+// Map the neighbours' arenas (CUDA IPC handles exchanged with ncclAllGather).  Falls back to NCCL
+// send/recv halos on every rank if any rank cannot map its neighbours.
+void setup_p2p(b200np* h)
+{
+    const int P = h->nranks, r = h->rank;
+    if (P == 1 || !h->use_p2p) return;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    std::vector<cudaIpcMemHandle_t> all(P);
+    cudaIpcMemHandle_t mine{};
+    double ok = cudaIpcGetMemHandle(&mine, h->arena.base) == cudaSuccess ? 1.0 : 0.0;
+    cudaGetLastError();
+    char* buf = reinterpret_cast<char*>(h->ipc_buf);
+    CK(cudaMemcpyAsync(buf + 64 * r, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+    NK(g_nccl.AllGather(buf + 64 * r, buf, 64, ncclChar, h->comm, h->stream));
+    CK(cudaMemcpyAsync(all.data(), buf, (size_t)64 * P, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const bool per = zper(h);
+    const bool has_lo = per || r > 0, has_hi = per || r < P - 1;
+    const int lo = (r - 1 + P) % P, hi = (r + 1) % P;
+    void *plo = nullptr, *phi = nullptr;
+    if (ok > 0 && has_lo && cudaIpcOpenMemHandle(&plo, all[lo], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.0;
+    if (ok > 0 && has_hi) {
+        if (has_lo && hi == lo) phi = plo;
+        else if (cudaIpcOpenMemHandle(&phi, all[hi], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.0;
+    }
+    cudaGetLastError();
+    CK(cudaMemcpyAsync(h->dscal + 4, &ok, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    NK(g_nccl.AllReduce(h->dscal + 4, h->dscal + 4, 1, ncclDouble, ncclMin, h->comm, h->stream));
+    CK(cudaMemcpyAsync(&ok, h->dscal + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->peer_lo = static_cast<char*>(plo); h->peer_hi = static_cast<char*>(phi);
+    h->p2p = ok > 0;
+    if (!h->p2p) {
+        if (plo) cudaIpcCloseMemHandle(plo);
+        if (phi && phi != plo) cudaIpcCloseMemHandle(phi);
+        h->peer_lo = h->peer_hi = nullptr;
+        cudaGetLastError();
+        if (r == 0) fprintf(stderr, "b200np: CUDA IPC peer mapping unavailable, slab halos use ncclSend/ncclRecv\n");
+    }
 }
 inline void halo_nodes(b200np* h, LevelData& L, double* x)
 {
-    if (L.dist) exchange_planes(h, x, L.g.ps, L.g.nzl, true);
+    if (L.dist) exchange_planes(h, x, L.g.ps, L.g.nzl, L.g.cnzl, true);
 }
 inline void halo_cells(b200np* h, LevelData& L, double* s)
 {
-    if (L.dist) exchange_planes(h, s, L.g.cps, L.g.cnzl, false);
+    if (L.dist) exchange_planes(h, s, L.g.cps, L.g.cnzl, L.g.cnzl, false);
 }
 // vel.FillBoundary(1 ghost) across slabs, written into the caller's ghost cell planes (compRHS, A.2)
 void halo_vel(b200np* h, Fab vel)
@@ -387,17 +537,51 @@ void coarsen_sigma(b200np* h)
 }
 
 // Gauss-Seidel sweeps (ping-pong x -> y, then swap); halo refresh before every sweep on slab levels
-void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double* rhs, int nsweeps)
+void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double* rhs, int nsweeps, bool zero_start = false)
 {
+    const bool iso_path = h->smoother_version >= 3 && L.iso;
+    const bool resident = L.tz <= SM_RES_TZ && (int)(L.gsm.x * L.gsm.y * L.gsm.z) <= h->res_max_ctas;
+    // slab level over NVLink peer memory: the halo exchange is part of the sweep kernel (HaloFused)
+    const bool fused = L.dist && h->p2p && h->fuse_halo && iso_path;
     for (int s = 0; s < nsweeps; ++s) {
+        if (fused) {
+            const int P = h->nranks, r = h->rank;
+            const bool per = zper(h);
+            const bool has_lo = per || r > 0, has_hi = per || r < P - 1;
+            const Lev& g = L.g;
+            // first sweep: the input halo comes from a standalone exchange (nothing to do if x == 0 everywhere)
+            if (s == 0 && !zero_start) halo_nodes(h, L, x);
+            HaloFused H{};
+            H.f = halo_flags(h);
+            H.pin_lo = has_lo ? x - g.ps : x + g.ps;                                    // ghost slot / reflection plane
+            H.pin_hi = has_hi ? x + (long long)g.nzl * g.ps : x + (long long)(g.nzl - 2) * g.ps;
+            // the lower neighbour owns cnzl planes (it is the last rank only through the periodic wrap)
+            H.out_lo = has_lo ? peer_ptr(h, h->peer_lo, y) + (long long)g.cnzl * g.ps : nullptr;
+            H.out_hi = has_hi ? peer_ptr(h, h->peer_hi, y) - g.ps : nullptr;
+            // same chunks as the unfused sweep; the top one (the remainder) is scheduled first
+            const int nch = (g.nzl + L.tz - 1) / L.tz;
+            H.tztop = g.nzl - (nch - 1) * L.tz;
+            H.first = s == 0; H.more = s + 1 < nsweeps;
+            h->exchanges++;
+            const dim3 grid(L.gsm.x, L.gsm.y, nch);
+            if (resident) {
+                if (h->var_sigma) launch_pdl(h, k_smooth_iso_res_dist<true>, grid, dim3(256), SM_RES_DOUBLES * sizeof(double), g, x, y, rhs, L.tz, H);
+                else              launch_pdl(h, k_smooth_iso_res_dist<false>, grid, dim3(256), (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), g, x, y, rhs, L.tz, H);
+            } else {
+                if (h->var_sigma) launch_pdl(h, k_smooth_iso_dist<true>, grid, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), g, x, y, rhs, L.tz, H);
+                else              launch_pdl(h, k_smooth_iso_dist<false>, grid, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), g, x, y, rhs, L.tz, H);
+            }
+            std::swap(x, y);
+            continue;
+        }
         halo_nodes(h, L, x);
         if (h->smoother_version == 1) {
             if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, L.tz);
             else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, L.tz);
-        } else if (h->smoother_version == 2 || !L.iso) {
+        } else if (!iso_path) {
             if (h->var_sigma) launch_pdl(h, k_smooth_v2<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, x, y, rhs, L.tz);
             else              launch_pdl(h, k_smooth_v2<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
-        } else if (L.tz <= SM_RES_TZ && (int)(L.gsm.x * L.gsm.y * L.gsm.z) <= h->res_max_ctas) {
+        } else if (resident) {
             // small isotropic level: whole chunk resident in shared memory, one CTA per SM
             if (h->var_sigma) launch_pdl(h, k_smooth_iso_res<true>, L.gsm, dim3(256), SM_RES_DOUBLES * sizeof(double), L.g, x, y, rhs, L.tz);
             else              launch_pdl(h, k_smooth_iso_res<false>, L.gsm, dim3(256), (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
@@ -460,8 +644,8 @@ void interp_add(b200np* h, int l)
         if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
         else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
     } else {
-        if (h->var_sigma) launch_pdl(h, k_interp_tile<true>, F.git, dim3(256), 0, F.g, C.g, F.cor, (const double*)C.cor);
-        else              launch_pdl(h, k_interp_tile<false>, F.git, dim3(256), 0, F.g, C.g, F.cor, (const double*)C.cor);
+        if (h->var_sigma) launch_pdl(h, k_interp_tile<true>, F.git, dim3(256), (IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
+        else              launch_pdl(h, k_interp_tile<false>, F.git, dim3(256), IT_V_DOUBLES * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
     }
 }
 
@@ -474,24 +658,37 @@ void vcycle_launch(b200np* h, int lev0)
         LevelData& L = h->lv[l];
         CK(cudaMemsetAsync(L.cor - L.g.ps, 0, (size_t)L.g.ps * (L.g.nzl + 2) * sizeof(double), h->stream));
         double *x = L.cor, *y = L.cor2;
-        smooth_sweeps(h, L, x, y, L.res, h->opts.num_pre_smooth * nsw);
-        if (x != L.cor) { CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); }
+        prof_mark(h, "zero cor", l);
+        smooth_sweeps(h, L, x, y, L.res, h->opts.num_pre_smooth * nsw, true);  // cor == 0, ghost slots included
+        if (x != L.cor) {  // odd sweep count: cor was pulled by the neighbours in the last exchange
+            if (L.dist) p2p_fence(h);
+            CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
+        prof_mark(h, "smooth", l);
         residual(h, L, L.cor, L.res, L.rescor, nullptr);
+        prof_mark(h, "residual", l);
         restrict_to(h, l);
+        prof_mark(h, "restrict", l);
     }
     bottom_solve(h);
+    prof_mark(h, "bottom");
     for (int l = nl - 2; l >= lev0; --l) {
         LevelData& L = h->lv[l];
         interp_add(h, l);
+        prof_mark(h, "interp", l);
         double *x = L.cor, *y = L.cor2;
         smooth_sweeps(h, L, x, y, L.res, h->opts.num_post_smooth * nsw);
-        if (x != L.cor) { CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); }
+        if (x != L.cor) {
+            if (L.dist) p2p_fence(h);
+            CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
+        prof_mark(h, "smooth", l);
     }
 }
 
 void vcycle(b200np* h)
 {
-    if (!h->opts.use_graph || (h->nranks > 1 && !h->dist_graph)) { vcycle_launch(h, 0); return; }
+    if (!h->opts.use_graph || h->profile || (h->nranks > 1 && !h->dist_graph)) { vcycle_launch(h, 0); return; }
     if (h->graph_exec && (h->graph_var != h->var_sigma || h->graph_csig != h->lv[0].g.csig)) {
         cudaGraphExecDestroy(h->graph_exec); cudaGraphDestroy(h->graph);
         h->graph_exec = nullptr; h->graph = nullptr;
@@ -553,11 +750,14 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
     if (talk && h->opts.verbose >= 1) printf("MLMG: Initial rhs               = %.12g\nMLMG: Initial residual (resid0) = %.12g\n", st->rhsnorm, st->resnorm0);
     if (st->resnorm0 <= target) return B200NP_OK;
     bool converged = false;
+    prof_mark(h, "mlmg setup");
     for (int it = 0; it < h->opts.maxiter; ++it) {
         vcycle(h);
         LAUNCH(h, k_axpy, L0.gn, 256, L0.g, L0.sol, L0.cor, 1.0);
         residual(h, L0, L0.sol, L0.rhs, L0.res, h->partial);
+        prof_mark(h, "top sol+=cor, residual");
         st->resnorm = norm_from_partials(h, resid_nblk(h, L0));
+        prof_mark(h, "top norm (allreduce+sync)");
         st->iters = it + 1;
         if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
         if (talk && h->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
@@ -649,9 +849,12 @@ int project_core(b200np* h, Fab vel, Fab velo, int add_old, Fab gphi, int acc_g,
                  double atol, b200np_stats* st)
 {
     LevelData& L0 = h->lv[0];
+    prof_mark(h, "start");
     coarsen_sigma(h);
+    prof_mark(h, "coarsen sigma");
     halo_vel(h, vel);
     LAUNCH(h, k_divu, L0.gn, 256, L0.g, vel, L0.rhs);
+    prof_mark(h, "halo vel + divu");
     CK(cudaMemsetAsync(L0.sol - L0.g.ps, 0, (size_t)L0.g.ps * (L0.g.nzl + 2) * sizeof(double), h->stream));
     CK(cudaEventRecord(h->ev[2], h->stream));
     int status = mlmg_solve(h, rtol, atol, st);
@@ -662,6 +865,8 @@ int project_core(b200np* h, Fab vel, Fab velo, int add_old, Fab gphi, int acc_g,
         dim3 g((pout.nx + 63) / 64, (pout.ny + 3) / 4, pout.nz);
         LAUNCH(h, k_copy_phi, g, 256, L0.g, L0.sol, pout, acc_p);
     }
+    prof_mark(h, "mknewu + copy out");
+    prof_report(h);
     return status;
 }
 
@@ -712,6 +917,9 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (const char* e = getenv("B200NP_RES_CTAS")) h->res_max_ctas = atoi(e);
         if (const char* e = getenv("B200NP_DIST_GRAPH")) h->dist_graph = atoi(e);
         if (const char* e = getenv("B200NP_PDL")) h->use_pdl = atoi(e);
+        if (const char* e = getenv("B200NP_PROFILE")) h->profile = atoi(e);
+        if (const char* e = getenv("B200NP_P2P")) h->use_p2p = atoi(e);
+        if (const char* e = getenv("B200NP_FUSE_HALO")) h->fuse_halo = atoi(e);
         if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) h->dist_min_planes = std::max(8, atoi(e));
         if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
         if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
@@ -723,6 +931,12 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         CK(cudaFuncSetAttribute(k_smooth_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_residual_iso<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_residual_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_interp_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_interp_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IT_V_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_iso_dist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_iso_dist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_iso_res_dist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_RES_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_smooth_iso_res_dist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso_res<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_RES_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso_res<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double))));
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -734,6 +948,7 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
             NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
         }
         build_hierarchy(h);
+        setup_p2p(h);
         CK(cudaDeviceSynchronize());
     } catch (int e) {
         b200np_destroy(h);
@@ -817,21 +1032,23 @@ void b200np_destroy(b200np_t* h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
+    if (h->p2p) {  // the neighbours may still be pulling from this arena: handshake before unmapping / freeing
+        try { p2p_fence(h); } catch (int) {}
+        cudaStreamSynchronize(h->stream);
+        if (h->peer_lo) cudaIpcCloseMemHandle(h->peer_lo);
+        if (h->peer_hi && h->peer_hi != h->peer_lo) cudaIpcCloseMemHandle(h->peer_hi);
+        h->p2p = false;
+    }
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
     if (h->comm) g_nccl.CommDestroy(h->comm);
-    for (auto& L : h->lv) {
-        for (double* p : L.allocs) cudaFree(p);
-        cudaFree(L.sigma_alloc);
-        if (L.part_nodal) cudaFree(L.part_nodal);
-        if (L.part_sigma) cudaFree(L.part_sigma);
-    }
-    cudaFree(h->partial); cudaFree(h->dscal); cudaFree(h->dinfo); cudaFree(h->bottom_work);
+    if (h->arena.base) cudaFree(h->arena.base);
     if (h->hscal) cudaFreeHost(h->hscal);
     if (h->hinfo) cudaFreeHost(h->hinfo);
     for (auto& s : h->stage) if (s.d) cudaFree(s.d);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }

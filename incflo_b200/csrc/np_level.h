@@ -45,6 +45,29 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // so that waiting successor CTAs do not take SM slots from this grid's later waves
 __device__ __forceinline__ bool pdl_small_grid() { return gridDim.x * gridDim.y * gridDim.z <= 296u; }
 
+// ---- NVLink peer-memory halo flags (slab-decomposed path; protocol in np_kernels.cuh K10) ----
+struct HaloFlags {
+    unsigned long long* my;       // [0] written by my lower neighbour, [1] by my upper neighbour, [2] epoch, [3] ticket
+    unsigned long long* lo_flag;  // lower neighbour's word [1] (peer pointer) or nullptr
+    unsigned long long* hi_flag;  // upper neighbour's word [0] (peer pointer) or nullptr
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // node index in [-1, n+1] -> unique storage index
 __host__ __device__ __forceinline__ int nmap(int i, int n, int per)
 {

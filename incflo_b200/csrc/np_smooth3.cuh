@@ -27,9 +27,47 @@ namespace b200np_dev {
 constexpr int SM_RES_TZ = 8;
 constexpr int SM_RES_DOUBLES = (SM_RES_TZ + 2) * SM_PHI_SLOT + (SM_RES_TZ + 1) * SM_SIG_SLOT;
 
-template <bool VAR, bool FULL, bool RES>
+// DIST: slab-decomposed level with the FillBoundary fused into the sweep (NVLink peer memory, flags of
+// np_kernels.cuh K10).  Push protocol: the CTAs that finish the slab's first / last plane also store it
+// into the lower / upper neighbour's ghost plane slot of the output array (remote stores), and the
+// last of them raises the neighbour's flag for the next exchange; the neighbour's next sweep reads its
+// LOCAL ghost slots.  Only the bottom / top chunk CTAs wait for a flag (not in the first sweep of a
+// smooth call, whose input halo was filled by a standalone exchange or is zero); every other CTA starts
+// at once.  To take the NVLink latency off the critical path the boundary planes are produced early:
+//   * the top chunk (`tztop` planes: the remainder chunk) is scheduled first (blockIdx.z = 0),
+//   * the bottom chunk (blockIdx.z = 1) reports right after its first plane.
+// (A deliberately short top chunk hides more latency but was measured to cost a V-cycle.)
+// A flag also tells the neighbour that its previous boundary plane is no longer being read (WAR).
+struct HaloFused {
+    HaloFlags f;           // my: [4], [5] count bottom / top chunk CTAs that have pushed their plane
+    const double* pin_lo;  // plane -1 of pin: my ghost slot, or the reflection plane at a physical end
+    const double* pin_hi;  // plane nzl of pin
+    double* out_lo;        // lower neighbour's ghost slot (its plane nzl) of pout, or nullptr
+    double* out_hi;        // upper neighbour's ghost slot (its plane -1) of pout, or nullptr
+    int tztop;             // planes of the top chunk
+    int first;             // 1: first sweep of a smooth call -> the input halo is already in place, do not wait
+    int more;              // 1: another fused sweep follows -> raise the neighbours' flags for it
+};
+
+// one thread of a bottom (SIDE 0) / top (SIDE 1) chunk CTA, after a CTA barrier that follows the push of
+// its boundary plane: count the CTA; the last one of the side raises the neighbour's flag for epoch ep+1
+template <int SIDE>
+__device__ __forceinline__ void halo_report(const HaloFused& H, unsigned long long ep)
+{
+    unsigned long long* flag = SIDE == 0 ? H.f.lo_flag : H.f.hi_flag;
+    if (!H.more || !flag) return;
+    __threadfence_system();   // this CTA's remote stores are performed before the count becomes visible
+    if (atomicAdd(H.f.my + 4 + SIDE, 1ull) == (unsigned long long)gridDim.x * gridDim.y - 1) {
+        H.f.my[4 + SIDE] = 0ull;
+        __threadfence_system();
+        st_release_sys(flag, ep + 1);
+    }
+}
+
+template <bool VAR, bool FULL, bool RES, bool DIST = false>
 __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __restrict__ pin, double* __restrict__ pout,
-                                                const double* __restrict__ rhs, const int TZ, double* smem)
+                                                const double* __restrict__ rhs, const int TZ, double* smem,
+                                                const HaloFused* H = nullptr)
 {
     double* sphi = smem;
     constexpr int NPS = RES ? SM_RES_TZ + 2 : 4, NSS = RES ? SM_RES_TZ + 1 : 3;
@@ -39,7 +77,10 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
 
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
-    const int kc0 = blockIdx.z * TZ, kc1 = min(kc0 + TZ, L.nzl);
+    // DIST: blockIdx.z = 0 is the top chunk, 1.. the other chunks from the bottom upwards
+    const int ztop = DIST ? L.nzl - H->tztop : L.nzl;
+    const int kc0 = DIST ? (blockIdx.z == 0 ? ztop : ((int)blockIdx.z - 1) * TZ) : (int)blockIdx.z * TZ;
+    const int kc1 = DIST ? (blockIdx.z == 0 ? L.nzl : min(kc0 + TZ, ztop)) : min(kc0 + TZ, L.nzl);
     const bool anyD = L.dlo[0] | L.dhi[0] | L.dlo[1] | L.dhi[1] | L.dlo[2] | L.dhi[2];
     // shared-memory slot of node plane p / sigma layer c
     auto pslot = [&](int p) { return RES ? p - kc0 + 1 : (p + 1) & 3; };
@@ -70,6 +111,7 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     }
     auto issue_phi = [&](int kl) {  // kl in [-1, nzl]
         const double* src = pin + zplane(L, kl) * L.ps;
+        if (DIST) { if (kl < 0) src = H->pin_lo; else if (kl >= L.nzl) src = H->pin_hi; }
         unsigned dst = sphi_a + pslot(kl) * (SM_PHI_SLOT * 8);
         asm volatile("" : "+l"(src), "+r"(dst));  // keep the plane base materialised (no per-copy 64-bit multiply)
 #pragma unroll
@@ -118,6 +160,17 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
 
     if (pdl_small_grid()) pdl_trigger();
     pdl_wait();   // everything above only touched kernel parameters and shared memory
+    unsigned long long ep = 0;
+    if (DIST) {
+        ep = ld_relaxed_gpu(H->f.my + 2) + 1ull;
+        if (!H->first) {
+            if (tid == 0) {
+                if (kc0 == 0 && H->f.lo_flag) while (ld_acquire_sys(H->f.my + 0) < ep) __nanosleep(20);
+                if (kc1 == L.nzl && H->f.hi_flag) while (ld_acquire_sys(H->f.my + 1) < ep) __nanosleep(20);
+            }
+            __syncthreads();
+        }
+    }
     double rcur[2][2], rnext[2][2];
     if (RES) {
         // the whole chunk: planes kc0-1 .. kc1, sigma layers kc0-1 .. kc1-1
@@ -168,6 +221,7 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
         load_rhs(kl + 1 < kc1 ? kl + 1 : kl, rnext);
         if (!RES) cp_async_wait<1>();   // plane kl+1 / sigma layer kl have landed (this thread's copies)
         __syncthreads();      // ... everybody else's, and plane kl-1's colours 2,3 are published
+        if (DIST && kc0 == 0 && kl == 1 && tid == 0) halo_report<0>(*H, ep);   // plane 0 has been pushed by every thread
         const int kg = kl + L.k0;
         const double* Pm = sphi + pslot(kl - 1) * SM_PHI_SLOT + rbase;   // plane kl-1 (this sweep)
         double* P0 = sphi + pslot(kl) * SM_PHI_SLOT + rbase;             // plane kl
@@ -335,6 +389,22 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
                 }
             }
         }
+        if (DIST) {  // the slab's first / last plane also goes into the neighbour's ghost plane slot
+            double* r0 = (kl == 0) ? H->out_lo : nullptr;
+            if (kl == L.nzl - 1 && H->out_hi) r0 = H->out_hi;   // (nzl >= 2: never both)
+            if (r0) {
+                r0 += roff;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    double* q = r0 + b * L.px;
+                    if (FULL) *reinterpret_cast<double2*>(q) = make_double2(v[b][0], v[b][1]);
+                    else if (rowok[b]) {
+                        if (colok[1]) *reinterpret_cast<double2*>(q) = make_double2(v[b][0], v[b][1]);
+                        else if (colok[0]) q[0] = v[b][0];
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
@@ -345,6 +415,39 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     }
     pdl_trigger();
     cp_async_wait<0>();
+    if (DIST) {
+        __syncthreads();   // every store of this CTA has been issued
+        if (tid == 0) {
+            if (kc0 == 0 && kc1 == 1) halo_report<0>(*H, ep);   // one-plane bottom chunk: not reported in the loop
+            if (kc1 == L.nzl) halo_report<1>(*H, ep);
+            __threadfence();
+            if (atomicAdd(H->f.my + 3, 1ull) == (unsigned long long)gridDim.x * gridDim.y * gridDim.z - 1) {
+                H->f.my[3] = 0ull; H->f.my[2] = ep; __threadfence();
+            }
+        }
+    }
+}
+
+// slab-decomposed variants with the halo exchange fused in (see HaloFused)
+template <bool VAR>
+__global__ void __launch_bounds__(256, 2) k_smooth_iso_dist(const Lev L, const double* __restrict__ pin, double* __restrict__ pout,
+                                                            const double* __restrict__ rhs, int TZ, const HaloFused H)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
+    const bool full = (i0 + SM_TX <= L.nn[0]) && (j0 + SM_TY <= L.nn[1]);
+    if (full) smooth_iso_body<VAR, true, false, true>(L, pin, pout, rhs, TZ, smem, &H);
+    else      smooth_iso_body<VAR, false, false, true>(L, pin, pout, rhs, TZ, smem, &H);
+}
+template <bool VAR>
+__global__ void __launch_bounds__(256, 1) k_smooth_iso_res_dist(const Lev L, const double* __restrict__ pin, double* __restrict__ pout,
+                                                                const double* __restrict__ rhs, int TZ, const HaloFused H)
+{
+    extern __shared__ __align__(16) double smem[];
+    const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
+    const bool full = (i0 + SM_TX <= L.nn[0]) && (j0 + SM_TY <= L.nn[1]);
+    if (full) smooth_iso_body<VAR, true, true, true>(L, pin, pout, rhs, TZ, smem, &H);
+    else      smooth_iso_body<VAR, false, true, true>(L, pin, pout, rhs, TZ, smem, &H);
 }
 
 template <bool VAR>

@@ -18,10 +18,16 @@ def _ngpus():
         return 0
 
 
+# B200NP_DIST_MIN_PLANES=8: every level down to 8 planes per rank stays slab-distributed (4 distributed
+# levels at 64^3 on 2 ranks); default (64): only level 0 is distributed, the rest is agglomerated.
+# B200NP_P2P=0: ncclSend/ncclRecv halos instead of NVLink peer memory; B200NP_FUSE_HALO=0: standalone pull kernel.
 @pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
-def test_two_slabs_match_oracle():
+@pytest.mark.parametrize("env", [{"B200NP_DIST_MIN_PLANES": "8"}, {}, {"B200NP_DIST_MIN_PLANES": "8", "B200NP_FUSE_HALO": "0"},
+                                 {"B200NP_DIST_MIN_PLANES": "8", "B200NP_P2P": "0"}],
+                         ids=["p2p_fused_4dist_levels", "default", "p2p_unfused", "nccl"])
+def test_two_slabs_match_oracle(env):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **env))
     sys.stdout.write(r.stdout[-4000:]); sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0 and "DIST OK" in r.stdout
