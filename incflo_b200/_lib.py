@@ -69,7 +69,8 @@ EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np
            "b200np_destroy", "b200np_set_stream", "b200np_project",
            "b200np_apply_nodal_projection", "b200np_strerror", "b200np_version", "b200np_nlevels",
            "b200np_level_dims", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
-           "b200np_time_op"]
+           "b200np_time_op", "b200np_composite_create", "b200np_composite_destroy", "b200np_composite_set_stream",
+           "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection"]
 
 _lib = None
 
@@ -105,5 +106,17 @@ def lib():
     L.b200np_level_get.argtypes = [vp, C.c_int, C.c_int, dp]
     L.b200np_level_op.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.b200np_time_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    i3 = C.POINTER(C.c_int * 3)
+    L.b200np_composite_create.argtypes = [C.POINTER(vp), C.POINTER(Geom), i3, i3, C.POINTER(Opts), C.c_int]
+    L.b200np_composite_destroy.argtypes = [vp]
+    L.b200np_composite_destroy.restype = None
+    L.b200np_composite_set_stream.argtypes = [vp, C.c_void_p]
+    L.b200np_composite_level.argtypes = [vp, C.c_int]
+    L.b200np_composite_level.restype = vp
+    L.b200np_composite_project.argtypes = [vp, dp, fb, dp, fb, dp, fb, dp, fb, C.c_double, dp, fb, dp, fb, dp, fb, dp, fb,
+                                           C.c_double, C.c_double, C.POINTER(Stats)]
+    p2, f2 = C.POINTER(C.c_void_p * 2), C.POINTER(fb * 2)
+    L.b200np_composite_apply_nodal_projection.argtypes = [vp, p2, f2, p2, p2, f2, C.c_double, p2, f2, p2, f2, dp, C.c_double,
+                                                          C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
     _lib = L
     return L

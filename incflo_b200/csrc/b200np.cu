@@ -13,6 +13,7 @@
 #include "np_kernels.cuh"
 #include "np_smooth.cuh"
 #include "np_smooth3.cuh"
+#include "np_composite.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -156,6 +157,7 @@ struct b200np {
     int smoother_version = 3, interp_version = 2, resid_version = 3;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
     // B200NP_PROFILE=1: per-phase device times (CUDA events between phases, graph capture off); printed per call
     int profile = 0;
+    bool no_bottom = false;   // fine AMR level of a composite solve: one MG level, never a bottom solve
     std::vector<cudaEvent_t> prof_ev;
     std::vector<std::string> prof_tag;
     size_t prof_n = 0;
@@ -336,7 +338,7 @@ void build_levels(b200np* h)
     h->ipc_buf = dev_alloc(h, (size_t)8 * std::max(P, 1) + 8);   // 64 bytes per rank
     h->dinfo = reinterpret_cast<int*>(dev_alloc(h, 8));
     const Lev& B = h->lv.back().g;
-    h->bottom_work = dev_alloc(h, (size_t)B.ps * B.nzl * 8);
+    h->bottom_work = dev_alloc(h, h->no_bottom ? 8 : (size_t)B.ps * B.nzl * 8);
 }
 
 void build_hierarchy(b200np* h)
@@ -593,19 +595,24 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
     }
 }
 
-// res = rhs - L phi (phi's ghost planes are refreshed first on slab levels)
-void residual(b200np* h, LevelData& L, double* phi, const double* rhs, double* res, double* norm_partial)
+// res = rhs - L phi (phi's ghost planes are refreshed first on slab levels).
+// gov / var_override: evaluate with another descriptor of the same arrays (other boundary conditions or
+// another sigma array) -- the composite solver's one-sided sums (np_composite.cuh).
+void residual(b200np* h, LevelData& L, double* phi, const double* rhs, double* res, double* norm_partial,
+              const Lev* gov = nullptr, int var_override = -1)
 {
     halo_nodes(h, L, phi);
+    const Lev& g = gov ? *gov : L.g;
+    const bool var = var_override >= 0 ? var_override != 0 : h->var_sigma;
     if (h->resid_version == 1) {
-        if (h->var_sigma) LAUNCH(h, k_residual<true>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
-        else              LAUNCH(h, k_residual<false>, L.gn, 256, L.g, phi, rhs, res, norm_partial);
+        if (var) LAUNCH(h, k_residual<true>, L.gn, 256, g, phi, rhs, res, norm_partial);
+        else     LAUNCH(h, k_residual<false>, L.gn, 256, g, phi, rhs, res, norm_partial);
     } else if (h->resid_version == 2 || !L.iso) {
-        if (h->var_sigma) launch_pdl(h, k_residual_v2<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, phi, rhs, res, L.tz, norm_partial);
-        else              launch_pdl(h, k_residual_v2<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, phi, rhs, res, L.tz, norm_partial);
+        if (var) launch_pdl(h, k_residual_v2<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), g, phi, rhs, res, L.tz, norm_partial);
+        else     launch_pdl(h, k_residual_v2<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), g, phi, rhs, res, L.tz, norm_partial);
     } else {
-        if (h->var_sigma) launch_pdl(h, k_residual_iso<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, phi, rhs, res, L.tz, norm_partial);
-        else              launch_pdl(h, k_residual_iso<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, phi, rhs, res, L.tz, norm_partial);
+        if (var) launch_pdl(h, k_residual_iso<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), g, phi, rhs, res, L.tz, norm_partial);
+        else     launch_pdl(h, k_residual_iso<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), g, phi, rhs, res, L.tz, norm_partial);
     }
 }
 // number of per-CTA norm partials the residual kernel writes
@@ -891,7 +898,7 @@ int check_geom(const b200np_geom* g)
 }
 
 int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* opts, int device, int rank, int nranks,
-                  const void* nccl_unique_id)
+                  const void* nccl_unique_id, bool fine_level = false)
 {
     if (!out || !geom) return B200NP_ERR_BAD_ARG;
     *out = nullptr;
@@ -908,6 +915,7 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
     try {
         CK(cudaSetDevice(device));
         h->device = device;
+        h->no_bottom = fine_level;
         h->rank = rank; h->nranks = nranks;
         h->geom = *geom;
         if (opts) h->opts = *opts; else b200np_default_opts(&h->opts);
@@ -956,6 +964,188 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
     }
     *out = h;
     return B200NP_OK;
+}
+
+
+// ============================================================================================
+// Composite (two AMR level) projection: coarse level + ONE fine box at ratio 2 (BASELINE configs[3]).
+// Algorithm and its justification: oracle/composite.py (MLMG::oneIter multi-level branch; with ratio 2
+// the fine AMR level has a single MG level, so its miniCycle is nu1 smooth calls).
+// ============================================================================================
+}  // namespace
+
+struct b200np_composite {
+    b200np* h0 = nullptr;   // coarse level: the ordinary single-level hierarchy over the whole domain
+    b200np* h1 = nullptr;   // fine box as a domain of its own with Dirichlet faces (coarse/fine interface nodes are not relaxed)
+    CBox box{};
+    int nb[3]{};            // covered coarse cells per direction
+    Lev view{};             // the box nodes inside the coarse level's arrays, seen as a level (restriction target / interpolation source)
+    long long off_n = 0;    // box node (lo) in a coarse nodal array
+    double* rhsN = nullptr; // D u1 with reflecting box faces (2^f x one-sided divergence on the box boundary)
+    double* s0z_alloc = nullptr;
+    double* s0z = nullptr;  // coarse sigma with 0 in the covered cells
+};
+
+namespace {
+
+// fine box with reflecting faces: one-sided sums x 2^f (np_composite.cuh)
+Lev comp_gN(const b200np_composite* C)
+{
+    Lev g = C->h1->lv[0].g;
+    for (int d = 0; d < 3; ++d) { g.rlo[d] = g.rhi[d] = 1; g.dlo[d] = g.dhi[d] = 0; }
+    return g;
+}
+dim3 box_grid(int nx, int ny, int nz) { return dim3((nx + 63) / 64, (ny + 3) / 4, nz); }
+
+void comp_set_sigma(b200np_composite* C, bool var, double csig)
+{
+    b200np *h0 = C->h0, *h1 = C->h1;
+    LevelData &L0 = h0->lv[0], &L1 = h1->lv[0];
+    set_level_sigma_ptrs(h0, var, csig);
+    set_level_sigma_ptrs(h1, var, csig);
+    LAUNCH(h0, k_comp_sigma, L0.gc, 256, L0.g, L1.g, C->box, var ? L0.sigma : (double*)nullptr, C->s0z,
+           var ? (const double*)L1.sigma : (const double*)nullptr, csig);
+    coarsen_sigma(h0);   // averageDownCoeffs of the coarse hierarchy, with the fine average in the covered cells
+}
+
+// composite residual on the coarse level (MLNodeLaplacian::reflux): L0.res = rhs0 - A_composite(sol0, sol1)
+void comp_coarse_residual(b200np_composite* C, const double* sol0, const double* sol1, const double* sums)
+{
+    b200np *h0 = C->h0, *h1 = C->h1;
+    LevelData &L0 = h0->lv[0], &L1 = h1->lv[0];
+    const Lev gN = comp_gN(C);
+    residual(h1, L1, const_cast<double*>(sol1), C->rhsN, L1.rescor, nullptr, &gN);   // 2^f x (b - A) fine-side sums
+    launch_pdl(h0, k_restrict, box_grid(C->nb[0] + 1, C->nb[1] + 1, C->nb[2] + 1), dim3(256), 0, gN, C->view,
+               (const double*)L1.rescor, L0.rescor + C->off_n);
+    Lev g0z = L0.g;
+    g0z.sigma = C->s0z;
+    residual(h0, L0, const_cast<double*>(sol0), L0.rhs, L0.res, nullptr, &g0z, 1);   // uncovered coarse cells only
+    LAUNCH(h0, k_comp_combine, L0.gn, 256, L0.g, C->box, L0.res, (const double*)L0.rescor, sums);
+}
+
+double comp_read_norm(b200np_composite* C, long long nb1)
+{
+    b200np *h0 = C->h0, *h1 = C->h1;
+    LevelData& L0 = h0->lv[0];
+    LAUNCH(h0, k_comp_norm_excl, L0.gn, 256, L0.g, C->box, (const double*)L0.res, h0->partial);
+    LAUNCH(h0, k_max_final, 1, 1024, h0->partial, L0.nblk_n, h0->dscal + 2);
+    LAUNCH(h0, k_max_final, 1, 1024, h1->partial, nb1, h0->dscal + 3);
+    CK(cudaMemcpyAsync(h0->hscal + 2, h0->dscal + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h0->stream));
+    CK(cudaStreamSynchronize(h0->stream));
+    return std::max(h0->hscal[2], h0->hscal[3]);
+}
+
+// Hydro::NodalProjector::project over two levels.  Fabs of the fine level are indexed relative to the
+// fine box (cell 0 = first fine cell of the box).
+int comp_core(b200np_composite* C, Fab vel0, Fab vel1, Fab velo0, Fab velo1, int add_old, Fab gphi0, Fab gphi1, int acc_g,
+              Fab p0, Fab p1, int acc_p, double rtol, double atol, b200np_stats* st)
+{
+    b200np *h0 = C->h0, *h1 = C->h1;
+    LevelData &L0 = h0->lv[0], &L1 = h1->lv[0];
+    const Lev gD = L1.g, gN = comp_gN(C);
+    const CBox& b = C->box;
+    const dim3 gbox = box_grid(C->nb[0], C->nb[1], C->nb[2]);
+    const size_t bytes0 = (size_t)L0.g.ps * L0.g.nzl * sizeof(double), bytes1 = (size_t)L1.g.ps * L1.g.nzl * sizeof(double);
+    const int nsw = h0->opts.smooth_num_sweeps;
+    st->iters = 0; st->bottom_iters = 0; st->status = B200NP_OK; st->nlevels = (int)h0->lv.size() + 1;
+    CK(cudaMemsetAsync(h0->dinfo, 0, 4 * sizeof(int), h0->stream));
+    // ---- rhs (compRHS): covered coarse cells do not count; fine ghost cells are zero (:137) ----
+    LAUNCH(h0, k_comp_zero_cells, gbox, 256, b, vel0, 3);
+    LAUNCH(h0, k_divu, L0.gn, 256, L0.g, vel0, L0.rhs);          // uncovered coarse cells
+    LAUNCH(h0, k_divu, L1.gn, 256, gD, vel1, L1.rhs);            // fine interior nodes (0 on the interface)
+    LAUNCH(h0, k_divu, L1.gn, 256, gN, vel1, C->rhsN);           // + 2^f x one-sided sums on the interface
+    CK(cudaMemsetAsync(L0.sol, 0, bytes0, h0->stream));
+    CK(cudaMemsetAsync(L1.sol, 0, bytes1, h0->stream));
+    CK(cudaMemsetAsync(L0.rescor, 0, bytes0, h0->stream));       // only its box nodes are ever written again
+    CK(cudaEventRecord(h0->ev[2], h0->stream));
+    // composite coarse rhs = residual of sol = 0: solvability offset (MLMG::makeSolvable, one offset for every level)
+    double* sums = nullptr;
+    comp_coarse_residual(C, L0.sol, L1.sol, nullptr);
+    if (h0->singular) {
+        LAUNCH(h0, k_wsum_partial, L0.gn, 256, L0.g, (const double*)L0.res, h0->partial);
+        LAUNCH(h0, k_sum2_final, 1, 1024, h0->partial, L0.nblk_n, h0->dscal + 8);
+        sums = h0->dscal + 8;
+        LAUNCH(h0, k_sub_mean, L0.gn, 256, L0.g, L0.res, (const double*)sums);
+        LAUNCH(h0, k_sub_mean, L1.gn, 256, gD, L1.rhs, (const double*)sums);
+        LAUNCH(h0, k_zero_masked, L1.gn, 256, gD, L1.rhs);
+    }
+    residual(h1, L1, L1.sol, L1.rhs, L1.res, h1->partial);       // = rhs1 (sol1 = 0), with its norm
+    const long long nb1 = resid_nblk(h1, L1);
+    st->rhsnorm = st->resnorm0 = comp_read_norm(C, nb1);
+    const double maxnorm = st->rhsnorm;
+    const double target = std::max(atol, std::max(rtol, 1e-16) * maxnorm);
+    st->resnorm = st->resnorm0;
+    st->resnorm_hist[0] = st->resnorm0;
+    const bool talk = h0->opts.verbose >= 1;
+    if (talk) printf("MLMG: Initial rhs               = %.12g\nMLMG: Initial residual (resid0) = %.12g\n", st->rhsnorm, st->resnorm0);
+    bool converged = st->resnorm0 <= target;
+    for (int it = 0; !converged && it < h0->opts.maxiter; ++it) {
+        // fine level: miniCycle = nu1 smooth calls on (cor, res), homogeneous Dirichlet on the interface
+        CK(cudaMemsetAsync(L1.cor, 0, bytes1, h0->stream));
+        double *x = L1.cor, *y = L1.cor2;
+        smooth_sweeps(h1, L1, x, y, L1.res, h0->opts.num_pre_smooth * nsw, true);
+        LAUNCH(h0, k_axpy, L1.gn, 256, gD, L1.sol, (const double*)x, 1.0);
+        // coarse level: composite residual, solvability, V-cycle
+        comp_coarse_residual(C, L0.sol, L1.sol, sums);
+        if (h0->singular) {
+            LAUNCH(h0, k_wsum_partial, L0.gn, 256, L0.g, (const double*)L0.res, h0->partial);
+            LAUNCH(h0, k_sum2_final, 1, 1024, h0->partial, L0.nblk_n, h0->dscal);
+            LAUNCH(h0, k_sub_mean, L0.gn, 256, L0.g, L0.res, (const double*)h0->dscal);
+        }
+        vcycle(h0);
+        LAUNCH(h0, k_axpy, L0.gn, 256, L0.g, L0.sol, (const double*)L0.cor, 1.0);
+        // interpolationAmr: cor1 = trilinear interpolant of cor0 on EVERY fine node; sol1 += cor1
+        CK(cudaMemsetAsync(L1.cor, 0, bytes1, h0->stream));
+        launch_pdl(h0, k_interp_tile<false>, L1.git, dim3(256), IT_V_DOUBLES * sizeof(double), gN, C->view, L1.cor,
+                   (const double*)(L0.cor + C->off_n));
+        LAUNCH(h0, k_axpy, L1.gn, 256, gD, L1.sol, (const double*)L1.cor, 1.0);
+        residual(h1, L1, L1.sol, L1.rhs, L1.res, nullptr);
+        CK(cudaMemsetAsync(L1.cor, 0, bytes1, h0->stream));
+        x = L1.cor; y = L1.cor2;
+        smooth_sweeps(h1, L1, x, y, L1.res, h0->opts.num_post_smooth * nsw, true);
+        LAUNCH(h0, k_axpy, L1.gn, 256, gD, L1.sol, (const double*)x, 1.0);
+        // convergence on the composite residual
+        residual(h1, L1, L1.sol, L1.rhs, L1.res, h1->partial);
+        comp_coarse_residual(C, L0.sol, L1.sol, sums);
+        st->resnorm = comp_read_norm(C, nb1);
+        st->iters = it + 1;
+        if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
+        if (h0->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
+        if (st->resnorm <= target) { converged = true; break; }
+        if (!(st->resnorm <= 1e20 * maxnorm)) { st->status = B200NP_ERR_DIVERGED; break; }
+    }
+    if (!converged && st->status == B200NP_OK) st->status = B200NP_ERR_NOT_CONVERGED;
+    CK(cudaMemcpyAsync(h0->hinfo, h0->dinfo, 4 * sizeof(int), cudaMemcpyDeviceToHost, h0->stream));
+    CK(cudaStreamSynchronize(h0->stream));
+    st->bottom_iters = h0->hinfo[0];
+    if (talk) printf("MLMG: Final Iter. %d resid, resid/bnorm = %.12g, %.12g\n", st->iters, st->resnorm, st->resnorm / maxnorm);
+    CK(cudaEventRecord(h0->ev[3], h0->stream));
+    // ---- finish: injection, u -= sigma G phi, gphi = G phi, average_down onto the covered cells ----
+    LAUNCH(h0, k_comp_inject, box_grid(C->nb[0] + 1, C->nb[1] + 1, C->nb[2] + 1), 256, L0.g, gD, b, L0.sol, (const double*)L1.sol);
+    LAUNCH(h0, k_mknewu, L1.gc, 256, gD, (const double*)L1.sol, vel1, velo1, add_old, gphi1, acc_g);
+    LAUNCH(h0, k_mknewu, L0.gc, 256, L0.g, (const double*)L0.sol, vel0, velo0, add_old, gphi0, acc_g);
+    LAUNCH(h0, k_comp_avgdown, gbox, 256, b, vel1, vel0, 3);
+    if (gphi0.p && gphi1.p) LAUNCH(h0, k_comp_avgdown, gbox, 256, b, gphi1, gphi0, 3);
+    if (p1.p) LAUNCH(h0, k_copy_phi, dim3((p1.nx + 63) / 64, (p1.ny + 3) / 4, p1.nz), 256, gN, (const double*)L1.sol, p1, acc_p);
+    if (p0.p) LAUNCH(h0, k_copy_phi, dim3((p0.nx + 63) / 64, (p0.ny + 3) / 4, p0.nz), 256, L0.g, (const double*)L0.sol, p0, acc_p);
+    return st->status;
+}
+
+// caller's fine-level box (fine index space) -> Fab indexed relative to the fine box
+Fab make_fab_fine(const b200np_composite* C, double* p, const b200np_fab* bx)
+{
+    Fab f = make_fab(p, bx);
+    if (bx) for (int d = 0; d < 3; ++d) f.lo[d] -= 2 * C->box.lo[d];
+    return f;
+}
+bool fine_box_ok(const b200np_composite* C, const b200np_fab* bx, int ncomp, int grow, bool nodal)
+{
+    if (!bx || bx->ncomp < ncomp) return false;
+    for (int d = 0; d < 3; ++d) {
+        const int lo = 2 * C->box.lo[d], hi = 2 * C->box.hi[d] + 1 + (nodal ? 1 : 0);
+        if (bx->lo[d] > lo - grow || bx->hi[d] < hi + grow) return false;
+    }
+    return true;
 }
 
 }  // namespace
@@ -1193,6 +1383,214 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
         float ms;
         CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); st->ms_h2d = ms;
         CK(cudaEventElapsedTime(&ms, h->ev[5], h->ev[1])); st->ms_d2h = ms;
+        return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+// ---- composite (two AMR level) projection -----------------------------------------------------
+int b200np_composite_create(b200np_composite_t** out, const b200np_geom* geom0, const int fine_lo[3], const int fine_hi[3],
+                            const b200np_opts* opts, int device)
+{
+    if (!out || !geom0 || !fine_lo || !fine_hi) return B200NP_ERR_BAD_ARG;
+    *out = nullptr;
+    for (int d = 0; d < 3; ++d)   // the fine box lies at least one coarse cell inside the domain (no contact with a face / the periodic seam)
+        if (fine_lo[d] < 1 || fine_hi[d] < fine_lo[d] || fine_hi[d] > geom0->n_cell[d] - 2) return B200NP_ERR_UNSUPPORTED;
+    b200np_composite* C = new b200np_composite();
+    int rc = create_common(&C->h0, geom0, opts, device, 0, 1, nullptr);
+    if (rc) { delete C; return rc; }
+    b200np_geom g1 = *geom0;
+    b200np_opts o1 = C->h0->opts;
+    o1.mg_max_coarsening_level = 0;   // ref ratio 2: the fine AMR level has ONE multigrid level
+    for (int d = 0; d < 3; ++d) {
+        C->box.lo[d] = fine_lo[d]; C->box.hi[d] = fine_hi[d];
+        C->nb[d] = fine_hi[d] - fine_lo[d] + 1;
+        g1.n_cell[d] = 2 * C->nb[d]; g1.dx[d] = 0.5 * geom0->dx[d];
+        g1.bc_lo[d] = g1.bc_hi[d] = B200NP_BC_DIRICHLET;
+    }
+    rc = create_common(&C->h1, &g1, &o1, device, 0, 1, nullptr, true);
+    if (rc) { b200np_destroy(C->h0); delete C; return rc; }
+    try {
+        CK(cudaSetDevice(device));
+        C->h1->stream = C->h0->stream;   // one stream for both levels
+        const Lev& g0 = C->h0->lv[0].g;
+        const Lev& gf = C->h1->lv[0].g;
+        Lev v = g0;
+        for (int d = 0; d < 3; ++d) {
+            v.n[d] = C->nb[d]; v.nn[d] = C->nb[d] + 1; v.per[d] = 0;
+            v.rlo[d] = v.rhi[d] = 0; v.dlo[d] = v.dhi[d] = 0;
+        }
+        v.k0 = 0; v.nzl = C->nb[2] + 1; v.ck0 = 0; v.cnzl = C->nb[2]; v.dist = 0; v.sigma = nullptr;
+        C->view = v;
+        C->off_n = (long long)fine_lo[2] * g0.ps + (long long)fine_lo[1] * g0.px + fine_lo[0];
+        CK(cudaMalloc(&C->rhsN, (size_t)gf.ps * gf.nzl * sizeof(double)));
+        CK(cudaMalloc(&C->s0z_alloc, (size_t)g0.cps * (g0.cnzl + 2) * sizeof(double)));
+        CK(cudaMemset(C->s0z_alloc, 0, (size_t)g0.cps * (g0.cnzl + 2) * sizeof(double)));
+        C->s0z = C->s0z_alloc + g0.cps;
+    } catch (int e) { b200np_composite_destroy(C); return e; }
+    *out = C;
+    return B200NP_OK;
+}
+
+void b200np_composite_destroy(b200np_composite_t* C)
+{
+    if (!C) return;
+    if (C->h0) { cudaSetDevice(C->h0->device); cudaStreamSynchronize(C->h0->stream); }
+    if (C->rhsN) cudaFree(C->rhsN);
+    if (C->s0z_alloc) cudaFree(C->s0z_alloc);
+    if (C->h1) { C->h1->stream = C->h1->own_stream; b200np_destroy(C->h1); }
+    if (C->h0) b200np_destroy(C->h0);
+    delete C;
+}
+
+int b200np_composite_set_stream(b200np_composite_t* C, void* stream)
+{
+    if (!C) return B200NP_ERR_BAD_ARG;
+    int rc = b200np_set_stream(C->h0, stream);
+    C->h1->stream = C->h0->stream;
+    return rc;
+}
+
+b200np_t* b200np_composite_level(b200np_composite_t* C, int amr_level)
+{
+    return !C ? nullptr : amr_level == 0 ? C->h0 : amr_level == 1 ? C->h1 : nullptr;
+}
+
+int b200np_composite_project(b200np_composite_t* C, double* vel0, const b200np_fab* vel0_box, double* vel1,
+                             const b200np_fab* vel1_box, const double* sigma0, const b200np_fab* sigma0_box,
+                             const double* sigma1, const b200np_fab* sigma1_box, double const_sigma, double* phi0,
+                             const b200np_fab* phi0_box, double* phi1, const b200np_fab* phi1_box, double* gphi0,
+                             const b200np_fab* gphi0_box, double* gphi1, const b200np_fab* gphi1_box, double rtol, double atol,
+                             b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!C || !vel0 || !vel0_box || !vel1 || !vel1_box) return st->status = B200NP_ERR_BAD_ARG;
+    if ((sigma0 == nullptr) != (sigma1 == nullptr)) return st->status = B200NP_ERR_BAD_ARG;
+    b200np *h0 = C->h0, *h1 = C->h1;
+    try {
+        CK(cudaSetDevice(h0->device));
+        LevelData &L0 = h0->lv[0], &L1 = h1->lv[0];
+        const Lev& g = L0.g;
+        const int clo[3] = {0, 0, 0}, chi[3] = {g.n[0] - 1, g.n[1] - 1, g.n[2] - 1};
+        if (!vel_box_ok(h0, vel0_box) || !fine_box_ok(C, vel1_box, 3, 1, false)) return st->status = B200NP_ERR_BAD_ARG;
+        if (sigma0 && (!box_covers(sigma0_box, clo, chi, 1) || !fine_box_ok(C, sigma1_box, 1, 0, false))) return st->status = B200NP_ERR_BAD_ARG;
+        if (gphi0 && !box_covers(gphi0_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
+        if (gphi1 && !fine_box_ok(C, gphi1_box, 3, 0, false)) return st->status = B200NP_ERR_BAD_ARG;
+        if ((phi0 && (!phi0_box || phi0_box->ncomp < 1)) || (phi1 && (!phi1_box || phi1_box->ncomp < 1))) return st->status = B200NP_ERR_BAD_ARG;
+        h0->launches = h1->launches = 0;
+        CK(cudaEventRecord(h0->ev[0], h0->stream));
+        bool s_v0, s_v1, s_s0, s_s1, s_p0 = false, s_p1 = false, s_g0 = false, s_g1 = false;
+        double* dv0 = stage_in(h0, 0, vel0, vel0_box, true, &s_v0, st);
+        double* dv1 = stage_in(h1, 0, vel1, vel1_box, true, &s_v1, st);
+        const double* ds0 = stage_in(h0, 3, sigma0, sigma0_box, true, &s_s0, st);
+        const double* ds1 = stage_in(h1, 3, sigma1, sigma1_box, true, &s_s1, st);
+        double* dp0 = phi0 ? stage_in(h0, 5, phi0, phi0_box, false, &s_p0, st) : nullptr;
+        double* dp1 = phi1 ? stage_in(h1, 5, phi1, phi1_box, false, &s_p1, st) : nullptr;
+        double* dg0 = gphi0 ? stage_in(h0, 4, gphi0, gphi0_box, false, &s_g0, st) : nullptr;
+        double* dg1 = gphi1 ? stage_in(h1, 4, gphi1, gphi1_box, false, &s_g1, st) : nullptr;
+        CK(cudaEventRecord(h0->ev[4], h0->stream));
+        Fab fv1 = make_fab_fine(C, dv1, vel1_box);
+        if (sigma0) {
+            LAUNCH(h0, k_copy_sigma, L0.gc, 256, L0.g, make_fab(const_cast<double*>(ds0), sigma0_box), L0.sigma);
+            LAUNCH(h0, k_copy_sigma, L1.gc, 256, L1.g, make_fab_fine(C, const_cast<double*>(ds1), sigma1_box), L1.sigma);
+        }
+        comp_set_sigma(C, sigma0 != nullptr, const_sigma);
+        {   // vel.setBndry(0.0) on the fine level (:137); the coarse ghost layer is the caller's input as in b200np_project
+            long long total = (long long)fv1.nx * fv1.ny * fv1.nz;
+            int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+            LAUNCH(h0, k_set_vel_ghosts, blocks, 256, L1.g, fv1, Fab{}, 0);
+        }
+        int status = comp_core(C, make_fab(dv0, vel0_box), fv1, Fab{}, Fab{}, 0, make_fab(dg0, gphi0_box), make_fab_fine(C, dg1, gphi1_box), 0,
+                               make_fab(dp0, phi0_box), make_fab_fine(C, dp1, phi1_box), 0, rtol, atol, st);
+        CK(cudaEventRecord(h0->ev[5], h0->stream));
+        stage_out(h0, 0, vel0, vel0_box, s_v0, st); stage_out(h1, 0, vel1, vel1_box, s_v1, st);
+        stage_out(h0, 5, phi0, phi0_box, s_p0, st); stage_out(h1, 5, phi1, phi1_box, s_p1, st);
+        stage_out(h0, 4, gphi0, gphi0_box, s_g0, st); stage_out(h1, 4, gphi1, gphi1_box, s_g1, st);
+        finish_stats(h0, st);
+        st->launches = h0->launches + h1->launches;
+        float ms;
+        CK(cudaEventElapsedTime(&ms, h0->ev[0], h0->ev[4])); st->ms_h2d = ms;
+        CK(cudaEventElapsedTime(&ms, h0->ev[5], h0->ev[1])); st->ms_d2h = ms;
+        return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+int b200np_composite_apply_nodal_projection(b200np_composite_t* C, double* const velocity[2], const b200np_fab* const vel_box[2],
+                                            const double* const velocity_o[2], const double* const density[2],
+                                            const b200np_fab* const rho_box[2], double ro_0, double* const gp[2],
+                                            const b200np_fab* const gp_box[2], double* const p_nd[2],
+                                            const b200np_fab* const p_box[2], const double* inflow_vel0, double scaling_factor,
+                                            int incremental, int proj_for_small_dt, double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!C || !velocity || !vel_box || !gp || !gp_box || !p_nd || !p_box) return st->status = B200NP_ERR_BAD_ARG;
+    for (int l = 0; l < 2; ++l)
+        if (!velocity[l] || !vel_box[l] || !gp[l] || !gp_box[l] || !p_nd[l] || !p_box[l]) return st->status = B200NP_ERR_BAD_ARG;
+    const int use_old = (incremental || proj_for_small_dt);
+    if (use_old && (!velocity_o || !velocity_o[0] || !velocity_o[1])) return st->status = B200NP_ERR_BAD_ARG;
+    const bool var = density && (density[0] || density[1]);
+    if (var && (!density[0] || !density[1] || !rho_box || !rho_box[0] || !rho_box[1])) return st->status = B200NP_ERR_BAD_ARG;
+    b200np* hh[2] = {C->h0, C->h1};
+    try {
+        CK(cudaSetDevice(hh[0]->device));
+        const Lev& g = hh[0]->lv[0].g;
+        const int clo[3] = {0, 0, 0}, chi[3] = {g.n[0] - 1, g.n[1] - 1, g.n[2] - 1};
+        if (!vel_box_ok(hh[0], vel_box[0]) || !box_covers(gp_box[0], clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
+        if (!fine_box_ok(C, vel_box[1], 3, 1, false) || !fine_box_ok(C, gp_box[1], 3, 0, false)) return st->status = B200NP_ERR_BAD_ARG;
+        if (var && (!box_covers(rho_box[0], clo, chi, 1) || !fine_box_ok(C, rho_box[1], 1, 0, false))) return st->status = B200NP_ERR_BAD_ARG;
+        hh[0]->launches = hh[1]->launches = 0;
+        cudaStream_t stream = hh[0]->stream;
+        CK(cudaEventRecord(hh[0]->ev[0], stream));
+        const int set_inflow = (!proj_for_small_dt && !incremental);   // :81
+        bool sv[2], so[2], sr[2], sg[2], sp[2], sin0;
+        Fab fvel[2], fvelo[2], frho[2], fgp[2], fp[2];
+        for (int l = 0; l < 2; ++l) {
+            b200np* h = hh[l];
+            double* dvel = stage_in(h, 0, velocity[l], vel_box[l], true, &sv[l], st);
+            double* dvelo = stage_in(h, 1, use_old ? velocity_o[l] : nullptr, vel_box[l], true, &so[l], st);
+            double* drho = stage_in(h, 2, var ? density[l] : nullptr, var ? rho_box[l] : nullptr, true, &sr[l], st);
+            double* dgp = stage_in(h, 4, gp[l], gp_box[l], true, &sg[l], st);
+            double* dp = stage_in(h, 5, p_nd[l], p_box[l], incremental != 0, &sp[l], st);
+            if (l == 0) {
+                fvel[l] = make_fab(dvel, vel_box[l]); fvelo[l] = make_fab(dvelo, vel_box[l]); frho[l] = make_fab(drho, var ? rho_box[l] : nullptr);
+                fgp[l] = make_fab(dgp, gp_box[l]); fp[l] = make_fab(dp, p_box[l]);
+            } else {
+                fvel[l] = make_fab_fine(C, dvel, vel_box[l]); fvelo[l] = make_fab_fine(C, dvelo, vel_box[l]);
+                frho[l] = make_fab_fine(C, drho, var ? rho_box[l] : nullptr);
+                fgp[l] = make_fab_fine(C, dgp, gp_box[l]); fp[l] = make_fab_fine(C, dp, p_box[l]);
+            }
+        }
+        double* din = stage_in(hh[0], 6, set_inflow ? inflow_vel0 : nullptr, vel_box[0], true, &sin0, st);
+        Fab fin = make_fab(din, vel_box[0]);
+        CK(cudaEventRecord(hh[0]->ev[4], stream));
+        // per level: u += s gp / rho, sigma = s / rho (:39-71, :101-121); vel.setBndry(0) + inflow fill on the coarse level (:137-163)
+        for (int l = 0; l < 2; ++l) {
+            LevelData& L = hh[l]->lv[0];
+            if (!incremental || use_old || var)
+                LAUNCH(hh[0], k_pre_add_sigma, L.gc, 256, L.g, fvel[l], fgp[l], frho[l], fvelo[l], scaling_factor, ro_0, incremental ? 0 : 1,
+                       use_old, var ? L.sigma : (double*)nullptr);
+            long long total = (long long)fvel[l].nx * fvel[l].ny * fvel[l].nz;
+            int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+            LAUNCH(hh[0], k_set_vel_ghosts, blocks, 256, L.g, fvel[l], l == 0 ? fin : Fab{}, l == 0 ? set_inflow : 0);
+        }
+        comp_set_sigma(C, var, scaling_factor / ro_0);
+        // :181-266 (gp, p_nd copy-out and average_down(gp) included)
+        int status = comp_core(C, fvel[0], fvel[1], fvelo[0], fvelo[1], use_old, fgp[0], fgp[1], incremental, fp[0], fp[1], incremental,
+                               rtol, atol, st);
+        CK(cudaEventRecord(hh[0]->ev[5], stream));
+        for (int l = 0; l < 2; ++l) {
+            stage_out(hh[l], 0, velocity[l], vel_box[l], sv[l], st);
+            stage_out(hh[l], 4, gp[l], gp_box[l], sg[l], st);
+            stage_out(hh[l], 5, p_nd[l], p_box[l], sp[l], st);
+        }
+        finish_stats(hh[0], st);
+        st->launches = hh[0]->launches + hh[1]->launches;
+        float ms;
+        CK(cudaEventElapsedTime(&ms, hh[0]->ev[0], hh[0]->ev[4])); st->ms_h2d = ms;
+        CK(cudaEventElapsedTime(&ms, hh[0]->ev[5], hh[0]->ev[1])); st->ms_d2h = ms;
         return st->status = status;
     } catch (int e) { return st->status = e; }
 }

@@ -315,3 +315,108 @@ class IncfloProjection:
             self.close()
         except Exception:
             pass
+
+
+class CompositeProjection:
+    """incflo::ApplyNodalProjection / Hydro::NodalProjector with amr.max_level = 1 (BASELINE configs[3]):
+    coarse level over the whole domain + ONE fine box at ratio 2, covered coarse cells [fine_lo, fine_hi]
+    (inclusive).  Level-1 arrays live in FINE index space (cells 2*fine_lo .. 2*fine_hi+1), grown by
+    their ghost width.  Backed by b200np_composite_* (include/b200np.h); algorithm: oracle/composite.py."""
+
+    def __init__(self, n_cell, dx, bclo, bchi, fine_lo, fine_hi, opts=None, device=0):
+        self._L = _lib.lib()
+        self.n = tuple(int(x) for x in n_cell)
+        self.flo = tuple(int(x) for x in fine_lo); self.fhi = tuple(int(x) for x in fine_hi)
+        self.nf = tuple(2 * (h - l + 1) for l, h in zip(self.flo, self.fhi))
+        g = Geom()
+        for d in range(3):
+            g.n_cell[d] = self.n[d]; g.dx[d] = float(dx[d]); g.bc_lo[d] = int(bclo[d]); g.bc_hi[d] = int(bchi[d])
+        self.opts = opts if opts is not None else nodal_proj_opts()
+        lo = (C.c_int * 3)(*self.flo); hi = (C.c_int * 3)(*self.fhi)
+        h = C.c_void_p()
+        rc = self._L.b200np_composite_create(C.byref(h), C.byref(g), C.byref(lo), C.byref(hi), C.byref(self.opts), device)
+        if rc != 0:
+            raise ProjectionError(rc)
+        self._h = h
+        self.stats = Stats()
+
+    def _flo(self, ng):
+        return tuple(2 * l - ng for l in self.flo)
+
+    def project(self, vel0, ng0, vel1, ng1, sigma0=None, sigma1=None, const_sigma=1.0, rtol=1e-11, atol=1e-14,
+                phi0=None, phi1=None, gphi0=None, gphi1=None):
+        """Hydro::NodalProjector::project over both levels; vel0 / vel1 are updated in place.
+        Returns (phi0, phi1, gphi0, gphi1) (allocated like vel0 when not given)."""
+        n, nf = self.n, self.nf
+        if phi0 is None:
+            phi0 = _empty_like(vel0, (n[2] + 1, n[1] + 1, n[0] + 1))
+        if phi1 is None:
+            phi1 = _empty_like(vel1, (nf[2] + 1, nf[1] + 1, nf[0] + 1))
+        if gphi0 is None:
+            gphi0 = _empty_like(vel0, (3, n[2], n[1], n[0]))
+        if gphi1 is None:
+            gphi1 = _empty_like(vel1, (3, nf[2], nf[1], nf[0]))
+        pv0, bv0, _ = _ptr_box(vel0, (-ng0,) * 3, 3)
+        pv1, bv1, _ = _ptr_box(vel1, self._flo(ng1), 3)
+        ps0, bs0, _ = _ptr_box(sigma0, (0, 0, 0), 1)
+        ps1, bs1, _ = _ptr_box(sigma1, self._flo(0), 1)
+        pp0, bp0, _ = _ptr_box(phi0, (0, 0, 0), 1)
+        pp1, bp1, _ = _ptr_box(phi1, self._flo(0), 1)
+        pg0, bg0, _ = _ptr_box(gphi0, (0, 0, 0), 3)
+        pg1, bg1, _ = _ptr_box(gphi1, self._flo(0), 3)
+        ref = lambda b: C.byref(b) if b is not None else None
+        rc = self._L.b200np_composite_project(self._h, pv0, ref(bv0), pv1, ref(bv1), ps0, ref(bs0), ps1, ref(bs1),
+                                              float(const_sigma), pp0, ref(bp0), pp1, ref(bp1), pg0, ref(bg0), pg1, ref(bg1),
+                                              float(rtol), float(atol), C.byref(self.stats))
+        if rc != 0:
+            raise ProjectionError(rc)
+        return phi0, phi1, gphi0, gphi1
+
+    def apply_nodal_projection(self, velocity, ng, gp, p_nd, density=None, ngd=(0, 0), ro_0=1.0, velocity_o=None,
+                               inflow_vel=None, scaling_factor=1.0, incremental=False, proj_for_small_dt=False,
+                               mg_rtol=1e-11, mg_atol=1e-14):
+        """incflo::ApplyNodalProjection with finest_level = 1: velocity, gp, p_nd, density, velocity_o are
+        pairs (level 0, level 1); ng / ngd the ghost widths per level."""
+        fbp = C.POINTER(FabBox)
+
+        def pair(arrs, los, ncomp):
+            ptrs = (C.c_void_p * 2)(); boxes = (fbp * 2)(); keep = []
+            if arrs is None:
+                return None, None, keep
+            for l in range(2):
+                p, b, _ = _ptr_box(arrs[l], los[l], ncomp)
+                ptrs[l] = p
+                if b is not None:
+                    keep.append(b); boxes[l] = C.pointer(b)
+            return ptrs, boxes, keep
+        lo_v = ((-ng[0],) * 3, self._flo(ng[1]))
+        lo_d = ((-ngd[0],) * 3, self._flo(ngd[1]))
+        lo_0 = ((0, 0, 0), self._flo(0))
+        pv, bv, k1 = pair(velocity, lo_v, 3)
+        po, _, k2 = pair(velocity_o, lo_v, 3)
+        pr, br, k3 = pair(density, lo_d, 1)
+        pg, bg, k4 = pair(gp, lo_0, 3)
+        pp, bp, k5 = pair(p_nd, lo_0, 1)
+        pi, _, _ = _ptr_box(inflow_vel, (-ng[0],) * 3, 3)
+        ref = lambda a: C.byref(a) if a is not None else None
+        rc = self._L.b200np_composite_apply_nodal_projection(self._h, ref(pv), ref(bv), ref(po), ref(pr), ref(br), float(ro_0),
+                                                             ref(pg), ref(bg), ref(pp), ref(bp), pi, float(scaling_factor),
+                                                             int(incremental), int(proj_for_small_dt), float(mg_rtol),
+                                                             float(mg_atol), C.byref(self.stats))
+        if rc != 0:
+            raise ProjectionError(rc)
+        return self.stats
+
+    def set_stream(self, cuda_stream):
+        self._L.b200np_composite_set_stream(self._h, C.c_void_p(cuda_stream))
+
+    def close(self):
+        if self._h is not None:
+            self._L.b200np_composite_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -39,7 +39,7 @@ enum b200np_status {
     B200NP_ERR_BAD_ARG = 4,
     B200NP_ERR_CUDA = 5,          /* no device / CUDA runtime error                            */
     B200NP_ERR_NCCL = 6,
-    B200NP_ERR_UNSUPPORTED = 7    /* multi-level AMR, EB, overset mask: not built yet          */
+    B200NP_ERR_UNSUPPORTED = 7    /* EB, overset mask, AMR beyond one fine box at ratio 2      */
 };
 
 /* amrex::Geometry + domain BCs of one level (NodalProjector ctor + setDomainBC, :187-194) */
@@ -162,6 +162,42 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
                                   const b200np_fab* p_box, const double* inflow_vel, double scaling_factor,
                                   int incremental, int proj_for_small_dt, double rtol, double atol,
                                   b200np_stats* stats);
+
+/* ---- composite (two AMR level) projection: BASELINE configs[3], amr.max_level = 1 -------------------
+ * incflo::ApplyNodalProjection loops over lev = 0..finest_level (:101-121, :130-164, :221-266) and hands
+ * Hydro::NodalProjector the vectors vel[], sigma[], Geom(0,finest_level) (:181-192); AMReX's MLMG then
+ * solves the composite problem (MLMG::oneIter multi-level branch, MLNodeLaplacian::reflux / compRHS /
+ * interpolationAmr; un-vendored, restated in oracle/composite.py).  Supported here: ONE fine box at
+ * amr.ref_ratio = 2 (every deck) that lies at least one coarse cell inside the domain; anything else
+ * returns B200NP_ERR_UNSUPPORTED.  fine_lo / fine_hi: the covered COARSE cells (inclusive).  Boxes of
+ * level-1 arrays are in FINE index space (fine cells 2*fine_lo .. 2*fine_hi+1), as amrex::MultiFab
+ * boxes of level 1 are.  Coarse cells under the fine box: their input velocity never counts; on return
+ * velocity, gp (gphi) there are the average of the fine values (amrex::average_down, :258-266 and
+ * NodalProjector::averageDown) and phi / p_nd on the covered coarse nodes is the fine value. */
+typedef struct b200np_composite b200np_composite_t;
+int  b200np_composite_create(b200np_composite_t** out, const b200np_geom* geom0, const int fine_lo[3], const int fine_hi[3],
+                             const b200np_opts* opts, int device);
+void b200np_composite_destroy(b200np_composite_t* c);
+int  b200np_composite_set_stream(b200np_composite_t* c, void* stream);
+/* the single-level handle of AMR level 0 / 1 (test hooks b200np_level_* / b200np_time_op; owned by c) */
+b200np_t* b200np_composite_level(b200np_composite_t* c, int amr_level);
+/* Hydro::NodalProjector::project over two levels + getPhi / getGradPhi (:215-219).  sigma0 and sigma1 are
+ * both given or both NULL (=> const_sigma).  One ghost layer of vel0 is an input at non-periodic domain
+ * faces as in b200np_project; the ghost cells of vel1 are zeroed (vel.setBndry(0.0), :137). */
+int  b200np_composite_project(b200np_composite_t* c, double* vel0, const b200np_fab* vel0_box, double* vel1,
+                              const b200np_fab* vel1_box, const double* sigma0, const b200np_fab* sigma0_box,
+                              const double* sigma1, const b200np_fab* sigma1_box, double const_sigma, double* phi0,
+                              const b200np_fab* phi0_box, double* phi1, const b200np_fab* phi1_box, double* gphi0,
+                              const b200np_fab* gphi0_box, double* gphi1, const b200np_fab* gphi1_box, double rtol, double atol,
+                              b200np_stats* stats);
+/* incflo::ApplyNodalProjection with finest_level = 1: every per-level argument of
+ * b200np_apply_nodal_projection becomes an array indexed by AMR level. */
+int  b200np_composite_apply_nodal_projection(b200np_composite_t* c, double* const velocity[2], const b200np_fab* const vel_box[2],
+                                             const double* const velocity_o[2], const double* const density[2],
+                                             const b200np_fab* const rho_box[2], double ro_0, double* const gp[2],
+                                             const b200np_fab* const gp_box[2], double* const p_nd[2],
+                                             const b200np_fab* const p_box[2], const double* inflow_vel0, double scaling_factor,
+                                             int incremental, int proj_for_small_dt, double rtol, double atol, b200np_stats* stats);
 
 const char* b200np_strerror(int status);
 int b200np_version(void);

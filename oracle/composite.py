@@ -227,3 +227,38 @@ class CompositeProjector:
             vel1[:, ng1:ng1 + nf[2], ng1:ng1 + nf[1], ng1:ng1 + nf[0]])
         return dict(status=status, iters=iters, phi0=sol0, phi1=sol1, gphi0=g0, gphi1=g1, rhsnorm=rhsnorm,
                     resnorm0=resnorm0, resnorm=hist[-1], hist=hist)
+
+
+def apply_nodal_projection(cp, velocity, ng, gp, p_nd, density=None, ngd=(0, 0), ro_0=1.0, scaling_factor=1.0,
+                           rtol=1e-11, atol=1e-14):
+    """incflo::ApplyNodalProjection with finest_level = 1, non-incremental branch (:39-71, :101-121,
+    :221-266): per level u += s gp / rho, sigma = s / rho, project, gp = G phi, p_nd = phi (nodal boxes
+    [0, n] per level, periodic image planes included), average_down(gp).  velocity / gp / p_nd / density
+    are pairs (level 0, level 1), updated in place."""
+    n = (cp.n0, cp.nf)
+    sig = [None, None]
+    for l in range(2):
+        nx, ny, nz = n[l]
+        g = ng[l]
+        v = velocity[l]
+        inner = (slice(None), slice(g, g + nz), slice(g, g + ny), slice(g, g + nx))
+        if density is not None:
+            d = ngd[l]
+            rho = density[l][d:d + nz, d:d + ny, d:d + nx]
+            sig[l] = scaling_factor / rho
+            v[inner] += gp[l] * sig[l][None]
+        else:
+            v[inner] += gp[l] * (scaling_factor / ro_0)
+        # vel.setBndry(0.0): ghost cells (no inflow faces in the composite cases)
+        keep = v[inner].copy()
+        v[...] = 0.0
+        v[inner] = keep
+    r = cp.project(velocity[0], ng[0], velocity[1], ng[1], sig[0], sig[1], scaling_factor / ro_0, rtol, atol)
+    gp[0][...] = r["gphi0"]; gp[1][...] = r["gphi1"]
+    p0 = r["phi0"]
+    for d, ax in ((0, 2), (1, 1), (2, 0)):
+        if cp.bclo[d] == PER:
+            p0 = np.concatenate([p0, np.take(p0, [0], axis=ax)], axis=ax)
+    p_nd[0][...] = p0
+    p_nd[1][...] = r["phi1"]
+    return r
