@@ -127,6 +127,7 @@ struct b200np {
     bool p2p = false;         // active (every rank mapped its neighbours)
     char *peer_lo = nullptr, *peer_hi = nullptr;
     unsigned long long* flags = nullptr;  // HaloFlags::my
+    unsigned long long xk = 0;            // exchanges issued since the epoch base was last advanced
     double* ipc_buf = nullptr;
     int nlev_dist = 0;       // levels [0, nlev_dist) are slab-distributed, the rest replicated on every rank
     int singular = 1;
@@ -157,6 +158,7 @@ struct b200np {
     int smoother_version = 3, interp_version = 2, resid_version = 3;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
     // B200NP_PROFILE=1: per-phase device times (CUDA events between phases, graph capture off); printed per call
     int profile = 0;
+    int dbg_halo = 0;         // B200NP_DBG_HALO: see smooth_sweeps (timing experiments, results are wrong)
     bool no_bottom = false;   // fine AMR level of a composite solve: one MG level, never a bottom solve
     std::vector<cudaEvent_t> prof_ev;
     std::vector<std::string> prof_tag;
@@ -366,7 +368,8 @@ inline T* peer_ptr(const b200np* h, const char* peer_base, T* mine)
 {
     return reinterpret_cast<T*>(const_cast<char*>(peer_base) + (reinterpret_cast<const char*>(mine) - h->arena.base));
 }
-inline HaloFlags halo_flags(const b200np* h)
+// flags of the next exchange (one call per exchange: it takes the next epoch number)
+inline HaloFlags halo_flags(b200np* h)
 {
     const int P = h->nranks, r = h->rank;
     const bool per = zper(h);
@@ -374,7 +377,15 @@ inline HaloFlags halo_flags(const b200np* h)
     f.my = h->flags;
     if (per || r > 0) f.lo_flag = peer_ptr(h, h->peer_lo, h->flags) + 1;      // I am my lower neighbour's upper neighbour
     if (per || r < P - 1) f.hi_flag = peer_ptr(h, h->peer_hi, h->flags) + 0;
+    f.k = h->xk++;
     return f;
+}
+// advance the device-side epoch base by the exchanges issued since the last advance (np_kernels.cuh K10)
+void epoch_advance(b200np* h)
+{
+    if (!h->p2p || h->xk == 0) return;
+    LAUNCH(h, k_epoch_advance, 1, 1, h->flags, h->xk);
+    h->xk = 0;
 }
 // handshake without data: everything both neighbours launched before it is complete when it returns
 void p2p_fence(b200np* h)
@@ -552,7 +563,7 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
             const bool has_lo = per || r > 0, has_hi = per || r < P - 1;
             const Lev& g = L.g;
             // first sweep: the input halo comes from a standalone exchange (nothing to do if x == 0 everywhere)
-            if (s == 0 && !zero_start) halo_nodes(h, L, x);
+            if (s == 0 && !zero_start && h->dbg_halo < 2) halo_nodes(h, L, x);
             HaloFused H{};
             H.f = halo_flags(h);
             H.pin_lo = has_lo ? x - g.ps : x + g.ps;                                    // ghost slot / reflection plane
@@ -564,6 +575,12 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
             const int nch = (g.nzl + L.tz - 1) / L.tz;
             H.tztop = g.nzl - (nch - 1) * L.tz;
             H.first = s == 0; H.more = s + 1 < nsweeps;
+            // timing experiments only (wrong halos): 1 no flags, 2 + no remote stores, 3 + no epoch ticket,
+            // 4 no flags, no ticket, remote stores kept; 5 (unfused path) no exchange at all
+            if (h->dbg_halo >= 1) { H.first = 1; H.more = 0; }
+            if (h->dbg_halo == 2 || h->dbg_halo == 3) { H.out_lo = nullptr; H.out_hi = nullptr; }
+            if (h->dbg_halo == 3 || h->dbg_halo == 4) H.first = 2;
+            if (s == 0 && h->dbg_halo >= 1) {}
             h->exchanges++;
             const dim3 grid(L.gsm.x, L.gsm.y, nch);
             if (resident) {
@@ -576,7 +593,7 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
             std::swap(x, y);
             continue;
         }
-        halo_nodes(h, L, x);
+        if (h->dbg_halo != 5) halo_nodes(h, L, x);
         if (h->smoother_version == 1) {
             if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, L.tz);
             else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, L.tz);
@@ -700,10 +717,12 @@ void vcycle(b200np* h)
         cudaGraphExecDestroy(h->graph_exec); cudaGraphDestroy(h->graph);
         h->graph_exec = nullptr; h->graph = nullptr;
     }
+    epoch_advance(h);   // the graph's exchanges are numbered from 0
     if (!h->graph_exec) {
         long long before = h->launches;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         vcycle_launch(h, 0);
+        epoch_advance(h);   // last node: every replay leaves the base advanced by the graph's exchanges
         CK(cudaStreamEndCapture(h->stream, &h->graph));
         CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
         h->launches_per_vcycle = h->launches - before;
@@ -926,6 +945,7 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (const char* e = getenv("B200NP_DIST_GRAPH")) h->dist_graph = atoi(e);
         if (const char* e = getenv("B200NP_PDL")) h->use_pdl = atoi(e);
         if (const char* e = getenv("B200NP_PROFILE")) h->profile = atoi(e);
+        if (const char* e = getenv("B200NP_DBG_HALO")) h->dbg_halo = atoi(e);
         if (const char* e = getenv("B200NP_P2P")) h->use_p2p = atoi(e);
         if (const char* e = getenv("B200NP_FUSE_HALO")) h->fuse_halo = atoi(e);
         if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) h->dist_min_planes = std::max(8, atoi(e));

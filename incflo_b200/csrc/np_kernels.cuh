@@ -806,12 +806,12 @@ __global__ void __launch_bounds__(512) k_bottom_bicgstab(const Lev L, double* __
 // K10: FillBoundary between z slabs over NVLink peer memory (replaces a grouped ncclSend/ncclRecv
 // pair per halo; MLNodeLinOp::applyBC's FillBoundary).  One process per GPU; every rank
 // maps its two neighbours' arenas with CUDA IPC.  Pull protocol, one kernel per exchange:
-//   1. epoch e = my[2] + 1.  Thread 0 of CTA 0 tells both neighbours "everything I launched before
+//   1. thread 0 of CTA 0 tells both neighbours "everything I launched before
 //      exchange e is complete" (st.release.sys of e into their flag words, over NVLink);
 //   2. every CTA waits until both neighbours have said the same (ld.acquire.sys on MY flag words,
 //      local polling), then copies the neighbours' boundary planes into my ghost plane slots with
 //      peer loads;
-//   3. the last CTA to finish publishes my[2] = e.
+//   (epoch e = base my[2] + 1 + k, k = kernel argument: see k_epoch_advance).
 // RAW: step 2.  WAR (a neighbour overwriting the plane I am still pulling): every overwrite of an
 // exchanged array is separated from its last pull by at least one later exchange with the same
 // neighbour (ping-pong sweeps; see exchange_planes), whose step 1 is stream-ordered after my pull.
@@ -819,10 +819,10 @@ __global__ void __launch_bounds__(512) k_bottom_bicgstab(const Lev L, double* __
 // At a physical (non-periodic) end the "source" is the local reflection / clamp plane and the
 // flag pointer is null.
 // ------------------------------------------------------------------------------------------
-// handshake part of an exchange (steps 1 and 2); returns the epoch
-__device__ __forceinline__ unsigned long long halo_handshake(const HaloFlags& f)
+// handshake part of an exchange (steps 1 and 2)
+__device__ __forceinline__ void halo_handshake(const HaloFlags& f)
 {
-    const unsigned long long e = ld_relaxed_gpu(f.my + 2) + 1ull;
+    const unsigned long long e = halo_epoch(f);
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
             __threadfence_system();
@@ -833,16 +833,6 @@ __device__ __forceinline__ unsigned long long halo_handshake(const HaloFlags& f)
         if (f.hi_flag) while (ld_acquire_sys(f.my + 1) < e) __nanosleep(20);
     }
     __syncthreads();
-    return e;
-}
-__device__ __forceinline__ void halo_publish(const HaloFlags& f, unsigned long long e)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned long long t = atomicAdd(f.my + 3, 1ull);
-        if (t == gridDim.x - 1) { f.my[3] = 0ull; f.my[2] = e; __threadfence(); }
-    }
 }
 // n2 = doubles per plane / 2 (planes are multiples of 64 B and 1 KiB aligned)
 __global__ void __launch_bounds__(256) k_halo_pull(const HaloFlags f, double2* __restrict__ ghost_lo, const double2* __restrict__ src_lo,
@@ -850,12 +840,15 @@ __global__ void __launch_bounds__(256) k_halo_pull(const HaloFlags f, double2* _
 {
     pdl_trigger();   // the successor may become resident; it still waits for this grid in its own pdl_wait()
     pdl_wait();      // the flag below promises that everything launched before this exchange is complete
-    const unsigned long long e = halo_handshake(f);
+    halo_handshake(f);
     for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n2; i += gridDim.x * 256ll) {
         const double2 a = __ldcv(src_lo + i), b = __ldcv(src_hi + i);   // .cv: never served from a stale line
         ghost_lo[i] = a; ghost_hi[i] = b;
     }
-    halo_publish(f, e);
 }
+// Epochs: an exchange kernel gets its number k since the last advance as an argument (so a captured
+// CUDA graph can be replayed) and the base lives in device memory; the base is advanced by the number
+// of exchanges issued, as the last node of the V-cycle graph and before a graph is launched.
+__global__ void k_epoch_advance(unsigned long long* my, unsigned long long n) { my[2] += n; }
 
 }  // namespace b200np_dev

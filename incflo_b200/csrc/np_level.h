@@ -47,10 +47,14 @@ __device__ __forceinline__ bool pdl_small_grid() { return gridDim.x * gridDim.y 
 
 // ---- NVLink peer-memory halo flags (slab-decomposed path; protocol in np_kernels.cuh K10) ----
 struct HaloFlags {
-    unsigned long long* my;       // [0] written by my lower neighbour, [1] by my upper neighbour, [2] epoch, [3] ticket
+    unsigned long long* my;       // [0] written by my lower neighbour, [1] by my upper neighbour, [2] epoch base,
+                                  // [4], [5] counters of the fused sweeps (np_smooth3.cuh)
     unsigned long long* lo_flag;  // lower neighbour's word [1] (peer pointer) or nullptr
     unsigned long long* hi_flag;  // upper neighbour's word [0] (peer pointer) or nullptr
+    unsigned long long k;         // this exchange is number k since the base was last advanced: epoch = my[2] + 1 + k
 };
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p);
+__device__ __forceinline__ unsigned long long halo_epoch(const HaloFlags& f) { return ld_relaxed_gpu(f.my + 2) + 1ull + f.k; }
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

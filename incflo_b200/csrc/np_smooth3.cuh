@@ -33,13 +33,15 @@ constexpr int SM_RES_DOUBLES = (SM_RES_TZ + 2) * SM_PHI_SLOT + (SM_RES_TZ + 1) *
 // last of them raises the neighbour's flag for the next exchange; the neighbour's next sweep reads its
 // LOCAL ghost slots.  Only the bottom / top chunk CTAs wait for a flag (not in the first sweep of a
 // smooth call, whose input halo was filled by a standalone exchange or is zero); every other CTA starts
-// at once.  To take the NVLink latency off the critical path the boundary planes are produced early:
-//   * the top chunk (`tztop` planes: the remainder chunk) is scheduled first (blockIdx.z = 0),
-//   * the bottom chunk (blockIdx.z = 1) reports right after its first plane.
-// (A deliberately short top chunk hides more latency but was measured to cost a V-cycle.)
+// at once, and the boundary chunks are scheduled first (blockIdx.z = 0 is the top chunk, 1 the bottom
+// chunk), so on a large level the flags arrive long before the neighbour's next sweep needs them.
+// The plane march itself is the single-GPU code, untouched: the pushes happen after the march (top
+// plane from registers, bottom plane re-read from this CTA's own output) -- in-loop pushes cost 10 %
+// of the sweep in extra shared-memory reloads (register pressure).  A deliberately short top chunk
+// hides more latency on small levels but was measured to cost a V-cycle.
 // A flag also tells the neighbour that its previous boundary plane is no longer being read (WAR).
 struct HaloFused {
-    HaloFlags f;           // my: [4], [5] count bottom / top chunk CTAs that have pushed their plane
+    HaloFlags f;           // my: [4], [5] count bottom / top chunk CTAs that have pushed their plane; f.k: this sweep's exchange
     const double* pin_lo;  // plane -1 of pin: my ghost slot, or the reflection plane at a physical end
     const double* pin_hi;  // plane nzl of pin
     double* out_lo;        // lower neighbour's ghost slot (its plane nzl) of pout, or nullptr
@@ -52,8 +54,9 @@ struct HaloFused {
 // one thread of a bottom (SIDE 0) / top (SIDE 1) chunk CTA, after a CTA barrier that follows the push of
 // its boundary plane: count the CTA; the last one of the side raises the neighbour's flag for epoch ep+1
 template <int SIDE>
-__device__ __forceinline__ void halo_report(const HaloFused& H, unsigned long long ep)
+__device__ __forceinline__ void halo_report(const HaloFused& H)
 {
+    const unsigned long long ep = halo_epoch(H.f);
     unsigned long long* flag = SIDE == 0 ? H.f.lo_flag : H.f.hi_flag;
     if (!H.more || !flag) return;
     __threadfence_system();   // this CTA's remote stores are performed before the count becomes visible
@@ -133,8 +136,8 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     const bool colok[2] = {FULL || gi0 < L.nn[0], FULL || gi0 + 1 < L.nn[0]};
     const bool rowok[2] = {FULL || gj0 < L.nn[1], FULL || gj0 + 1 < L.nn[1]};
     const int roff = gj0 * L.px + gi0;
-    auto load_rhs = [&](int kl, double (&r)[2][2]) {
-        const double* q0 = rhs + kl * L.ps + roff;
+    auto load_rhs = [&](int kl, double (&r)[2][2], const double* arr = nullptr) {
+        const double* q0 = (arr ? arr : rhs) + kl * L.ps + roff;
         asm volatile("" : "+l"(q0));
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
@@ -160,16 +163,13 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
 
     if (pdl_small_grid()) pdl_trigger();
     pdl_wait();   // everything above only touched kernel parameters and shared memory
-    unsigned long long ep = 0;
-    if (DIST) {
-        ep = ld_relaxed_gpu(H->f.my + 2) + 1ull;
-        if (!H->first) {
-            if (tid == 0) {
-                if (kc0 == 0 && H->f.lo_flag) while (ld_acquire_sys(H->f.my + 0) < ep) __nanosleep(20);
-                if (kc1 == L.nzl && H->f.hi_flag) while (ld_acquire_sys(H->f.my + 1) < ep) __nanosleep(20);
-            }
-            __syncthreads();
+    if (DIST && !H->first) {
+        if (tid == 0) {
+            const unsigned long long ep = halo_epoch(H->f);
+            if (kc0 == 0 && H->f.lo_flag) while (ld_acquire_sys(H->f.my + 0) < ep) __nanosleep(20);
+            if (kc1 == L.nzl && H->f.hi_flag) while (ld_acquire_sys(H->f.my + 1) < ep) __nanosleep(20);
         }
+        __syncthreads();
     }
     double rcur[2][2], rnext[2][2];
     if (RES) {
@@ -221,7 +221,6 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
         load_rhs(kl + 1 < kc1 ? kl + 1 : kl, rnext);
         if (!RES) cp_async_wait<1>();   // plane kl+1 / sigma layer kl have landed (this thread's copies)
         __syncthreads();      // ... everybody else's, and plane kl-1's colours 2,3 are published
-        if (DIST && kc0 == 0 && kl == 1 && tid == 0) halo_report<0>(*H, ep);   // plane 0 has been pushed by every thread
         const int kg = kl + L.k0;
         const double* Pm = sphi + pslot(kl - 1) * SM_PHI_SLOT + rbase;   // plane kl-1 (this sweep)
         double* P0 = sphi + pslot(kl) * SM_PHI_SLOT + rbase;             // plane kl
@@ -389,22 +388,6 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
                 }
             }
         }
-        if (DIST) {  // the slab's first / last plane also goes into the neighbour's ghost plane slot
-            double* r0 = (kl == 0) ? H->out_lo : nullptr;
-            if (kl == L.nzl - 1 && H->out_hi) r0 = H->out_hi;   // (nzl >= 2: never both)
-            if (r0) {
-                r0 += roff;
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    double* q = r0 + b * L.px;
-                    if (FULL) *reinterpret_cast<double2*>(q) = make_double2(v[b][0], v[b][1]);
-                    else if (rowok[b]) {
-                        if (colok[1]) *reinterpret_cast<double2*>(q) = make_double2(v[b][0], v[b][1]);
-                        else if (colok[0]) q[0] = v[b][0];
-                    }
-                }
-            }
-        }
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
@@ -416,13 +399,32 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     pdl_trigger();
     cp_async_wait<0>();
     if (DIST) {
-        __syncthreads();   // every store of this CTA has been issued
-        if (tid == 0) {
-            if (kc0 == 0 && kc1 == 1) halo_report<0>(*H, ep);   // one-plane bottom chunk: not reported in the loop
-            if (kc1 == L.nzl) halo_report<1>(*H, ep);
-            __threadfence();
-            if (atomicAdd(H->f.my + 3, 1ull) == (unsigned long long)gridDim.x * gridDim.y * gridDim.z - 1) {
-                H->f.my[3] = 0ull; H->f.my[2] = ep; __threadfence();
+        // push the slab's first / last plane into the neighbour's ghost plane slot of pout, then report
+        const bool bot = kc0 == 0 && H->out_lo, top = kc1 == L.nzl && H->out_hi;
+        if (bot || top) {
+            auto push = [&](double* r0, const double (&w)[2][2]) {
+                r0 += roff;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    double* q = r0 + b * L.px;
+                    if (FULL) *reinterpret_cast<double2*>(q) = make_double2(w[b][0], w[b][1]);
+                    else if (rowok[b]) {
+                        if (colok[1]) *reinterpret_cast<double2*>(q) = make_double2(w[b][0], w[b][1]);
+                        else if (colok[0]) q[0] = w[b][0];
+                    }
+                }
+            };
+            if (top) push(H->out_hi, ownp);            // ownp: this thread's values of the last plane of the chunk
+            if (bot) {
+                double w[2][2];
+                if (kc1 - kc0 == 1) { w[0][0] = ownp[0][0]; w[0][1] = ownp[0][1]; w[1][0] = ownp[1][0]; w[1][1] = ownp[1][1]; }
+                else load_rhs(0, w, pout);             // plane 0 of this CTA's own output (written by this very thread)
+                push(H->out_lo, w);
+            }
+            __syncthreads();   // every thread's remote stores have been issued
+            if (tid == 0) {
+                if (bot) halo_report<0>(*H);
+                if (top) halo_report<1>(*H);
             }
         }
     }
