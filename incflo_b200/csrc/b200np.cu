@@ -283,8 +283,12 @@ void build_levels(b200np* h)
         fill_lev(G, n, dx, g);
         L.iso = (dx[0] == dx[1] && dx[1] == dx[2]);
         // level 0 is always distributed; a coarser level stays distributed while every rank keeps an even
-        // number (>= dist_min_planes) of cell planes
-        if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && (lev == 0 || n[2] / P >= h->dist_min_planes)) {
+        // number (>= dist_min_planes) of cell planes, or while it is too big to replicate (> 128^3 nodes)
+        // (a replicated level costs every rank a sweep over ALL its nodes, so a big level with thin slabs --
+        // 512^3 on 8 GPUs: level 1 = 256^3 with 32 planes per rank -- stays distributed down to 8 planes)
+        const double gnodes = (double)(n[0] + 1) * (n[1] + 1) * (n[2] + 1);
+        const bool keep = n[2] / P >= h->dist_min_planes || (gnodes > 2.2e6 && n[2] / P >= 8);
+        if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && (lev == 0 || keep)) {
             set_slab(g, h->rank, P, zper(h));
             L.dist = true;
             h->nlev_dist = lev + 1;

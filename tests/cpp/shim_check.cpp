@@ -55,10 +55,25 @@ static int host_checks()
         try { np.project(1e-11, 1e-14); } catch (const std::runtime_error&) { threw = true; }
         EXPECT(threw);
     }
+    // two levels: level 1 must be one box at ratio 2 aligned with the coarse cells; three levels abort
     threw = false;
-    try { NodalProjector np2({Fab::make(v.data(), n, 1, 3), Fab::make(v.data(), n, 1, 3)}, 1.0, {g, g}); }
+    try { NodalProjector np2({Fab::make(v.data(), n, 1, 3), Fab::make(v.data(), n, 1, 3)}, 1.0, {g, g}); }   // geom[1] is not the refined geometry
     catch (const std::runtime_error&) { threw = true; }
     EXPECT(threw);
+    threw = false;
+    try { NodalProjector np3({Fab::make(v.data(), n, 1, 3), Fab::make(v.data(), n, 1, 3), Fab::make(v.data(), n, 1, 3)}, 1.0, {g, g, g}); }
+    catch (const std::runtime_error&) { threw = true; }
+    EXPECT(threw);
+    {
+        Geometry g1{{16, 16, 16}, {0.0625, 0.0625, 0.0625}, {true, true, true}};
+        const int vlo[3] = {4, 4, 4}, vhi[3] = {11, 11, 11};   // fine cells 4..11 = coarse cells 2..5
+        NodalProjector np4({Fab::make(v.data(), n, 1, 3), Fab::make_box(v.data(), vlo, vhi, 1, 3)}, 1.0, {g, g1});
+        const int odd[3] = {5, 4, 4};
+        threw = false;
+        try { NodalProjector np5({Fab::make(v.data(), n, 1, 3), Fab::make_box(v.data(), odd, vhi, 1, 3)}, 1.0, {g, g1}); }
+        catch (const std::runtime_error&) { threw = true; }
+        EXPECT(threw);
+    }
     // Fab geometry: ld.velocity (ng=3), ld.p_nd (nodal, ng=0)   src/setup/incflo_arrays.cpp:9-26
     Fab f = Fab::make(nullptr, n, 3, 3);
     EXPECT(f.box.lo[0] == -3 && f.box.hi[2] == 10 && f.size() == (size_t)3 * 14 * 14 * 14);

@@ -25,8 +25,13 @@ def _ngpus():
 @pytest.mark.parametrize("env", [{"B200NP_DIST_MIN_PLANES": "8"}, {}, {"B200NP_DIST_MIN_PLANES": "8", "B200NP_FUSE_HALO": "0"},
                                  {"B200NP_DIST_MIN_PLANES": "8", "B200NP_P2P": "0"}],
                          ids=["p2p_fused_4dist_levels", "default", "p2p_unfused", "nccl"])
-def test_two_slabs_match_oracle(env):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+@pytest.mark.parametrize("nproc", [2, 4])   # 4: interior ranks with two distinct neighbours
+def test_slabs_match_oracle(env, nproc):
+    if _ngpus() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    if nproc == 4 and env.get("B200NP_FUSE_HALO") == "0":
+        pytest.skip("covered at 2 ranks")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **env))
     sys.stdout.write(r.stdout[-4000:]); sys.stderr.write(r.stderr[-4000:])
