@@ -1015,8 +1015,11 @@ namespace {
 // fine box with reflecting faces: one-sided sums x 2^f (np_composite.cuh)
 Lev comp_gN(const b200np_composite* C)
 {
-    Lev g = C->h1->lv[0].g;
-    for (int d = 0; d < 3; ++d) { g.rlo[d] = g.rhi[d] = 1; g.dlo[d] = g.dhi[d] = 0; }
+    Lev g = C->h1->lv[0].g;   // interface faces: Dirichlet -> reflecting; wall / outflow / periodic faces stay what they are
+    for (int d = 0; d < 3; ++d) {
+        if (C->box.cf_lo[d]) { g.rlo[d] = 1; g.dlo[d] = 0; }
+        if (C->box.cf_hi[d]) { g.rhi[d] = 1; g.dhi[d] = 0; }
+    }
     return g;
 }
 dim3 box_grid(int nx, int ny, int nz) { return dim3((nx + 63) / 64, (ny + 3) / 4, nz); }
@@ -1039,7 +1042,7 @@ void comp_coarse_residual(b200np_composite* C, const double* sol0, const double*
     LevelData &L0 = h0->lv[0], &L1 = h1->lv[0];
     const Lev gN = comp_gN(C);
     residual(h1, L1, const_cast<double*>(sol1), C->rhsN, L1.rescor, nullptr, &gN);   // 2^f x (b - A) fine-side sums
-    launch_pdl(h0, k_restrict, box_grid(C->nb[0] + 1, C->nb[1] + 1, C->nb[2] + 1), dim3(256), 0, gN, C->view,
+    launch_pdl(h0, k_restrict, box_grid(C->box.nbn[0], C->box.nbn[1], C->box.nbn[2]), dim3(256), 0, gN, C->view,
                (const double*)L1.rescor, L0.rescor + C->off_n);
     Lev g0z = L0.g;
     g0z.sigma = C->s0z;
@@ -1145,7 +1148,7 @@ int comp_core(b200np_composite* C, Fab vel0, Fab vel1, Fab velo0, Fab velo1, int
     if (talk) printf("MLMG: Final Iter. %d resid, resid/bnorm = %.12g, %.12g\n", st->iters, st->resnorm, st->resnorm / maxnorm);
     CK(cudaEventRecord(h0->ev[3], h0->stream));
     // ---- finish: injection, u -= sigma G phi, gphi = G phi, average_down onto the covered cells ----
-    LAUNCH(h0, k_comp_inject, box_grid(C->nb[0] + 1, C->nb[1] + 1, C->nb[2] + 1), 256, L0.g, gD, b, L0.sol, (const double*)L1.sol);
+    LAUNCH(h0, k_comp_inject, box_grid(b.nbn[0], b.nbn[1], b.nbn[2]), 256, L0.g, gD, b, L0.sol, (const double*)L1.sol);
     LAUNCH(h0, k_mknewu, L1.gc, 256, gD, (const double*)L1.sol, vel1, velo1, add_old, gphi1, acc_g);
     LAUNCH(h0, k_mknewu, L0.gc, 256, L0.g, (const double*)L0.sol, vel0, velo0, add_old, gphi0, acc_g);
     LAUNCH(h0, k_comp_avgdown, gbox, 256, b, vel1, vel0, 3);
@@ -1167,7 +1170,8 @@ bool fine_box_ok(const b200np_composite* C, const b200np_fab* bx, int ncomp, int
     if (!bx || bx->ncomp < ncomp) return false;
     for (int d = 0; d < 3; ++d) {
         const int lo = 2 * C->box.lo[d], hi = 2 * C->box.hi[d] + 1 + (nodal ? 1 : 0);
-        if (bx->lo[d] > lo - grow || bx->hi[d] < hi + grow) return false;
+        const int gr = C->box.span[d] ? 0 : grow;   // periodic ghosts are never read (the library wraps)
+        if (bx->lo[d] > lo - gr || bx->hi[d] < hi + gr) return false;
     }
     return true;
 }
@@ -1417,8 +1421,23 @@ int b200np_composite_create(b200np_composite_t** out, const b200np_geom* geom0, 
 {
     if (!out || !geom0 || !fine_lo || !fine_hi) return B200NP_ERR_BAD_ARG;
     *out = nullptr;
-    for (int d = 0; d < 3; ++d)   // the fine box lies at least one coarse cell inside the domain (no contact with a face / the periodic seam)
-        if (fine_lo[d] < 1 || fine_hi[d] < fine_lo[d] || fine_hi[d] > geom0->n_cell[d] - 2) return B200NP_ERR_UNSUPPORTED;
+    int rcg = check_geom(geom0);
+    if (rcg) return rcg;
+    int span[3], cflo[3], cfhi[3], ncf = 0;
+    for (int d = 0; d < 3; ++d) {
+        if (fine_lo[d] < 0 || fine_hi[d] < fine_lo[d] || fine_hi[d] > geom0->n_cell[d] - 1) return B200NP_ERR_BAD_ARG;
+        const bool at_lo = fine_lo[d] == 0, at_hi = fine_hi[d] == geom0->n_cell[d] - 1;
+        span[d] = 0; cflo[d] = !at_lo; cfhi[d] = !at_hi;
+        if (geom0->bc_lo[d] == B200NP_BC_PERIODIC) {
+            if (at_lo != at_hi) return B200NP_ERR_UNSUPPORTED;   // touches the periodic seam without spanning the direction
+            span[d] = at_lo;
+        } else {   // a fine box on an inflow face would need the inflow profile on the fine level too
+            if (at_lo && geom0->bc_lo[d] == B200NP_BC_INFLOW) return B200NP_ERR_UNSUPPORTED;
+            if (at_hi && geom0->bc_hi[d] == B200NP_BC_INFLOW) return B200NP_ERR_UNSUPPORTED;
+        }
+        ncf += cflo[d] + cfhi[d];
+    }
+    if (ncf == 0) return B200NP_ERR_UNSUPPORTED;   // the "fine box" is the whole domain
     b200np_composite* C = new b200np_composite();
     int rc = create_common(&C->h0, geom0, opts, device, 0, 1, nullptr);
     if (rc) { delete C; return rc; }
@@ -1427,9 +1446,13 @@ int b200np_composite_create(b200np_composite_t** out, const b200np_geom* geom0, 
     o1.mg_max_coarsening_level = 0;   // ref ratio 2: the fine AMR level has ONE multigrid level
     for (int d = 0; d < 3; ++d) {
         C->box.lo[d] = fine_lo[d]; C->box.hi[d] = fine_hi[d];
+        C->box.cf_lo[d] = cflo[d]; C->box.cf_hi[d] = cfhi[d]; C->box.span[d] = span[d];
         C->nb[d] = fine_hi[d] - fine_lo[d] + 1;
+        C->box.nbn[d] = span[d] ? C->nb[d] : C->nb[d] + 1;
         g1.n_cell[d] = 2 * C->nb[d]; g1.dx[d] = 0.5 * geom0->dx[d];
-        g1.bc_lo[d] = g1.bc_hi[d] = B200NP_BC_DIRICHLET;
+        // interface: Dirichlet (not relaxed); otherwise the fine level inherits the domain's BC on that side
+        g1.bc_lo[d] = cflo[d] ? B200NP_BC_DIRICHLET : geom0->bc_lo[d];
+        g1.bc_hi[d] = cfhi[d] ? B200NP_BC_DIRICHLET : geom0->bc_hi[d];
     }
     rc = create_common(&C->h1, &g1, &o1, device, 0, 1, nullptr, true);
     if (rc) { b200np_destroy(C->h0); delete C; return rc; }
@@ -1440,10 +1463,10 @@ int b200np_composite_create(b200np_composite_t** out, const b200np_geom* geom0, 
         const Lev& gf = C->h1->lv[0].g;
         Lev v = g0;
         for (int d = 0; d < 3; ++d) {
-            v.n[d] = C->nb[d]; v.nn[d] = C->nb[d] + 1; v.per[d] = 0;
+            v.n[d] = C->nb[d]; v.nn[d] = C->box.nbn[d]; v.per[d] = C->box.span[d];
             v.rlo[d] = v.rhi[d] = 0; v.dlo[d] = v.dhi[d] = 0;
         }
-        v.k0 = 0; v.nzl = C->nb[2] + 1; v.ck0 = 0; v.cnzl = C->nb[2]; v.dist = 0; v.sigma = nullptr;
+        v.k0 = 0; v.nzl = C->box.nbn[2]; v.ck0 = 0; v.cnzl = C->nb[2]; v.dist = 0; v.sigma = nullptr;
         C->view = v;
         C->off_n = (long long)fine_lo[2] * g0.ps + (long long)fine_lo[1] * g0.px + fine_lo[0];
         CK(cudaMalloc(&C->rhsN, (size_t)gf.ps * gf.nzl * sizeof(double)));

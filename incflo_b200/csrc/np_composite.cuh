@@ -12,15 +12,27 @@
 
 namespace b200np_dev {
 
+// Per direction the box either has a coarse/fine interface on a side (cf_lo / cf_hi), or touches a wall /
+// outflow face of the domain there (the fine level inherits the BC), or spans a periodic direction.
 struct CBox {
-    int lo[3], hi[3];  // covered coarse cells, inclusive; box nodes are lo .. hi+1
+    int lo[3], hi[3];        // covered coarse cells, inclusive
+    int cf_lo[3], cf_hi[3];  // 1: coarse/fine interface on this side
+    int span[3];             // 1: the box spans this (periodic) direction
+    int nbn[3];              // coarse nodes of the box per direction: hi-lo+2, or n when it spans a periodic direction
 };
 
-// number of box faces the coarse node (i,j,k) lies on; -1 if outside the closed box
+// number of coarse/fine interface faces the coarse node (i,j,k) lies on; -1 if outside the closed box
 __device__ __forceinline__ int box_faces(const CBox& b, int i, int j, int k)
 {
-    if (i < b.lo[0] || i > b.hi[0] + 1 || j < b.lo[1] || j > b.hi[1] + 1 || k < b.lo[2] || k > b.hi[2] + 1) return -1;
-    return (i == b.lo[0]) + (i == b.hi[0] + 1) + (j == b.lo[1]) + (j == b.hi[1] + 1) + (k == b.lo[2]) + (k == b.hi[2] + 1);
+    const int id[3] = {i, j, k};
+    int f = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (b.span[d]) continue;
+        if (id[d] < b.lo[d] || id[d] > b.hi[d] + 1) return -1;
+        f += (b.cf_lo[d] && id[d] == b.lo[d]) + (b.cf_hi[d] && id[d] == b.hi[d] + 1);
+    }
+    return f;
 }
 
 // reflux: res0 (sums over uncovered coarse cells) += R / 2^f on the box nodes, R = restriction of the
@@ -37,7 +49,7 @@ __global__ void __launch_bounds__(256) k_comp_combine(const Lev L, const CBox b,
     const int f = box_faces(b, i, j, k);
     if (f >= 0) v += R[id] * (f == 0 ? 1.0 : f == 1 ? 0.5 : f == 2 ? 0.25 : 0.125);
     if (sums) v -= sums[0] / sums[1];
-    res0[id] = v;
+    res0[id] = node_masked(L, i, j, k) ? 0.0 : v;
 }
 
 // inf-norm partials over the coarse nodes that are not strictly inside the box
@@ -98,7 +110,7 @@ __global__ void __launch_bounds__(256) k_comp_inject(const Lev L0, const Lev L1,
     const int i = b.lo[0] + blockIdx.x * 64 + (threadIdx.x & 63);
     const int j = b.lo[1] + blockIdx.y * 4 + (threadIdx.x >> 6);
     const int k = b.lo[2] + blockIdx.z;
-    if (i > b.hi[0] + 1 || j > b.hi[1] + 1) return;
+    if (i >= b.lo[0] + b.nbn[0] || j >= b.lo[1] + b.nbn[1]) return;
     sol0[k * L0.ps + (long long)j * L0.px + i] =
         sol1[2 * (k - b.lo[2]) * L1.ps + (long long)(2 * (j - b.lo[1])) * L1.px + 2 * (i - b.lo[0])];
 }

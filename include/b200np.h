@@ -168,7 +168,11 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
  * Hydro::NodalProjector the vectors vel[], sigma[], Geom(0,finest_level) (:181-192); AMReX's MLMG then
  * solves the composite problem (MLMG::oneIter multi-level branch, MLNodeLaplacian::reflux / compRHS /
  * interpolationAmr; un-vendored, restated in oracle/composite.py).  Supported here: ONE fine box at
- * amr.ref_ratio = 2 (every deck) that lies at least one coarse cell inside the domain; anything else
+ * amr.ref_ratio = 2 (every deck).  Per direction and side the box either ends at least one coarse cell
+ * inside the domain (a coarse/fine interface), or spans a periodic direction completely (e.g. a refined
+ * slab around the rayleigh_taylor interface), or touches a wall (Neumann) / outflow (Dirichlet) face, whose
+ * BC the fine level then inherits.  A box on an inflow face, or touching the periodic seam without
+ * spanning the direction, several boxes, or a third level
  * returns B200NP_ERR_UNSUPPORTED.  fine_lo / fine_hi: the covered COARSE cells (inclusive).  Boxes of
  * level-1 arrays are in FINE index space (fine cells 2*fine_lo .. 2*fine_hi+1), as amrex::MultiFab
  * boxes of level 1 are.  Coarse cells under the fine box: their input velocity never counts; on return

@@ -44,17 +44,19 @@ from . import pyoracle as po
 PER, NEU, DIR, INF = 0, 1, 2, 3
 
 
-def _trilinear(c):
-    """(nb+1)^3 coarse nodal values -> (2nb+1)^3 fine nodal values (mlmg_lin_nd_interp_r2)"""
+def _trilinear(c, periodic=(False, False, False)):
+    """coarse nodal values of the box -> fine nodal values (mlmg_lin_nd_interp_r2).  Array axes are (z, y, x);
+    periodic[d] (d = x, y, z): the box spans the periodic direction d (n unique nodes -> 2n), else nb+1 -> 2nb+1"""
     f = c
     for ax in range(3):
+        per = periodic[2 - ax]
         sh = list(f.shape)
-        sh[ax] = 2 * sh[ax] - 1
+        sh[ax] = 2 * sh[ax] if per else 2 * sh[ax] - 1
         g = np.empty(sh)
         ev = [slice(None)] * 3; od = [slice(None)] * 3; lo = [slice(None)] * 3; hi = [slice(None)] * 3
         ev[ax] = slice(0, None, 2); od[ax] = slice(1, None, 2); lo[ax] = slice(0, -1); hi[ax] = slice(1, None)
         g[tuple(ev)] = f
-        g[tuple(od)] = 0.5 * (f[tuple(lo)] + f[tuple(hi)])
+        g[tuple(od)] = 0.5 * (f + np.roll(f, -1, axis=ax)) if per else 0.5 * (f[tuple(lo)] + f[tuple(hi)])
         f = g
     return f
 
@@ -93,8 +95,11 @@ def vcycle(mg, res0, nu1=2, nu2=2, nsweeps=4):
 
 class CompositeProjector:
     """Two-level composite nodal projection; coarse domain params0 (pyoracle.Params), fine box =
-    coarse cells [clo, chi] (inclusive) refined by 2.  The box must lie at least one coarse cell inside
-    the domain in every direction (no contact with a domain face or the periodic seam)."""
+    coarse cells [clo, chi] (inclusive) refined by 2.  Per direction the box either
+      * lies at least one coarse cell inside the domain on that side (a coarse/fine interface), or
+      * spans a periodic direction completely (the fine level is periodic there), or
+      * touches a Neumann (wall) or Dirichlet (outflow) domain face (the fine level inherits that BC).
+    Touching an inflow face or the periodic seam without spanning the direction is not supported."""
 
     def __init__(self, params0, clo, chi, smoother_kw=None):
         self.p0 = params0
@@ -102,25 +107,54 @@ class CompositeProjector:
         self.dx0 = tuple(params0.dx)
         self.bclo = tuple(params0.bclo); self.bchi = tuple(params0.bchi)
         self.clo = tuple(int(x) for x in clo); self.chi = tuple(int(x) for x in chi)
+        n0 = self.n0
+        self.span = [False] * 3; self.cf_lo = [True] * 3; self.cf_hi = [True] * 3
+        bD_lo, bD_hi, bN_lo, bN_hi = [DIR] * 3, [DIR] * 3, [NEU] * 3, [NEU] * 3
         for d in range(3):
-            assert 1 <= self.clo[d] <= self.chi[d] <= self.n0[d] - 2, "fine box must be strictly inside the domain"
+            assert 0 <= self.clo[d] <= self.chi[d] <= n0[d] - 1
+            at_lo, at_hi = self.clo[d] == 0, self.chi[d] == n0[d] - 1
+            if self.bclo[d] == PER:
+                assert at_lo == at_hi, "a fine box may span a periodic direction but not touch its seam"
+                if at_lo:
+                    self.span[d] = True; self.cf_lo[d] = self.cf_hi[d] = False
+                    bD_lo[d] = bD_hi[d] = bN_lo[d] = bN_hi[d] = PER
+            else:
+                if at_lo:
+                    assert self.bclo[d] in (NEU, DIR), "fine box on an inflow face is not supported"
+                    self.cf_lo[d] = False; bD_lo[d] = bN_lo[d] = self.bclo[d]
+                if at_hi:
+                    assert self.bchi[d] in (NEU, DIR), "fine box on an inflow face is not supported"
+                    self.cf_hi[d] = False; bD_hi[d] = bN_hi[d] = self.bchi[d]
+        assert any(self.cf_lo) or any(self.cf_hi), "the fine box covers the whole domain"
         self.nb = tuple(self.chi[d] - self.clo[d] + 1 for d in range(3))
         self.nf = tuple(2 * x for x in self.nb)
         self.dx1 = tuple(0.5 * x for x in self.dx0)
         kw = dict(smoother_kw or {})
-        self.pD = po.make_params(self.nf, self.dx1, (DIR,) * 3, (DIR,) * 3, **kw)
-        self.pN = po.make_params(self.nf, self.dx1, (NEU,) * 3, (NEU,) * 3, **kw)
+        self.pD = po.make_params(self.nf, self.dx1, tuple(bD_lo), tuple(bD_hi), **kw)   # interface nodes are not relaxed
+        self.pN = po.make_params(self.nf, self.dx1, tuple(bN_lo), tuple(bN_hi), **kw)   # reflecting interface: one-sided sums
         self.singular = all(b != DIR for b in self.bclo + self.bchi)
         self.nu1 = self.nu2 = 2
         self.nsweeps = 4
         self.maxiter = 100
-        # slices of the box in the coarse arrays (cells, nodes of the unique-node layout) and its interior nodes
+        # slices (z, y, x) of the box in the coarse arrays: cells, nodes (unique-node layout), strictly covered nodes
         c, h = self.clo, self.chi
-        self.cbox = (slice(c[2], h[2] + 1), slice(c[1], h[1] + 1), slice(c[0], h[0] + 1))
-        self.nbox = (slice(c[2], h[2] + 2), slice(c[1], h[1] + 2), slice(c[0], h[0] + 2))
-        self.nint = (slice(c[2] + 1, h[2] + 1), slice(c[1] + 1, h[1] + 1), slice(c[0] + 1, h[0] + 1))
-        fc = _face_count(self.nb)
-        self.scale = np.where(fc > 0, 0.5 ** fc, 1.0)     # 1 / 2^f on the box boundary, 1 inside
+        self.cbox = tuple(slice(c[d], h[d] + 1) for d in (2, 1, 0))
+        self.nbox = tuple(slice(0, n0[d]) if self.span[d] else slice(c[d], h[d] + 2) for d in (2, 1, 0))
+        self.nint = tuple(slice(c[d] + (1 if self.cf_lo[d] else 0), (h[d] + 1) if self.cf_hi[d] else (n0[d] if self.span[d] else h[d] + 2))
+                          for d in (2, 1, 0))
+        # number of coarse/fine interface faces each box node lies on -> 1 / 2^f; Dirichlet mask of the fine level
+        shape = tuple(n0[d] if self.span[d] else self.nb[d] + 1 for d in (2, 1, 0))
+        fc = np.zeros(shape, dtype=np.int64)
+        fshape = tuple(self.nf[d] if self.span[d] else self.nf[d] + 1 for d in (2, 1, 0))
+        self.fmask = np.zeros(fshape, dtype=bool)      # fine nodes that are not unknowns of the fine level
+        for ax, d in enumerate((2, 1, 0)):
+            lo = [slice(None)] * 3; hi = [slice(None)] * 3
+            lo[ax] = 0; hi[ax] = -1
+            if self.cf_lo[d]: fc[tuple(lo)] += 1
+            if self.cf_hi[d]: fc[tuple(hi)] += 1
+            if bD_lo[d] == DIR: self.fmask[tuple(lo)] = True
+            if bD_hi[d] == DIR: self.fmask[tuple(hi)] = True
+        self.scale = 0.5 ** fc
 
     # ---- composite pieces --------------------------------------------------------------------
     def _add_fine_part(self, r0, RN):
@@ -173,7 +207,7 @@ class CompositeProjector:
             self.offset = float((w * rhs0).sum() / w.sum())
         rhs0 -= self.offset
         rhs1 = self.rhs1.copy()
-        rhs1[1:-1, 1:-1, 1:-1] -= self.offset
+        rhs1[~self.fmask] -= self.offset
         sol0 = np.zeros_like(rhs0)
         sol1 = np.zeros_like(rhs1)
         res1 = self.mgD.residual(0, sol1, rhs1)
@@ -199,7 +233,7 @@ class CompositeProjector:
                 cor0 = vcycle(self.mg0, np.ascontiguousarray(res0), self.nu1, self.nu2, self.nsweeps)
                 sol0 += cor0
                 # interpolate the coarse correction to every fine node, then post-smooth its residual
-                cor1 = np.ascontiguousarray(_trilinear(cor0[self.nbox]))
+                cor1 = np.ascontiguousarray(_trilinear(cor0[self.nbox], self.span))
                 sol1 += cor1
                 res1 = self.mgD.residual(0, sol1, rhs1)
                 cor1 = np.zeros_like(sol1)

@@ -28,8 +28,15 @@ from make_golden import PER, NEU, DIR, fe_operator, gradT, grad_cells, node_coun
 OUT = os.path.join(HERE, "composite")
 
 
-def interp1d(nb):
-    """(2nb+1) x (nb+1) linear interpolation"""
+def interp1d(nb, periodic=False):
+    """linear interpolation of the box's coarse nodes onto its fine nodes in one direction:
+    (2nb+1) x (nb+1), or 2nb x nb with wrap when the box spans a periodic direction"""
+    if periodic:
+        m = sp.lil_matrix((2 * nb, nb))
+        for i in range(nb):
+            m[2 * i, i] = 1.0
+            m[2 * i + 1, i] += 0.5; m[2 * i + 1, (i + 1) % nb] += 0.5
+        return m.tocsr()
     m = sp.lil_matrix((2 * nb + 1, nb + 1))
     for i in range(nb + 1):
         m[2 * i, i] = 1.0
@@ -47,6 +54,14 @@ def solve(n0, dx0, bclo, bchi, clo, chi, vel0, ng0, vel1, ng1, sigma0, sigma1):
     nf = [2 * x for x in nb]
     dx1 = [0.5 * x for x in dx0]
     H3, h3 = float(np.prod(dx0)), float(np.prod(dx1))
+    # per direction: the box spans a periodic direction / touches a wall / has a coarse-fine interface
+    span = [bclo[d] == PER and clo[d] == 0 and chi[d] == n0[d] - 1 for d in range(3)]
+    cf_lo = [not span[d] and clo[d] > 0 for d in range(3)]
+    cf_hi = [not span[d] and chi[d] < n0[d] - 1 for d in range(3)]
+    for d in range(3):
+        assert span[d] or bclo[d] != PER or (clo[d] > 0 and chi[d] < n0[d] - 1)
+        assert bclo[d] in (PER, NEU) and bchi[d] in (PER, NEU), "golden cases: periodic or wall faces only"
+    bc1 = tuple(PER if span[d] else NEU for d in range(3))     # natural (one-sided) sums on every non-periodic face
     cbox = (slice(clo[2], chi[2] + 1), slice(clo[1], chi[1] + 1), slice(clo[0], chi[0] + 1))
     s0 = sigma0.copy()
     s0z = s0.copy(); s0z[cbox] = 0.0
@@ -57,31 +72,38 @@ def solve(n0, dx0, bclo, bchi, clo, chi, vel0, ng0, vel1, ng1, sigma0, sigma1):
     K0, nn0 = fe_operator(n0, dx0, bclo, bchi, s0z)
     K0 = K0 * H3
     f0 = -H3 * gradT(u0z, n0, dx0, bclo).ravel()
-    nat = (NEU, NEU, NEU)
-    K1, nn1 = fe_operator(nf, dx1, nat, nat, sigma1)
+    K1, nn1 = fe_operator(nf, dx1, bc1, bc1, sigma1)
     K1 = K1 * h3
-    f1 = -h3 * gradT(u1, nf, dx1, nat).ravel()
+    f1 = -h3 * gradT(u1, nf, dx1, bc1).ravel()
     N0, N1 = K0.shape[0], K1.shape[0]
-    # fine node classification
-    kk, jj, ii = np.meshgrid(np.arange(nf[2] + 1), np.arange(nf[1] + 1), np.arange(nf[0] + 1), indexing="ij")
-    bnd = ((ii == 0) | (ii == nf[0]) | (jj == 0) | (jj == nf[1]) | (kk == 0) | (kk == nf[2])).ravel()
+    # fine nodes on a coarse/fine interface are hanging nodes
+    kk, jj, ii = np.meshgrid(np.arange(nn1[2]), np.arange(nn1[1]), np.arange(nn1[0]), indexing="ij")
+    idx = (ii, jj, kk)
+    bnd = np.zeros(kk.shape, dtype=bool)
+    for d in range(3):
+        if cf_lo[d]: bnd |= idx[d] == 0
+        if cf_hi[d]: bnd |= idx[d] == nf[d]
+    bnd = bnd.ravel()
     int_ids = np.flatnonzero(~bnd)
     Ni = int_ids.size
     # trilinear interpolation box coarse nodes -> fine nodes, and box coarse nodes -> global coarse ids
-    Bbox = sp.kron(interp1d(nb[2]), sp.kron(interp1d(nb[1]), interp1d(nb[0]))).tocsr()
-    ck, cj, ci = np.meshgrid(np.arange(clo[2], chi[2] + 2), np.arange(clo[1], chi[1] + 2), np.arange(clo[0], chi[0] + 2), indexing="ij")
-    gid = ((ck * nn0[1] + cj) * nn0[0] + ci).ravel()     # box strictly inside: no periodic wrap
+    I1 = [interp1d(nb[d], span[d]) for d in range(3)]
+    Bbox = sp.kron(I1[2], sp.kron(I1[1], I1[0])).tocsr()
+    rng = [np.arange(n0[d]) if span[d] else np.arange(clo[d], chi[d] + 2) for d in range(3)]
+    ck, cj, ci = np.meshgrid(rng[2], rng[1], rng[0], indexing="ij")
+    gid = ((ck * nn0[1] + cj) * nn0[0] + ci).ravel()
     S = sp.csr_matrix((np.ones(gid.size), (np.arange(gid.size), gid)), shape=(gid.size, N0))
     Mb = sp.diags(bnd.astype(float))
     E = sp.csr_matrix((np.ones(Ni), (int_ids, np.arange(Ni))), shape=(N1, Ni))
     T = sp.hstack([Mb @ Bbox @ S, E]).tocsr()            # phi1_all = T [phi0; phi1_int]
     A = sp.bmat([[K0, None], [None, sp.csr_matrix((Ni, Ni))]]).tocsr() + T.T @ K1 @ T
     b = np.concatenate([f0, np.zeros(Ni)]) + T.T @ f1
-    # active unknowns: coarse nodes not strictly inside the box, fine interior nodes
+    # active unknowns: coarse nodes not strictly covered, fine nodes that are not hanging
     cin = np.zeros(nn0[::-1], dtype=bool)
-    cin[clo[2] + 1:chi[2] + 1, clo[1] + 1:chi[1] + 1, clo[0] + 1:chi[0] + 1] = True
+    sl = tuple(slice(clo[d] + (1 if cf_lo[d] else 0), (chi[d] + 1) if cf_hi[d] else (n0[d] if span[d] else chi[d] + 2)) for d in (2, 1, 0))
+    cin[sl] = True
     act = np.concatenate([~cin.ravel(), np.ones(Ni, dtype=bool)])
-    assert abs(A[~act].sum()) == 0.0 and np.abs(b[~act]).max() == 0.0
+    assert abs(A[~act]).sum() == 0.0 and np.abs(b[~act]).max() == 0.0
     Aa = A[act][:, act].tocsc()
     ba = b[act]
     assert all(x != DIR for x in tuple(bclo) + tuple(bchi)), "only singular (no Dirichlet face) cases here"
@@ -91,9 +113,11 @@ def solve(n0, dx0, bclo, bchi, clo, chi, vel0, ng0, vel1, ng1, sigma0, sigma1):
     x = spl.spsolve(Ksys, np.concatenate([ba, [0.0]]))[:-1]
     full = np.zeros(N0 + Ni); full[act] = x
     phi0_u = full[:N0].reshape(nn0[::-1])
-    phi1 = (T @ full).reshape(nf[2] + 1, nf[1] + 1, nf[0] + 1)
-    phi0_u[clo[2]:chi[2] + 2, clo[1]:chi[1] + 2, clo[0]:chi[0] + 2] = phi1[::2, ::2, ::2]   # injection (interface: identical)
+    phi1_u = (T @ full).reshape(nn1[::-1])
+    nsl = tuple(slice(0, n0[d]) if span[d] else slice(clo[d], chi[d] + 2) for d in (2, 1, 0))
+    phi0_u[nsl] = phi1_u[::2, ::2, ::2]                  # injection (interface nodes: identical)
     phi0 = to_full(phi0_u, n0, bclo)
+    phi1 = to_full(phi1_u, nf, bc1)
     g1 = grad_cells(phi1, dx1)
     g0 = grad_cells(phi0, dx0)
     s0[cbox] = avg_down(sigma1)
@@ -125,6 +149,25 @@ def cases():
     out.append(dict(name="walls_box_offcentre_var", n0=n0, dx0=dx0, bclo=bclo, bchi=bchi, clo=clo, chi=chi, ng0=1, ng1=1,
                     vel0=smooth_random_velocity(n0, 1, bclo, bchi, 61), vel1=smooth_random_velocity(nf, 1, (NEU,) * 3, (NEU,) * 3, 62),
                     sigma0=rng.uniform(0.5, 2.0, size=n0[::-1]), sigma1=rng.uniform(0.5, 2.0, size=nf[::-1]), var=True))
+    # 3. rayleigh_taylor-like refinement of the interface region: the fine level spans the periodic x, y
+    #    directions completely (a refined slab), walls in z, variable density
+    n0, dx0 = (16, 16, 16), (1 / 16,) * 3
+    bclo = bchi = (PER, PER, NEU)
+    clo, chi = (0, 0, 5), (15, 15, 10)
+    nf = tuple(2 * (chi[d] - clo[d] + 1) for d in range(3))
+    bc1 = (PER, PER, NEU)
+    rng = np.random.default_rng(8)
+    out.append(dict(name="rt_slab_periodic_span_var", n0=n0, dx0=dx0, bclo=bclo, bchi=bchi, clo=clo, chi=chi, ng0=1, ng1=1,
+                    vel0=smooth_random_velocity(n0, 1, bclo, bchi, 71), vel1=smooth_random_velocity(nf, 1, bc1, bc1, 72),
+                    sigma0=rng.uniform(0.5, 2.0, size=n0[::-1]), sigma1=rng.uniform(0.5, 2.0, size=nf[::-1]), var=True))
+    # 4. closed box, fine box in a corner: touches the x-lo and z-hi walls, interface on the other four faces
+    n0, dx0 = (12, 12, 12), (1 / 12,) * 3
+    bclo = bchi = (NEU, NEU, NEU)
+    clo, chi = (0, 3, 6), (5, 8, 11)
+    nf = tuple(2 * (chi[d] - clo[d] + 1) for d in range(3))
+    out.append(dict(name="closed_box_corner_walls_const", n0=n0, dx0=dx0, bclo=bclo, bchi=bchi, clo=clo, chi=chi, ng0=2, ng1=1,
+                    vel0=smooth_random_velocity(n0, 2, bclo, bchi, 81), vel1=smooth_random_velocity(nf, 1, bclo, bchi, 82),
+                    sigma0=np.full(n0[::-1], 0.8), sigma1=np.full(nf[::-1], 0.8), var=False))
     return out
 
 
