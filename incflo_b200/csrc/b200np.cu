@@ -158,6 +158,8 @@ struct b200np {
     int smoother_version = 3, interp_version = 2, resid_version = 3;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
     // B200NP_PROFILE=1: per-phase device times (CUDA events between phases, graph capture off); printed per call
     int profile = 0;
+    int interp_tz = 4;        // B200NP_INTERP_TZ = 8 | 4: fine planes per interpolation tile (4: 35 KB of shared memory,
+                              // 5-6 CTAs per SM; measured 7-12 % faster than 8)
     int dbg_halo = 0;         // B200NP_DBG_HALO: see smooth_sweeps (timing experiments, results are wrong)
     bool no_bottom = false;   // fine AMR level of a composite solve: one MG level, never a bottom solve
     std::vector<cudaEvent_t> prof_ev;
@@ -320,7 +322,7 @@ void build_levels(b200np* h)
             L.tz = std::max(mn, std::min(h->TZ, (nzp + nch - 1) / nch));
         }
         L.gsm = dim3((g.nn[0] + NP_TX - 1) / NP_TX, (g.nn[1] + NP_TY - 1) / NP_TY, (g.nzl + L.tz - 1) / L.tz);
-        L.git = dim3((g.nn[0] + IT_X - 1) / IT_X, (g.nn[1] + IT_Y - 1) / IT_Y, (g.nzl + IT_Z - 1) / IT_Z);
+        L.git = dim3((g.nn[0] + IT_X - 1) / IT_X, (g.nn[1] + IT_Y - 1) / IT_Y, (g.nzl + h->interp_tz - 1) / h->interp_tz);
         L.nblk_n = (long long)L.gn.x * L.gn.y * L.gn.z;
         L.nzl_alloc = L.dist ? n[2] / P + 1 : g.nzl;   // the last slab of a non-periodic domain owns one more plane
         L.sigma_alloc = dev_alloc(h, (size_t)g.cps * (g.cnzl + 2));
@@ -672,8 +674,13 @@ void interp_add(b200np* h, int l)
         if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
         else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
     } else {
-        if (h->var_sigma) launch_pdl(h, k_interp_tile<true>, F.git, dim3(256), (IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
-        else              launch_pdl(h, k_interp_tile<false>, F.git, dim3(256), IT_V_DOUBLES * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
+        if (h->interp_tz == 4) {
+            if (h->var_sigma) launch_pdl(h, k_interp_tile<true, 4>, F.git, dim3(256), (it_v_doubles(4) + it_s_doubles(4)) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
+            else              launch_pdl(h, k_interp_tile<false, 4>, F.git, dim3(256), it_v_doubles(4) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
+        } else {
+            if (h->var_sigma) launch_pdl(h, k_interp_tile<true>, F.git, dim3(256), (IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
+            else              launch_pdl(h, k_interp_tile<false>, F.git, dim3(256), IT_V_DOUBLES * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
+        }
     }
 }
 
@@ -954,6 +961,7 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (const char* e = getenv("B200NP_FUSE_HALO")) h->fuse_halo = atoi(e);
         if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) h->dist_min_planes = std::max(8, atoi(e));
         if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
+        if (const char* e = getenv("B200NP_INTERP_TZ")) h->interp_tz = atoi(e) == 8 ? 8 : 4;
         if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
         CK(cudaFuncSetAttribute(k_residual_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_residual_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
@@ -965,6 +973,8 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         CK(cudaFuncSetAttribute(k_residual_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IT_V_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_interp_tile<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((it_v_doubles(4) + it_s_doubles(4)) * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_interp_tile<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(it_v_doubles(4) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso_dist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso_dist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso_res_dist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_RES_DOUBLES * sizeof(double))));
@@ -1123,8 +1133,12 @@ int comp_core(b200np_composite* C, Fab vel0, Fab vel1, Fab velo0, Fab velo1, int
         LAUNCH(h0, k_axpy, L0.gn, 256, L0.g, L0.sol, (const double*)L0.cor, 1.0);
         // interpolationAmr: cor1 = trilinear interpolant of cor0 on EVERY fine node; sol1 += cor1
         CK(cudaMemsetAsync(L1.cor, 0, bytes1, h0->stream));
-        launch_pdl(h0, k_interp_tile<false>, L1.git, dim3(256), IT_V_DOUBLES * sizeof(double), gN, C->view, L1.cor,
-                   (const double*)(L0.cor + C->off_n));
+        if (h1->interp_tz == 4)
+            launch_pdl(h0, k_interp_tile<false, 4>, L1.git, dim3(256), it_v_doubles(4) * sizeof(double), gN, C->view, L1.cor,
+                       (const double*)(L0.cor + C->off_n));
+        else
+            launch_pdl(h0, k_interp_tile<false>, L1.git, dim3(256), IT_V_DOUBLES * sizeof(double), gN, C->view, L1.cor,
+                       (const double*)(L0.cor + C->off_n));
         LAUNCH(h0, k_axpy, L1.gn, 256, gD, L1.sol, (const double*)L1.cor, 1.0);
         residual(h1, L1, L1.sol, L1.rhs, L1.res, nullptr);
         CK(cudaMemsetAsync(L1.cor, 0, bytes1, h0->stream));
