@@ -65,7 +65,7 @@ class Stats(C.Structure):
 
 
 # every symbol include/b200np.h declares
-EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np_nccl_unique_id", "b200np_slab_range",
+EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np_nccl_unique_id", "b200np_slab_range", "b200np_dist_plan",
            "b200np_destroy", "b200np_set_stream", "b200np_project",
            "b200np_apply_nodal_projection", "b200np_strerror", "b200np_version", "b200np_nlevels",
            "b200np_level_dims", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
@@ -90,6 +90,7 @@ def lib():
     L.b200np_create_dist.argtypes = [C.POINTER(vp), C.POINTER(Geom), C.POINTER(Opts), C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.b200np_nccl_unique_id.argtypes = [C.c_void_p]
     L.b200np_slab_range.argtypes = [C.POINTER(Geom), C.c_int, C.c_int] + [C.POINTER(C.c_int)] * 4
+    L.b200np_dist_plan.argtypes = [C.POINTER(Geom), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.b200np_destroy.argtypes = [vp]
     L.b200np_destroy.restype = None
     L.b200np_set_stream.argtypes = [vp, C.c_void_p]

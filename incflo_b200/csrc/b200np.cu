@@ -266,6 +266,26 @@ void set_slab(Lev& g, int rank, int P, bool periodic_z)
     g.dist = 1;
 }
 
+// ---- hierarchy plan (pure host logic; also exported as b200np_dist_plan for the CPU tests) ----
+// level 0 is always distributed; a coarser level stays distributed while every rank keeps an even
+// number (>= min_planes) of cell planes, or while it is too big to replicate (> 128^3 nodes)
+// (a replicated level costs every rank a sweep over ALL its nodes, so a big level with thin slabs --
+// 512^3 on 8 GPUs: level 1 = 256^3 with 32 planes per rank -- stays distributed down to 8 planes)
+bool level_stays_dist(const int n[3], int P, int lev, int min_planes)
+{
+    if (n[2] % P != 0 || (n[2] / P) % 2 != 0) return false;
+    if (lev == 0) return true;
+    const double gnodes = (double)(n[0] + 1) * (n[1] + 1) * (n[2] + 1);
+    return n[2] / P >= min_planes || (gnodes > 2.2e6 && n[2] / P >= 8);
+}
+// coarsen by 2 while every direction stays even and >= 2 cells wide (A.8)
+bool can_coarsen(const int n[3], int lev_next, int max_coarsening_level)
+{
+    if (lev_next > max_coarsening_level || lev_next >= 30) return false;
+    for (int d = 0; d < 3; ++d) if (n[d] % 2 != 0 || n[d] / 2 < 2) return false;
+    return true;
+}
+
 void build_levels(b200np* h)
 {
     const b200np_geom& G = h->geom;
@@ -284,13 +304,7 @@ void build_levels(b200np* h)
         Lev& g = L.g;
         fill_lev(G, n, dx, g);
         L.iso = (dx[0] == dx[1] && dx[1] == dx[2]);
-        // level 0 is always distributed; a coarser level stays distributed while every rank keeps an even
-        // number (>= dist_min_planes) of cell planes, or while it is too big to replicate (> 128^3 nodes)
-        // (a replicated level costs every rank a sweep over ALL its nodes, so a big level with thin slabs --
-        // 512^3 on 8 GPUs: level 1 = 256^3 with 32 planes per rank -- stays distributed down to 8 planes)
-        const double gnodes = (double)(n[0] + 1) * (n[1] + 1) * (n[2] + 1);
-        const bool keep = n[2] / P >= h->dist_min_planes || (gnodes > 2.2e6 && n[2] / P >= 8);
-        if (still_dist && n[2] % P == 0 && (n[2] / P) % 2 == 0 && (lev == 0 || keep)) {
+        if (still_dist && level_stays_dist(n, P, lev, h->dist_min_planes)) {
             set_slab(g, h->rank, P, zper(h));
             L.dist = true;
             h->nlev_dist = lev + 1;
@@ -331,10 +345,7 @@ void build_levels(b200np* h)
         if (lev == 0) { L.sol = alloc_nodal(h, L); L.rhs = alloc_nodal(h, L); }
         h->lv.push_back(L);
         ++lev;
-        // coarsen by 2 while every direction stays even and >= 2 cells wide (A.8)
-        bool ok = lev <= h->opts.mg_max_coarsening_level && lev < 30;
-        for (int d = 0; d < 3; ++d) if (n[d] % 2 != 0 || n[d] / 2 < 2) ok = false;
-        if (!ok) break;
+        if (!can_coarsen(n, lev, h->opts.mg_max_coarsening_level)) break;
         for (int d = 0; d < 3; ++d) { n[d] /= 2; dx[d] *= 2; }
     }
     if (P > 1 && h->nlev_dist >= (int)h->lv.size()) throw int(B200NP_ERR_BAD_ARG);  // needs a replicated coarse level
@@ -1257,6 +1268,34 @@ int b200np_slab_range(const b200np_geom* geom, int rank, int nranks, int* cell_l
     if (cell_hi) *cell_hi = (rank + 1) * m - 1;
     if (node_lo) *node_lo = rank * m;
     if (node_hi) *node_hi = (rank + 1) * m - 1 + ((!per && rank == nranks - 1) ? 1 : 0);  // owned (unique) node planes
+    return B200NP_OK;
+}
+
+int b200np_dist_plan(const b200np_geom* geom, int nranks, int min_planes, int max_coarsening_level, int* nlev_dist, int* nlev)
+{
+    if (!geom || nranks < 1) return B200NP_ERR_BAD_ARG;
+    int rc = check_geom(geom);
+    if (rc) return rc;
+    if (min_planes <= 0) {
+        min_planes = 64;
+        if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) min_planes = std::max(8, atoi(e));
+    }
+    int n[3] = {geom->n_cell[0], geom->n_cell[1], geom->n_cell[2]};
+    int lev = 0, nd = 0;
+    bool still = nranks > 1;
+    for (;;) {
+        if (still && level_stays_dist(n, nranks, lev, min_planes)) nd = lev + 1;
+        else {
+            if (still && lev == 0) return B200NP_ERR_BAD_ARG;   // level 0 must be distributable
+            still = false;
+        }
+        ++lev;
+        if (!can_coarsen(n, lev, max_coarsening_level)) break;
+        for (int d = 0; d < 3; ++d) n[d] /= 2;
+    }
+    if (nranks > 1 && nd >= lev) return B200NP_ERR_BAD_ARG;   // needs a replicated coarse level
+    if (nlev_dist) *nlev_dist = nd;
+    if (nlev) *nlev = lev;
     return B200NP_OK;
 }
 

@@ -29,14 +29,21 @@ def halo_plan(rank, nranks, periodic_z):
     return sends, recvs
 
 
-def distributed_levels(n_cell_z, nranks, max_levels=30):
-    """number of multigrid levels that stay slab-distributed: every rank keeps an even number
-    (>= 8) of cell planes; coarser levels are replicated on every rank (agglomeration)."""
-    n, lev = n_cell_z, 0
-    while lev < max_levels and n % nranks == 0 and (n // nranks) % 2 == 0 and n // nranks >= 8:
-        lev += 1
-        n //= 2
-    return lev
+def distributed_levels(n_cell, nranks, min_planes=0, bclo=(0, 0, 0), max_coarsening_level=100):
+    """(levels that stay slab-distributed, levels in total) for the domain n_cell = (nx, ny, nz) on nranks
+    ranks (b200np_dist_plan; needs no GPU).  Level 0 is always distributed; a coarser level stays distributed
+    while every rank keeps >= min_planes (default 64) cell planes or while it is too big to replicate
+    (> 128^3 nodes, down to 8 planes per rank); the rest is replicated on every rank (agglomeration)."""
+    import ctypes as C
+    from . import _lib
+    g = _lib.Geom()
+    for d in range(3):
+        g.n_cell[d] = int(n_cell[d]); g.dx[d] = 1.0; g.bc_lo[d] = int(bclo[d]); g.bc_hi[d] = int(bclo[d])
+    nd, nl = C.c_int(), C.c_int()
+    rc = _lib.lib().b200np_dist_plan(C.byref(g), int(nranks), int(min_planes), int(max_coarsening_level), C.byref(nd), C.byref(nl))
+    if rc != 0:
+        raise npj.ProjectionError(rc)
+    return nd.value, nl.value
 
 
 def cut(global_arr, zlo, zhi, ng, node=False):

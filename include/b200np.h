@@ -118,7 +118,12 @@ int b200np_create_dist(b200np_t** out, const b200np_geom* geom, const b200np_opt
  * b200np_slab_range: the z range of cells [cell_lo, cell_hi] and of uniquely owned node planes
  *   [node_lo, node_hi] of `rank` (the node plane shared with the upper neighbour belongs to the
  *   upper neighbour; the last rank of a non-periodic domain also owns the top boundary plane).
- *   Needs no GPU. */
+ *   Needs no GPU.
+ * b200np_dist_plan: how many multigrid levels of `geom` stay slab-distributed over nranks ranks (the
+ *   coarser ones are agglomerated by replication) and how many levels there are; min_planes <= 0 takes the
+ *   default (64 cell planes per rank, B200NP_DIST_MIN_PLANES).  Replaces the agglomeration / consolidation
+ *   decisions of MLLinOp::defineGrids.  Needs no GPU. */
+int b200np_dist_plan(const b200np_geom* geom, int nranks, int min_planes, int max_coarsening_level, int* nlev_dist, int* nlev);
 int b200np_nccl_unique_id(void* out128);
 int b200np_slab_range(const b200np_geom* geom, int rank, int nranks, int* cell_lo, int* cell_hi, int* node_lo,
                       int* node_hi);

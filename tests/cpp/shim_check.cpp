@@ -3,6 +3,9 @@
 //   shim_check host                         : host-logic checks, no GPU needed (BC map, options, abort behaviour)
 //   shim_check project in.bin out.bin nx ny nz dx bclo(3) bchi(3) var
 //       in.bin : vel (3,(nz+2),(ny+2),(nx+2)) [+ sigma (nz,ny,nx) if var]; out.bin: vel, phi, gphi, iters
+//   shim_check composite in.bin out.bin nx ny nz dx bclo(3) bchi(3) flo(3) fhi(3)
+//       two AMR levels, constant sigma 0.37, fine box = coarse cells [flo, fhi] refined by 2, 1 ghost cell per level;
+//       in.bin: vel0, vel1; out.bin: vel0, vel1, phi0, phi1, gphi0, gphi1, iters
 #include "../../include/B200NodalProjector.H"
 
 #include <cstring>
@@ -83,9 +86,58 @@ static int host_checks()
     return 0;
 }
 
+// the call sequence of incflo_apply_nodal_projection.cpp:181-219 with finest_level = 1
+static int composite(int argc, char** argv)
+{
+    if (argc < 20) { std::printf("usage: see header comment\n"); return 2; }
+    abort_handler() = throwing_abort;
+    const int n[3] = {std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6])};
+    const double dx = std::atof(argv[7]);
+    std::array<LinOpBCType, 3> lo, hi;
+    Geometry g0, g1;
+    int flo[3], fhi[3], vlo[3], vhi[3], nf[3];
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = (LinOpBCType)std::atoi(argv[8 + d]); hi[d] = (LinOpBCType)std::atoi(argv[11 + d]);
+        flo[d] = std::atoi(argv[14 + d]); fhi[d] = std::atoi(argv[17 + d]);
+        g0.n_cell[d] = n[d]; g0.dx[d] = dx; g0.is_periodic[d] = lo[d] == LinOpBCType::Periodic;
+        g1.n_cell[d] = 2 * n[d]; g1.dx[d] = 0.5 * dx; g1.is_periodic[d] = g0.is_periodic[d];
+        vlo[d] = 2 * flo[d]; vhi[d] = 2 * fhi[d] + 1; nf[d] = vhi[d] - vlo[d] + 1;
+    }
+    const size_t nv0 = (size_t)3 * (n[0] + 2) * (n[1] + 2) * (n[2] + 2), nv1 = (size_t)3 * (nf[0] + 2) * (nf[1] + 2) * (nf[2] + 2);
+    std::vector<double> vel0(nv0), vel1(nv1);
+    std::ifstream in(argv[2], std::ios::binary);
+    in.read((char*)vel0.data(), nv0 * 8);
+    in.read((char*)vel1.data(), nv1 * 8);
+    if (!in) { std::printf("short input\n"); return 3; }
+    try {
+        LPInfo info;
+        info.setMaxCoarseningLevel(100);
+        std::vector<Fab> velv{Fab::make(vel0.data(), n, 1, 3), Fab::make_box(vel1.data(), vlo, vhi, 1, 3)};
+        auto nodal_projector = std::make_unique<NodalProjector>(velv, 0.37, std::vector<Geometry>{g0, g1}, info);
+        nodal_projector->setDomainBC(lo, hi);
+        nodal_projector->project(1e-11, 1e-14);
+        auto phi = nodal_projector->getPhi();
+        auto gradphi = nodal_projector->getGradPhi();
+        if (phi.size() != 2 || gradphi.size() != 2) { std::printf("expected two levels\n"); return 4; }
+        std::ofstream out(argv[3], std::ios::binary);
+        out.write((const char*)vel0.data(), nv0 * 8);
+        out.write((const char*)vel1.data(), nv1 * 8);
+        for (int l = 0; l < 2; ++l) out.write((const char*)phi[l]->p, phi[l]->size() * 8);
+        for (int l = 0; l < 2; ++l) out.write((const char*)gradphi[l]->p, gradphi[l]->size() * 8);
+        double it = nodal_projector->stats().iters;
+        out.write((const char*)&it, 8);
+        std::printf("shim composite OK: %d iterations\n", nodal_projector->stats().iters);
+    } catch (const std::runtime_error& e) {
+        std::printf("amrex::Abort::%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
     if (argc >= 2 && !std::strcmp(argv[1], "host")) return host_checks();
+    if (argc >= 2 && !std::strcmp(argv[1], "composite")) return composite(argc, argv);
     if (argc < 15 || std::strcmp(argv[1], "project")) { std::printf("usage: see header comment\n"); return 2; }
     abort_handler() = throwing_abort;
     const int n[3] = {std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6])};

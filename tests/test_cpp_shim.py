@@ -64,3 +64,52 @@ def test_shim_project_matches_oracle(shim_exe, tmp_path, config, N, oracle):
     assert rel_l2(ggrad, r["gphi"]) < 1e-9
     inner = (slice(None), slice(1, -1), slice(1, -1), slice(1, -1))
     assert rel_l2(gvel[inner], ovel[inner]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_shim_two_level_project_matches_oracle(shim_exe, tmp_path, oracle):
+    """Hydro::NodalProjector with two-element vectors (finest_level = 1) through the C++ mirror, against the
+    composite oracle: periodic x/y, walls z, central box (bouss_bubble-like, BASELINE configs[3] scaled down)"""
+    from oracle import composite as oc
+    N = 16
+    n0, dx = (N, N, N), 1.0 / N
+    bclo = bchi = (0, 0, 1)
+    flo, fhi = (4, 4, 4), (11, 11, 11)
+    nf = (16, 16, 16)
+    rng = np.random.default_rng(21)
+
+    def field(n):
+        v = rng.standard_normal((3,) + n[::-1])
+        for ax in (1, 2, 3):
+            v = 0.5 * v + 0.25 * (np.roll(v, 1, ax) + np.roll(v, -1, ax))
+        out = np.zeros((3, n[2] + 2, n[1] + 2, n[0] + 2)); out[:, 1:-1, 1:-1, 1:-1] = v
+        return out
+    vel0, vel1 = field(n0), field(nf)
+    fin, fout = str(tmp_path / "cin.bin"), str(tmp_path / "cout.bin")
+    with open(fin, "wb") as f:
+        f.write(vel0.tobytes()); f.write(vel1.tobytes())
+    args = [shim_exe, "composite", fin, fout] + [str(x) for x in n0] + [repr(dx)] + [str(b) for b in bclo] + \
+           [str(b) for b in bchi] + [str(x) for x in flo] + [str(x) for x in fhi]
+    out = subprocess.run(args, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = np.fromfile(fout)
+    sizes = [vel0.size, vel1.size, (N + 1) ** 3, 17 ** 3, 3 * N ** 3, 3 * 16 ** 3, 1]
+    assert raw.size == sum(sizes)
+    parts = np.split(raw, np.cumsum(sizes)[:-1])
+    gv0 = parts[0].reshape(vel0.shape); gv1 = parts[1].reshape(vel1.shape)
+    gp0 = parts[2].reshape(N + 1, N + 1, N + 1); gp1 = parts[3].reshape(17, 17, 17)
+    gg0 = parts[4].reshape(3, N, N, N); gg1 = parts[5].reshape(3, 16, 16, 16)
+    iters = int(parts[6][0])
+    cp = oc.CompositeProjector(oracle_params(n0, (dx,) * 3, bclo, bchi, tile=(64, 16, 64)), flo, fhi,
+                               smoother_kw=dict(smoother=oracle.SM_BOX, box=(64, 16, 64), box_order=oracle.SM_PLANE4, box_stale_per_call=0))
+    ov0, ov1 = vel0.copy(), vel1.copy()
+    r = cp.project(ov0, 1, ov1, 1, const_sigma=0.37, rtol=1e-11, atol=1e-14)
+    assert r["status"] == 0 and abs(iters - r["iters"]) <= 1
+    c = gp1.mean() - r["phi1"].mean()
+    p0 = r["phi0"]
+    for ax in (1, 2):   # periodic x, y: append the image plane (the mirror returns the full nodal box)
+        p0 = np.concatenate([p0, np.take(p0, [0], axis=ax)], axis=ax)
+    assert rel_l2(gp1 - c, r["phi1"]) < 1e-9 and rel_l2(gp0 - c, p0) < 1e-9
+    assert rel_l2(gg1, r["gphi1"]) < 1e-9 and rel_l2(gg0, r["gphi0"]) < 1e-9
+    inner = (slice(None), slice(1, -1), slice(1, -1), slice(1, -1))
+    assert rel_l2(gv0[inner], ov0[inner]) < 1e-9 and rel_l2(gv1[inner], ov1[inner]) < 1e-9

@@ -27,13 +27,23 @@ def test_slab_partition_covers_domain():
         slab.slab_range((16, 16, 30), (0, 0, 0), 0, 4)
 
 
-def test_distributed_level_count():
-    from incflo_b200 import slab
-    assert slab.distributed_levels(512, 8) == 4   # 64, 32, 16, 8 cell planes per rank
-    assert slab.distributed_levels(256, 2) == 5
-    assert slab.distributed_levels(64, 2) == 3
-    assert slab.distributed_levels(64, 1) >= 3
-    assert slab.distributed_levels(60, 8) == 0
+def test_distributed_level_plan():
+    """agglomeration plan of the C ABI (b200np_dist_plan): which levels stay slab-distributed"""
+    from incflo_b200 import nodal_projector as npj, slab
+    # bench weak scaling, 256^3 per GPU: levels with 256, 128, 64 planes per rank are distributed
+    assert slab.distributed_levels((256, 256, 512), 2) == (3, 8)
+    assert slab.distributed_levels((256, 256, 2048), 8) == (3, 8)
+    # strong scaling 512^3 / 1024^3 on 8 GPUs: big levels with thin slabs must NOT be replicated
+    assert slab.distributed_levels((512, 512, 512), 8)[0] == 2      # 64, 32 (256^3 nodes: too big to replicate)
+    assert slab.distributed_levels((1024, 1024, 1024), 8)[0] == 3   # 128, 64, 32
+    assert slab.distributed_levels((1024, 1024, 1024), 4)[0] == 3   # 256, 128, 64; 128^3 with 32 planes is replicated
+    # explicit threshold (the slab parity tests run with 8): every level down to 8 planes per rank
+    assert slab.distributed_levels((64, 64, 64), 2, min_planes=8)[0] == 3
+    assert slab.distributed_levels((64, 64, 64), 4, min_planes=8)[0] == 2
+    assert slab.distributed_levels((64, 64, 64), 2)[0] == 1         # default: only level 0
+    assert slab.distributed_levels((64, 64, 64), 1) == (0, 6)
+    with pytest.raises(npj.ProjectionError):                        # level 0 cannot be cut into even slabs
+        slab.distributed_levels((64, 64, 60), 8)
 
 
 def _worker(rank, world, port, periodic, q):
