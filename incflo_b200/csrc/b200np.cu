@@ -158,6 +158,8 @@ struct b200np {
     int smoother_version = 3, interp_version = 2, resid_version = 3;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
     // B200NP_PROFILE=1: per-phase device times (CUDA events between phases, graph capture off); printed per call
     int profile = 0;
+    int zero_start = -1;      // skip the memset of cor before a pre-smooth and the read of it in the first sweep (-1.6 % per solve);
+                              // default: on for one GPU, off on slabs (not yet measured there); B200NP_ZERO_START=0|1 overrides
     int interp_tz = 4;        // B200NP_INTERP_TZ = 8 | 4: fine planes per interpolation tile (4: 35 KB of shared memory,
                               // 5-6 CTAs per SM; measured 7-12 % faster than 8)
     int dbg_halo = 0;         // B200NP_DBG_HALO: see smooth_sweeps (timing experiments, results are wrong)
@@ -574,6 +576,8 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
     // slab level over NVLink peer memory: the halo exchange is part of the sweep kernel (HaloFused)
     const bool fused = L.dist && h->p2p && h->fuse_halo && iso_path;
     for (int s = 0; s < nsweeps; ++s) {
+        // first sweep of a zero-start smooth call: the kernel does not read x at all (and nobody zeroed it)
+        const int tzarg = L.tz | ((zero_start && s == 0 && h->zero_start && iso_path) ? SM_ZERO_IN : 0);
         if (fused) {
             const int P = h->nranks, r = h->rank;
             const bool per = zper(h);
@@ -601,11 +605,11 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
             h->exchanges++;
             const dim3 grid(L.gsm.x, L.gsm.y, nch);
             if (resident) {
-                if (h->var_sigma) launch_pdl(h, k_smooth_iso_res_dist<true>, grid, dim3(256), SM_RES_DOUBLES * sizeof(double), g, x, y, rhs, L.tz, H);
-                else              launch_pdl(h, k_smooth_iso_res_dist<false>, grid, dim3(256), (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), g, x, y, rhs, L.tz, H);
+                if (h->var_sigma) launch_pdl(h, k_smooth_iso_res_dist<true>, grid, dim3(256), SM_RES_DOUBLES * sizeof(double), g, x, y, rhs, tzarg, H);
+                else              launch_pdl(h, k_smooth_iso_res_dist<false>, grid, dim3(256), (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), g, x, y, rhs, tzarg, H);
             } else {
-                if (h->var_sigma) launch_pdl(h, k_smooth_iso_dist<true>, grid, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), g, x, y, rhs, L.tz, H);
-                else              launch_pdl(h, k_smooth_iso_dist<false>, grid, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), g, x, y, rhs, L.tz, H);
+                if (h->var_sigma) launch_pdl(h, k_smooth_iso_dist<true>, grid, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), g, x, y, rhs, tzarg, H);
+                else              launch_pdl(h, k_smooth_iso_dist<false>, grid, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), g, x, y, rhs, tzarg, H);
             }
             std::swap(x, y);
             continue;
@@ -619,11 +623,11 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
             else              launch_pdl(h, k_smooth_v2<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
         } else if (resident) {
             // small isotropic level: whole chunk resident in shared memory, one CTA per SM
-            if (h->var_sigma) launch_pdl(h, k_smooth_iso_res<true>, L.gsm, dim3(256), SM_RES_DOUBLES * sizeof(double), L.g, x, y, rhs, L.tz);
-            else              launch_pdl(h, k_smooth_iso_res<false>, L.gsm, dim3(256), (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
+            if (h->var_sigma) launch_pdl(h, k_smooth_iso_res<true>, L.gsm, dim3(256), SM_RES_DOUBLES * sizeof(double), L.g, x, y, rhs, tzarg);
+            else              launch_pdl(h, k_smooth_iso_res<false>, L.gsm, dim3(256), (SM_RES_TZ + 2) * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, tzarg);
         } else {  // isotropic level: 2-barrier / register-carried variant, same semantics
-            if (h->var_sigma) launch_pdl(h, k_smooth_iso<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, x, y, rhs, L.tz);
-            else              launch_pdl(h, k_smooth_iso<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
+            if (h->var_sigma) launch_pdl(h, k_smooth_iso<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, x, y, rhs, tzarg);
+            else              launch_pdl(h, k_smooth_iso<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, tzarg);
         }
         std::swap(x, y);
     }
@@ -702,7 +706,9 @@ void vcycle_launch(b200np* h, int lev0)
     const int nsw = h->opts.smooth_num_sweeps;
     for (int l = lev0; l < nl - 1; ++l) {
         LevelData& L = h->lv[l];
-        CK(cudaMemsetAsync(L.cor - L.g.ps, 0, (size_t)L.g.ps * (L.g.nzl + 2) * sizeof(double), h->stream));
+        // cor = 0 (ghost slots included) -- unless the first sweep knows it and never reads cor
+        const bool skip_zero = h->zero_start && h->smoother_version >= 3 && L.iso && h->opts.num_pre_smooth * nsw >= 1;
+        if (!skip_zero) CK(cudaMemsetAsync(L.cor - L.g.ps, 0, (size_t)L.g.ps * (L.g.nzl + 2) * sizeof(double), h->stream));
         double *x = L.cor, *y = L.cor2;
         prof_mark(h, "zero cor", l);
         smooth_sweeps(h, L, x, y, L.res, h->opts.num_pre_smooth * nsw, true);  // cor == 0, ghost slots included
@@ -972,6 +978,7 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (const char* e = getenv("B200NP_FUSE_HALO")) h->fuse_halo = atoi(e);
         if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) h->dist_min_planes = std::max(8, atoi(e));
         if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
+        if (const char* e = getenv("B200NP_ZERO_START")) h->zero_start = atoi(e);
         if (const char* e = getenv("B200NP_INTERP_TZ")) h->interp_tz = atoi(e) == 8 ? 8 : 4;
         if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
         CK(cudaFuncSetAttribute(k_residual_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
@@ -1000,6 +1007,7 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
             memcpy(&id, nccl_unique_id, sizeof(id));
             NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
         }
+        if (h->zero_start < 0) h->zero_start = nranks == 1 ? 1 : 0;
         build_hierarchy(h);
         setup_p2p(h);
         CK(cudaDeviceSynchronize());

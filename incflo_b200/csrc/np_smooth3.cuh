@@ -67,11 +67,18 @@ __device__ __forceinline__ void halo_report(const HaloFused& H)
     }
 }
 
+// tzarg: the z-chunk height; bit 30 (SM_ZERO_IN) set: pin is known to be zero everywhere (first sweep of a
+// pre-smooth, cor = 0) -- the staged planes are filled with zeros instead of being read, and the caller
+// skips the memset of pin (8 B/node written + 8 B/node read saved on 1 of 16 sweeps per level and V-cycle)
+constexpr int SM_ZERO_IN = 1 << 30;
+
 template <bool VAR, bool FULL, bool RES, bool DIST = false>
 __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __restrict__ pin, double* __restrict__ pout,
-                                                const double* __restrict__ rhs, const int TZ, double* smem,
+                                                const double* __restrict__ rhs, const int tzarg, double* smem,
                                                 const HaloFused* H = nullptr)
 {
+    const int TZ = tzarg & (SM_ZERO_IN - 1);
+    const bool zin = (tzarg & SM_ZERO_IN) != 0;
     double* sphi = smem;
     constexpr int NPS = RES ? SM_RES_TZ + 2 : 4, NSS = RES ? SM_RES_TZ + 1 : 3;
     double* ssig = smem + NPS * SM_PHI_SLOT;
@@ -117,6 +124,12 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
         if (DIST) { if (kl < 0) src = H->pin_lo; else if (kl >= L.nzl) src = H->pin_hi; }
         unsigned dst = sphi_a + pslot(kl) * (SM_PHI_SLOT * 8);
         asm volatile("" : "+l"(src), "+r"(dst));  // keep the plane base materialised (no per-copy 64-bit multiply)
+        if (zin) {   // the slot being refilled was last read before the previous iteration's mid-plane barrier
+#pragma unroll
+            for (int s = 0; s < 5; ++s)
+                if (psrc[s] >= 0) asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst + pdst[s]), "d"(0.0) : "memory");
+            return;
+        }
 #pragma unroll
         for (int s = 0; s < 5; ++s)
             if (psrc[s] >= 0) cp_async8(dst + pdst[s], src + psrc[s]);
