@@ -176,10 +176,10 @@ class CompositeProjector:
         return max(np.abs(res0[m]).max(), np.abs(res1).max())
 
     # ---- Hydro::NodalProjector::project over two levels -------------------------------------------
-    def project(self, vel0, ng0, vel1, ng1, sigma0=None, sigma1=None, const_sigma=1.0, rtol=1e-11, atol=1e-14):
-        """vel0 (3, n0z+2ng0, ...) and vel1 (3, nfz+2ng1, ...) are updated in place (valid cells).
-        sigma0 / sigma1: cell arrays or None => const_sigma on both levels."""
-        n0, nf, nb = self.n0, self.nf, self.nb
+    def setup(self, sigma0=None, sigma1=None, const_sigma=1.0):
+        """the four single-level hierarchies: coarse (sigma averaged down under the box), coarse with sigma = 0 in
+        the covered cells, fine box with Dirichlet / with reflecting interface faces"""
+        n0, nf = self.n0, self.nf
         s1 = np.full((nf[2], nf[1], nf[0]), float(const_sigma)) if sigma1 is None else np.ascontiguousarray(sigma1, dtype=np.float64)
         s0 = np.full((n0[2], n0[1], n0[0]), float(const_sigma)) if sigma0 is None else np.array(sigma0, dtype=np.float64)
         s0[self.cbox] = _avg_down_cells(s1)                  # averageDownCoeffsToCoarseAmrLevel
@@ -189,6 +189,33 @@ class CompositeProjector:
         self.mg0z = po.MG(self.p0, s0z, 1.0)
         self.mgD = po.MG(self.pD, s1 if var else None, const_sigma)
         self.mgN = po.MG(self.pN, s1 if var else None, const_sigma)
+        self.rhsN = np.zeros(self.mgN.node_shape(0)); self.rhs0z = np.zeros(self.mg0.node_shape(0)); self.offset = 0.0
+
+    def fill_hanging(self, sol0, sol1):
+        """fine nodes on the coarse/fine interface <- trilinear interpolant of the coarse solution (what the
+        iteration maintains implicitly: they only ever change by interpolationAmr)"""
+        interp = _trilinear(sol0[self.nbox], self.span)
+        hang = np.zeros(sol1.shape, dtype=bool)
+        for ax, d in enumerate((2, 1, 0)):
+            lo = [slice(None)] * 3; hi = [slice(None)] * 3
+            lo[ax] = 0; hi[ax] = -1
+            if self.cf_lo[d]: hang[tuple(lo)] = True
+            if self.cf_hi[d]: hang[tuple(hi)] = True
+        sol1[hang] = interp[hang]
+        return hang
+
+    def composite_residual(self, sol0, sol1):
+        """(res0, res1) = rhs - A_composite(sol0, sol1) with the current rhs (zero after setup())"""
+        rhs1 = getattr(self, "rhs1_off", None)
+        if rhs1 is None:
+            rhs1 = np.zeros_like(sol1)
+        return self._coarse_residual(sol0, sol1), self.mgD.residual(0, sol1, rhs1)
+
+    def project(self, vel0, ng0, vel1, ng1, sigma0=None, sigma1=None, const_sigma=1.0, rtol=1e-11, atol=1e-14):
+        """vel0 (3, n0z+2ng0, ...) and vel1 (3, nfz+2ng1, ...) are updated in place (valid cells).
+        sigma0 / sigma1: cell arrays or None => const_sigma on both levels."""
+        n0, nf, nb = self.n0, self.nf, self.nb
+        self.setup(sigma0, sigma1, const_sigma)
         # velocities: ghost cells of the fine level are zero (vel.setBndry(0.0), :137), covered coarse cells do not count
         v1 = vel1.copy()
         gz = np.zeros_like(v1)

@@ -49,7 +49,7 @@ def avg_down(f):
     return 0.125 * sum(f[..., c::2, b::2, a::2] for c in range(2) for b in range(2) for a in range(2))
 
 
-def solve(n0, dx0, bclo, bchi, clo, chi, vel0, ng0, vel1, ng1, sigma0, sigma1):
+def solve(n0, dx0, bclo, bchi, clo, chi, vel0, ng0, vel1, ng1, sigma0, sigma1, assemble_only=False):
     nb = [chi[d] - clo[d] + 1 for d in range(3)]
     nf = [2 * x for x in nb]
     dx1 = [0.5 * x for x in dx0]
@@ -106,6 +106,8 @@ def solve(n0, dx0, bclo, bchi, clo, chi, vel0, ng0, vel1, ng1, sigma0, sigma1):
     assert abs(A[~act]).sum() == 0.0 and np.abs(b[~act]).max() == 0.0
     Aa = A[act][:, act].tocsc()
     ba = b[act]
+    if assemble_only:
+        return dict(A=Aa, b=ba, act=act, N0=N0, int_ids=int_ids, nn0=nn0, nn1=nn1, H3=H3, h3=h3)
     assert all(x != DIR for x in tuple(bclo) + tuple(bchi)), "only singular (no Dirichlet face) cases here"
     print(f"   compatibility: sum(b) = {ba.sum():.3e} (|b|max {np.abs(ba).max():.3e})")
     c = sp.csc_matrix(np.ones((ba.size, 1)))

@@ -90,3 +90,84 @@ def test_composite_converges_and_removes_a_gradient(oracle):
     assert r["resnorm"] <= 1e-11 * max(r["rhsnorm"], r["resnorm0"])
     assert np.abs(vel1[:, 1:-1, 1:-1, 1:-1]).max() < 0.05 * u1      # O(h^2) remainder on the fine level
     assert np.abs(vel0[:, 1:-1, 1:-1, 1:-1]).max() < 0.12 * u0      # coarser level: 4x larger
+
+
+@pytest.mark.parametrize("case", ["interior_box", "periodic_span_slab", "corner_on_walls"])
+def test_composite_operator_equals_assembled_finite_element_matrix(case, oracle):
+    """Column by column: the oracle's composite residual operator (reflux through the reflected fine box and
+    the sigma-masked coarse level) against the Q1 finite-element matrix A of the composite mesh with hanging-node
+    constraints, assembled independently in tests/golden/make_golden_composite.py -- entry-wise, not just for
+    one right-hand side.  Rows are compared in natural (element-sum) scaling: the oracle's equations are the
+    element sums divided by the cell volume and by the node weight 1/2 per wall face.
+    Fine rows must be identical.  A coarse row I on the interface is the FE row PLUS the full-weighting share
+    of the residuals of the fine UNKNOWNS next to the interface (restriction does not stop at the hanging
+    nodes; AMReX's reflux restricts the fine residual the same way): op = [[1, W], [0, 1]] A with W the trilinear
+    weights -- an equivalent system (same solutions), which is why the golden solutions agree to 1e-13."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_composite as mg
+    from oracle import composite as oc
+    PER, NEU = 0, 1
+    if case == "interior_box":
+        n0, bc, clo, chi = (8, 8, 6), (PER, NEU, NEU), (2, 3, 1), (5, 5, 3)
+    elif case == "periodic_span_slab":
+        n0, bc, clo, chi = (6, 6, 8), (PER, PER, NEU), (0, 0, 2), (5, 5, 4)
+    else:
+        n0, bc, clo, chi = (6, 6, 6), (NEU, NEU, NEU), (0, 2, 3), (2, 4, 5)
+    dx0 = (1.0 / 8, 1.0 / 8, 1.0 / 8)
+    nf = tuple(2 * (h - l + 1) for l, h in zip(clo, chi))
+    rng = np.random.default_rng(3)
+    s0 = rng.uniform(0.5, 2.0, size=n0[::-1]); s1 = rng.uniform(0.5, 2.0, size=nf[::-1])
+    z0 = np.zeros((3, n0[2] + 2, n0[1] + 2, n0[0] + 2)); z1 = np.zeros((3, nf[2] + 2, nf[1] + 2, nf[0] + 2))
+    sysm = mg.solve(n0, dx0, bc, bc, clo, chi, z0, 1, z1, 1, s0, s1, assemble_only=True)
+    A = sysm["A"].toarray()
+    cp = oc.CompositeProjector(oracle.make_params(n0, dx0, bc, bc), clo, chi)
+    cp.setup(s0, s1)
+    shape0, shape1 = cp.mg0.node_shape(0), cp.mgD.node_shape(0)
+    N0 = int(np.prod(shape0))
+    act0 = sysm["act"][:N0].reshape(shape0)                 # coarse nodes that are unknowns
+    int1 = np.zeros(int(np.prod(shape1)), dtype=bool); int1[sysm["int_ids"]] = True
+    int1 = int1.reshape(shape1)                              # fine nodes that are unknowns (not hanging)
+    w0 = cp.mg0.dot_weights(0); w1 = cp.mgN.dot_weights(0)   # 1/2 per wall face
+    idx0, idx1 = np.argwhere(act0), np.argwhere(int1)
+    n_act0 = len(idx0); n_unk = n_act0 + len(idx1)
+    assert A.shape == (n_unk, n_unk)
+    op = np.zeros_like(A)
+    for j in range(n_unk):
+        sol0 = np.zeros(shape0); sol1 = np.zeros(shape1)
+        if j < n_act0:
+            sol0[tuple(idx0[j])] = 1.0
+        else:
+            sol1[tuple(idx1[j - n_act0])] = 1.0
+        cp.fill_hanging(sol0, sol1)
+        r0, r1 = cp.composite_residual(sol0, sol1)           # = -A_composite x in the oracle's row scaling
+        op[:n_act0, j] = -(r0 * w0)[act0] * sysm["H3"]
+        op[n_act0:, j] = -(r1 * w1)[int1] * sysm["h3"]
+    # W: trilinear weight of the fine unknown j in the coarse basis function of the interface node I
+    fid = -np.ones(shape1, dtype=np.int64); fid[int1] = np.arange(len(idx1))
+    W = np.zeros((n_act0, len(idx1)))
+    lo = (clo[2], clo[1], clo[0]); span = cp.span[::-1]; cf = (list(zip(cp.cf_lo, cp.cf_hi)))[::-1]
+    for I, (k, j, i) in enumerate(idx0):
+        c = (k, j, i)
+        inside = all(span[a] or lo[a] <= c[a] <= lo[a] + cp.nb[2 - a] for a in range(3))
+        on_cf = any((cf[a][0] and c[a] == lo[a]) or (cf[a][1] and c[a] == lo[a] + cp.nb[2 - a]) for a in range(3))
+        if not (inside and on_cf):
+            continue
+        for dz in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    f = [2 * (c[a] - lo[a]) + d for a, d in enumerate((dz, dy, dx))]
+                    ok = True
+                    for a in range(3):
+                        if span[a]:
+                            f[a] %= shape1[a]
+                        elif not 0 <= f[a] < shape1[a]:
+                            ok = False
+                    if ok and fid[tuple(f)] >= 0:
+                        W[I, fid[tuple(f)]] += (1 - abs(dz) / 2) * (1 - abs(dy) / 2) * (1 - abs(dx) / 2)
+    expected = A.copy()
+    expected[:n_act0] += W @ A[n_act0:]
+    scale = np.abs(A).max()
+    assert np.abs(op[n_act0:] - A[n_act0:]).max() < 1e-12 * scale      # fine rows: the FE rows themselves
+    assert np.abs(op - expected).max() < 1e-12 * scale                  # coarse rows: FE row + restricted fine rows
+    assert np.abs(A - A.T).max() < 1e-12 * scale and np.abs(op.sum(axis=1)).max() < 1e-11 * scale
