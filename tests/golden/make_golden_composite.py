@@ -60,7 +60,7 @@ def solve(n0, dx0, bclo, bchi, clo, chi, vel0, ng0, vel1, ng1, sigma0, sigma1, a
     cf_hi = [not span[d] and chi[d] < n0[d] - 1 for d in range(3)]
     for d in range(3):
         assert span[d] or bclo[d] != PER or (clo[d] > 0 and chi[d] < n0[d] - 1)
-        assert bclo[d] in (PER, NEU) and bchi[d] in (PER, NEU), "golden cases: periodic or wall faces only"
+        assert bclo[d] in (PER, NEU, DIR) and bchi[d] in (PER, NEU, DIR), "golden cases: periodic, wall or outflow faces"
     bc1 = tuple(PER if span[d] else NEU for d in range(3))     # natural (one-sided) sums on every non-periodic face
     cbox = (slice(clo[2], chi[2] + 1), slice(clo[1], chi[1] + 1), slice(clo[0], chi[0] + 1))
     s0 = sigma0.copy()
@@ -102,17 +102,32 @@ def solve(n0, dx0, bclo, bchi, clo, chi, vel0, ng0, vel1, ng1, sigma0, sigma1, a
     cin = np.zeros(nn0[::-1], dtype=bool)
     sl = tuple(slice(clo[d] + (1 if cf_lo[d] else 0), (chi[d] + 1) if cf_hi[d] else (n0[d] if span[d] else chi[d] + 2)) for d in (2, 1, 0))
     cin[sl] = True
-    act = np.concatenate([~cin.ravel(), np.ones(Ni, dtype=bool)])
-    assert abs(A[~act]).sum() == 0.0 and np.abs(b[~act]).max() == 0.0
+    # Dirichlet (outflow) faces of the domain: phi = 0 there, on the coarse level and -- where the box touches
+    # the face -- on the fine level
+    dir0 = np.zeros(nn0[::-1], dtype=bool); dir1 = np.zeros(nn1[::-1], dtype=bool)
+    for d, ax in ((0, 2), (1, 1), (2, 0)):
+        lo_ = [slice(None)] * 3; hi_ = [slice(None)] * 3
+        lo_[ax] = 0; hi_[ax] = -1
+        if bclo[d] == DIR:
+            dir0[tuple(lo_)] = True
+            if clo[d] == 0: dir1[tuple(lo_)] = True
+        if bchi[d] == DIR:
+            dir0[tuple(hi_)] = True
+            if chi[d] == n0[d] - 1: dir1[tuple(hi_)] = True
+    act = np.concatenate([~cin.ravel() & ~dir0.ravel(), ~dir1.ravel()[int_ids]])
+    inact_free = ~act & ~np.concatenate([dir0.ravel(), dir1.ravel()[int_ids]])   # strictly covered coarse nodes
+    assert abs(A[inact_free]).sum() == 0.0 and np.abs(b[inact_free]).max() == 0.0
     Aa = A[act][:, act].tocsc()
     ba = b[act]
     if assemble_only:
         return dict(A=Aa, b=ba, act=act, N0=N0, int_ids=int_ids, nn0=nn0, nn1=nn1, H3=H3, h3=h3)
-    assert all(x != DIR for x in tuple(bclo) + tuple(bchi)), "only singular (no Dirichlet face) cases here"
-    print(f"   compatibility: sum(b) = {ba.sum():.3e} (|b|max {np.abs(ba).max():.3e})")
-    c = sp.csc_matrix(np.ones((ba.size, 1)))
-    Ksys = sp.bmat([[Aa, c], [c.T, None]]).tocsc()
-    x = spl.spsolve(Ksys, np.concatenate([ba, [0.0]]))[:-1]
+    if all(x != DIR for x in tuple(bclo) + tuple(bchi)):
+        print(f"   compatibility: sum(b) = {ba.sum():.3e} (|b|max {np.abs(ba).max():.3e})")
+        c = sp.csc_matrix(np.ones((ba.size, 1)))
+        Ksys = sp.bmat([[Aa, c], [c.T, None]]).tocsc()
+        x = spl.spsolve(Ksys, np.concatenate([ba, [0.0]]))[:-1]
+    else:
+        x = spl.spsolve(Aa, ba)
     full = np.zeros(N0 + Ni); full[act] = x
     phi0_u = full[:N0].reshape(nn0[::-1])
     phi1_u = (T @ full).reshape(nn1[::-1])
@@ -173,13 +188,37 @@ def cases():
     return out
 
 
+def cases_dirichlet():
+    """non-singular problems (an outflow face): tests/golden/composite_dirichlet/ -- pins the oracle; the CUDA
+    path for them has no GPU run yet (tests/test_gpu_composite.py marks them xfail(strict=False))"""
+    out = []
+    # 1. channel-like: wall x-lo, outflow x-hi, walls y, periodic z; interior box
+    n0, dx0 = (16, 8, 8), (1 / 16,) * 3
+    bclo, bchi = (NEU, NEU, PER), (DIR, NEU, PER)
+    clo, chi = (4, 2, 2), (9, 5, 5)
+    nf = tuple(2 * (chi[d] - clo[d] + 1) for d in range(3))
+    nat = (NEU,) * 3
+    rng = np.random.default_rng(9)
+    out.append(dict(name="channel_outflow_interior_box_var", n0=n0, dx0=dx0, bclo=bclo, bchi=bchi, clo=clo, chi=chi, ng0=1, ng1=1,
+                    vel0=smooth_random_velocity(n0, 1, nat, nat, 91), vel1=smooth_random_velocity(nf, 1, nat, nat, 92),
+                    sigma0=rng.uniform(0.5, 2.0, size=n0[::-1]), sigma1=rng.uniform(0.5, 2.0, size=nf[::-1]), var=True))
+    # 2. the fine box sits ON the outflow face (and spans the periodic direction)
+    clo, chi = (10, 2, 0), (15, 5, 7)
+    nf = tuple(2 * (chi[d] - clo[d] + 1) for d in range(3))
+    out.append(dict(name="channel_box_on_outflow_face_const", n0=n0, dx0=dx0, bclo=bclo, bchi=bchi, clo=clo, chi=chi, ng0=1, ng1=1,
+                    vel0=smooth_random_velocity(n0, 1, nat, nat, 93), vel1=smooth_random_velocity(nf, 1, nat, nat, 94),
+                    sigma0=np.full(n0[::-1], 0.6), sigma1=np.full(nf[::-1], 0.6), var=False))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for c in cases():
+    os.makedirs(OUT + "_dirichlet", exist_ok=True)
+    for c in cases() + cases_dirichlet():
         print(c["name"])
         r = solve(c["n0"], c["dx0"], c["bclo"], c["bchi"], c["clo"], c["chi"], c["vel0"], c["ng0"], c["vel1"], c["ng1"],
                   c["sigma0"], c["sigma1"])
-        path = os.path.join(OUT, c["name"] + ".npz")
+        path = os.path.join(OUT + ("_dirichlet" if DIR in tuple(c["bclo"]) + tuple(c["bchi"]) else ""), c["name"] + ".npz")
         np.savez_compressed(path, n0=np.array(c["n0"]), dx0=np.array(c["dx0"]), bclo=np.array(c["bclo"]), bchi=np.array(c["bchi"]),
                             clo=np.array(c["clo"]), chi=np.array(c["chi"]), ng0=c["ng0"], ng1=c["ng1"], vel0_in=c["vel0"],
                             vel1_in=c["vel1"], sigma0=c["sigma0"], sigma1=c["sigma1"], var=c["var"], **r)

@@ -11,6 +11,7 @@ import pytest
 from helpers import oracle_params, rel_l2
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "composite", "*.npz")))
+GOLD_DIR = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "composite_dirichlet", "*.npz")))
 TOL = 1e-9
 
 
@@ -50,10 +51,10 @@ def check(g, vel0, vel1, phi0_full, phi1, gphi0, gphi1, tol=TOL):
 
 
 def test_fixtures_present():
-    assert len(GOLD) >= 4
+    assert len(GOLD) >= 4 and len(GOLD_DIR) >= 2
 
 
-@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+@pytest.mark.parametrize("path", GOLD + GOLD_DIR, ids=[os.path.basename(p)[:-4] for p in GOLD + GOLD_DIR])
 def test_composite_oracle_reproduces_golden(path, oracle):
     from oracle import composite as oc
     g = load(path)

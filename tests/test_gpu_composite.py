@@ -9,10 +9,14 @@ import numpy as np
 import pytest
 
 from helpers import TILE, oracle_params, rel_l2
-from test_composite_oracle import GOLD, check, fine_per, load, to_full
+from test_composite_oracle import GOLD, GOLD_DIR, check, fine_per, load, to_full
 
 pytestmark = pytest.mark.gpu
-MIRROR = None
+# non-singular fixtures (an outflow face; tests/golden/composite_dirichlet/): the oracle reproduces them on CPU, the
+# CUDA path for them was written after the last GPU visit of round 1 -> not yet a hard requirement
+ALL_GOLD = [pytest.param(p, id=os.path.basename(p)[:-4]) for p in GOLD] + \
+           [pytest.param(p, id=os.path.basename(p)[:-4], marks=pytest.mark.xfail(strict=False, reason="no GPU run yet (round 2)"))
+            for p in GOLD_DIR]
 
 
 def _mirror(oracle):
@@ -29,7 +33,7 @@ def _np(a):
 
 
 @pytest.mark.parametrize("host", [False, True], ids=["device_ptrs", "host_ptrs"])
-@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+@pytest.mark.parametrize("path", ALL_GOLD)
 def test_composite_cuda_reproduces_golden(path, host):
     from incflo_b200 import nodal_projector as npj
     g = load(path)
@@ -38,7 +42,7 @@ def test_composite_cuda_reproduces_golden(path, host):
     s0 = _cuda(g["sigma0"], host) if g["var"] else None
     s1 = _cuda(g["sigma1"], host) if g["var"] else None
     phi0, phi1, g0, g1 = cp.project(v0, g["ng0"], v1, g["ng1"], s0, s1, float(g["sigma0"].flat[0]), rtol=1e-12, atol=0.0)
-    assert cp.stats.status == 0 and cp.stats.iters <= 20
+    assert cp.stats.status == 0 and cp.stats.iters <= 25
     check(g, _np(v0), _np(v1), _np(phi0), _np(phi1), _np(g0), _np(g1))
     cp.close()
 
