@@ -688,6 +688,12 @@ void interp_add(b200np* h, int l)
     if (h->interp_version == 1) {
         if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
         else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
+    } else if (h->interp_version == 3) {   // persistent, software-pipelined variant (see np_smooth.cuh K6 version 3)
+        const int ntx = (F.g.nn[0] + IT_X - 1) / IT_X, nty = (F.g.nn[1] + IT_Y - 1) / IT_Y, ntz = (F.g.nzl + IP_TZ - 1) / IP_TZ;
+        const long long nt = (long long)ntx * nty * ntz;
+        const int grid = (int)std::min<long long>(nt, 148 * 3);
+        if (h->var_sigma) launch_pdl(h, k_interp_pipe<true>, dim3(grid), dim3(256), 2 * IP_BUF_DOUBLES * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor, ntx, nty, ntz);
+        else              launch_pdl(h, k_interp_pipe<false>, dim3(grid), dim3(256), 2 * IP_BUF_DOUBLES * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor, ntx, nty, ntz);
     } else {
         if (h->interp_tz == 4) {
             if (h->var_sigma) launch_pdl(h, k_interp_tile<true, 4>, F.git, dim3(256), (it_v_doubles(4) + it_s_doubles(4)) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
@@ -991,6 +997,8 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         CK(cudaFuncSetAttribute(k_residual_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IT_V_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_interp_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * IP_BUF_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_interp_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * IP_BUF_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((it_v_doubles(4) + it_s_doubles(4)) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(it_v_doubles(4) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso_dist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));

@@ -155,3 +155,20 @@ def test_vcycle(var, oracle):
     phi = np.zeros_like(res)
     mg2.solve(phi, res.copy(), 1e-30, 0.0)
     _close(got, phi, 1e-8)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("B200NP_TEST_EXPERIMENTAL"),
+                    reason="k_interp_pipe (B200NP_INTERP=3) was written after the last GPU visit of round 1; opt-in until measured")
+@pytest.mark.parametrize("var", [False, True])
+@pytest.mark.parametrize("case", BC_CASES, ids=[c[0] for c in BC_CASES])
+def test_interpolation_pipelined_variant(case, var, oracle, monkeypatch):
+    """the persistent, software-pipelined interpolation kernel must give what the tile kernel gives"""
+    from incflo_b200.nodal_projector import A_COR, OP_INTERP
+    monkeypatch.setenv("B200NP_INTERP", "3")
+    mg, proj, rng = _setup(case, var, oracle)
+    for lev in range(mg.nlev - 1):
+        fine = _masked_random(mg, lev, rng)
+        crse = _masked_random(mg, lev + 1, rng)
+        proj.level_set(lev, A_COR, fine); proj.level_set(lev + 1, A_COR, crse)
+        proj.level_op(lev, OP_INTERP)
+        _close(proj.level_get(lev, A_COR), mg.interp_add(lev, fine.copy(), crse))
