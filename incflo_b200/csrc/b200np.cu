@@ -163,6 +163,8 @@ struct b200np {
     int interp_tz = 4;        // B200NP_INTERP_TZ = 8 | 4: fine planes per interpolation tile (4: 35 KB of shared memory,
                               // 5-6 CTAs per SM; measured 7-12 % faster than 8)
     int dbg_halo = 0;         // B200NP_DBG_HALO: see smooth_sweeps (timing experiments, results are wrong)
+    bool has_profile = false; // b200np_set_inflow_profile: IncfloVelFill evaluated on the device
+    InflowProfile profile_data{};
     bool no_bottom = false;   // fine AMR level of a composite solve: one MG level, never a bottom solve
     std::vector<cudaEvent_t> prof_ev;
     std::vector<std::string> prof_tag;
@@ -1349,6 +1351,19 @@ int b200np_set_stream(b200np_t* h, void* stream)
     return B200NP_OK;
 }
 
+int b200np_set_inflow_profile(b200np_t* h, int probtype, const double* bcv_vel, double time)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    if (!bcv_vel) { h->has_profile = false; return B200NP_OK; }
+    if (probtype == 1101 || probtype == 1102) return B200NP_ERR_UNSUPPORTED;   // mixed BCs (EB decks), overset mask
+    h->profile_data.probtype = probtype;
+    h->profile_data.time = time;
+    for (int o = 0; o < 6; ++o)
+        for (int c = 0; c < 3; ++c) h->profile_data.bcv[o][c] = bcv_vel[3 * o + c];
+    h->has_profile = true;
+    return B200NP_OK;
+}
+
 int b200np_nlevels(const b200np_t* h) { return h ? (int)h->lv.size() : 0; }
 
 int b200np_level_dims(const b200np_t* h, int lev, int n_cell[3], int n_node[3])
@@ -1469,6 +1484,8 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
             long long total = (long long)fvel.nx * fvel.ny * fvel.nz;
             int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
             LAUNCH(h, k_set_vel_ghosts, blocks, 256, L0.g, fvel, fin, set_inflow);
+            // no caller-filled array: IncfloVelFill on the device (:138-163), when a profile has been set
+            if (set_inflow && !fin.p && h->has_profile) LAUNCH(h, k_incflo_vel_fill, blocks, 256, L0.g, fvel, h->profile_data);
         }
         // :181-256
         int status = project_core(h, fvel, fvelo, use_old, fgp, incremental, fp, incremental, rtol, atol, st);

@@ -482,6 +482,75 @@ __global__ void __launch_bounds__(256) k_set_vel_ghosts(const Lev L, Fab vel, Fa
     }
 }
 
+// IncfloVelFill (src/prob/prob_bc.H:8-351), the mass-inflow (BCType::ext_dir) part, evaluated on the device:
+// fills the FIRST ghost layer of the velocity at inflow faces (:138-163 of incflo_apply_nodal_projection.cpp
+// call it with nghost = 1) from the face's boundary velocity bcv_vel and the probtype-specific profile of
+// the normal component.  The face blocks are applied in the reference's order (x-lo, x-hi, y-lo, y-hi, z-lo,
+// z-hi), so a ghost cell outside the domain in two directions ends up with the later face's value, as there.
+// bcv[o][c]: o = amrex::Orientation index (dir + 3 * side), c = velocity component (m_bc_velocity).
+// direction_dependent faces (copy of the interior value when the flow leaves) and the mixed-BC probtypes
+// 1101 / 1102 are not handled here (the host refuses them: B200NP_ERR_UNSUPPORTED).
+struct InflowProfile {
+    int probtype;
+    double time;
+    double bcv[6][3];
+};
+__device__ __forceinline__ double parab6(int idx, int n) { const double s = (idx + 0.5) / n; return 6.0 * s * (1.0 - s); }
+// value of component nc in ghost cell (i,j,k); returns false if no inflow face claims the cell
+__device__ __forceinline__ bool incflo_vel_fill(const InflowProfile& P, const Lev& L, int i, int j, int k, int nc, double& out)
+{
+    bool hit = false;
+    const int idx[3] = {i, j, k};
+#pragma unroll
+    for (int dir = 0; dir < 3; ++dir)
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const bool outside = side == 0 ? idx[dir] < 0 : idx[dir] >= L.n[dir];
+            const int kind = side == 0 ? L.rlo[dir] : L.rhi[dir];   // 2 = inflow (np_level.h)
+            if (!outside || kind != 2 || L.per[dir]) continue;
+            const double* b = P.bcv[dir + 3 * side];
+            double norm_vel = b[dir];
+            const int pt = P.probtype;
+            if (dir == 0 && side == 0) {          // prob_bc.H:57-84
+                if (pt == 42) norm_vel = P.time;
+                else if (pt == 31) norm_vel = parab6(j, L.n[1]);
+                else if (pt == 43) norm_vel = parab6(j, L.n[1]) - 1.0;
+                else if (pt == 311) norm_vel = parab6(k, L.n[2]);
+                else if (pt == 41) norm_vel = 0.5 * ((k + 0.5) / L.n[2]);
+            } else if (dir == 0 && side == 1) {   // :129-138
+                if (pt == 42) norm_vel = P.time;
+                else if (pt == 43) norm_vel = parab6(j, L.n[1]) - 1.0;
+            } else if (dir == 1 && side == 0) {   // :190-202
+                if (pt == 32) norm_vel *= parab6(k, L.n[2]);
+                if (pt == 322) norm_vel *= parab6(i, L.n[0]);
+            } else if (dir == 1 && side == 1) {   // :241-246
+                if (pt == 16) { const double x = (i + 0.5) / L.n[0]; norm_vel = 16.0 * (x * x * x * x - 2.0 * x * x * x + x * x); }
+            } else if (dir == 2 && side == 0) {   // :298-308
+                if (pt == 33) norm_vel *= parab6(i, L.n[0]);
+                else if (pt == 333) norm_vel *= parab6(j, L.n[1]);
+            }
+            out = nc == dir ? norm_vel : b[nc];   // normal component: the profile; tangential: bcv_vel
+            hit = true;
+        }
+    return hit;
+}
+// one thread per cell of the domain grown by one; only ghost cells at inflow faces are written
+__global__ void __launch_bounds__(256) k_incflo_vel_fill(const Lev L, Fab vel, const InflowProfile P)
+{
+    const int nx = L.n[0] + 2, ny = L.n[1] + 2;
+    const long long total = (long long)nx * ny * (L.cnzl + 2);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx) - 1, j = (int)((t / nx) % ny) - 1, k = (int)(t / ((long long)nx * ny)) - 1 + L.ck0;
+        const bool out = i < 0 || i >= L.n[0] || j < 0 || j >= L.n[1] || k < 0 || k >= L.n[2];
+        if (!out || !vel.has(i, j, k)) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double v;
+            if (incflo_vel_fill(P, L, i, j, k, c, v)) vel.p[vel.idx(i, j, k, c)] = v;
+        }
+    }
+}
+
 // K2: rhs = D u with the Neumann/inflow treatment of A.2.  One thread per owned node.
 // Traffic 24 B/cell R + 8 B/node W.
 __global__ void __launch_bounds__(256) k_divu(const Lev L, Fab vel, double* __restrict__ rhs)

@@ -289,6 +289,18 @@ class IncfloProjection:
             raise ProjectionError(rc)
         return self.stats
 
+    def set_inflow_profile(self, probtype, bcv_vel, time=0.0):
+        """IncfloVelFill (src/prob/prob_bc.H) on the device: apply_nodal_projection(inflow_vel=None) then fills the
+        first ghost layer at mass-inflow faces itself.  bcv_vel: 6 x 3 (Orientation x-lo, y-lo, z-lo, x-hi, y-hi, z-hi);
+        None switches it off."""
+        if bcv_vel is None:
+            rc = self._L.b200np_set_inflow_profile(self._h, 0, None, 0.0)
+        else:
+            arr = (C.c_double * 18)(*[float(x) for x in np.asarray(bcv_vel, dtype=np.float64).reshape(18)])
+            rc = self._L.b200np_set_inflow_profile(self._h, int(probtype), C.byref(arr), float(time))
+        if rc != 0:
+            raise ProjectionError(rc)
+
     def set_stream(self, cuda_stream):
         """run on the caller's stream (int handle of a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)"""
         self._L.b200np_set_stream(self._h, C.c_void_p(cuda_stream))

@@ -208,6 +208,16 @@ int  b200np_composite_apply_nodal_projection(b200np_composite_t* c, double* cons
                                              const b200np_fab* const p_box[2], const double* inflow_vel0, double scaling_factor,
                                              int incremental, int proj_for_small_dt, double rtol, double atol, b200np_stats* stats);
 
+/* IncfloVelFill (src/prob/prob_bc.H:8-351) evaluated by the library: after this call,
+ * b200np_apply_nodal_projection with inflow_vel == NULL fills the first ghost layer of the velocity at INFLOW
+ * faces itself (:138-163, PhysBCFunct<GpuBndryFuncFab<IncfloVelFill>> with nghost = 1) from
+ *   bcv_vel[6][3]  m_bc_velocity: boundary velocity per amrex::Orientation (x-lo, y-lo, z-lo, x-hi, y-hi, z-hi),
+ *   probtype       the profile of the normal component (16, 31, 311, 32, 322, 33, 333, 41, 42, 43; else bcv_vel),
+ *   time           probtype 42.
+ * Mass-inflow (ext_dir) faces only: direction_dependent faces need the caller's inflow_vel array, probtypes
+ * 1101 / 1102 (mixed BCs) return B200NP_ERR_UNSUPPORTED.  bcv_vel == NULL switches the profile off again. */
+int b200np_set_inflow_profile(b200np_t* h, int probtype, const double* bcv_vel, double time);
+
 const char* b200np_strerror(int status);
 int b200np_version(void);
 
