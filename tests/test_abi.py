@@ -85,3 +85,38 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in src and "nodal_oracle" not in src and "liboracle" not in src, f
+
+
+def test_composite_create_validates_the_fine_box_without_a_gpu():
+    """b200np_composite_create: which fine boxes are supported is decided before any CUDA call"""
+    mod, L = _lib()
+    g = mod.Geom()
+    for d in range(3):
+        g.n_cell[d] = 16; g.dx[d] = 1 / 16
+    g.bc_lo[0] = g.bc_hi[0] = 0          # periodic x
+    g.bc_lo[1] = 3; g.bc_hi[1] = 2       # inflow y-lo, outflow y-hi
+    g.bc_lo[2] = g.bc_hi[2] = 1          # walls z
+
+    def create(lo, hi):
+        h = C.c_void_p()
+        rc = L.b200np_composite_create(C.byref(h), C.byref(g), C.byref((C.c_int * 3)(*lo)), C.byref((C.c_int * 3)(*hi)), None, 0)
+        if rc == 0:
+            L.b200np_composite_destroy(h)
+        return rc
+    ok = 0 if has_gpu() else 5                                  # a supported box needs a device (no CPU fallback)
+    assert create((4, 4, 4), (11, 11, 11)) == ok               # interior box
+    assert create((0, 4, 4), (15, 11, 11)) == ok               # spans the periodic direction
+    assert create((4, 4, 0), (11, 11, 7)) == ok                # touches a wall
+    assert create((4, 8, 4), (11, 15, 11)) == ok               # touches the outflow face
+    assert create((0, 4, 4), (7, 11, 11)) == 7                 # on the periodic seam without spanning: unsupported
+    assert create((4, 0, 4), (11, 7, 11)) == 7                 # on the inflow face: unsupported
+    assert create((4, 4, 4), (3, 11, 11)) == 4                 # hi < lo
+    assert create((4, 4, 4), (11, 11, 16)) == 4                # outside the domain
+    g.bc_lo[1] = g.bc_hi[1] = 1
+    assert create((0, 0, 0), (15, 15, 15)) == 7                # the "fine box" is the whole domain
+
+
+def test_inflow_profile_argument_checks():
+    mod, L = _lib()
+    arr = (C.c_double * 18)()
+    assert L.b200np_set_inflow_profile(None, 31, C.byref(arr), 0.0) == 4   # no handle
