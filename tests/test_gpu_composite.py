@@ -9,14 +9,10 @@ import numpy as np
 import pytest
 
 from helpers import TILE, oracle_params, rel_l2
-from test_composite_oracle import GOLD, GOLD_DIR, check, fine_per, load, to_full
+from test_composite_oracle import GOLD, check, fine_per, load, to_full
 
 pytestmark = pytest.mark.gpu
-# non-singular fixtures (an outflow face; tests/golden/composite_dirichlet/): the oracle reproduces them on CPU, the
-# CUDA path for them was written after the last GPU visit of round 1 -> not yet a hard requirement
-ALL_GOLD = [pytest.param(p, id=os.path.basename(p)[:-4]) for p in GOLD] + \
-           [pytest.param(p, id=os.path.basename(p)[:-4], marks=pytest.mark.xfail(strict=False, reason="no GPU run yet (round 2)"))
-            for p in GOLD_DIR]
+MIRROR = None
 
 
 def _mirror(oracle):
@@ -33,8 +29,12 @@ def _np(a):
 
 
 @pytest.mark.parametrize("host", [False, True], ids=["device_ptrs", "host_ptrs"])
-@pytest.mark.parametrize("path", ALL_GOLD)
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_composite_cuda_reproduces_golden(path, host):
+    _golden_case(path, host)
+
+
+def _golden_case(path, host):
     from incflo_b200 import nodal_projector as npj
     g = load(path)
     cp = npj.CompositeProjection(g["n0"], g["dx0"], g["bclo"], g["bchi"], g["clo"], g["chi"], opts=npj.nodal_proj_opts(tile=TILE))
