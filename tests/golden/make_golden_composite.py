@@ -189,8 +189,7 @@ def cases():
 
 
 def cases_dirichlet():
-    """non-singular problems (an outflow face): tests/golden/composite_dirichlet/ -- pins the oracle; the CUDA
-    path for them has no GPU run yet (tests/test_gpu_composite.py marks them xfail(strict=False))"""
+    """non-singular problems (an outflow face): tests/golden/composite_dirichlet/"""
     out = []
     # 1. channel-like: wall x-lo, outflow x-hi, walls y, periodic z; interior box
     n0, dx0 = (16, 8, 8), (1 / 16,) * 3

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from helpers import TILE, oracle_params, rel_l2
-from test_composite_oracle import GOLD, check, fine_per, load, to_full
+from test_composite_oracle import GOLD, GOLD_DIR, check, fine_per, load, to_full
 
 pytestmark = pytest.mark.gpu
 MIRROR = None
@@ -29,12 +29,9 @@ def _np(a):
 
 
 @pytest.mark.parametrize("host", [False, True], ids=["device_ptrs", "host_ptrs"])
-@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+@pytest.mark.parametrize("path", GOLD + GOLD_DIR, ids=[os.path.basename(p)[:-4] for p in GOLD + GOLD_DIR])
 def test_composite_cuda_reproduces_golden(path, host):
-    _golden_case(path, host)
-
-
-def _golden_case(path, host):
+    """singular (periodic / wall) and non-singular (outflow face, also with the box ON the outflow face) fixtures"""
     from incflo_b200 import nodal_projector as npj
     g = load(path)
     cp = npj.CompositeProjection(g["n0"], g["dx0"], g["bclo"], g["bchi"], g["clo"], g["chi"], opts=npj.nodal_proj_opts(tile=TILE))
