@@ -50,6 +50,15 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def solve_roofline(nodes, cells, vcycles, var_sigma=True):
+    """algorithmic HBM bytes of one projection from SURVEY 8(d)'s per-kernel table: one V(2,2) x 4-sweep cycle is
+    16 sweeps + residual + restriction + interpolation + (sol += cor, top residual) = 634 B per fine node (variable
+    sigma; 490 B constant), x 8/7 for the hierarchy, plus rhs (32 B/node) and pre-add + final update (88 + 96 B/cell)"""
+    per_node_cycle = (16 * 32 + 32 + 9 + 25 + 56) if var_sigma else (16 * 24 + 24 + 9 + 17 + 48)
+    per_cell = (88 + 96) if var_sigma else (72 + 88)
+    return nodes * (per_node_cycle * 8.0 / 7.0 * vcycles + 32.0) + cells * float(per_cell)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region"""
 
@@ -279,6 +288,10 @@ def run_ours(args):
                 "launches_per_step": sweeps_per_step, "share_of_step": sweeps_per_step * ms_sm / ms_per_step,
                 "residual_kernel": {"us_per_launch": ms_res * 1e3, "achieved": alg_bytes / (ms_res * 1e-3) / 1e9,
                                     "frac": alg_bytes / (ms_res * 1e-3) / 1e9 / peak}}
+    # the whole projection against the same peak (per rank: local nodes / cells, the realised V-cycle count)
+    solve_bytes = solve_roofline(nodes, ncell, iters, True)
+    roofline["whole_solve"] = {"algorithmic_bytes": solve_bytes, "achieved": solve_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": solve_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
 
     # ---------------- e2e arm: host (pinned) buffers through the same C-ABI call ----------------
     Ke = 0 if args.no_e2e else min(K, 3)
