@@ -172,3 +172,37 @@ def test_composite_operator_equals_assembled_finite_element_matrix(case, oracle)
     assert np.abs(op[n_act0:] - A[n_act0:]).max() < 1e-12 * scale      # fine rows: the FE rows themselves
     assert np.abs(op - expected).max() < 1e-12 * scale                  # coarse rows: FE row + restricted fine rows
     assert np.abs(A - A.T).max() < 1e-12 * scale and np.abs(op.sum(axis=1)).max() < 1e-11 * scale
+
+
+def test_composite_solution_converges_at_second_order(oracle):
+    """u = grad(psi) on both levels: the composite phi must approach psi (up to a constant) at O(h^2) on the fine
+    AND on the coarse level when the whole hierarchy is refined (pins sign and scaling conventions of the
+    composite rhs, reflux and interpolation against an analytic solution, like SURVEY 8(c).4 does for one level)"""
+    from oracle import composite as oc
+    tp = 2 * np.pi
+
+    def psi(x, y, z):
+        return np.cos(tp * x) * np.cos(tp * y) * np.cos(np.pi * z)
+
+    def grad_psi(n, h, off):
+        z, y, x = np.meshgrid(*[(np.arange(m) + 0.5) * h + o for m, o in zip(n[::-1], off[::-1])], indexing="ij")
+        return np.stack([-tp * np.sin(tp * x) * np.cos(tp * y) * np.cos(np.pi * z),
+                         -tp * np.cos(tp * x) * np.sin(tp * y) * np.cos(np.pi * z),
+                         -np.pi * np.cos(tp * x) * np.cos(tp * y) * np.sin(np.pi * z)])
+    errs = []
+    for N in (16, 32):
+        p0 = oracle_params((N, N, N), (1.0 / N,) * 3, (0, 0, 1), (0, 0, 1))
+        clo, chi = (N // 4,) * 3, (3 * N // 4 - 1,) * 3
+        vel0 = np.zeros((3, N + 2, N + 2, N + 2)); vel0[:, 1:-1, 1:-1, 1:-1] = grad_psi((N, N, N), 1.0 / N, (0, 0, 0))
+        vel1 = np.zeros((3, N + 2, N + 2, N + 2)); vel1[:, 1:-1, 1:-1, 1:-1] = grad_psi((N, N, N), 0.5 / N, (clo[0] / N,) * 3)
+        r = oc.CompositeProjector(p0, clo, chi).project(vel0, 1, vel1, 1, const_sigma=1.0, rtol=1e-12, atol=0.0)
+        assert r["status"] == 0
+        c0 = np.arange(N + 1) / N
+        Z, Y, X = np.meshgrid(c0, c0, c0, indexing="ij")
+        f0 = clo[0] / N + np.arange(N + 1) * 0.5 / N
+        Zf, Yf, Xf = np.meshgrid(f0, f0, f0, indexing="ij")
+        phi0 = to_full(r["phi0"], (0, 0, 1))
+        c = (phi0 - psi(X, Y, Z)).mean()
+        errs.append((np.abs(phi0 - c - psi(X, Y, Z)).max(), np.abs(r["phi1"] - c - psi(Xf, Yf, Zf)).max()))
+    assert errs[1][0] < 0.3 * errs[0][0] and errs[1][1] < 0.3 * errs[0][1]     # ~ 1/4 per halving of h
+    assert errs[1][0] < 5e-3 and errs[1][1] < 5e-3
