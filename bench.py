@@ -14,17 +14,23 @@ value  : Mcell-updates/s = cells * K / t with every input already resident in HB
          pointers through the C ABI), timed with CUDA events on the launching stream.
 e2e    : same metric through the same C-ABI call with HOST (pinned) buffers: H2D of
          velocity/density/gp and D2H of velocity/gp/p_nd inside the timed region.
-roofline: the dominant kernel (tile-resident Gauss-Seidel sweep k_smooth_iso, level 0): algorithmic
-         bytes (32 B/node variable sigma) / CUDA-event time per launch vs MEASURED_PEAKS.json hbm_gbs
+roofline: the dominant kernel (tile-resident Gauss-Seidel sweep, level 0): algorithmic bytes
+         (32 B/node variable sigma) / CUDA-event time per launch vs MEASURED_PEAKS.json hbm_gbs
          (burst copy figure; the kernel is timed alone, back to back); traffic = dram bytes of one
          launch from the committed ncu --set full capture (profiles/ncu_traffic.json).
-cpu_baseline: the CPU oracle (a port of the reference algorithm, NOT incflo/AMReX itself, which
-         cannot be built offline) on the box's host cores, on a bounded sample (128^3 of the same
-         workload).
---impl reference: times that CPU port alone (the reference's own CPU build needs the un-vendored
-         AMReX + AMReX-Hydro and MPI, none of which exist offline).
-N > 1  : z-slab decomposition, one process per GPU (torchrun), weak scaling: every rank owns
-         256 x 256 x 256 cells of a 256 x 256 x 256N domain.
+parity : before anything is timed, the same C-ABI call is checked against the CPU oracle (mirrored
+         smoother ordering) on a size whose level 0 runs the PRODUCTION kernels: N = 1: 128^3;
+         N > 1: 256 x 256 x 32N cells on N ranks (level 0 = the fused NVLink-halo sweep).  rel-L2 of
+         p, u, gp must be < 1e-9 (north_star), else the run exits non-zero.
+cpu_baseline / --impl reference: the CPU oracle configured as the REFERENCE's CPU algorithm
+         (AMReX multi-box semantics, SURVEY A.4: lexicographic Gauss-Seidel inside each
+         max_grid_size box, 4 sweeps per smooth call without halo refresh) on the FULL 256^3
+         workload with OpenMP on all host cores (the count in effect is printed).  It is a port:
+         incflo/AMReX itself cannot be built offline (AMReX, AMReX-Hydro, MPI are not vendored).
+N > 1  : z-slab decomposition, one process per GPU (torchrun).  Headline = weak scaling: every rank
+         owns 256 x 256 x 256 cells of a 256 x 256 x 256N domain.  The line also carries a `strong`
+         record: 512^3 and 1024^3 in total on the N GPUs against the same solve MEASURED on one GPU
+         (rank 0) in the same run.
 """
 import argparse
 import json
@@ -40,6 +46,8 @@ sys.path.insert(0, ROOT)
 METRIC = "nodal_projection_Mcell_updates_per_s"
 UNIT = "Mcell-updates/s"
 RTOL, ATOL = 1e-11, 1e-14
+PARITY_TOL = 1e-9            # north_star: pressure and projected velocity within 1e-9 relative L2
+REF_BOX = 64                 # amr.max_grid_size of the CPU reference arm at 256^3 (64 boxes)
 
 
 def peaks():
@@ -109,72 +117,300 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload(N, nranks, rank, device, ng=3, strong=False):
-    """per-rank slab of the rayleigh_taylor workload.  weak scaling: N x N x N cells per rank
-    (domain N x N x N*nranks); strong scaling: the N^3 domain cut into nranks z slabs."""
-    import torch
+# ------------------------------------------------------------------------------------------
+# workloads (closed forms, filled in z chunks so that a 1024^3 slab never needs a second copy)
+# ------------------------------------------------------------------------------------------
+def fill_inputs(vel, gp, n_glob, zlo, nz, ng, rho=None, chunk=64):
+    """(re)generate this rank's inputs in place: velocity (valid cells; ghost cells zero), gp, and optionally rho"""
     from incflo_b200 import problems
-    n_glob = (N, N, N) if strong else (N, N, N * nranks)
-    nz = N // nranks if strong else N
-    dt = 0.45 / N
-    with problems.slab(rank * nz, nz):   # this rank's cell planes [rank*nz, (rank+1)*nz) of the global closed forms
-        vel = problems.rayleigh_taylor_velocity(n_glob, ng, device, "b")
-        rho = problems.rayleigh_taylor_density(n_glob, ng, device)
-    gp = torch.zeros((3, nz, N, N), dtype=torch.float64, device=device)
+    N0, N1 = n_glob[0], n_glob[1]
+    vel.zero_()
+    for z0 in range(0, nz, chunk):
+        c = min(chunk, nz - z0)
+        with problems.slab(zlo + z0, c):   # cell planes [zlo+z0, zlo+z0+c) of the global closed forms
+            v = problems.rayleigh_taylor_velocity(n_glob, 0, vel.device, "b")
+            vel[:, ng + z0:ng + z0 + c, ng:ng + N1, ng:ng + N0] = v
+            if rho is not None:
+                rho[ng + z0:ng + z0 + c, ng:ng + N1, ng:ng + N0] = problems.rayleigh_taylor_density(n_glob, 0, vel.device)
+        del v
+    gp.zero_()
     gp[2] = -0.05  # a hydrostatic-like old pressure gradient so the pre-add does work
-    p = torch.zeros((nz + 1, N + 1, N + 1), dtype=torch.float64, device=device)
-    return dict(n=n_glob, dx=(1.0 / N,) * 3, dt=dt, vel=vel, rho=rho, gp=gp, p=p, ng=ng,
+
+
+def workload(n_glob, nranks, rank, device, ng=3):
+    """this rank's z slab of the rayleigh_taylor workload on the global domain n_glob (dx = 1/n_glob[0], isotropic)"""
+    import torch
+    N0, N1, N2 = n_glob
+    nz = N2 // nranks
+    zlo = rank * nz
+    vel = torch.empty((3, nz + 2 * ng, N1 + 2 * ng, N0 + 2 * ng), dtype=torch.float64, device=device)
+    rho = torch.ones((nz + 2 * ng, N1 + 2 * ng, N0 + 2 * ng), dtype=torch.float64, device=device)
+    gp = torch.empty((3, nz, N1, N0), dtype=torch.float64, device=device)
+    p = torch.zeros((nz + 1, N1 + 1, N0 + 1), dtype=torch.float64, device=device)
+    fill_inputs(vel, gp, n_glob, zlo, nz, ng, rho)
+    return dict(n=tuple(n_glob), dx=(1.0 / N0,) * 3, dt=0.45 / N0, vel=vel, rho=rho, gp=gp, p=p, ng=ng, zlo=zlo, nz=nz,
                 bclo=(0, 0, 1), bchi=(0, 0, 1))
 
 
-def cpu_port_run(N, steps, warmup):
-    """the CPU oracle (port of the reference algorithm) on a bounded sample; returns list of seconds"""
+# ------------------------------------------------------------------------------------------
+# CPU oracle legs (checker for `parity`, CPU baseline; never part of the product path)
+# ------------------------------------------------------------------------------------------
+def oracle_threads():
+    """torchrun exports OMP_NUM_THREADS=1: set the team size explicitly, report what is in effect"""
+    from oracle import pyoracle as po
+    return po.set_num_threads(os.cpu_count() or 1)
+
+
+def oracle_params(n, mode):
+    from oracle import pyoracle as po
+    dx = (1.0 / n[0],) * 3
+    if mode == "mirror":      # the GPU's tile ordering: sweep-by-sweep comparable
+        return po.make_params(n, dx, (0, 0, 1), (0, 0, 1), smoother=po.SM_BOX, box=(64, 16, 64), box_order=po.SM_PLANE4,
+                              box_stale_per_call=0)
+    b = min(REF_BOX, n[0] // 2)   # the reference's CPU algorithm (SURVEY A.4): multi-box lexicographic GS, 4 stale sweeps
+    return po.make_params(n, dx, (0, 0, 1), (0, 0, 1), smoother=po.SM_BOX, box=(b, b, b), box_order=po.SM_LEX,
+                          box_stale_per_call=1, box_amrex=1)
+
+
+def cpu_port_run(n, steps, warmup, mode="reference", keep=False):
+    """the CPU oracle on the rayleigh_taylor workload of global size n; returns (seconds per step, V-cycles, fields)"""
     import numpy as np
-    from incflo_b200 import problems
     from oracle import pyoracle as po
     ng = 3
-    n = (N, N, N)
-    vel0 = problems.rayleigh_taylor_velocity(n, ng, "cpu", "b").numpy()
-    rho = problems.rayleigh_taylor_density(n, ng, "cpu").numpy()
-    gp0 = np.zeros((3, N, N, N)); gp0[2] = -0.05
-    prm = po.make_params(n, (1.0 / N,) * 3, (0, 0, 1), (0, 0, 1), smoother=po.SM_BOX, box=(64, 16, 64),
-                         box_order=po.SM_PLANE4, box_stale_per_call=0)
-    times, iters = [], 0
+    wl = workload(n, 1, 0, "cpu", ng)
+    vel0, rho, gp0 = wl["vel"].numpy(), wl["rho"].numpy(), wl["gp"].numpy()
+    prm = oracle_params(n, mode)
+    times, iters, out = [], 0, None
     for s in range(warmup + steps):
-        vel = vel0.copy(); gp = gp0.copy(); p = np.zeros((N + 1,) * 3)
+        vel = vel0.copy(); gp = gp0.copy(); p = np.zeros((n[2] + 1, n[1] + 1, n[0] + 1))
         t0 = time.perf_counter()
-        status, st = po.apply_nodal_projection(prm, vel, ng, gp, p, density=rho, ngd=ng, scaling_factor=0.45 / N,
+        status, st = po.apply_nodal_projection(prm, vel, ng, gp, p, density=rho, ngd=ng, scaling_factor=wl["dt"],
                                                rtol=RTOL, atol=ATOL)
         dt = time.perf_counter() - t0
         assert status == 0
         iters = st.iters
         if s >= warmup:
             times.append(dt)
-    return times, iters
+        if keep:
+            out = dict(vel=vel, gp=gp, p=p)
+    return times, iters, out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    Ns = 128  # bounded sample: 1/8 of the 256^3 workload per step
-    cores = os.cpu_count()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
-    times, iters = cpu_port_run(Ns, steps, warmup)
+    threads = oracle_threads()
+    n = (args.n,) * 3
+    steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
+    times, iters, _ = cpu_port_run(n, steps, warmup, "reference")
     t = sum(times) / len(times)
-    val = Ns ** 3 / t / 1e6
-    sample = f"{Ns}^3 rayleigh_taylor variable-density projection per step (1/8 of the {args.n}^3 workload), {len(times)} steps"
+    val = args.n ** 3 / t / 1e6
+    what = (f"CPU restatement of the reference algorithm (AMReX multi-box semantics: lexicographic Gauss-Seidel inside "
+            f"{min(REF_BOX, args.n // 2)}^3-cell boxes, 4 sweeps per smooth call without halo refresh, V(2,2), BiCGStab bottom), OpenMP")
+    sample = (f"the full {args.n}^3 rayleigh_taylor variable-density projection per step"
+              + (f" (= the per-GPU share of the {args.gpus}-GPU weak-scaling workload)" if args.gpus > 1 else "")
+              + f", {len(times)} timed steps after {warmup} warm-up")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
             "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"rayleigh_taylor variable-density {args.n}^3 nodal projection (BASELINE configs[1]); "
-                                   f"CPU arm runs the bounded {Ns}^3 sample", "rtol": RTOL, "atol": ATOL, "vcycles": iters},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "note": "CPU restatement of AMReX MLMG nodal projection (OpenMP); incflo/AMReX itself cannot be "
-                                     "built offline (AMReX, AMReX-Hydro, MPI not vendored)"},
+            "config": {"workload": f"rayleigh_taylor variable-density (sigma=dt/rho, 4:1) {args.n}^3, periodic x/y + walls z, nodal "
+                                   f"projection to rtol 1e-11 (BASELINE configs[1])", "rtol": RTOL, "atol": ATOL, "vcycles": iters,
+                       "cycle": "V(2,2) x 4 sweeps (reference defaults)", "algorithm": what},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count(),
+                             "note": "port, not incflo/AMReX itself: AMReX, AMReX-Hydro and MPI are not vendored and cannot be built offline"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def make_projection(ctx, n_glob, nranks=None):
+    """a handle over the global domain n_glob on all ranks (or on this rank alone when nranks == 1)"""
+    import torch
+    import torch.distributed as dist
+    from incflo_b200 import nodal_projector as npj
+    nranks = ctx.nranks if nranks is None else nranks
+    nccl_id = None
+    if nranks > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=ctx.device)
+        if ctx.rank == 0:
+            idt.copy_(torch.tensor(list(npj.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+    proj = npj.IncfloProjection(n_glob, (1.0 / n_glob[0],) * 3, (0, 0, 1), (0, 0, 1), device=ctx.local,
+                                rank=ctx.rank if nranks > 1 else 0, nranks=nranks, nccl_id=nccl_id)
+    proj.set_stream(ctx.stream.cuda_stream)
+    return proj
+
+
+def allmax(ctx, x):
+    import torch
+    import torch.distributed as dist
+    if ctx.nranks == 1:
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64, device=ctx.device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def parity_block(ctx):
+    """C-ABI call vs the CPU oracle (mirrored ordering) on a size whose level 0 runs the production kernels"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    P, rank = ctx.nranks, ctx.rank
+    n = (128, 128, 128) if P == 1 else (256, 256, 32 * P)
+    wl = workload(n, P, rank, ctx.device)
+    proj = make_projection(ctx, n)
+    with torch.cuda.stream(ctx.stream):
+        st = proj.apply_nodal_projection(wl["vel"], wl["ng"], wl["gp"], wl["p"], density=wl["rho"], ngd=wl["ng"],
+                                         scaling_factor=wl["dt"], mg_rtol=RTOL, mg_atol=ATOL)
+    torch.cuda.synchronize()
+    transport = proj.halo_transport()
+    proj.close()
+    ng, nz, zlo = wl["ng"], wl["nz"], wl["zlo"]
+    # oracle on the GLOBAL problem (rank 0), results broadcast as device tensors
+    shapes = dict(vel=(3, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng), gp=(3, n[2], n[1], n[0]), p=(n[2] + 1, n[1] + 1, n[0] + 1))
+    ref, info = {}, torch.zeros(3, dtype=torch.float64, device=ctx.device)
+    if rank == 0:
+        t0 = time.perf_counter()
+        _, it_m, out = cpu_port_run(n, 1, 0, "mirror", keep=True)
+        info[0] = it_m; info[1] = time.perf_counter() - t0
+        if P == 1:   # the reference's CPU algorithm on the same input: V-cycle count for the 20 % band
+            _, it_r, _ = cpu_port_run(n, 1, 0, "reference")
+            info[2] = it_r
+    for k in ("vel", "gp", "p"):
+        ref[k] = torch.from_numpy(out[k]).to(ctx.device) if rank == 0 else torch.empty(shapes[k], dtype=torch.float64, device=ctx.device)
+        if P > 1:
+            dist.broadcast(ref[k], 0)
+    if P > 1:
+        dist.broadcast(info, 0)
+    inner = (slice(None), slice(ng, ng + nz), slice(ng, -ng), slice(ng, -ng))
+    rv = ref["vel"][:, zlo:zlo + nz + 2 * ng][inner]
+    rg = ref["gp"][:, zlo:zlo + nz]
+    own = nz + (1 if rank == P - 1 else 0)          # uniquely owned node planes
+    rp = ref["p"][zlo:zlo + own]
+    dp = wl["p"][:own] - rp
+    sums = torch.stack([((wl["vel"][inner] - rv) ** 2).sum(), (rv ** 2).sum(), ((wl["gp"] - rg) ** 2).sum(), (rg ** 2).sum(),
+                        dp.sum(), torch.tensor(float(dp.numel()), dtype=torch.float64, device=ctx.device), rp.sum()])
+    if P > 1:
+        dist.all_reduce(sums)
+    mean_d, mean_r = sums[4] / sums[5], sums[6] / sums[5]   # the problem is singular: compare p up to a constant
+    s2 = torch.stack([((dp - mean_d) ** 2).sum(), ((rp - mean_r) ** 2).sum()])
+    if P > 1:
+        dist.all_reduce(s2)
+    res = {"n_cell": list(n), "ranks": P, "checker": "CPU oracle, mirrored smoother ordering (oracle/nodal_oracle.c)",
+           "rel_l2_u": float(torch.sqrt(sums[0] / sums[1])), "rel_l2_gp": float(torch.sqrt(sums[2] / sums[3])),
+           "rel_l2_p": float(torch.sqrt(s2[0] / s2[1])), "tol": PARITY_TOL, "vcycles_gpu": int(st.iters),
+           "vcycles_oracle_mirrored": int(info[0].item()), "oracle_seconds": float(info[1].item()),
+           "halo_transport": {0: "none (1 GPU)", 1: "ipc", 2: "nccl"}[transport]}
+    if P == 1:
+        res["vcycles_reference_cpu_algorithm"] = int(info[2].item())
+    res["ok"] = bool(st.status == 0 and max(res["rel_l2_u"], res["rel_l2_gp"], res["rel_l2_p"]) < PARITY_TOL
+                     and abs(res["vcycles_gpu"] - res["vcycles_oracle_mirrored"]) <= 1)
+    del wl, ref
+    torch.cuda.empty_cache()
+    return res
+
+
+def timed_solves(ctx, proj, wl, K, W, n_glob, restore="clone"):
+    """W warm-up + K timed steps; returns (ms per step (max over ranks), per-step list, last stats, launches)"""
+    import torch
+    import torch.distributed as dist
+    ng = wl["ng"]
+
+    def step(vel, gp, p):
+        return proj.apply_nodal_projection(vel, ng, gp, p, density=wl["rho"], ngd=ng, scaling_factor=wl["dt"],
+                                           mg_rtol=RTOL, mg_atol=ATOL)
+    if restore == "clone":      # every timed step of a chunk gets its own untouched inputs
+        nbuf = min(K, 16)
+        vels = [wl["vel"].clone() for _ in range(nbuf)]
+        gps = [wl["gp"].clone() for _ in range(nbuf)]
+
+        def refill():
+            for i in range(nbuf):
+                vels[i].copy_(wl["vel"]); gps[i].copy_(wl["gp"])
+    else:                       # big slabs: one buffer, regenerated in place between steps
+        nbuf = 1
+        vels, gps = [wl["vel"]], [wl["gp"]]
+
+        def refill():
+            fill_inputs(wl["vel"], wl["gp"], n_glob, wl["zlo"], wl["nz"], ng)
+    st = None
+    for s_ in range(W):
+        with torch.cuda.stream(ctx.stream):
+            st = step(vels[s_ % nbuf], gps[s_ % nbuf], wl["p"])
+        if nbuf == 1:
+            torch.cuda.synchronize(); refill()
+    torch.cuda.synchronize()
+    refill()
+    torch.cuda.synchronize()
+    if ctx.nranks > 1:
+        dist.barrier()
+    t_dev, launches, done, step_ms = 0.0, 0, 0, []
+    while done < K:
+        chunk = min(nbuf, K - done)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(chunk + 1)]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(ctx.stream):
+            ev[0].record(ctx.stream)
+            for i in range(chunk):
+                st = step(vels[i], gps[i], wl["p"])
+                launches += st.launches
+                ev[i + 1].record(ctx.stream)
+        torch.cuda.synchronize()
+        t_dev += ev[0].elapsed_time(ev[chunk])
+        step_ms += [ev[i].elapsed_time(ev[i + 1]) for i in range(chunk)]
+        done += chunk
+        if done < K:
+            refill()   # restore inputs between chunks, outside the event brackets
+            torch.cuda.synchronize()
+    return allmax(ctx, t_dev) / K, step_ms, st, launches
+
+
+def strong_block(ctx, sizes):
+    """strong scaling: the n^3 problem on all N GPUs vs the SAME solve measured on one GPU (rank 0) in this run"""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    for n1 in sizes:
+        n = (n1, n1, n1)
+        rec = {"n_cell": list(n)}
+        restore = "clone" if n1 <= 512 else "regen"
+        K, W = (3, 2) if n1 <= 512 else (2, 1)
+        # one GPU (rank 0 alone; the other ranks wait at the barrier)
+        if ctx.rank == 0:
+            try:
+                wl = workload(n, 1, 0, ctx.device)
+                solo = Ctx(); solo.__dict__.update(ctx.__dict__); solo.nranks = 1
+                proj = make_projection(solo, n, nranks=1)
+                ms1, _, st1, _ = timed_solves(solo, proj, wl, K, W, n, restore)
+                proj.close()
+                rec.update(ms_per_solve_1gpu=ms1, vcycles_1gpu=int(st1.iters))
+                del wl, proj
+            except Exception as e:   # e.g. out of memory for the one-GPU 1024^3 problem next to other tenants
+                rec.update(ms_per_solve_1gpu=None, error_1gpu=repr(e)[:200])
+            torch.cuda.empty_cache()
+        dist.barrier()
+        wl = workload(n, ctx.nranks, ctx.rank, ctx.device)
+        proj = make_projection(ctx, n)
+        msN, _, stN, _ = timed_solves(ctx, proj, wl, K, W, n, restore)
+        rec.update(ms_per_solve=msN, vcycles=int(stN.iters), resid_over_bnorm=stN.resnorm / max(stN.rhsnorm, stN.resnorm0),
+                   Mcell_updates_per_s=n1 ** 3 / msN / 1e3, steps=K, warmup=W)
+        proj.close()
+        del wl, proj
+        torch.cuda.empty_cache()
+        if ctx.rank == 0 and rec.get("ms_per_solve_1gpu"):
+            rec["speedup_vs_1gpu"] = rec["ms_per_solve_1gpu"] / msN
+        out[str(n1)] = rec
+    return out
 
 
 def run_ours(args):
@@ -182,87 +418,44 @@ def run_ours(args):
     import torch.distributed as dist
     from incflo_b200 import nodal_projector as npj
 
-    nranks = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx = Ctx()
+    ctx.nranks = nranks = int(os.environ.get("WORLD_SIZE", "1"))
+    ctx.rank = rank = int(os.environ.get("RANK", "0"))
+    ctx.local = local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product path has no CPU fallback"
     torch.cuda.set_device(local)
-    device = f"cuda:{local}"
+    ctx.device = device = f"cuda:{local}"
     if nranks > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
+    ctx.stream = torch.cuda.Stream()   # the launching stream: the handle runs on it, the events are recorded on it
     N, K, W = args.n, args.steps, args.warmup
     strong = args.scaling == "strong" and nranks > 1
-    wl = workload(N, nranks, rank, device, strong=strong)   # weak (default): every rank owns an N^3 slab of an N x N x (N*nranks) domain
-    nccl_id = None
-    if nranks > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=device)
-        if rank == 0:
-            idt.copy_(torch.tensor(list(npj.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().tolist())
-    ng = wl["ng"]
-    proj = npj.IncfloProjection(wl["n"], wl["dx"], wl["bclo"], wl["bchi"], device=local, rank=rank, nranks=nranks,
-                                nccl_id=nccl_id)
-    stream = torch.cuda.Stream()           # the launching stream: the handle runs on it, the events are recorded on it
-    proj.set_stream(stream.cuda_stream)
-    ncell = N ** 3 // nranks if strong else N ** 3   # cells per rank
+    threads = oracle_threads() if rank == 0 else 0
 
-    def step(vel, gp, p, rho):
-        return proj.apply_nodal_projection(vel, ng, gp, p, density=rho, ngd=ng, scaling_factor=wl["dt"],
-                                           mg_rtol=RTOL, mg_atol=ATOL)
+    # ---------------- parity first: a fast wrong answer is not a result ----------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(ctx)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "parity check failed", "parity": parity}))
+            sys.stdout.flush()
+            sys.exit(3)
 
     # ---------------- device-resident arm ----------------
-    nbuf = min(K, 16)                      # every timed step gets its own untouched inputs
-    vels = [wl["vel"].clone() for _ in range(nbuf)]
-    gps = [wl["gp"].clone() for _ in range(nbuf)]
-    ps = [wl["p"].clone() for _ in range(nbuf)]
-
-    def refill():
-        for i in range(nbuf):
-            vels[i].copy_(wl["vel"]); gps[i].copy_(wl["gp"])
-        torch.cuda.synchronize()
-
-    with torch.cuda.stream(stream):
-        for s_ in range(W):
-            st = step(vels[s_ % nbuf], gps[s_ % nbuf], ps[s_ % nbuf], wl["rho"])
-    torch.cuda.synchronize()
-    refill()
-    if nranks > 1:
-        dist.barrier()
+    n_glob = (N, N, N) if (strong or nranks == 1) else (N, N, N * nranks)   # weak (default): an N^3 slab per rank
+    wl = workload(n_glob, nranks, rank, device)
+    proj = make_projection(ctx, n_glob)
+    transport = proj.halo_transport()
+    ncell = n_glob[0] * n_glob[1] * n_glob[2] // nranks   # cells per rank
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    t_dev = 0.0
-    launches = 0
-    iters = 0
     t0 = time.perf_counter()
-    done = 0
-    step_ms = []
-    while done < K:
-        chunk = min(nbuf, K - done)
-        # one event bracket around the chunk (the reported time) + one event after every step (median / min)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(chunk + 1)]
-        torch.cuda.synchronize()
-        with torch.cuda.stream(stream):
-            ev[0].record(stream)
-            for i in range(chunk):
-                st = step(vels[i], gps[i], ps[i], wl["rho"])
-                launches += st.launches
-                iters = st.iters
-                ev[i + 1].record(stream)
-        torch.cuda.synchronize()
-        t_dev += ev[0].elapsed_time(ev[chunk])
-        step_ms += [ev[i].elapsed_time(ev[i + 1]) for i in range(chunk)]
-        done += chunk
-        if done < K:
-            refill()   # restore inputs between chunks, outside the event brackets
+    ms_per_step, step_ms, st, launches = timed_solves(ctx, proj, wl, K, W, n_glob, "clone" if N <= 512 else "regen")
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    if nranks > 1:
-        tt = torch.tensor([t_dev], dtype=torch.float64, device=device)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev = float(tt.item())
-    ms_per_step = t_dev / K
+    iters = st.iters
     value = ncell * nranks / (ms_per_step * 1e-3) / 1e6
     resid_ratio = st.resnorm / max(st.rhsnorm, st.resnorm0)
 
@@ -282,8 +475,10 @@ def run_ours(args):
     except Exception:
         pass
     sweeps_per_step = iters * 16
-    roofline = {"bound": "hbm", "kernel": "k_smooth_iso<variable sigma> level 0 (one Gauss-Seidel sweep)",
+    roofline = {"bound": "hbm", "kernel": "level-0 Gauss-Seidel sweep, variable sigma (one launch = one sweep over the level)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "profiles/ncu_traffic.json (committed ncu --set full capture of this kernel at this size)",
+                "frac_of_nominal_8TBs": achieved / 8000.0,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms_sm * 1e3,
                 "launches_per_step": sweeps_per_step, "share_of_step": sweeps_per_step * ms_sm / ms_per_step,
                 "residual_kernel": {"us_per_launch": ms_res * 1e3, "achieved": alg_bytes / (ms_res * 1e-3) / 1e9,
@@ -294,6 +489,11 @@ def run_ours(args):
                                "frac": solve_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
 
     # ---------------- e2e arm: host (pinned) buffers through the same C-ABI call ----------------
+    ng = wl["ng"]
+
+    def step(vel, gp, p, rho):
+        return proj.apply_nodal_projection(vel, ng, gp, p, density=rho, ngd=ng, scaling_factor=wl["dt"],
+                                           mg_rtol=RTOL, mg_atol=ATOL)
     Ke = 0 if args.no_e2e else min(K, 3)
     hv = [wl["vel"].cpu().pin_memory() for _ in range(Ke)]
     hg = [wl["gp"].cpu().pin_memory() for _ in range(Ke)]
@@ -312,13 +512,25 @@ def run_ours(args):
         ste = step(hv[i].numpy(), hg[i].numpy(), hp[i].numpy(), hr.numpy())
         te += time.perf_counter() - a
         h2d, d2h = ste.h2d_bytes, ste.d2h_bytes
-    if nranks > 1:
-        tt = torch.tensor([te], dtype=torch.float64, device=device)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        te = float(tt.item())
+    te = allmax(ctx, te)
     e2e_val = ncell * nranks / (te / Ke) / 1e6 if Ke else None
+    proj.close()
+    del wl, hv, hg, hp, hr
+    torch.cuda.empty_cache()
+
+    # ---------------- strong-scaling record (N > 1): 512^3 / 1024^3 in total vs one GPU, measured here ----------------
+    strong_rec = None
+    if nranks > 1 and not args.no_strong and not strong:
+        sizes = [s for s in (512, 1024) if s % nranks == 0]
+        strong_rec = strong_block(ctx, sizes)
 
     if rank == 0:
+        tname = {0: "none (1 GPU)", 1: "ipc", 2: "nccl"}[transport]
+        par = "1 GPU" if nranks == 1 else (
+            f"z-slab decomposition over {nranks} GPUs; halo planes: "
+            + ("stores / loads into the neighbours' arenas over NVLink peer memory (CUDA IPC), issued by the solver kernels"
+               if transport == 1 else "FALLBACK grouped ncclSend/ncclRecv (CUDA IPC mapping unavailable)")
+            + f"; ncclAllReduce for norms / solvability; domain {n_glob[0]}x{n_glob[1]}x{n_glob[2]}")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
@@ -326,24 +538,23 @@ def run_ours(args):
                                        f"walls z, nodal projection to rtol 1e-11 (BASELINE configs[1])",
                            "rtol": RTOL, "atol": ATOL, "vcycles": iters, "resid_over_bnorm": resid_ratio,
                            "cycle": "V(2,2) x 4 sweeps (reference defaults)", "inputs_vs_l2": "working set >> 126 MB L2",
-                           "parallelism": "1 GPU" if nranks == 1 else f"z-slab decomposition over {nranks} GPUs (NCCL halo planes + allreduce), "
-                                                                                 f"domain {N}x{N}x{N if strong else N * nranks}",
+                           "parallelism": par, "halo_transport": tname,
                            "solves_per_s": 1e3 / ms_per_step,   # projections of the whole (global) domain per second
                            "ms_per_step_median": sorted(step_ms)[len(step_ms) // 2], "ms_per_step_min": min(step_ms)},
                 "clocks": clocks, "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                                           "d2h_bytes_per_step": int(d2h), "steps": Ke, "ms_per_step": te / Ke * 1e3 if Ke else None},
-                "gpu_launches": int(launches), "roofline": roofline, "wall_s_timed_region": wall}
+                "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "wall_s_timed_region": wall}
+        if strong_rec is not None:
+            line["strong"] = strong_rec
         if nranks == 1 and not args.no_cpu:
-            cores = os.cpu_count()
-            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-            Ns = 128
-            times, it_cpu = cpu_port_run(Ns, 2, 0)
+            times, it_cpu, _ = cpu_port_run((N, N, N), 1, 0, "reference")
             tcpu = min(times)
-            line["cpu_baseline"] = {"value": Ns ** 3 / tcpu / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{Ns}^3 of the same workload (1/8 of the cells), best of {len(times)} runs, "
-                                              f"{it_cpu} V-cycles; CPU restatement of the AMReX algorithm, not incflo/AMReX"}
+            line["cpu_baseline"] = {"value": N ** 3 / tcpu / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+                                    "sample": f"one full {N}^3 projection of the same workload ({tcpu:.1f} s, {it_cpu} V-cycles) with the "
+                                              f"reference's CPU algorithm (AMReX multi-box semantics: lexicographic Gauss-Seidel in "
+                                              f"{min(REF_BOX, N // 2)}^3 boxes, 4 sweeps per smooth call without halo refresh); CPU restatement, "
+                                              f"not incflo/AMReX"}
         print(json.dumps(line))
-    proj.close()
     if nranks > 1:
         dist.destroy_process_group()
 
@@ -369,6 +580,8 @@ def main():
                     help="N > 1: weak = n^3 cells per GPU (default, the driver's scaling run); strong = n^3 in total")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer arm (the line is then not a valid bench line)")
+    ap.add_argument("--no-parity", action="store_true", help="tuning sweeps only: skip the oracle check before timing")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the 512^3 / 1024^3 strong-scaling record")
     args = ap.parse_args()
     real_stdout = _json_only_stdout()
     sys.stdout = real_stdout

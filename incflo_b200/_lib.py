@@ -14,7 +14,6 @@ CSRC = os.path.join(_PKG, "csrc")
 LIBDIR = os.path.join(_PKG, "lib")
 SO = os.path.join(LIBDIR, "libb200np.so")
 SOURCES = ["b200np.cu"]
-HEADERS = ["np_level.h", "np_kernels.cuh", "np_smooth.cuh", "np_smooth3.cuh", os.path.join(ROOT, "include", "b200np.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -24,8 +23,10 @@ def _stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    # every file of csrc/ (sources and headers alike) and the public header
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(ROOT, "include", "b200np.h"))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
 def build(force=False, verbose=False):
@@ -33,11 +34,13 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    nvcc = os.environ.get("NVCC", os.path.join(cuda_home, "bin", "nvcc"))
+    ccbin = os.environ.get("B200NP_CCBIN", "/usr/bin/g++")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
-    subprocess.check_call(cmd + ["-ccbin", "/usr/bin/g++"], env=env)
+    subprocess.check_call(cmd + ["-ccbin", ccbin], env=env)
     return SO
 
 
@@ -68,7 +71,7 @@ class Stats(C.Structure):
 EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np_nccl_unique_id", "b200np_slab_range", "b200np_dist_plan",
            "b200np_destroy", "b200np_set_stream", "b200np_project",
            "b200np_apply_nodal_projection", "b200np_set_inflow_profile", "b200np_strerror", "b200np_version", "b200np_nlevels",
-           "b200np_level_dims", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
+           "b200np_level_dims", "b200np_halo_transport", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
            "b200np_time_op", "b200np_composite_create", "b200np_composite_destroy", "b200np_composite_set_stream",
            "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection"]
 
@@ -102,6 +105,7 @@ def lib():
     L.b200np_strerror.restype = C.c_char_p
     L.b200np_version.restype = C.c_int
     L.b200np_nlevels.argtypes = [vp]
+    L.b200np_halo_transport.argtypes = [vp]
     L.b200np_level_dims.argtypes = [vp, C.c_int, ip, ip]
     L.b200np_set_sigma.argtypes = [vp, dp, fb, C.c_double]
     L.b200np_level_set.argtypes = [vp, C.c_int, C.c_int, dp]

@@ -458,8 +458,15 @@ void setup_p2p(b200np* h)
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
     std::vector<cudaIpcMemHandle_t> all(P);
     cudaIpcMemHandle_t mine{};
-    double ok = cudaIpcGetMemHandle(&mine, h->arena.base) == cudaSuccess ? 1.0 : 0.0;
-    cudaGetLastError();
+    double ok = 1.0;
+    {
+        cudaError_t e = cudaIpcGetMemHandle(&mine, h->arena.base);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "b200np[rank %d]: cudaIpcGetMemHandle failed: %s\n", r, cudaGetErrorString(e));
+            ok = 0.0;
+        }
+        cudaGetLastError();
+    }
     char* buf = reinterpret_cast<char*>(h->ipc_buf);
     CK(cudaMemcpyAsync(buf + 64 * r, &mine, 64, cudaMemcpyHostToDevice, h->stream));
     NK(g_nccl.AllGather(buf + 64 * r, buf, 64, ncclChar, h->comm, h->stream));
@@ -469,12 +476,21 @@ void setup_p2p(b200np* h)
     const bool has_lo = per || r > 0, has_hi = per || r < P - 1;
     const int lo = (r - 1 + P) % P, hi = (r + 1) % P;
     void *plo = nullptr, *phi = nullptr;
-    if (ok > 0 && has_lo && cudaIpcOpenMemHandle(&plo, all[lo], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.0;
+    auto open_peer = [&](void** p, int peer) {
+        cudaError_t e = cudaIpcOpenMemHandle(p, all[peer], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "b200np[rank %d]: cudaIpcOpenMemHandle(arena of rank %d, %zu bytes) failed: %s\n", r, peer, h->arena.size,
+                    cudaGetErrorString(e));
+            *p = nullptr;
+            ok = 0.0;
+        }
+        cudaGetLastError();
+    };
+    if (ok > 0 && has_lo) open_peer(&plo, lo);
     if (ok > 0 && has_hi) {
         if (has_lo && hi == lo) phi = plo;
-        else if (cudaIpcOpenMemHandle(&phi, all[hi], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.0;
+        else open_peer(&phi, hi);
     }
-    cudaGetLastError();
     CK(cudaMemcpyAsync(h->dscal + 4, &ok, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     NK(g_nccl.AllReduce(h->dscal + 4, h->dscal + 4, 1, ncclDouble, ncclMin, h->comm, h->stream));
     CK(cudaMemcpyAsync(&ok, h->dscal + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -486,7 +502,8 @@ void setup_p2p(b200np* h)
         if (phi && phi != plo) cudaIpcCloseMemHandle(phi);
         h->peer_lo = h->peer_hi = nullptr;
         cudaGetLastError();
-        if (r == 0) fprintf(stderr, "b200np: CUDA IPC peer mapping unavailable, slab halos use ncclSend/ncclRecv\n");
+        if (r == 0) fprintf(stderr, "b200np: WARNING: CUDA IPC peer mapping unavailable on at least one rank, slab halos FALL BACK to ncclSend/ncclRecv "
+                                    "(b200np_halo_transport() == 2)\n");
     }
 }
 inline void halo_nodes(b200np* h, LevelData& L, double* x)
@@ -757,8 +774,16 @@ void vcycle(b200np* h)
     if (!h->graph_exec) {
         long long before = h->launches;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        vcycle_launch(h, 0);
-        epoch_advance(h);   // last node: every replay leaves the base advanced by the graph's exchanges
+        try {
+            vcycle_launch(h, 0);
+            epoch_advance(h);   // last node: every replay leaves the base advanced by the graph's exchanges
+        } catch (int) {   // never leave the (possibly caller-owned) stream in capture mode
+            cudaGraph_t broken = nullptr;
+            cudaStreamEndCapture(h->stream, &broken);
+            if (broken) cudaGraphDestroy(broken);
+            cudaGetLastError();
+            throw;
+        }
         CK(cudaStreamEndCapture(h->stream, &h->graph));
         CK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
         h->launches_per_vcycle = h->launches - before;
@@ -903,6 +928,18 @@ bool vel_box_ok(const b200np* h, const b200np_fab* vb)
         const bool need = !g.per[d] || (d == 2 && h->nranks > 1);
         if (need && (vb->lo[d] > clo[d] - 1 || vb->hi[d] < chi[d] + 1)) return false;
     }
+    return true;
+}
+
+// the caller's nodal box (phi / p_nd) must hold every node plane this rank writes: all nodes [0, n] in x and y and, in z,
+// the rank's cell slab's nodes [ck0, ck0 + cnzl]; on a slab it must not reach beyond them (k_copy_phi reads the node
+// plane above the slab from the ghost slot and nothing further away)
+bool nodal_box_ok(const b200np* h, const b200np_fab* pb)
+{
+    const Lev& g = h->lv[0].g;
+    const int nlo[3] = {0, 0, g.ck0}, nhi[3] = {g.n[0], g.n[1], g.ck0 + g.cnzl};
+    if (!box_covers(pb, nlo, nhi, 1)) return false;
+    if (h->nranks > 1 && (pb->lo[2] < nlo[2] - (g.ck0 > 0 || g.per[2] ? 1 : 0) || pb->hi[2] > nhi[2])) return false;
     return true;
 }
 
@@ -1192,9 +1229,15 @@ int comp_core(b200np_composite* C, Fab vel0, Fab vel1, Fab velo0, Fab velo1, int
     CK(cudaEventRecord(h0->ev[3], h0->stream));
     // ---- finish: injection, u -= sigma G phi, gphi = G phi, average_down onto the covered cells ----
     LAUNCH(h0, k_comp_inject, box_grid(b.nbn[0], b.nbn[1], b.nbn[2]), 256, L0.g, gD, b, L0.sol, (const double*)L1.sol);
-    LAUNCH(h0, k_mknewu, L1.gc, 256, gD, (const double*)L1.sol, vel1, velo1, add_old, gphi1, acc_g);
-    LAUNCH(h0, k_mknewu, L0.gc, 256, L0.g, (const double*)L0.sol, vel0, velo0, add_old, gphi0, acc_g);
+    // NodalProjector::project averages the projected velocity down; ApplyNodalProjection (:84-91) adds velocity_o back
+    // afterwards, level by level -- so covered coarse cells end up with avg(u1) + uo0, not avg(u1 + uo1)
+    LAUNCH(h0, k_mknewu, L1.gc, 256, gD, (const double*)L1.sol, vel1, Fab{}, 0, gphi1, acc_g);
+    LAUNCH(h0, k_mknewu, L0.gc, 256, L0.g, (const double*)L0.sol, vel0, Fab{}, 0, gphi0, acc_g);
     LAUNCH(h0, k_comp_avgdown, gbox, 256, b, vel1, vel0, 3);
+    if (add_old) {
+        LAUNCH(h0, k_add_cells, L1.gc, 256, gD, vel1, velo1, 3);
+        LAUNCH(h0, k_add_cells, L0.gc, 256, L0.g, vel0, velo0, 3);
+    }
     if (gphi0.p && gphi1.p) LAUNCH(h0, k_comp_avgdown, gbox, 256, b, gphi1, gphi0, 3);
     if (p1.p) LAUNCH(h0, k_copy_phi, dim3((p1.nx + 63) / 64, (p1.ny + 3) / 4, p1.nz), 256, gN, (const double*)L1.sol, p1, acc_p);
     if (p0.p) LAUNCH(h0, k_copy_phi, dim3((p0.nx + 63) / 64, (p0.ny + 3) / 4, p0.nz), 256, L0.g, (const double*)L0.sol, p0, acc_p);
@@ -1366,6 +1409,8 @@ int b200np_set_inflow_profile(b200np_t* h, int probtype, const double* bcv_vel, 
 
 int b200np_nlevels(const b200np_t* h) { return h ? (int)h->lv.size() : 0; }
 
+int b200np_halo_transport(const b200np_t* h) { return !h ? -1 : h->nranks == 1 ? 0 : h->p2p ? 1 : 2; }
+
 int b200np_level_dims(const b200np_t* h, int lev, int n_cell[3], int n_node[3])
 {
     if (!h || lev < 0 || lev >= (int)h->lv.size()) return B200NP_ERR_BAD_ARG;
@@ -1413,7 +1458,7 @@ int b200np_project(b200np_t* h, double* vel, const b200np_fab* vel_box, const do
         if (!vel_box_ok(h, vel_box)) return st->status = B200NP_ERR_BAD_ARG;
         if (sigma && !box_covers(sigma_box, clo, chi, 1)) return st->status = B200NP_ERR_BAD_ARG;
         if (gphi && !box_covers(gphi_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
-        if (phi && (!phi_box || phi_box->ncomp < 1)) return st->status = B200NP_ERR_BAD_ARG;
+        if (phi && !nodal_box_ok(h, phi_box)) return st->status = B200NP_ERR_BAD_ARG;
         h->launches = 0; h->exchanges = 0;
         CK(cudaEventRecord(h->ev[0], h->stream));
         bool s_vel, s_sig, s_phi = false, s_g = false;
@@ -1461,6 +1506,7 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
         const int clo[3] = {0, 0, g.ck0}, chi[3] = {g.n[0] - 1, g.n[1] - 1, g.ck0 + g.cnzl - 1};
         if (!vel_box_ok(h, vel_box) || !box_covers(gp_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
         if (density && !box_covers(rho_box, clo, chi, 1)) return st->status = B200NP_ERR_BAD_ARG;
+        if (!nodal_box_ok(h, p_box)) return st->status = B200NP_ERR_BAD_ARG;
         h->launches = 0; h->exchanges = 0;
         CK(cudaEventRecord(h->ev[0], h->stream));
         bool s_vel, s_velo, s_rho, s_gp, s_p, s_in;
@@ -1610,7 +1656,7 @@ int b200np_composite_project(b200np_composite_t* C, double* vel0, const b200np_f
         if (sigma0 && (!box_covers(sigma0_box, clo, chi, 1) || !fine_box_ok(C, sigma1_box, 1, 0, false))) return st->status = B200NP_ERR_BAD_ARG;
         if (gphi0 && !box_covers(gphi0_box, clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
         if (gphi1 && !fine_box_ok(C, gphi1_box, 3, 0, false)) return st->status = B200NP_ERR_BAD_ARG;
-        if ((phi0 && (!phi0_box || phi0_box->ncomp < 1)) || (phi1 && (!phi1_box || phi1_box->ncomp < 1))) return st->status = B200NP_ERR_BAD_ARG;
+        if ((phi0 && !nodal_box_ok(h0, phi0_box)) || (phi1 && !fine_box_ok(C, phi1_box, 1, 0, true))) return st->status = B200NP_ERR_BAD_ARG;
         h0->launches = h1->launches = 0;
         CK(cudaEventRecord(h0->ev[0], h0->stream));
         bool s_v0, s_v1, s_s0, s_s1, s_p0 = false, s_p1 = false, s_g0 = false, s_g1 = false;
@@ -1674,6 +1720,7 @@ int b200np_composite_apply_nodal_projection(b200np_composite_t* C, double* const
         if (!vel_box_ok(hh[0], vel_box[0]) || !box_covers(gp_box[0], clo, chi, 3)) return st->status = B200NP_ERR_BAD_ARG;
         if (!fine_box_ok(C, vel_box[1], 3, 1, false) || !fine_box_ok(C, gp_box[1], 3, 0, false)) return st->status = B200NP_ERR_BAD_ARG;
         if (var && (!box_covers(rho_box[0], clo, chi, 1) || !fine_box_ok(C, rho_box[1], 1, 0, false))) return st->status = B200NP_ERR_BAD_ARG;
+        if (!nodal_box_ok(hh[0], p_box[0]) || !fine_box_ok(C, p_box[1], 1, 0, true)) return st->status = B200NP_ERR_BAD_ARG;
         hh[0]->launches = hh[1]->launches = 0;
         cudaStream_t stream = hh[0]->stream;
         CK(cudaEventRecord(hh[0]->ev[0], stream));
@@ -1790,7 +1837,12 @@ static int run_op(b200np* h, int lev, int op, int arg)
     switch (op) {
     case B200NP_OP_SMOOTH: {
         double *x = L.cor, *y = L.cor2;
-        smooth_sweeps(h, L, x, y, L.res, arg);
+        // arg bit 16: "cor is zero" smooth call exactly as the V-cycle's pre-smooth issues it: either the first sweep
+        // never reads cor (zero-start kernels), or cor is cleared first
+        const bool zs = (arg & B200NP_SMOOTH_ZERO_START) != 0;
+        if (zs && !(h->zero_start && h->smoother_version >= 3 && L.iso))
+            CK(cudaMemsetAsync(L.cor - L.g.ps, 0, (size_t)L.g.ps * (L.g.nzl + 2) * sizeof(double), h->stream));
+        smooth_sweeps(h, L, x, y, L.res, arg & 0xffff, zs);
         if (x != L.cor) CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         break;
     }

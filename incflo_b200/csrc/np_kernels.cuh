@@ -637,6 +637,16 @@ __global__ void __launch_bounds__(256) k_mknewu(const Lev L, const double* __res
     }
 }
 
+// y += x on the valid cells of two caller arrays (vel += vel_old after the composite average-down)
+__global__ void __launch_bounds__(256) k_add_cells(const Lev L, Fab y, Fab x, int ncomp)
+{
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int kg = blockIdx.z + L.ck0;
+    if (i >= L.n[0] || j >= L.n[1]) return;
+    for (int c = 0; c < ncomp; ++c) y.p[y.idx(i, j, kg, c)] += x.p[x.idx(i, j, kg, c)];
+}
+
 // copy-out of phi into the caller's nodal box (p_nd (=|+=) phi, :235-253); duplicates the
 // periodic image nodes that the unique-node storage does not hold.
 __global__ void __launch_bounds__(256) k_copy_phi(const Lev L, const double* __restrict__ phi, Fab out, int accumulate)
@@ -646,6 +656,7 @@ __global__ void __launch_bounds__(256) k_copy_phi(const Lev L, const double* __r
     const int k = blockIdx.z + out.lo[2];
     if (i >= out.lo[0] + out.nx || j >= out.lo[1] + out.ny) return;
     if (i < 0 || i > L.n[0] || j < 0 || j > L.n[1] || k < 0 || k > L.n[2]) return;
+    if (L.dist && (k - L.k0 < -1 || k - L.k0 > L.nzl)) return;   // beyond this slab's planes and ghost slots
     int kl = zplane(L, k - L.k0);
     double v = phi[kl * L.ps + (long long)nmap(j, L.n[1], L.per[1]) * L.px + nmap(i, L.n[0], L.per[0])];
     long long o = out.idx(i, j, k, 0);

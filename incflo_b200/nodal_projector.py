@@ -23,6 +23,7 @@ from ._lib import FabBox, Geom, Opts, Stats
 BC_PERIODIC, BC_NEUMANN, BC_DIRICHLET, BC_INFLOW = 0, 1, 2, 3
 A_SOL, A_RHS, A_RES, A_COR, A_RESCOR, A_SIGMA = range(6)
 OP_SMOOTH, OP_RESIDUAL, OP_RESTRICT, OP_INTERP, OP_BOTTOM, OP_VCYCLE, OP_COARSEN_SIGMA = range(7)
+SMOOTH_ZERO_START = 0x10000   # B200NP_SMOOTH_ZERO_START: OP_SMOOTH as the V-cycle's "cor = 0" pre-smooth
 
 # incflo BC names (src/boundary_conditions/boundary_conditions.cpp:30-222) -> LinOpBCType
 _INCFLO_BC = {"pi": BC_DIRICHLET, "pressure_inflow": BC_DIRICHLET, "po": BC_DIRICHLET, "pressure_outflow": BC_DIRICHLET,
@@ -304,6 +305,10 @@ class IncfloProjection:
     def set_stream(self, cuda_stream):
         """run on the caller's stream (int handle of a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)"""
         self._L.b200np_set_stream(self._h, C.c_void_p(cuda_stream))
+
+    def halo_transport(self):
+        """0: one GPU; 1: NVLink peer memory (CUDA IPC); 2: ncclSend/ncclRecv fallback"""
+        return self._L.b200np_halo_transport(self._h)
 
     def time_op(self, lev, op, arg=1, reps=10):
         ms = C.c_double()

@@ -234,7 +234,13 @@ enum b200np_op { B200NP_OP_SMOOTH = 0,   /* cor <- nsweeps sweeps on (cor, res) 
                  B200NP_OP_BOTTOM = 4,   /* cor[bottom] <- bottom solve of res[bottom]  */
                  B200NP_OP_VCYCLE = 5,   /* one V-cycle on (cor, res) from level 0      */
                  B200NP_OP_COARSEN_SIGMA = 6 };
+/* B200NP_OP_SMOOTH: arg = number of sweeps, optionally | B200NP_SMOOTH_ZERO_START: "cor is zero" smooth call as in the
+ * V-cycle's pre-smooth (MLMG::mgVcycle sets cor = 0 first, A.9) -- the first sweep does not read cor at all */
+#define B200NP_SMOOTH_ZERO_START 0x10000
 int b200np_nlevels(const b200np_t* h);
+/* how the slab halos travel: 0 = single GPU (none), 1 = NVLink peer memory (CUDA IPC mapped neighbour arenas, stores /
+ * loads issued by the solver kernels), 2 = grouped ncclSend/ncclRecv (fallback when a rank cannot map its neighbours) */
+int b200np_halo_transport(const b200np_t* h);
 int b200np_level_dims(const b200np_t* h, int lev, int n_cell[3], int n_node[3]);
 int b200np_set_sigma(b200np_t* h, const double* sigma, const b200np_fab* sigma_box, double const_sigma);
 int b200np_level_set(b200np_t* h, int lev, int which, const double* host);

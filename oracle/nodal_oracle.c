@@ -61,6 +61,12 @@ void orc_default_params(orc_params* p)
     p->smoother = ORC_SM_LEX; p->box_order = ORC_SM_LEX; p->box_stale_per_call = 1;
 }
 
+int orc_set_num_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+
 /* ---------------------------------------------------------------- index maps */
 static inline int is_per(const orc_mg* mg, int d) { return mg->p.bclo[d] == ORC_BC_PERIODIC; }
 static inline int refl_lo(const orc_mg* mg, int d) { return mg->p.bclo[d] == ORC_BC_NEUMANN || mg->p.bclo[d] == ORC_BC_INFLOW; }
@@ -123,16 +129,19 @@ static inline void gather_phi(const orc_mg* mg, const level* L, const double* ph
         for (int c = 0; c < 3; ++c) for (int b = 0; b < 3; ++b) for (int a = 0; a < 3; ++a)
             P[a][b][c] = phi[NIDX(L, ix[a], jy[b], kz[c])];
     } else {
-        int bi = i / bsz[0], bj = j / bsz[1], bk = k / bsz[2];
+        /* bsz[3..5]: number of boxes per direction (the last box may own one more node plane) */
+#define BOXOF(idx, d) ((idx) / bsz[d] < bsz[3 + (d)] ? (idx) / bsz[d] : bsz[3 + (d)] - 1)
+        int bi = BOXOF(i, 0), bj = BOXOF(j, 1), bk = BOXOF(k, 2);
         int inx[3], iny[3], inz[3];
         /* a neighbour reached through a periodic wrap or a reflection counts as outside the box
          * (its value is the previous sweep's), exactly like a halo cell of the GPU tile */
         for (int a = 0; a < 3; ++a) {
             int ri = i - 1 + a, rj = j - 1 + a, rk = k - 1 + a;
-            inx[a] = (ri >= 0 && ri < L->nn[0] && ri / bsz[0] == bi);
-            iny[a] = (rj >= 0 && rj < L->nn[1] && rj / bsz[1] == bj);
-            inz[a] = (rk >= 0 && rk < L->nn[2] && rk / bsz[2] == bk);
+            inx[a] = (ri >= 0 && ri < L->nn[0] && BOXOF(ri, 0) == bi);
+            iny[a] = (rj >= 0 && rj < L->nn[1] && BOXOF(rj, 1) == bj);
+            inz[a] = (rk >= 0 && rk < L->nn[2] && BOXOF(rk, 2) == bk);
         }
+#undef BOXOF
         for (int c = 0; c < 3; ++c) for (int b = 0; b < 3; ++b) for (int a = 0; a < 3; ++a) {
             long id = NIDX(L, ix[a], jy[b], kz[c]);
             P[a][b][c] = (inx[a] && iny[b] && inz[c]) ? phi[id] : old[id];
@@ -342,8 +351,17 @@ static void smooth_level(const orc_mg* mg, level* L, double* phi, const double* 
     if (p->smoother == ORC_SM_BOX) {
         /* z-chunk rule shared with the CUDA smoother: aim at 592 tile-chunks per sweep (148 SMs x 2
          * resident CTAs x 2 waves), chunk height between 4 and the cap box[2] */
-        int bsz[3] = {p->box[0], p->box[1], p->box[2]};
-        {
+        int bsz[6] = {p->box[0], p->box[1], p->box[2], 0, 0, 0};
+        int* nb = bsz + 3;
+        if (p->box_amrex) {   /* the reference's grids: max_grid_size boxes, coarsened with the level */
+            int lev = (int)(L - mg->L);
+            for (int d = 0; d < 3; ++d) {
+                int b = p->box[d] >> lev; if (b < 2) b = 2;
+                if (b > L->n[d]) b = L->n[d];
+                bsz[d] = b;
+                nb[d] = (L->n[d] + b - 1) / b;   /* cell boxes; the last one also owns the top node plane */
+            }
+        } else {
             int ntiles = ((L->nn[0] + bsz[0] - 1) / bsz[0]) * ((L->nn[1] + bsz[1] - 1) / bsz[1]);
             int nch = 592 / ntiles; if (nch < 1) nch = 1;
             int c = (L->nn[2] + nch - 1) / nch;
@@ -353,18 +371,17 @@ static void smooth_level(const orc_mg* mg, level* L, double* phi, const double* 
              * (same residual history to 2 digits), so they use 4 / 2 / 1 to expose more parallel chunks */
             { int mn = L->nn[2] > 33 ? 8 : L->nn[2] > 17 ? 4 : L->nn[2] > 9 ? 2 : 1;
               if (bsz[2] < mn) bsz[2] = mn; }
+            for (int d = 0; d < 3; ++d) nb[d] = (L->nn[d] + bsz[d] - 1) / bsz[d];
         }
-        int nb[3];
-        for (int d = 0; d < 3; ++d) nb[d] = (L->nn[d] + bsz[d] - 1) / bsz[d];
         int outer = p->box_stale_per_call ? 1 : nsweeps, inner = p->box_stale_per_call ? nsweeps : 1;
         for (int so = 0; so < outer; ++so) {
             memcpy(L->old, phi, sizeof(double) * L->nnodes);
 #pragma omp parallel for collapse(3) schedule(dynamic)
             for (int bk = 0; bk < nb[2]; ++bk) for (int bj = 0; bj < nb[1]; ++bj) for (int bi = 0; bi < nb[0]; ++bi) {
                 int lo0 = bi * bsz[0], lo1 = bj * bsz[1], lo2 = bk * bsz[2];
-                int hi0 = lo0 + bsz[0] < L->nn[0] ? lo0 + bsz[0] : L->nn[0];
-                int hi1 = lo1 + bsz[1] < L->nn[1] ? lo1 + bsz[1] : L->nn[1];
-                int hi2 = lo2 + bsz[2] < L->nn[2] ? lo2 + bsz[2] : L->nn[2];
+                int hi0 = (bi + 1 < nb[0] && lo0 + bsz[0] < L->nn[0]) ? lo0 + bsz[0] : L->nn[0];
+                int hi1 = (bj + 1 < nb[1] && lo1 + bsz[1] < L->nn[1]) ? lo1 + bsz[1] : L->nn[1];
+                int hi2 = (bk + 1 < nb[2] && lo2 + bsz[2] < L->nn[2]) ? lo2 + bsz[2] : L->nn[2];
                 for (int si = 0; si < inner; ++si)
                     sweep_ordered(mg, L, phi, L->old, bsz, rhs, p->box_order, lo0, hi0, lo1, hi1, lo2, hi2, 0);
             }
@@ -568,6 +585,12 @@ static double wdot(const orc_mg* mg, int lev, const double* x, const double* y)
         s += orc_dot_weight(mg, lev, i, j, k) * x[id] * y[id];
     }
     return s;
+}
+void orc_dot_weights(const orc_mg* mg, int lev, double* w)
+{
+    const level* L = &mg->L[lev];
+    for (int k = 0; k < L->nn[2]; ++k) for (int j = 0; j < L->nn[1]; ++j) for (int i = 0; i < L->nn[0]; ++i)
+        w[NIDX(L, i, j, k)] = orc_dot_weight(mg, lev, i, j, k);
 }
 /* subtract the weighted mean (singular problems, A.8) */
 static void make_solvable(const orc_mg* mg, int lev, double* rhs)

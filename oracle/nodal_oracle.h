@@ -60,6 +60,11 @@ typedef struct {
     int    box_order;              /* in-box ordering: LEX / COLOR8 / COLOR4XY / PLANE4 */
     int    box_stale_per_call;     /* 1: snapshot once per smooth call; 0: per sweep  */
     int    verbose;
+    int    box_amrex;              /* ORC_SM_BOX only.  1 = AMReX grid semantics (the reference's CPU path):
+                                      box[] is amr.max_grid_size in CELLS on level 0 and is coarsened together with the
+                                      multigrid level (never below 2 cells), the top node plane of a non-periodic
+                                      direction belongs to the last box, and the GPU smoother's z-chunk rule is NOT
+                                      applied.  Use with box_order = ORC_SM_LEX, box_stale_per_call = 1.            */
 } orc_params;
 
 typedef struct {
@@ -76,6 +81,9 @@ typedef struct {
 } orc_stats;
 
 void orc_default_params(orc_params* p);
+/* OpenMP threads used by every orc_* call from now on (torchrun exports OMP_NUM_THREADS=1); returns the
+ * number actually in effect (omp_get_max_threads) */
+int  orc_set_num_threads(int n);
 
 /*
  * Hydro::NodalProjector::project.  Arrays are Fortran order
@@ -126,6 +134,7 @@ void    orc_mknewu(const orc_mg* mg, const double* phi, double* vel, int ng, dou
 int     orc_bottom_solve(const orc_mg* mg, double* x, const double* b);   /* returns iterations */
 int     orc_mlmg_solve(const orc_mg* mg, double* phi, double* rhs, double rtol, double atol, orc_stats* st);
 double  orc_dot_weight(const orc_mg* mg, int lev, int i, int j, int k);
+void    orc_dot_weights(const orc_mg* mg, int lev, double* w);   /* the whole level, unique-node layout */
 
 #ifdef __cplusplus
 }

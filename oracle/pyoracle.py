@@ -25,6 +25,7 @@ class Params(C.Structure):
         ("bottom_rtol", C.c_double), ("bottom_atol", C.c_double),
         ("nu1", C.c_int), ("nu2", C.c_int), ("nsweeps", C.c_int), ("smoother", C.c_int),
         ("box", C.c_int * 3), ("box_order", C.c_int), ("box_stale_per_call", C.c_int), ("verbose", C.c_int),
+        ("box_amrex", C.c_int),
     ]
 
 
@@ -52,6 +53,8 @@ def lib():
         dp = C.POINTER(C.c_double)
         L = _LIB
         L.orc_default_params.argtypes = [C.POINTER(Params)]
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_set_num_threads.restype = C.c_int
         L.orc_project.argtypes = [C.POINTER(Params), dp, C.c_int, dp, C.c_double, dp, dp, dp, C.c_double,
                                   C.c_double, C.POINTER(Stats)]
         L.orc_project.restype = C.c_int
@@ -80,7 +83,13 @@ def lib():
         L.orc_mlmg_solve.restype = C.c_int
         L.orc_dot_weight.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_dot_weight.restype = C.c_double
+        L.orc_dot_weights.argtypes = [C.c_void_p, C.c_int, dp]
     return _LIB
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle from now on (torchrun exports OMP_NUM_THREADS=1); returns the count in effect"""
+    return lib().orc_set_num_threads(int(n))
 
 
 def _p(a):
@@ -169,10 +178,7 @@ class MG:
     def dot_weights(self, lev):
         _, nn = self.dims(lev)
         w = np.empty((nn[2], nn[1], nn[0]))
-        for k in range(nn[2]):
-            for j in range(nn[1]):
-                for i in range(nn[0]):
-                    w[k, j, i] = lib().orc_dot_weight(self.h, lev, i, j, k)
+        lib().orc_dot_weights(self.h, lev, _p(w))
         return w
 
 

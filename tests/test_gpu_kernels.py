@@ -172,3 +172,100 @@ def test_interpolation_pipelined_variant(case, var, oracle, monkeypatch):
         proj.level_set(lev, A_COR, fine); proj.level_set(lev + 1, A_COR, crse)
         proj.level_op(lev, OP_INTERP)
         _close(proj.level_get(lev, A_COR), mg.interp_add(lev, fine.copy(), crse))
+
+
+# ---- the kernels that run at BENCHMARK size ------------------------------------------------------
+# b200np.cu routes a level with <= 148 smoother CTAs to the resident-chunk kernel (k_smooth_iso_res); every grid
+# above is that small.  B200NP_RES_CTAS=0 forces the ring-slot kernel k_smooth_iso (50 % of a 256^3 solve) onto the
+# same cases, and the 128^3 cases below reach it with the default routing (272 CTAs on level 0).
+@pytest.mark.parametrize("zero_start", [False, True], ids=["read_cor", "zero_start"])
+@pytest.mark.parametrize("nsweeps", [1, 4])
+@pytest.mark.parametrize("var", [False, True])
+@pytest.mark.parametrize("case", BC_CASES, ids=[c[0] for c in BC_CASES])
+def test_smoother_sweeps_nonresident_kernel(case, var, nsweeps, zero_start, oracle, monkeypatch):
+    """k_smooth_iso<VAR, FULL|edge, RES=false> (+ its SM_ZERO_IN path) == oracle, sweep by sweep"""
+    from incflo_b200.nodal_projector import A_COR, A_RES, OP_SMOOTH, SMOOTH_ZERO_START
+    monkeypatch.setenv("B200NP_RES_CTAS", "0")
+    mg, proj, rng = _setup(case, var, oracle)
+    for lev in range(mg.nlev):
+        junk = rng.standard_normal(mg.node_shape(lev))          # zero start: cor must never be read
+        phi = junk if zero_start else _masked_random(mg, lev, rng)
+        rhs = _masked_random(mg, lev, rng)
+        proj.level_set(lev, A_COR, phi); proj.level_set(lev, A_RES, rhs)
+        proj.level_op(lev, OP_SMOOTH, nsweeps | (SMOOTH_ZERO_START if zero_start else 0))
+        got = proj.level_get(lev, A_COR)
+        start = np.zeros_like(phi) if zero_start else phi.copy()
+        _close(got, mg.smooth(lev, start, rhs, nsweeps), 1e-11)
+
+
+@pytest.mark.parametrize("zero_start", [False, True], ids=["read_cor", "zero_start"])
+@pytest.mark.parametrize("var", [False, True])
+def test_smoother_zero_start_resident_kernel(var, zero_start, oracle):
+    """the same zero-start contract on the default routing (k_smooth_iso_res at these sizes)"""
+    from incflo_b200.nodal_projector import A_COR, A_RES, OP_SMOOTH, SMOOTH_ZERO_START
+    mg, proj, rng = _setup(BC_CASES[1], var, oracle)
+    for lev in range(mg.nlev):
+        phi = rng.standard_normal(mg.node_shape(lev)) if zero_start else _masked_random(mg, lev, rng)
+        rhs = _masked_random(mg, lev, rng)
+        proj.level_set(lev, A_COR, phi); proj.level_set(lev, A_RES, rhs)
+        proj.level_op(lev, OP_SMOOTH, 4 | (SMOOTH_ZERO_START if zero_start else 0))
+        start = np.zeros_like(phi) if zero_start else phi.copy()
+        _close(proj.level_get(lev, A_COR), mg.smooth(lev, start, rhs, 4), 1e-11)
+
+
+@pytest.mark.parametrize("env", [{}, {"B200NP_RES_CTAS": "0"}, {"B200NP_ZERO_START": "0"}, {"B200NP_RES_CTAS": "0", "B200NP_ZERO_START": "0"}],
+                         ids=["default", "nonresident", "no_zero_start", "nonresident_no_zero_start"])
+@pytest.mark.parametrize("var", [False, True])
+def test_vcycle_kernel_routing(var, env, oracle, monkeypatch):
+    """one whole V-cycle with every smoother routing (resident / ring-slot kernel, zero-start on / off)"""
+    from incflo_b200.nodal_projector import A_COR, A_RES, OP_VCYCLE
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    mg, proj, rng = _setup(BC_CASES[1], var, oracle)
+    res = _masked_random(mg, 0, rng)
+    w = mg.dot_weights(0)
+    res -= (w * res).sum() / w.sum()
+    proj.level_set(0, A_RES, res)
+    proj.level_set(0, A_COR, rng.standard_normal(mg.node_shape(0)))   # junk: the V-cycle starts from cor = 0 (A.9)
+    proj.level_op(0, OP_VCYCLE)
+    got = proj.level_get(0, A_COR)
+    mg.params.maxiter = 1
+    mg2 = oracle.MG(mg.params, mg.sigma(0), 0.7)
+    phi = np.zeros_like(res)
+    mg2.solve(phi, res.copy(), 1e-30, 0.0)
+    _close(got, phi, 1e-8)
+
+
+CASES_128 = [
+    ("rt128", (128, 128, 128), (1 / 128,) * 3, (0, 0, 1), (0, 0, 1)),          # BASELINE configs[1] layout
+    ("periodic128", (128, 128, 128), (1 / 128,) * 3, (0, 0, 0), (0, 0, 0)),    # configs[0] / [2] layout
+    ("channel_160x64x48", (160, 64, 48), (1 / 160,) * 3, (3, 1, 0), (2, 1, 0)),  # inflow / outflow, edge tiles, multi-tile
+]
+
+
+@pytest.mark.parametrize("var", [False, True])
+@pytest.mark.parametrize("case", CASES_128, ids=[c[0] for c in CASES_128])
+def test_production_size_kernels(case, var, oracle):
+    """128^3-class grids: level 0 has 272 smoother CTAs and several interpolation / residual tiles per direction, i.e.
+    the kernels and the routing of the 256^3 benchmark (k_smooth_iso, k_residual_iso, k_interp_tile, k_restrict)"""
+    from incflo_b200.nodal_projector import A_COR, A_RES, A_RESCOR, OP_INTERP, OP_RESIDUAL, OP_RESTRICT, OP_SMOOTH, SMOOTH_ZERO_START
+    mg, proj, rng = _setup(case, var, oracle)
+    for lev in range(2):
+        phi = _masked_random(mg, lev, rng)
+        rhs = _masked_random(mg, lev, rng)
+        proj.level_set(lev, A_COR, phi); proj.level_set(lev, A_RES, rhs)
+        proj.level_op(lev, OP_SMOOTH, 2)
+        _close(proj.level_get(lev, A_COR), mg.smooth(lev, phi.copy(), rhs, 2), 1e-11)
+        proj.level_set(lev, A_COR, rng.standard_normal(mg.node_shape(lev)))
+        proj.level_op(lev, OP_SMOOTH, 2 | SMOOTH_ZERO_START)
+        _close(proj.level_get(lev, A_COR), mg.smooth(lev, np.zeros_like(phi), rhs, 2), 1e-11)
+        proj.level_set(lev, A_COR, phi)
+        proj.level_op(lev, OP_RESIDUAL)
+        r = proj.level_get(lev, A_RESCOR)
+        _close(r, mg.residual(lev, phi, rhs))
+        proj.level_op(lev, OP_RESTRICT)
+        _close(proj.level_get(lev + 1, A_RES), mg.restrict(lev, r))
+        crse = _masked_random(mg, lev + 1, rng)
+        proj.level_set(lev + 1, A_COR, crse)
+        proj.level_op(lev, OP_INTERP)
+        _close(proj.level_get(lev, A_COR), mg.interp_add(lev, phi.copy(), crse))

@@ -14,7 +14,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = f"cuda:{local}"
 dist.init_process_group("nccl", device_id=torch.device(dev))
-wl = bench.workload(N, world, rank, dev)
+wl = bench.workload((N, N, N * world), world, rank, dev)
 idt = torch.zeros(128, dtype=torch.uint8, device=dev)
 if rank == 0:
     idt.copy_(torch.tensor(list(npj.nccl_unique_id()), dtype=torch.uint8))
