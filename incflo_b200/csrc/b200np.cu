@@ -14,6 +14,7 @@
 #include "np_smooth.cuh"
 #include "np_smooth3.cuh"
 #include "np_composite.cuh"
+#include "np_tail.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -155,7 +156,11 @@ struct b200np {
                               // measured at 2 GPUs, 256^3 per GPU: 8 -> 33.1 ms, 64 -> 30.6 ms per solve)
     int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200NP_PDL)
     int res_max_ctas = 148;   // levels with at most this many smoother CTAs use the resident-chunk kernel (B200NP_RES_CTAS)
-    int smoother_version = 3, interp_version = 2, resid_version = 3;  // B200NP_SMOOTHER/_INTERP/_RESID=1: simple kernels
+    int smoother_version = 3, resid_version = 3;  // B200NP_SMOOTHER=2 / B200NP_RESID=2: the general (anisotropic) kernels on isotropic levels too
+    // coarse tail (np_tail.cuh): levels [tail_lev0, nlev) run in one single-CTA kernel; -1: none (B200NP_TAIL=0)
+    int use_tail = 1, tail_lev0 = -1;
+    TailPlan tail{};
+    size_t tail_smem = 0;
     // B200NP_PROFILE=1: per-phase device times (CUDA events between phases, graph capture off); printed per call
     int profile = 0;
     int zero_start = -1;      // skip the memset of cor before a pre-smooth and the read of it in the first sweep (-1.6 % per solve);
@@ -364,6 +369,8 @@ void build_levels(b200np* h)
     h->bottom_work = dev_alloc(h, h->no_bottom ? 8 : (size_t)B.ps * B.nzl * 8);
 }
 
+void plan_tail(b200np* h);
+
 void build_hierarchy(b200np* h)
 {
     h->arena = Arena{};
@@ -375,8 +382,52 @@ void build_hierarchy(b200np* h)
     h->arena.base = static_cast<char*>(base);
     h->arena.off = 0; h->arena.measure = false;
     build_levels(h);                       // pass 2: pointers
+    plan_tail(h);
     CK(cudaMallocHost(&h->hscal, 16 * sizeof(double)));
     CK(cudaMallocHost(&h->hinfo, 4 * sizeof(int)));
+}
+
+// Coarse tail (np_tail.cuh): the longest run of bottom-most levels that fits one CTA's shared memory -- every level
+// replicated (not slab-distributed) and at most TAIL_MAX_NODES nodes.  Shared-memory need per level: ping, pong,
+// rhs (+ sigma cells); the bottom level also the 7 work vectors of BiCGStab.
+void plan_tail(b200np* h)
+{
+    h->tail_lev0 = -1;
+    const int nl = (int)h->lv.size();
+    if (!h->use_tail || h->no_bottom) return;
+    auto nodes_of = [&](int l) { const Lev& g = h->lv[l].g; return (long long)g.nn[0] * g.nn[1] * g.nn[2]; };
+    auto cells_of = [&](int l) { const Lev& g = h->lv[l].g; return (long long)g.n[0] * g.n[1] * g.n[2]; };
+    long long need = 7 * nodes_of(nl - 1);
+    int l0 = nl;
+    for (int l = nl - 1; l >= std::max(0, h->nlev_dist); --l) {
+        const long long add = 3 * nodes_of(l) + cells_of(l) + 8;
+        if (nodes_of(l) > TAIL_MAX_NODES || need + add > TAIL_SMEM_DOUBLES || nl - l > TAIL_MAX_LEV) break;
+        need += add;
+        l0 = l;
+    }
+    if (l0 >= nl) return;   // not even the bottom level fits: the per-level kernels do everything
+    TailPlan& P = h->tail;
+    P = TailPlan{};
+    P.nlev = nl - l0;
+    int off = 0;
+    auto take = [&](long long n) { int o = off; off += (int)((n + 1) & ~1ll); return o; };
+    for (int t = 0; t < P.nlev; ++t) {
+        const LevelData& L = h->lv[l0 + t];
+        TailLev& T = P.lv[t];
+        T.g = L.g;
+        T.g.px = L.g.nn[0]; T.g.ps = (long long)L.g.nn[0] * L.g.nn[1];
+        T.g.cpx = L.g.n[0]; T.g.cps = (long long)L.g.n[0] * L.g.n[1];
+        T.g.k0 = 0; T.g.nzl = L.g.nn[2]; T.g.ck0 = 0; T.g.cnzl = L.g.n[2]; T.g.dist = 0;
+        T.a = take(nodes_of(l0 + t)); T.b = take(nodes_of(l0 + t)); T.r = take(nodes_of(l0 + t)); T.s = take(cells_of(l0 + t));
+        T.tz = L.tz;
+        T.cpx_g = L.g.cpx; T.cps_g = L.g.cps;
+        T.sigma_g = L.sigma;
+    }
+    P.work = take(7 * nodes_of(nl - 1));
+    P.px_io = h->lv[l0].g.px; P.ps_io = h->lv[l0].g.ps;
+    P.res_in = h->lv[l0].res; P.cor_out = h->lv[l0].cor;
+    h->tail_smem = (size_t)off * sizeof(double);
+    h->tail_lev0 = l0;
 }
 
 // ---- slab communication (MLNodeLinOp::applyBC's FillBoundary) ------------------------
@@ -634,10 +685,7 @@ void smooth_sweeps(b200np* h, LevelData& L, double*& x, double*& y, const double
             continue;
         }
         if (h->dbg_halo != 5) halo_nodes(h, L, x);
-        if (h->smoother_version == 1) {
-            if (h->var_sigma) LAUNCH(h, k_smooth_tile<true>, L.gsm, 256, L.g, x, y, rhs, L.tz);
-            else              LAUNCH(h, k_smooth_tile<false>, L.gsm, 256, L.g, x, y, rhs, L.tz);
-        } else if (!iso_path) {
+        if (!iso_path) {
             if (h->var_sigma) launch_pdl(h, k_smooth_v2<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), L.g, x, y, rhs, L.tz);
             else              launch_pdl(h, k_smooth_v2<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), L.g, x, y, rhs, L.tz);
         } else if (resident) {
@@ -661,10 +709,7 @@ void residual(b200np* h, LevelData& L, double* phi, const double* rhs, double* r
     halo_nodes(h, L, phi);
     const Lev& g = gov ? *gov : L.g;
     const bool var = var_override >= 0 ? var_override != 0 : h->var_sigma;
-    if (h->resid_version == 1) {
-        if (var) LAUNCH(h, k_residual<true>, L.gn, 256, g, phi, rhs, res, norm_partial);
-        else     LAUNCH(h, k_residual<false>, L.gn, 256, g, phi, rhs, res, norm_partial);
-    } else if (h->resid_version == 2 || !L.iso) {
+    if (h->resid_version == 2 || !L.iso) {
         if (var) launch_pdl(h, k_residual_v2<true>, L.gsm, dim3(256), SM_SMOOTH_DOUBLES * sizeof(double), g, phi, rhs, res, L.tz, norm_partial);
         else     launch_pdl(h, k_residual_v2<false>, L.gsm, dim3(256), 4 * SM_PHI_SLOT * sizeof(double), g, phi, rhs, res, L.tz, norm_partial);
     } else {
@@ -675,7 +720,7 @@ void residual(b200np* h, LevelData& L, double* phi, const double* rhs, double* r
 // number of per-CTA norm partials the residual kernel writes
 long long resid_nblk(b200np* h, LevelData& L)
 {
-    return h->resid_version == 1 ? L.nblk_n : (long long)L.gsm.x * L.gsm.y * L.gsm.z;
+    return (long long)L.gsm.x * L.gsm.y * L.gsm.z;
 }
 
 void bottom_solve(b200np* h)
@@ -687,6 +732,21 @@ void bottom_solve(b200np* h)
     else
         launch_pdl(h, k_bottom_bicgstab<false>, dim3(1), dim3(512), 0, B.g, B.cor, B.res, h->bottom_work, h->opts.bottom_maxiter,
                h->opts.bottom_rtol, h->opts.bottom_atol, h->singular, h->opts.smooth_num_sweeps, h->opts.bottom_solver, h->dinfo);
+}
+
+// levels [tail_lev0, nlev): down-leg, bottom solve and up-leg in one CTA (np_tail.cuh)
+void coarse_tail(b200np* h)
+{
+    TailPlan P = h->tail;
+    for (int t = 0; t < P.nlev; ++t) {
+        P.lv[t].g.csig = h->lv[h->tail_lev0 + t].g.csig;
+        if (!h->var_sigma) P.lv[t].sigma_g = nullptr;
+    }
+    P.nu1 = h->opts.num_pre_smooth; P.nu2 = h->opts.num_post_smooth; P.nsw = h->opts.smooth_num_sweeps;
+    P.maxiter = h->opts.bottom_maxiter; P.rtol = h->opts.bottom_rtol; P.atol = h->opts.bottom_atol;
+    P.singular = h->singular; P.bottom_solver = h->opts.bottom_solver; P.info = h->dinfo;
+    if (h->var_sigma) launch_pdl(h, k_coarse_tail<true>, dim3(1), dim3(TAIL_THREADS), h->tail_smem, P);
+    else              launch_pdl(h, k_coarse_tail<false>, dim3(1), dim3(TAIL_THREADS), h->tail_smem, P);
 }
 
 void restrict_to(b200np* h, int l)
@@ -704,16 +764,7 @@ void interp_add(b200np* h, int l)
 {
     LevelData &F = h->lv[l], &C = h->lv[l + 1];
     halo_nodes(h, C, C.cor);
-    if (h->interp_version == 1) {
-        if (h->var_sigma) LAUNCH(h, k_interp_add<true>, F.gn, 256, F.g, C.g, F.cor, C.cor);
-        else              LAUNCH(h, k_interp_add<false>, F.gn, 256, F.g, C.g, F.cor, C.cor);
-    } else if (h->interp_version == 3) {   // persistent, software-pipelined variant (see np_smooth.cuh K6 version 3)
-        const int ntx = (F.g.nn[0] + IT_X - 1) / IT_X, nty = (F.g.nn[1] + IT_Y - 1) / IT_Y, ntz = (F.g.nzl + IP_TZ - 1) / IP_TZ;
-        const long long nt = (long long)ntx * nty * ntz;
-        const int grid = (int)std::min<long long>(nt, 148 * 3);
-        if (h->var_sigma) launch_pdl(h, k_interp_pipe<true>, dim3(grid), dim3(256), 2 * IP_BUF_DOUBLES * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor, ntx, nty, ntz);
-        else              launch_pdl(h, k_interp_pipe<false>, dim3(grid), dim3(256), 2 * IP_BUF_DOUBLES * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor, ntx, nty, ntz);
-    } else {
+    {
         if (h->interp_tz == 4) {
             if (h->var_sigma) launch_pdl(h, k_interp_tile<true, 4>, F.git, dim3(256), (it_v_doubles(4) + it_s_doubles(4)) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
             else              launch_pdl(h, k_interp_tile<false, 4>, F.git, dim3(256), it_v_doubles(4) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
@@ -727,8 +778,10 @@ void interp_add(b200np* h, int l)
 // MLMG::mgVcycle (A.9) on (cor, res), all launches on h->stream, no host synchronisation
 void vcycle_launch(b200np* h, int lev0)
 {
-    const int nl = (int)h->lv.size();
     const int nsw = h->opts.smooth_num_sweeps;
+    // levels [nl - 1, ...) -- the bottom level alone, or the whole coarse tail -- are one kernel
+    const bool tail = h->tail_lev0 >= lev0 && h->tail_lev0 >= 0;
+    const int nl = tail ? h->tail_lev0 + 1 : (int)h->lv.size();
     for (int l = lev0; l < nl - 1; ++l) {
         LevelData& L = h->lv[l];
         // cor = 0 (ghost slots included) -- unless the first sweep knows it and never reads cor
@@ -747,8 +800,9 @@ void vcycle_launch(b200np* h, int lev0)
         restrict_to(h, l);
         prof_mark(h, "restrict", l);
     }
-    bottom_solve(h);
-    prof_mark(h, "bottom");
+    if (tail) coarse_tail(h);
+    else bottom_solve(h);
+    prof_mark(h, tail ? "coarse tail + bottom" : "bottom");
     for (int l = nl - 2; l >= lev0; --l) {
         LevelData& L = h->lv[l];
         interp_add(h, l);
@@ -1022,7 +1076,7 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (const char* e = getenv("B200NP_P2P")) h->use_p2p = atoi(e);
         if (const char* e = getenv("B200NP_FUSE_HALO")) h->fuse_halo = atoi(e);
         if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) h->dist_min_planes = std::max(8, atoi(e));
-        if (const char* e = getenv("B200NP_INTERP")) h->interp_version = atoi(e);
+        if (const char* e = getenv("B200NP_TAIL")) h->use_tail = atoi(e);
         if (const char* e = getenv("B200NP_ZERO_START")) h->zero_start = atoi(e);
         if (const char* e = getenv("B200NP_INTERP_TZ")) h->interp_tz = atoi(e) == 8 ? 8 : 4;
         if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
@@ -1036,8 +1090,8 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         CK(cudaFuncSetAttribute(k_residual_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IT_V_DOUBLES * sizeof(double))));
-        CK(cudaFuncSetAttribute(k_interp_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * IP_BUF_DOUBLES * sizeof(double))));
-        CK(cudaFuncSetAttribute(k_interp_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * IP_BUF_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_coarse_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TAIL_SMEM_DOUBLES * sizeof(double))));
+        CK(cudaFuncSetAttribute(k_coarse_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TAIL_SMEM_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((it_v_doubles(4) + it_s_doubles(4)) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(it_v_doubles(4) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso_dist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));

@@ -3,10 +3,11 @@
 // Kernel inventory (reference function replaced -> kernel), SURVEY.md 2.4 / DESIGN.md section 4:
 //   K1  incflo_apply_nodal_projection.cpp:53-59,:68,:115-118      -> k_pre_add_sigma
 //   K2  mlndlap_divu + mlndlap_impose_neumann_bc (A.2)            -> k_divu
-//   K3  mlndlap_adotx_{aa,c} / solutionResidual (A.3)             -> k_residual
-//   K4  mlndlap_gauss_seidel_{aa,c} / mlndlap_gscolor (A.4)       -> k_smooth_tile
+//   K3  mlndlap_adotx_{aa,c} / solutionResidual (A.3)             -> k_residual_iso / k_residual_v2 (np_smooth*.cuh)
+//   K4  mlndlap_gauss_seidel_{aa,c} / mlndlap_gscolor (A.4)       -> k_smooth_iso* / k_smooth_v2 (np_smooth*.cuh)
 //   K5  mlndlap_restriction (A.5)                                 -> k_restrict
-//   K6  mlndlap_interpadd_{aa,c} (A.6)                            -> k_interp_add
+//   K6  mlndlap_interpadd_{aa,c} (A.6)                            -> k_interp_tile (np_smooth.cuh), Interp (node form)
+//   K11 the levels below ~17^3 nodes, all of the above in one CTA -> k_coarse_tail (np_tail.cuh)
 //   K7  mlndlap_mknewu{,_c} + copy-out :221-256 (A.7)             -> k_mknewu, k_copy_phi
 //   K8  MLCGSolver BiCGStab / CG (A.10)                           -> k_bottom_bicgstab (one CTA)
 //   K9  average_down of sigma (A.8)                               -> k_coarsen_sigma
@@ -33,7 +34,7 @@ __device__ __forceinline__ void gather_sigma_g(const Lev& L, int i, int j, int k
 #pragma unroll
         for (int b = 0; b < 2; ++b)
 #pragma unroll
-            for (int a = 0; a < 2; ++a) S[c][b][a] = __ldg(L.sigma + ck[c] * L.cps + (long long)cj[b] * L.cpx + ci[a]);
+            for (int a = 0; a < 2; ++a) S[c][b][a] = L.sigma[ck[c] * L.cps + (long long)cj[b] * L.cpx + ci[a]];
 }
 
 __device__ __forceinline__ void gather_phi_g(const Lev& L, const double* __restrict__ phi, int i, int j, int kl,
@@ -101,158 +102,6 @@ __device__ __forceinline__ double block_reduce(double v, double* sh /* >= 33 dou
 }
 
 // ------------------------------------------------------------------------------------------
-// K4: tile-resident Gauss-Seidel sweep.
-// One CTA owns a tile of NP_TX x NP_TY node columns and marches through TZ planes.  Inside the
-// tile the update order is: planes in ascending k, and inside a plane the 4 colours
-// c = (i&1) + 2(j&1) in order 0..3 (nodes of one colour in a plane are not coupled).  Values
-// outside the tile (x/y halo ring, the plane below the chunk and the plane above it) are taken
-// from the previous sweep (pin); results go to pout (ping-pong), so the sweep is deterministic
-// and independent of CTA scheduling and of the number of GPUs as long as chunk boundaries are
-// aligned with slab boundaries.  This is AMReX's multi-box Gauss-Seidel semantics (A.4: no halo
-// refresh inside a box sweep) with box == tile and one sweep per refresh.
-// Algorithmic traffic: 8 R + 8 W (phi) + 8 R (rhs) + 8 R (sigma) = 32 B/node (24 B const sigma).
-// ------------------------------------------------------------------------------------------
-template <bool VAR>
-__global__ void __launch_bounds__(256) k_smooth_tile(const Lev L, const double* __restrict__ pin,
-                                                     double* __restrict__ pout, const double* __restrict__ rhs, int TZ)
-{
-    constexpr int SX = NP_TX + 2, SY = NP_TY + 2, CX = NP_TX + 1, CY = NP_TY + 1;
-    __shared__ double sphi[3][SY][SX];
-    __shared__ double ssig[VAR ? 2 : 1][VAR ? CY : 1][VAR ? CX : 1];
-
-    const int tid = threadIdx.x;
-    const int i0 = blockIdx.x * NP_TX, j0 = blockIdx.y * NP_TY;
-    const int kc0 = blockIdx.z * TZ;
-    const int kc1 = min(kc0 + TZ, L.nzl);
-
-    // per-thread column offsets for the staged loads (fixed for the whole march)
-    int poff[5], coff[5];
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-        int idx = tid + s * 256;
-        poff[s] = -1; coff[s] = -1;
-        if (idx < SX * SY) {
-            int lx = idx % SX, ly = idx / SX;
-            int gi = i0 - 1 + lx, gj = j0 - 1 + ly;
-            if (gi <= L.n[0] + 1 && gj <= L.n[1] + 1 && (L.per[0] ? gi <= L.n[0] : true) && (L.per[1] ? gj <= L.n[1] : true))
-                poff[s] = nmap(gj, L.n[1], L.per[1]) * L.px + nmap(gi, L.n[0], L.per[0]);
-        }
-        if (VAR && idx < CX * CY) {
-            int lx = idx % CX, ly = idx / CX;
-            int gi = i0 - 1 + lx, gj = j0 - 1 + ly;
-            if (gi <= L.n[0] && gj <= L.n[1])
-                coff[s] = cmap(gj, L.n[1], L.per[1]) * L.cpx + cmap(gi, L.n[0], L.per[0]);
-        }
-    }
-    auto load_phi = [&](int kl) {  // kl in [-1, nzl]
-        const double* src = pin + zplane(L, kl) * L.ps;
-        double* dst = &sphi[(kl + 1) % 3][0][0];
-#pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            int idx = tid + s * 256;
-            if (idx < SX * SY) dst[idx] = poff[s] >= 0 ? src[poff[s]] : 0.0;
-        }
-    };
-    auto load_sig = [&](int cl) {  // cell layer cl in [-1, cnzl]
-        if (!VAR) return;
-        const double* src = L.sigma + czplane(L, cl) * L.cps;
-        double* dst = &ssig[(cl + 1) & 1][0][0];
-#pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            int idx = tid + s * 256;
-            if (idx < CX * CY) dst[idx] = coff[s] >= 0 ? __ldg(src + coff[s]) : 0.0;
-        }
-    };
-
-    load_phi(kc0 - 1);
-    load_phi(kc0);
-    load_sig(kc0 - 1);
-
-    const int tx = tid & 31, ty = tid >> 5;
-    for (int kl = kc0; kl < kc1; ++kl) {
-        load_phi(kl + 1);
-        load_sig(kl);
-        __syncthreads();
-        const int kg = kl + L.k0;
-        const double(*pm)[SX] = sphi[(kl) % 3];      // plane kl-1
-        double(*p0)[SX] = sphi[(kl + 1) % 3];        // plane kl
-        const double(*pp)[SX] = sphi[(kl + 2) % 3];  // plane kl+1
-#pragma unroll 1
-        for (int color = 0; color < 4; ++color) {
-            const int li = 2 * tx + (color & 1), lj = 2 * ty + (color >> 1);
-            const int gi = i0 + li, gj = j0 + lj;
-            if (gi < L.nn[0] && gj < L.nn[1]) {
-                double P[3][3][3];
-#pragma unroll
-                for (int b = 0; b < 3; ++b)
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        P[0][b][a] = pm[lj + b][li + a];
-                        P[1][b][a] = p0[lj + b][li + a];
-                        P[2][b][a] = pp[lj + b][li + a];
-                    }
-                double s0, Ax;
-                if (VAR) {
-                    double S[2][2][2];
-#pragma unroll
-                    for (int c = 0; c < 2; ++c)
-#pragma unroll
-                        for (int b = 0; b < 2; ++b)
-#pragma unroll
-                            for (int a = 0; a < 2; ++a) S[c][b][a] = ssig[(kl + c) & 1][lj + b][li + a];
-                    Ax = stencil27(L, S, P, s0);
-                } else {
-                    Ax = stencil27_c(L, L.csig, P, s0);
-                }
-                double r = rhs[kl * L.ps + (long long)gj * L.px + gi];
-                double v = node_masked(L, gi, gj, kg) ? 0.0 : P[1][1][1] + (r - Ax) / s0;
-                p0[lj + 1][li + 1] = v;
-            }
-            __syncthreads();
-        }
-        // write the finished plane (interior of the tile) to the output array
-        double* dst = pout + kl * L.ps;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            int idx = tid + s * 256;
-            int lx = idx % NP_TX, ly = idx / NP_TX;
-            int gi = i0 + lx, gj = j0 + ly;
-            if (gi < L.nn[0] && gj < L.nn[1]) dst[(long long)gj * L.px + gi] = p0[ly + 1][lx + 1];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// K3: res = rhs - L phi (masked nodes -> 0); optional fused inf-norm partials.
-// Algorithmic traffic 32 B/node (24 B const sigma).
-// ------------------------------------------------------------------------------------------
-template <bool VAR>
-__global__ void __launch_bounds__(256) k_residual(const Lev L, const double* __restrict__ phi,
-                                                  const double* __restrict__ rhs, double* __restrict__ res,
-                                                  double* __restrict__ norm_partial)
-{
-    __shared__ double sh[34];
-    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
-    const int kl = blockIdx.z;
-    double a = 0.0;
-    if (i < L.nn[0] && j < L.nn[1]) {
-        long long id = kl * L.ps + (long long)j * L.px + i;
-        double r = 0.0;
-        if (!node_masked(L, i, j, kl + L.k0)) {
-            double s0;
-            r = rhs[id] - node_Lphi_g<VAR>(L, phi, i, j, kl, s0);
-        }
-        res[id] = r;
-        a = fabs(r);
-    }
-    if (norm_partial) {
-        a = block_reduce<true>(a, sh);
-        if (threadIdx.x == 0) norm_partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = a;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // K5: full-weighting restriction (A.5).  One thread per coarse node.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_restrict(const Lev F, const Lev C, const double* __restrict__ fine,
@@ -285,7 +134,8 @@ __global__ void __launch_bounds__(256) k_restrict(const Lev F, const Lev C, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// K6: sigma-weighted trilinear prolongation, added to the fine correction (A.6).
+// K6, node-by-node form of the sigma-weighted trilinear prolongation (A.6) -- used by the coarse-tail kernel
+// (np_tail.cuh); the tiled kernel of the big levels is k_interp_tile (np_smooth.cuh).
 // ------------------------------------------------------------------------------------------
 template <bool VAR>
 struct Interp {
@@ -296,7 +146,7 @@ struct Interp {
     __device__ __forceinline__ double sg(int i, int j, int kl) const
     {
         if (!VAR) return 1.0;
-        return __ldg(F.sigma + czplane(F, kl) * F.cps + (long long)cmap(j, F.n[1], F.per[1]) * F.cpx + cmap(i, F.n[0], F.per[0]));
+        return F.sigma[czplane(F, kl) * F.cps + (long long)cmap(j, F.n[1], F.per[1]) * F.cpx + cmap(i, F.n[0], F.per[0])];
     }
     // coarse value at coarse global index (ic, jc, kcg)
     __device__ __forceinline__ double cr(int ic, int jc, int kcg) const
@@ -352,38 +202,28 @@ struct Interp {
         return (w1 * line_z(i, j - 1, k, ic, jc, kc) + w2 * line_z(i, j + 1, k, ic, jc + 1, kc) +
                 w3 * line_y(i, j, k - 1, ic, jc, kc) + w4 * line_y(i, j, k + 1, ic, jc, kc + 1)) / (w1 + w2 + w3 + w4);
     }
+    // the interpolant at fine node (i, j, k local plane / kg global plane)
+    __device__ double value(int i, int j, int k, int kg) const
+    {
+        const int ic = i >> 1, jc = j >> 1, kc = kg >> 1;
+        const int io = i & 1, jo = j & 1, ko = kg & 1;
+        if (io && jo && ko) {
+            double w1 = qx(i, j, k, 0), w2 = qx(i, j, k, 1), w3 = qy(i, j, k, 0), w4 = qy(i, j, k, 1), w5 = qz(i, j, k, 0),
+                   w6 = qz(i, j, k, 1);
+            return (w1 * face_yz(i - 1, j, k, ic, jc, kc) + w2 * face_yz(i + 1, j, k, ic + 1, jc, kc) +
+                    w3 * face_xz(i, j - 1, k, ic, jc, kc) + w4 * face_xz(i, j + 1, k, ic, jc + 1, kc) +
+                    w5 * face_xy(i, j, k - 1, ic, jc, kc) + w6 * face_xy(i, j, k + 1, ic, jc, kc + 1)) /
+                   (w1 + w2 + w3 + w4 + w5 + w6);
+        }
+        if (jo && ko) return face_yz(i, j, k, ic, jc, kc);
+        if (io && ko) return face_xz(i, j, k, ic, jc, kc);
+        if (io && jo) return face_xy(i, j, k, ic, jc, kc);
+        if (io) return line_x(i, j, k, ic, jc, kc);
+        if (jo) return line_y(i, j, k, ic, jc, kc);
+        if (ko) return line_z(i, j, k, ic, jc, kc);
+        return cr(ic, jc, kc);
+    }
 };
-
-template <bool VAR>
-__global__ void __launch_bounds__(256) k_interp_add(const Lev F, const Lev C, double* __restrict__ fine,
-                                                    const double* __restrict__ crse)
-{
-    const int i = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
-    const int k = blockIdx.z;  // fine local plane
-    if (i >= F.nn[0] || j >= F.nn[1]) return;
-    const int kg = k + F.k0;
-    if (node_masked(F, i, j, kg)) return;
-    Interp<VAR> x{F, C, crse, F.k0};
-    const int ic = i >> 1, jc = j >> 1, kc = kg >> 1;
-    const int io = i & 1, jo = j & 1, ko = kg & 1;
-    double v;
-    if (io && jo && ko) {
-        double w1 = x.qx(i, j, k, 0), w2 = x.qx(i, j, k, 1), w3 = x.qy(i, j, k, 0), w4 = x.qy(i, j, k, 1),
-               w5 = x.qz(i, j, k, 0), w6 = x.qz(i, j, k, 1);
-        v = (w1 * x.face_yz(i - 1, j, k, ic, jc, kc) + w2 * x.face_yz(i + 1, j, k, ic + 1, jc, kc) +
-             w3 * x.face_xz(i, j - 1, k, ic, jc, kc) + w4 * x.face_xz(i, j + 1, k, ic, jc + 1, kc) +
-             w5 * x.face_xy(i, j, k - 1, ic, jc, kc) + w6 * x.face_xy(i, j, k + 1, ic, jc, kc + 1)) /
-            (w1 + w2 + w3 + w4 + w5 + w6);
-    } else if (jo && ko) v = x.face_yz(i, j, k, ic, jc, kc);
-    else if (io && ko)   v = x.face_xz(i, j, k, ic, jc, kc);
-    else if (io && jo)   v = x.face_xy(i, j, k, ic, jc, kc);
-    else if (io)         v = x.line_x(i, j, k, ic, jc, kc);
-    else if (jo)         v = x.line_y(i, j, k, ic, jc, kc);
-    else if (ko)         v = x.line_z(i, j, k, ic, jc, kc);
-    else                 v = x.cr(ic, jc, kc);
-    fine[k * F.ps + (long long)j * F.px + i] += v;
-}
 
 // ------------------------------------------------------------------------------------------
 // K9: sigma on the next-coarser level = arithmetic mean of the 8 children (A.8)
@@ -769,13 +609,10 @@ __device__ void bottom_apply(const Lev& L, const double* __restrict__ x, double*
     }
 
 template <bool VAR>
-__global__ void __launch_bounds__(512) k_bottom_bicgstab(const Lev L, double* __restrict__ x, const double* __restrict__ b,
-                                                         double* __restrict__ work, int maxiter, double rtol, double atol,
-                                                         int singular, int nsweeps, int bottom_solver, int* __restrict__ info)
+__device__ void bottom_bicgstab_body(const Lev& L, double* __restrict__ x, const double* __restrict__ b, double* __restrict__ work,
+                                     int maxiter, double rtol, double atol, int singular, int nsweeps, int bottom_solver,
+                                     int* __restrict__ info, double* sh /* >= 33 doubles of shared memory */)
 {
-    __shared__ double sh[34];
-    pdl_trigger();
-    pdl_wait();
     const int nxy = L.nn[0] * L.nn[1], ntot = nxy * L.nzl;
     const long long vs = L.ps * L.nzl;
     double *r = work, *rh = work + vs, *p = work + 2 * vs, *v = work + 3 * vs, *s = work + 4 * vs, *t_ = work + 5 * vs,
@@ -880,6 +717,17 @@ __global__ void __launch_bounds__(512) k_bottom_bicgstab(const Lev L, double* __
     }
     __syncthreads();
     if (threadIdx.x == 0) { atomicAdd(&info[0], total_iters); info[1] = ret; }
+}
+
+template <bool VAR>
+__global__ void __launch_bounds__(512) k_bottom_bicgstab(const Lev L, double* __restrict__ x, const double* __restrict__ b,
+                                                         double* __restrict__ work, int maxiter, double rtol, double atol,
+                                                         int singular, int nsweeps, int bottom_solver, int* __restrict__ info)
+{
+    __shared__ double sh[34];
+    pdl_trigger();
+    pdl_wait();
+    bottom_bicgstab_body<VAR>(L, x, b, work, maxiter, rtol, atol, singular, nsweeps, bottom_solver, info, sh);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -213,15 +213,18 @@ def test_smoother_zero_start_resident_kernel(var, zero_start, oracle):
         _close(proj.level_get(lev, A_COR), mg.smooth(lev, start, rhs, 4), 1e-11)
 
 
-@pytest.mark.parametrize("env", [{}, {"B200NP_RES_CTAS": "0"}, {"B200NP_ZERO_START": "0"}, {"B200NP_RES_CTAS": "0", "B200NP_ZERO_START": "0"}],
-                         ids=["default", "nonresident", "no_zero_start", "nonresident_no_zero_start"])
+@pytest.mark.parametrize("env", [{}, {"B200NP_RES_CTAS": "0"}, {"B200NP_ZERO_START": "0"}, {"B200NP_RES_CTAS": "0", "B200NP_ZERO_START": "0"},
+                                 {"B200NP_TAIL": "0"}],
+                         ids=["default", "nonresident", "no_zero_start", "nonresident_no_zero_start", "no_coarse_tail"])
 @pytest.mark.parametrize("var", [False, True])
-def test_vcycle_kernel_routing(var, env, oracle, monkeypatch):
-    """one whole V-cycle with every smoother routing (resident / ring-slot kernel, zero-start on / off)"""
+@pytest.mark.parametrize("case", BC_CASES, ids=[c[0] for c in BC_CASES])
+def test_vcycle_kernel_routing(case, var, env, oracle, monkeypatch):
+    """one whole V-cycle with every kernel routing: resident / ring-slot smoother, zero-start on / off, and the coarse
+    levels either in the single-CTA tail kernel k_coarse_tail (default) or in the per-level kernels"""
     from incflo_b200.nodal_projector import A_COR, A_RES, OP_VCYCLE
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    mg, proj, rng = _setup(BC_CASES[1], var, oracle)
+    mg, proj, rng = _setup(case, var, oracle)
     res = _masked_random(mg, 0, rng)
     w = mg.dot_weights(0)
     res -= (w * res).sum() / w.sum()
@@ -230,7 +233,7 @@ def test_vcycle_kernel_routing(var, env, oracle, monkeypatch):
     proj.level_op(0, OP_VCYCLE)
     got = proj.level_get(0, A_COR)
     mg.params.maxiter = 1
-    mg2 = oracle.MG(mg.params, mg.sigma(0), 0.7)
+    mg2 = oracle.MG(mg.params, mg.sigma(0) if var else None, 0.7)
     phi = np.zeros_like(res)
     mg2.solve(phi, res.copy(), 1e-30, 0.0)
     _close(got, phi, 1e-8)
