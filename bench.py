@@ -274,6 +274,7 @@ def parity_block(ctx):
                                          scaling_factor=wl["dt"], mg_rtol=RTOL, mg_atol=ATOL)
     torch.cuda.synchronize()
     transport = proj.halo_transport()
+    pmap = proj.peer_map()
     proj.close()
     ng, nz, zlo = wl["ng"], wl["nz"], wl["zlo"]
     # oracle on the GLOBAL problem (rank 0), results broadcast as device tensors
@@ -310,7 +311,8 @@ def parity_block(ctx):
            "rel_l2_u": float(torch.sqrt(sums[0] / sums[1])), "rel_l2_gp": float(torch.sqrt(sums[2] / sums[3])),
            "rel_l2_p": float(torch.sqrt(s2[0] / s2[1])), "tol": PARITY_TOL, "vcycles_gpu": int(st.iters),
            "vcycles_oracle_mirrored": int(info[0].item()), "oracle_seconds": float(info[1].item()),
-           "halo_transport": {0: "none (1 GPU)", 1: "ipc", 2: "nccl"}[transport]}
+           "halo_transport": {0: "none (1 GPU)", 1: "peer memory", 2: "nccl"}[transport],
+           "peer_map": {0: None, 1: "cuMem + POSIX fd", 2: "cudaIpc"}[pmap]}
     if P == 1:
         res["vcycles_reference_cpu_algorithm"] = int(info[2].item())
     res["ok"] = bool(st.status == 0 and max(res["rel_l2_u"], res["rel_l2_gp"], res["rel_l2_p"]) < PARITY_TOL
@@ -447,6 +449,7 @@ def run_ours(args):
     wl = workload(n_glob, nranks, rank, device)
     proj = make_projection(ctx, n_glob)
     transport = proj.halo_transport()
+    pmap = proj.peer_map()
     ncell = n_glob[0] * n_glob[1] * n_glob[2] // nranks   # cells per rank
     sampler = ClockSampler(local)
     if rank == 0:
@@ -525,11 +528,11 @@ def run_ours(args):
         strong_rec = strong_block(ctx, sizes)
 
     if rank == 0:
-        tname = {0: "none (1 GPU)", 1: "ipc", 2: "nccl"}[transport]
+        tname = {0: "none (1 GPU)", 1: "peer memory (" + {1: "cuMem + POSIX fd", 2: "cudaIpc"}.get(pmap, "?") + ")", 2: "nccl"}[transport]
         par = "1 GPU" if nranks == 1 else (
             f"z-slab decomposition over {nranks} GPUs; halo planes: "
-            + ("stores / loads into the neighbours' arenas over NVLink peer memory (CUDA IPC), issued by the solver kernels"
-               if transport == 1 else "FALLBACK grouped ncclSend/ncclRecv (CUDA IPC mapping unavailable)")
+            + ("stores / loads into the neighbours' arenas over NVLink peer memory, issued by the solver kernels"
+               if transport == 1 else "FALLBACK grouped ncclSend/ncclRecv (peer mapping unavailable)")
             + f"; ncclAllReduce for norms / solvability; domain {n_glob[0]}x{n_glob[1]}x{n_glob[2]}")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,

@@ -70,8 +70,8 @@ class Stats(C.Structure):
 # every symbol include/b200np.h declares
 EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np_nccl_unique_id", "b200np_slab_range", "b200np_dist_plan",
            "b200np_destroy", "b200np_set_stream", "b200np_project",
-           "b200np_apply_nodal_projection", "b200np_set_inflow_profile", "b200np_strerror", "b200np_version", "b200np_nlevels",
-           "b200np_level_dims", "b200np_halo_transport", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
+           "b200np_apply_nodal_projection", "b200np_set_inflow_profile", "b200np_set_face_types", "b200np_check_overset_mask", "b200np_inout_flux", "b200np_strerror", "b200np_version", "b200np_nlevels",
+           "b200np_level_dims", "b200np_halo_transport", "b200np_peer_map", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
            "b200np_time_op", "b200np_composite_create", "b200np_composite_destroy", "b200np_composite_set_stream",
            "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection"]
 
@@ -101,11 +101,15 @@ def lib():
     L.b200np_apply_nodal_projection.argtypes = [vp, dp, fb, dp, dp, fb, C.c_double, dp, fb, dp, fb, dp, C.c_double,
                                                 C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
     L.b200np_set_inflow_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_double * 18), C.c_double]
+    L.b200np_set_face_types.argtypes = [vp, C.POINTER(C.c_int * 6), C.c_int, C.c_int]
+    L.b200np_check_overset_mask.argtypes = [vp, C.c_void_p, fb]
+    L.b200np_inout_flux.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.b200np_strerror.argtypes = [C.c_int]
     L.b200np_strerror.restype = C.c_char_p
     L.b200np_version.restype = C.c_int
     L.b200np_nlevels.argtypes = [vp]
     L.b200np_halo_transport.argtypes = [vp]
+    L.b200np_peer_map.argtypes = [vp]
     L.b200np_level_dims.argtypes = [vp, C.c_int, ip, ip]
     L.b200np_set_sigma.argtypes = [vp, dp, fb, C.c_double]
     L.b200np_level_set.argtypes = [vp, C.c_int, C.c_int, dp]

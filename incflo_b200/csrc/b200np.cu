@@ -14,12 +14,14 @@
 #include "np_smooth.cuh"
 #include "np_smooth3.cuh"
 #include "np_composite.cuh"
-#include "np_tail.cuh"
+#include "np_peer.h"
 
 #include <dlfcn.h>
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -78,6 +80,9 @@ NcclApi g_nccl;
         }                                                                                              \
     } while (0)
 
+b200np_peer::DriverApi g_drv;
+std::atomic<unsigned long long> g_peer_serial{0};
+
 // Every device array of a handle lives in ONE allocation.  Sizes are rank-independent, so an array
 // sits at the same offset on every rank and a neighbour's copy is (peer base + my offset) once the
 // neighbour's arena is mapped with CUDA IPC (slab-decomposed path).  Pass 1 measures, pass 2 places.
@@ -127,6 +132,10 @@ struct b200np {
     int fuse_halo = 1;        // B200NP_FUSE_HALO=0: separate k_halo_pull before every sweep
     bool p2p = false;         // active (every rank mapped its neighbours)
     char *peer_lo = nullptr, *peer_hi = nullptr;
+    // how the neighbours' arenas are mapped: 0 none, 1 cuMem* allocation + POSIX fd (np_peer.h), 2 legacy CUDA IPC
+    int peer_map = 0;
+    int peer_map_want = 1;    // B200NP_PEER_MAP=vmm|ipc (default vmm: legacy IPC refuses >= 1 GB arenas on some boxes)
+    b200np_peer::VmmMapping arena_vmm{}, peer_lo_vmm{}, peer_hi_vmm{};
     unsigned long long* flags = nullptr;  // HaloFlags::my
     unsigned long long xk = 0;            // exchanges issued since the epoch base was last advanced
     double* ipc_buf = nullptr;
@@ -145,6 +154,8 @@ struct b200np {
     double* bottom_work = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    bool graph_direct = false;   // the captured V-cycle relaxes (sol, rhs) on level 0 (vcycle_launch's direct form)
+    int top_direct = 1;          // B200NP_TOP_DIRECT=0: MLMG's correction form on level 0 too (cor = 0, smooth, sol += cor)
     bool graph_var = false;
     double graph_csig = 0.0;  // kernel parameters (Lev by value) are baked into the captured graph
     long long launches = 0, launches_per_vcycle = 0, exchanges = 0;
@@ -157,10 +168,6 @@ struct b200np {
     int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200NP_PDL)
     int res_max_ctas = 148;   // levels with at most this many smoother CTAs use the resident-chunk kernel (B200NP_RES_CTAS)
     int smoother_version = 3, resid_version = 3;  // B200NP_SMOOTHER=2 / B200NP_RESID=2: the general (anisotropic) kernels on isotropic levels too
-    // coarse tail (np_tail.cuh): levels [tail_lev0, nlev) run in one single-CTA kernel; -1: none (B200NP_TAIL=0)
-    int use_tail = 1, tail_lev0 = -1;
-    TailPlan tail{};
-    size_t tail_smem = 0;
     // B200NP_PROFILE=1: per-phase device times (CUDA events between phases, graph capture off); printed per call
     int profile = 0;
     int zero_start = -1;      // skip the memset of cor before a pre-smooth and the read of it in the first sweep (-1.6 % per solve);
@@ -170,6 +177,9 @@ struct b200np {
     int dbg_halo = 0;         // B200NP_DBG_HALO: see smooth_sweeps (timing experiments, results are wrong)
     bool has_profile = false; // b200np_set_inflow_profile: IncfloVelFill evaluated on the device
     InflowProfile profile_data{};
+    int face_type[6] = {0, 0, 0, 0, 0, 0};   // b200np_set_face_types (enum b200np_face_type), amrex::Orientation order
+    bool has_dd = false;                      // some face is direction_dependent: enforceInOutSolvability applies
+    double inout_flux[2] = {0.0, 0.0};        // influx / outflux of the last call (b200np_inout_flux)
     bool no_bottom = false;   // fine AMR level of a composite solve: one MG level, never a bottom solve
     std::vector<cudaEvent_t> prof_ev;
     std::vector<std::string> prof_tag;
@@ -369,65 +379,26 @@ void build_levels(b200np* h)
     h->bottom_work = dev_alloc(h, h->no_bottom ? 8 : (size_t)B.ps * B.nzl * 8);
 }
 
-void plan_tail(b200np* h);
-
 void build_hierarchy(b200np* h)
 {
     h->arena = Arena{};
     build_levels(h);                       // pass 1: sizes
     h->arena.size = h->arena.off;
     void* base = nullptr;
-    CK(cudaMalloc(&base, h->arena.size));
+    // slab handles: an exportable cuMem* allocation, so the neighbours can map it over a POSIX fd (setup_p2p)
+    if (h->nranks > 1 && h->use_p2p && h->peer_map_want == 1) {
+        std::string why;
+        if (g_drv.load() && b200np_peer::vmm_alloc(g_drv, h->device, h->arena.size, h->arena_vmm, &why)) base = (void*)h->arena_vmm.ptr;
+        else fprintf(stderr, "b200np[rank %d]: cuMem* arena unavailable (%s), using cudaMalloc + legacy CUDA IPC\n", h->rank, why.c_str());
+        cudaGetLastError();
+    }
+    if (!base) CK(cudaMalloc(&base, h->arena.size));
     CK(cudaMemset(base, 0, h->arena.size));
     h->arena.base = static_cast<char*>(base);
     h->arena.off = 0; h->arena.measure = false;
     build_levels(h);                       // pass 2: pointers
-    plan_tail(h);
     CK(cudaMallocHost(&h->hscal, 16 * sizeof(double)));
-    CK(cudaMallocHost(&h->hinfo, 4 * sizeof(int)));
-}
-
-// Coarse tail (np_tail.cuh): the longest run of bottom-most levels that fits one CTA's shared memory -- every level
-// replicated (not slab-distributed) and at most TAIL_MAX_NODES nodes.  Shared-memory need per level: ping, pong,
-// rhs (+ sigma cells); the bottom level also the 7 work vectors of BiCGStab.
-void plan_tail(b200np* h)
-{
-    h->tail_lev0 = -1;
-    const int nl = (int)h->lv.size();
-    if (!h->use_tail || h->no_bottom) return;
-    auto nodes_of = [&](int l) { const Lev& g = h->lv[l].g; return (long long)g.nn[0] * g.nn[1] * g.nn[2]; };
-    auto cells_of = [&](int l) { const Lev& g = h->lv[l].g; return (long long)g.n[0] * g.n[1] * g.n[2]; };
-    long long need = 7 * nodes_of(nl - 1);
-    int l0 = nl;
-    for (int l = nl - 1; l >= std::max(0, h->nlev_dist); --l) {
-        const long long add = 3 * nodes_of(l) + cells_of(l) + 8;
-        if (nodes_of(l) > TAIL_MAX_NODES || need + add > TAIL_SMEM_DOUBLES || nl - l > TAIL_MAX_LEV) break;
-        need += add;
-        l0 = l;
-    }
-    if (l0 >= nl) return;   // not even the bottom level fits: the per-level kernels do everything
-    TailPlan& P = h->tail;
-    P = TailPlan{};
-    P.nlev = nl - l0;
-    int off = 0;
-    auto take = [&](long long n) { int o = off; off += (int)((n + 1) & ~1ll); return o; };
-    for (int t = 0; t < P.nlev; ++t) {
-        const LevelData& L = h->lv[l0 + t];
-        TailLev& T = P.lv[t];
-        T.g = L.g;
-        T.g.px = L.g.nn[0]; T.g.ps = (long long)L.g.nn[0] * L.g.nn[1];
-        T.g.cpx = L.g.n[0]; T.g.cps = (long long)L.g.n[0] * L.g.n[1];
-        T.g.k0 = 0; T.g.nzl = L.g.nn[2]; T.g.ck0 = 0; T.g.cnzl = L.g.n[2]; T.g.dist = 0;
-        T.a = take(nodes_of(l0 + t)); T.b = take(nodes_of(l0 + t)); T.r = take(nodes_of(l0 + t)); T.s = take(cells_of(l0 + t));
-        T.tz = L.tz;
-        T.cpx_g = L.g.cpx; T.cps_g = L.g.cps;
-        T.sigma_g = L.sigma;
-    }
-    P.work = take(7 * nodes_of(nl - 1));
-    P.px_io = h->lv[l0].g.px; P.ps_io = h->lv[l0].g.ps;
-    P.res_in = h->lv[l0].res; P.cor_out = h->lv[l0].cor;
-    h->tail_smem = (size_t)off * sizeof(double);
-    h->tail_lev0 = l0;
+    CK(cudaMallocHost(&h->hinfo, 16 * sizeof(int)));
 }
 
 // ---- slab communication (MLNodeLinOp::applyBC's FillBoundary) ------------------------
@@ -500,62 +471,140 @@ void exchange_planes(b200np* h, double* base, long long plane, int nown, int m, 
     if (!has_lo) CK(cudaMemcpyAsync(ghost_lo, end_lo, plane * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (!has_hi) CK(cudaMemcpyAsync(ghost_hi, end_hi, plane * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
 }
-// Map the neighbours' arenas (CUDA IPC handles exchanged with ncclAllGather).  Falls back to NCCL
-// send/recv halos on every rank if any rank cannot map its neighbours.
+// Map the neighbours' arenas.  Preferred: the arena is a cuMem* allocation whose POSIX file descriptor goes to
+// the neighbours over a UNIX socket (np_peer.h); else legacy CUDA IPC handles exchanged with ncclAllGather.
+// Falls back -- loudly -- to NCCL send/recv halos on every rank if any rank cannot map its neighbours.
 void setup_p2p(b200np* h)
 {
     const int P = h->nranks, r = h->rank;
     if (P == 1 || !h->use_p2p) return;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
-    std::vector<cudaIpcMemHandle_t> all(P);
-    cudaIpcMemHandle_t mine{};
-    double ok = 1.0;
-    {
-        cudaError_t e = cudaIpcGetMemHandle(&mine, h->arena.base);
-        if (e != cudaSuccess) {
-            fprintf(stderr, "b200np[rank %d]: cudaIpcGetMemHandle failed: %s\n", r, cudaGetErrorString(e));
-            ok = 0.0;
-        }
-        cudaGetLastError();
-    }
-    char* buf = reinterpret_cast<char*>(h->ipc_buf);
-    CK(cudaMemcpyAsync(buf + 64 * r, &mine, 64, cudaMemcpyHostToDevice, h->stream));
-    NK(g_nccl.AllGather(buf + 64 * r, buf, 64, ncclChar, h->comm, h->stream));
-    CK(cudaMemcpyAsync(all.data(), buf, (size_t)64 * P, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
     const bool per = zper(h);
     const bool has_lo = per || r > 0, has_hi = per || r < P - 1;
     const int lo = (r - 1 + P) % P, hi = (r + 1) % P;
-    void *plo = nullptr, *phi = nullptr;
-    auto open_peer = [&](void** p, int peer) {
-        cudaError_t e = cudaIpcOpenMemHandle(p, all[peer], cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            fprintf(stderr, "b200np[rank %d]: cudaIpcOpenMemHandle(arena of rank %d, %zu bytes) failed: %s\n", r, peer, h->arena.size,
-                    cudaGetErrorString(e));
-            *p = nullptr;
-            ok = 0.0;
-        }
-        cudaGetLastError();
+    char* buf = reinterpret_cast<char*>(h->ipc_buf);
+    double ok = 1.0;
+    auto all_min = [&](double v) {
+        CK(cudaMemcpyAsync(h->dscal + 4, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        NK(g_nccl.AllReduce(h->dscal + 4, h->dscal + 4, 1, ncclDouble, ncclMin, h->comm, h->stream));
+        CK(cudaMemcpyAsync(&v, h->dscal + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return v;
     };
-    if (ok > 0 && has_lo) open_peer(&plo, lo);
-    if (ok > 0 && has_hi) {
-        if (has_lo && hi == lo) phi = plo;
-        else open_peer(&phi, hi);
+    // ---- (1) cuMem* arena + POSIX fd ----
+    struct Rec { long long pid; unsigned long long serial, size; long long vmm; char pad[32]; };
+    static_assert(sizeof(Rec) == 64, "record size");
+    std::vector<Rec> recs(P);
+    Rec me{};
+    me.pid = (long long)getpid(); me.serial = g_peer_serial.fetch_add(1); me.size = h->arena_vmm.size; me.vmm = h->arena_vmm.mapped ? 1 : 0;
+    int sock = -1;
+    if (me.vmm) {
+        sock = b200np_peer::fd_socket_bind(me.pid, me.serial);
+        if (sock < 0) { fprintf(stderr, "b200np[rank %d]: UNIX socket for the arena descriptor: %s\n", r, strerror(errno)); me.vmm = 0; }
     }
-    CK(cudaMemcpyAsync(h->dscal + 4, &ok, sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    NK(g_nccl.AllReduce(h->dscal + 4, h->dscal + 4, 1, ncclDouble, ncclMin, h->comm, h->stream));
-    CK(cudaMemcpyAsync(&ok, h->dscal + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(buf + 64 * r, &me, 64, cudaMemcpyHostToDevice, h->stream));
+    NK(g_nccl.AllGather(buf + 64 * r, buf, 64, ncclChar, h->comm, h->stream));
+    CK(cudaMemcpyAsync(recs.data(), buf, (size_t)64 * P, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->peer_lo = static_cast<char*>(plo); h->peer_hi = static_cast<char*>(phi);
-    h->p2p = ok > 0;
-    if (!h->p2p) {
+    bool all_vmm = true;
+    for (const Rec& q : recs) all_vmm = all_vmm && q.vmm;
+    if (all_vmm) {
+        std::string why;
+        int fd = b200np_peer::vmm_export_fd(g_drv, h->arena_vmm, &why);
+        if (fd < 0) { fprintf(stderr, "b200np[rank %d]: %s\n", r, why.c_str()); ok = 0.0; }
+        int expect = 0;
+        auto send_to = [&](int peer) {
+            if (fd >= 0 && !b200np_peer::fd_send(sock, recs[peer].pid, recs[peer].serial, fd, r)) {
+                fprintf(stderr, "b200np[rank %d]: sending the arena descriptor to rank %d: %s\n", r, peer, strerror(errno));
+                ok = 0.0;
+            }
+            ++expect;
+        };
+        // every rank sends even after a local failure would leave a neighbour waiting: recv has a 20 s timeout
+        if (has_lo) send_to(lo);
+        if (has_hi && !(has_lo && hi == lo)) send_to(hi);
+        for (int i = 0; i < expect; ++i) {
+            int from = -1;
+            const int pfd = b200np_peer::fd_recv(sock, &from);
+            if (pfd < 0 || from < 0 || from >= P) {
+                fprintf(stderr, "b200np[rank %d]: no arena descriptor from a neighbour (%s)\n", r, strerror(errno));
+                ok = 0.0;
+                if (pfd >= 0) close(pfd);
+                continue;
+            }
+            b200np_peer::VmmMapping m;
+            if (!b200np_peer::vmm_import(g_drv, h->device, pfd, recs[from].size, m, &why)) {
+                fprintf(stderr, "b200np[rank %d]: mapping the arena of rank %d (%llu bytes): %s\n", r, from, recs[from].size, why.c_str());
+                ok = 0.0;
+            } else if (from == lo && has_lo && !h->peer_lo_vmm.mapped) h->peer_lo_vmm = m;
+            else if (from == hi && has_hi && !h->peer_hi_vmm.mapped) h->peer_hi_vmm = m;
+            else b200np_peer::vmm_free(g_drv, m);
+            close(pfd);
+        }
+        if (fd >= 0) close(fd);
+        cudaGetLastError();
+        if (has_lo && !h->peer_lo_vmm.mapped) ok = 0.0;
+        if (has_hi && !(has_lo && hi == lo) && !h->peer_hi_vmm.mapped) ok = 0.0;
+        ok = all_min(ok);
+        if (sock >= 0) close(sock);
+        if (ok > 0) {
+            h->peer_lo = has_lo ? (char*)h->peer_lo_vmm.ptr : nullptr;
+            h->peer_hi = !has_hi ? nullptr : (has_lo && hi == lo) ? h->peer_lo : (char*)h->peer_hi_vmm.ptr;
+            h->p2p = true; h->peer_map = 1;
+            return;
+        }
+        b200np_peer::vmm_free(g_drv, h->peer_lo_vmm);
+        b200np_peer::vmm_free(g_drv, h->peer_hi_vmm);
+    } else {
+        if (sock >= 0) close(sock);
+        // ---- (2) legacy CUDA IPC (only when no rank holds a cuMem* arena: those cannot be exported this way) ----
+        bool none_vmm = true;
+        for (const Rec& q : recs) none_vmm = none_vmm && !q.vmm && q.size == 0;
+        std::vector<cudaIpcMemHandle_t> all(P);
+        cudaIpcMemHandle_t mine{};
+        if (!none_vmm) ok = 0.0;
+        else {
+            cudaError_t e = cudaIpcGetMemHandle(&mine, h->arena.base);
+            if (e != cudaSuccess) {
+                fprintf(stderr, "b200np[rank %d]: cudaIpcGetMemHandle failed: %s\n", r, cudaGetErrorString(e));
+                ok = 0.0;
+            }
+            cudaGetLastError();
+        }
+        CK(cudaMemcpyAsync(buf + 64 * r, &mine, 64, cudaMemcpyHostToDevice, h->stream));
+        NK(g_nccl.AllGather(buf + 64 * r, buf, 64, ncclChar, h->comm, h->stream));
+        CK(cudaMemcpyAsync(all.data(), buf, (size_t)64 * P, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        void *plo = nullptr, *phi = nullptr;
+        auto open_peer = [&](void** p, int peer) {
+            cudaError_t e = cudaIpcOpenMemHandle(p, all[peer], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                fprintf(stderr, "b200np[rank %d]: cudaIpcOpenMemHandle(arena of rank %d, %zu bytes) failed: %s\n", r, peer, h->arena.size,
+                        cudaGetErrorString(e));
+                *p = nullptr;
+                ok = 0.0;
+            }
+            cudaGetLastError();
+        };
+        if (ok > 0 && has_lo) open_peer(&plo, lo);
+        if (ok > 0 && has_hi) {
+            if (has_lo && hi == lo) phi = plo;
+            else open_peer(&phi, hi);
+        }
+        ok = all_min(ok);
+        if (ok > 0) {
+            h->peer_lo = static_cast<char*>(plo); h->peer_hi = static_cast<char*>(phi);
+            h->p2p = true; h->peer_map = 2;
+            return;
+        }
         if (plo) cudaIpcCloseMemHandle(plo);
         if (phi && phi != plo) cudaIpcCloseMemHandle(phi);
-        h->peer_lo = h->peer_hi = nullptr;
         cudaGetLastError();
-        if (r == 0) fprintf(stderr, "b200np: WARNING: CUDA IPC peer mapping unavailable on at least one rank, slab halos FALL BACK to ncclSend/ncclRecv "
-                                    "(b200np_halo_transport() == 2)\n");
     }
+    h->peer_lo = h->peer_hi = nullptr;
+    h->p2p = false; h->peer_map = 0;
+    if (r == 0) fprintf(stderr, "b200np: WARNING: peer mapping of the neighbours' arenas unavailable on at least one rank, slab halos FALL BACK to "
+                                "ncclSend/ncclRecv (b200np_halo_transport() == 2)\n");
 }
 inline void halo_nodes(b200np* h, LevelData& L, double* x)
 {
@@ -734,21 +783,6 @@ void bottom_solve(b200np* h)
                h->opts.bottom_rtol, h->opts.bottom_atol, h->singular, h->opts.smooth_num_sweeps, h->opts.bottom_solver, h->dinfo);
 }
 
-// levels [tail_lev0, nlev): down-leg, bottom solve and up-leg in one CTA (np_tail.cuh)
-void coarse_tail(b200np* h)
-{
-    TailPlan P = h->tail;
-    for (int t = 0; t < P.nlev; ++t) {
-        P.lv[t].g.csig = h->lv[h->tail_lev0 + t].g.csig;
-        if (!h->var_sigma) P.lv[t].sigma_g = nullptr;
-    }
-    P.nu1 = h->opts.num_pre_smooth; P.nu2 = h->opts.num_post_smooth; P.nsw = h->opts.smooth_num_sweeps;
-    P.maxiter = h->opts.bottom_maxiter; P.rtol = h->opts.bottom_rtol; P.atol = h->opts.bottom_atol;
-    P.singular = h->singular; P.bottom_solver = h->opts.bottom_solver; P.info = h->dinfo;
-    if (h->var_sigma) launch_pdl(h, k_coarse_tail<true>, dim3(1), dim3(TAIL_THREADS), h->tail_smem, P);
-    else              launch_pdl(h, k_coarse_tail<false>, dim3(1), dim3(TAIL_THREADS), h->tail_smem, P);
-}
-
 void restrict_to(b200np* h, int l)
 {
     LevelData &F = h->lv[l], &C = h->lv[l + 1];
@@ -760,67 +794,74 @@ void restrict_to(b200np* h, int l)
         launch_pdl(h, k_restrict, C.gn, dim3(256), 0, F.g, C.g, (const double*)F.rescor, C.res);
     }
 }
-void interp_add(b200np* h, int l)
+void interp_add(b200np* h, int l, double* fine = nullptr)
 {
     LevelData &F = h->lv[l], &C = h->lv[l + 1];
+    if (!fine) fine = F.cor;
     halo_nodes(h, C, C.cor);
     {
         if (h->interp_tz == 4) {
-            if (h->var_sigma) launch_pdl(h, k_interp_tile<true, 4>, F.git, dim3(256), (it_v_doubles(4) + it_s_doubles(4)) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
-            else              launch_pdl(h, k_interp_tile<false, 4>, F.git, dim3(256), it_v_doubles(4) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
+            if (h->var_sigma) launch_pdl(h, k_interp_tile<true, 4>, F.git, dim3(256), (it_v_doubles(4) + it_s_doubles(4)) * sizeof(double), F.g, C.g, fine, (const double*)C.cor);
+            else              launch_pdl(h, k_interp_tile<false, 4>, F.git, dim3(256), it_v_doubles(4) * sizeof(double), F.g, C.g, fine, (const double*)C.cor);
         } else {
-            if (h->var_sigma) launch_pdl(h, k_interp_tile<true>, F.git, dim3(256), (IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
-            else              launch_pdl(h, k_interp_tile<false>, F.git, dim3(256), IT_V_DOUBLES * sizeof(double), F.g, C.g, F.cor, (const double*)C.cor);
+            if (h->var_sigma) launch_pdl(h, k_interp_tile<true>, F.git, dim3(256), (IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double), F.g, C.g, fine, (const double*)C.cor);
+            else              launch_pdl(h, k_interp_tile<false>, F.git, dim3(256), IT_V_DOUBLES * sizeof(double), F.g, C.g, fine, (const double*)C.cor);
         }
     }
 }
 
-// MLMG::mgVcycle (A.9) on (cor, res), all launches on h->stream, no host synchronisation
-void vcycle_launch(b200np* h, int lev0)
+// MLMG::mgVcycle (A.9) on (cor, res), all launches on h->stream, no host synchronisation.
+// direct (level 0 of mlmg_solve only): the cycle relaxes (sol, rhs) in place of (cor, res) on the finest level.  The
+// smoother is a stationary linear iteration, so smoothing cor from 0 against res = rhs - L sol and adding it to sol is
+// the same arithmetic as smoothing sol against rhs (rounding aside); the direct form needs neither the zeroed cor,
+// nor `sol += cor` (24 B/node), nor the stored top residual (8 B/node) -- MLMG::oneIter's result is unchanged.
+void vcycle_launch(b200np* h, int lev0, bool direct = false)
 {
     const int nsw = h->opts.smooth_num_sweeps;
-    // levels [nl - 1, ...) -- the bottom level alone, or the whole coarse tail -- are one kernel
-    const bool tail = h->tail_lev0 >= lev0 && h->tail_lev0 >= 0;
-    const int nl = tail ? h->tail_lev0 + 1 : (int)h->lv.size();
+    const int nl = (int)h->lv.size();
     for (int l = lev0; l < nl - 1; ++l) {
         LevelData& L = h->lv[l];
+        const bool dtop = direct && l == 0;
+        double* X = dtop ? L.sol : L.cor;
+        const double* R = dtop ? L.rhs : L.res;
         // cor = 0 (ghost slots included) -- unless the first sweep knows it and never reads cor
-        const bool skip_zero = h->zero_start && h->smoother_version >= 3 && L.iso && h->opts.num_pre_smooth * nsw >= 1;
+        const bool skip_zero = dtop || (h->zero_start && h->smoother_version >= 3 && L.iso && h->opts.num_pre_smooth * nsw >= 1);
         if (!skip_zero) CK(cudaMemsetAsync(L.cor - L.g.ps, 0, (size_t)L.g.ps * (L.g.nzl + 2) * sizeof(double), h->stream));
-        double *x = L.cor, *y = L.cor2;
+        double *x = X, *y = L.cor2;
         prof_mark(h, "zero cor", l);
-        smooth_sweeps(h, L, x, y, L.res, h->opts.num_pre_smooth * nsw, true);  // cor == 0, ghost slots included
-        if (x != L.cor) {  // odd sweep count: cor was pulled by the neighbours in the last exchange
+        smooth_sweeps(h, L, x, y, R, h->opts.num_pre_smooth * nsw, !dtop);  // cor == 0, ghost slots included
+        if (x != X) {  // odd sweep count: cor was pulled by the neighbours in the last exchange
             if (L.dist) p2p_fence(h);
-            CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            CK(cudaMemcpyAsync(X, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         }
         prof_mark(h, "smooth", l);
-        residual(h, L, L.cor, L.res, L.rescor, nullptr);
+        residual(h, L, X, R, L.rescor, nullptr);
         prof_mark(h, "residual", l);
         restrict_to(h, l);
         prof_mark(h, "restrict", l);
     }
-    if (tail) coarse_tail(h);
-    else bottom_solve(h);
-    prof_mark(h, tail ? "coarse tail + bottom" : "bottom");
+    bottom_solve(h);
+    prof_mark(h, "bottom");
     for (int l = nl - 2; l >= lev0; --l) {
         LevelData& L = h->lv[l];
-        interp_add(h, l);
+        const bool dtop = direct && l == 0;
+        double* X = dtop ? L.sol : L.cor;
+        interp_add(h, l, X);
         prof_mark(h, "interp", l);
-        double *x = L.cor, *y = L.cor2;
-        smooth_sweeps(h, L, x, y, L.res, h->opts.num_post_smooth * nsw);
-        if (x != L.cor) {
+        double *x = X, *y = L.cor2;
+        smooth_sweeps(h, L, x, y, dtop ? L.rhs : L.res, h->opts.num_post_smooth * nsw);
+        if (x != X) {
             if (L.dist) p2p_fence(h);
-            CK(cudaMemcpyAsync(L.cor, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            CK(cudaMemcpyAsync(X, x, (size_t)L.g.ps * L.g.nzl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         }
         prof_mark(h, "smooth", l);
     }
 }
 
-void vcycle(b200np* h)
+void vcycle(b200np* h, bool direct = false)
 {
-    if (!h->opts.use_graph || h->profile || (h->nranks > 1 && !h->dist_graph)) { vcycle_launch(h, 0); return; }
-    if (h->graph_exec && (h->graph_var != h->var_sigma || h->graph_csig != h->lv[0].g.csig)) {
+    if (!h->opts.use_graph || h->profile || (h->nranks > 1 && !h->dist_graph)) { vcycle_launch(h, 0, direct); return; }
+    if (h->graph_exec && (h->graph_var != h->var_sigma || h->graph_csig != h->lv[0].g.csig || h->graph_direct != direct)) {
         cudaGraphExecDestroy(h->graph_exec); cudaGraphDestroy(h->graph);
         h->graph_exec = nullptr; h->graph = nullptr;
     }
@@ -829,7 +870,7 @@ void vcycle(b200np* h)
         long long before = h->launches;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         try {
-            vcycle_launch(h, 0);
+            vcycle_launch(h, 0, direct);
             epoch_advance(h);   // last node: every replay leaves the base advanced by the graph's exchanges
         } catch (int) {   // never leave the (possibly caller-owned) stream in capture mode
             cudaGraph_t broken = nullptr;
@@ -843,6 +884,7 @@ void vcycle(b200np* h)
         h->launches_per_vcycle = h->launches - before;
         h->launches = before;
         h->graph_var = h->var_sigma;
+        h->graph_direct = direct;
         h->graph_csig = h->lv[0].g.csig;
     }
     CK(cudaGraphLaunch(h->graph_exec, h->stream));
@@ -893,10 +935,12 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
     bool converged = false;
     prof_mark(h, "mlmg setup");
     for (int it = 0; it < h->opts.maxiter; ++it) {
-        vcycle(h);
-        LAUNCH(h, k_axpy, L0.gn, 256, L0.g, L0.sol, L0.cor, 1.0);
-        residual(h, L0, L0.sol, L0.rhs, L0.res, h->partial);
-        prof_mark(h, "top sol+=cor, residual");
+        const bool direct = h->top_direct && h->lv.size() > 1;
+        vcycle(h, direct);
+        if (!direct) LAUNCH(h, k_axpy, L0.gn, 256, L0.g, L0.sol, L0.cor, 1.0);
+        // direct form: only the norm of the new residual is needed (the next cycle never reads res)
+        residual(h, L0, L0.sol, L0.rhs, direct ? nullptr : L0.res, h->partial);
+        prof_mark(h, direct ? "top residual norm" : "top sol+=cor, residual");
         st->resnorm = norm_from_partials(h, resid_nblk(h, L0));
         prof_mark(h, "top norm (allreduce+sync)");
         st->iters = it + 1;
@@ -1074,9 +1118,10 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         if (const char* e = getenv("B200NP_PROFILE")) h->profile = atoi(e);
         if (const char* e = getenv("B200NP_DBG_HALO")) h->dbg_halo = atoi(e);
         if (const char* e = getenv("B200NP_P2P")) h->use_p2p = atoi(e);
+        if (const char* e = getenv("B200NP_PEER_MAP")) h->peer_map_want = strcmp(e, "ipc") == 0 ? 2 : 1;
         if (const char* e = getenv("B200NP_FUSE_HALO")) h->fuse_halo = atoi(e);
         if (const char* e = getenv("B200NP_DIST_MIN_PLANES")) h->dist_min_planes = std::max(8, atoi(e));
-        if (const char* e = getenv("B200NP_TAIL")) h->use_tail = atoi(e);
+        if (const char* e = getenv("B200NP_TOP_DIRECT")) h->top_direct = atoi(e);
         if (const char* e = getenv("B200NP_ZERO_START")) h->zero_start = atoi(e);
         if (const char* e = getenv("B200NP_INTERP_TZ")) h->interp_tz = atoi(e) == 8 ? 8 : 4;
         if (const char* e = getenv("B200NP_RESID")) h->resid_version = atoi(e);
@@ -1090,8 +1135,6 @@ int create_common(b200np_t** out, const b200np_geom* geom, const b200np_opts* op
         CK(cudaFuncSetAttribute(k_residual_iso<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SM_PHI_SLOT * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((IT_V_DOUBLES + IT_S_DOUBLES) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(IT_V_DOUBLES * sizeof(double))));
-        CK(cudaFuncSetAttribute(k_coarse_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TAIL_SMEM_DOUBLES * sizeof(double))));
-        CK(cudaFuncSetAttribute(k_coarse_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TAIL_SMEM_DOUBLES * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((it_v_doubles(4) + it_s_doubles(4)) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_interp_tile<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(it_v_doubles(4) * sizeof(double))));
         CK(cudaFuncSetAttribute(k_smooth_iso_dist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMOOTH_DOUBLES * sizeof(double))));
@@ -1349,6 +1392,7 @@ const char* b200np_strerror(int s)
     case B200NP_ERR_CUDA: return "CUDA error / no usable sm_100 device (there is no CPU fallback)";
     case B200NP_ERR_NCCL: return "NCCL error";
     case B200NP_ERR_UNSUPPORTED: return "not supported by this build";
+    case B200NP_ERR_INOUT_FLUX: return "cannot enforce solvability: inflow without outflow through the direction_dependent faces, or the reverse";
     default: return "unknown status";
     }
 }
@@ -1421,15 +1465,21 @@ void b200np_destroy(b200np_t* h)
     if (h->p2p) {  // the neighbours may still be pulling from this arena: handshake before unmapping / freeing
         try { p2p_fence(h); } catch (int) {}
         cudaStreamSynchronize(h->stream);
-        if (h->peer_lo) cudaIpcCloseMemHandle(h->peer_lo);
-        if (h->peer_hi && h->peer_hi != h->peer_lo) cudaIpcCloseMemHandle(h->peer_hi);
+        if (h->peer_map == 1) {
+            b200np_peer::vmm_free(g_drv, h->peer_lo_vmm);
+            b200np_peer::vmm_free(g_drv, h->peer_hi_vmm);
+        } else {
+            if (h->peer_lo) cudaIpcCloseMemHandle(h->peer_lo);
+            if (h->peer_hi && h->peer_hi != h->peer_lo) cudaIpcCloseMemHandle(h->peer_hi);
+        }
         h->p2p = false;
     }
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
     if (h->graph) cudaGraphDestroy(h->graph);
     if (h->comm) g_nccl.CommDestroy(h->comm);
-    if (h->arena.base) cudaFree(h->arena.base);
+    if (h->arena_vmm.mapped) b200np_peer::vmm_free(g_drv, h->arena_vmm);
+    else if (h->arena.base) cudaFree(h->arena.base);
     if (h->hscal) cudaFreeHost(h->hscal);
     if (h->hinfo) cudaFreeHost(h->hinfo);
     for (auto& s : h->stage) if (s.d) cudaFree(s.d);
@@ -1448,11 +1498,97 @@ int b200np_set_stream(b200np_t* h, void* stream)
     return B200NP_OK;
 }
 
+// device-side face kinds of the profile: INFLOW faces are mass inflow unless b200np_set_face_types said otherwise
+static void sync_profile_faces(b200np* h)
+{
+    for (int o = 0; o < 6; ++o) {
+        const int d = o % 3, bc = o < 3 ? h->geom.bc_lo[d] : h->geom.bc_hi[d];
+        int ft = FACE_PLAIN;
+        if (bc == B200NP_BC_INFLOW)
+            ft = h->face_type[o] == B200NP_FACE_DIRECTION_DEPENDENT ? FACE_DIRECTION_DEPENDENT
+               : h->face_type[o] == B200NP_FACE_MIXED ? FACE_MIXED : FACE_MASS_INFLOW;
+        h->profile_data.face[o] = ft;
+    }
+}
+
+int b200np_set_face_types(b200np_t* h, const int face_type[6], int mixed_split_dir, int mixed_half_num_cells)
+{
+    if (!h || !face_type) return B200NP_ERR_BAD_ARG;
+    int mixm = 0;
+    bool dd = false;
+    for (int o = 0; o < 6; ++o) {
+        const int d = o % 3, bc = o < 3 ? h->geom.bc_lo[d] : h->geom.bc_hi[d];
+        if (face_type[o] < B200NP_FACE_DEFAULT || face_type[o] > B200NP_FACE_MIXED) return B200NP_ERR_BAD_ARG;
+        // get_projection_bc maps both kinds to LinOpBCType::inflow (incflo_projection_bc.cpp:21-27)
+        if (face_type[o] != B200NP_FACE_DEFAULT && bc != B200NP_BC_INFLOW) return B200NP_ERR_BAD_BC;
+        if (face_type[o] == B200NP_FACE_MIXED) mixm |= 1 << o;
+        if (face_type[o] == B200NP_FACE_DIRECTION_DEPENDENT) dd = true;
+    }
+    if (mixm) {
+        if (mixed_split_dir < 0 || mixed_split_dir > 2) return B200NP_ERR_BAD_ARG;
+        if (mixed_half_num_cells < 0 || mixed_half_num_cells > h->geom.n_cell[mixed_split_dir]) return B200NP_ERR_BAD_ARG;
+        for (int o = 0; o < 6; ++o)   // prob_set_BC_MF splits a face along a direction inside the face
+            if ((mixm >> o & 1) && o % 3 == mixed_split_dir) return B200NP_ERR_BAD_ARG;
+    }
+    for (int o = 0; o < 6; ++o) h->face_type[o] = face_type[o];
+    h->has_dd = dd;
+    // the overset mask of the mixed faces on every multigrid level (injection: half >> level)
+    for (size_t l = 0; l < h->lv.size(); ++l) {
+        for (Lev* g : {&h->lv[l].g, &h->lv[l].gpart}) {
+            g->mixm = mixm; g->mixdir = mixm ? mixed_split_dir : 0; g->mixhalf = mixm ? mixed_half_num_cells >> l : 0;
+        }
+    }
+    h->singular = 1;
+    for (int d = 0; d < 3; ++d)
+        if (h->geom.bc_lo[d] == B200NP_BC_DIRICHLET || h->geom.bc_hi[d] == B200NP_BC_DIRICHLET) h->singular = 0;
+    if (mixm) h->singular = 0;
+    // the level descriptors are kernel parameters baked into the captured V-cycle
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); cudaGraphDestroy(h->graph); h->graph_exec = nullptr; h->graph = nullptr; }
+    sync_profile_faces(h);
+    return B200NP_OK;
+}
+
+int b200np_check_overset_mask(b200np_t* h, const int* mask, const b200np_fab* mask_box)
+{
+    if (!h || !mask || !mask_box) return B200NP_ERR_BAD_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        const int nx = mask_box->hi[0] - mask_box->lo[0] + 1, ny = mask_box->hi[1] - mask_box->lo[1] + 1, nz = mask_box->hi[2] - mask_box->lo[2] + 1;
+        if (nx < 1 || ny < 1 || nz < 1) return B200NP_ERR_BAD_ARG;
+        const size_t bytes = (size_t)nx * ny * nz * sizeof(int);
+        const int* d = mask;
+        int* staged = nullptr;
+        if (!is_device_ptr(mask)) {
+            CK(cudaMalloc(&staged, bytes));
+            CK(cudaMemcpyAsync(staged, mask, bytes, cudaMemcpyHostToDevice, h->stream));
+            d = staged;
+        }
+        Lev Lm = h->lv[0].g;
+        for (int dd = 0; dd < 3; ++dd) Lm.dlo[dd] = Lm.dhi[dd] = 0;
+        CK(cudaMemsetAsync(h->dinfo + 8, 0, sizeof(int), h->stream));
+        const long long total = (long long)nx * ny * nz;
+        LAUNCH(h, k_check_overset, (int)std::min<long long>((total + 255) / 256, 148 * 8), 256, Lm, d, mask_box->lo[0], mask_box->lo[1],
+               mask_box->lo[2], nx, ny, nz, h->dinfo + 8);
+        CK(cudaMemcpyAsync(h->hinfo + 8, h->dinfo + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (staged) CK(cudaFree(staged));
+        return h->hinfo[8] == 0 ? B200NP_OK : B200NP_ERR_UNSUPPORTED;
+    } catch (int e) { return e; }
+}
+
+int b200np_inout_flux(const b200np_t* h, double* influx, double* outflux)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    if (influx) *influx = h->inout_flux[0];
+    if (outflux) *outflux = h->inout_flux[1];
+    return B200NP_OK;
+}
+
 int b200np_set_inflow_profile(b200np_t* h, int probtype, const double* bcv_vel, double time)
 {
     if (!h) return B200NP_ERR_BAD_ARG;
     if (!bcv_vel) { h->has_profile = false; return B200NP_OK; }
-    if (probtype == 1101 || probtype == 1102) return B200NP_ERR_UNSUPPORTED;   // mixed BCs (EB decks), overset mask
+    sync_profile_faces(h);
     h->profile_data.probtype = probtype;
     h->profile_data.time = time;
     for (int o = 0; o < 6; ++o)
@@ -1464,6 +1600,7 @@ int b200np_set_inflow_profile(b200np_t* h, int probtype, const double* bcv_vel, 
 int b200np_nlevels(const b200np_t* h) { return h ? (int)h->lv.size() : 0; }
 
 int b200np_halo_transport(const b200np_t* h) { return !h ? -1 : h->nranks == 1 ? 0 : h->p2p ? 1 : 2; }
+int b200np_peer_map(const b200np_t* h) { return !h ? -1 : h->p2p ? h->peer_map : 0; }
 
 int b200np_level_dims(const b200np_t* h, int lev, int n_cell[3], int n_node[3])
 {
@@ -1541,6 +1678,29 @@ int b200np_project(b200np_t* h, double* vel, const b200np_fab* vel_box, const do
     } catch (int e) { return st->status = e; }
 }
 
+// HydroUtils::enforceInOutSolvability (call site incflo_apply_nodal_projection.cpp:166-179) on the ghost layer of
+// the direction_dependent faces.  AMReX-Hydro aborts when only one of influx / outflux is non-zero; here that is
+// B200NP_ERR_INOUT_FLUX.
+namespace {
+int enforce_inout_solvability(b200np* h, Fab fvel)
+{
+    constexpr double small_vel = 1.0e-8;
+    const Lev& g = h->lv[0].g;
+    sync_profile_faces(h);
+    const int blocks = 148;
+    LAUNCH(h, k_inout_flux, blocks, 256, g, fvel, h->profile_data, h->partial);
+    LAUNCH(h, k_sum2_final, 1, 1024, h->partial, (long long)blocks, h->dscal);
+    allreduce(h, h->dscal, 2, ncclSum);
+    CK(cudaMemcpyAsync(h->hscal, h->dscal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    LAUNCH(h, k_inout_correct, blocks, 256, g, fvel, h->profile_data, h->dscal, small_vel);
+    CK(cudaStreamSynchronize(h->stream));
+    h->inout_flux[0] = h->hscal[0]; h->inout_flux[1] = h->hscal[1];
+    const bool in = h->hscal[0] > small_vel, out = h->hscal[1] > small_vel;
+    if (in != out) return B200NP_ERR_INOUT_FLUX;   // "Cannot enforce solvability": inflow without outflow, or the reverse
+    return B200NP_OK;
+}
+}  // namespace
+
 int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fab* vel_box, const double* velocity_o,
                                   const double* density, const b200np_fab* rho_box, double ro_0, double* gp,
                                   const b200np_fab* gp_box, double* p_nd, const b200np_fab* p_box, const double* inflow_vel,
@@ -1586,6 +1746,11 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
             LAUNCH(h, k_set_vel_ghosts, blocks, 256, L0.g, fvel, fin, set_inflow);
             // no caller-filled array: IncfloVelFill on the device (:138-163), when a profile has been set
             if (set_inflow && !fin.p && h->has_profile) LAUNCH(h, k_incflo_vel_fill, blocks, 256, L0.g, fvel, h->profile_data);
+            // :166-179 enforceInOutSolvability over the direction_dependent faces
+            if (set_inflow && h->has_dd) {
+                int rc = enforce_inout_solvability(h, fvel);
+                if (rc) return st->status = rc;
+            }
         }
         // :181-256
         int status = project_core(h, fvel, fvelo, use_old, fgp, incremental, fp, incremental, rtol, atol, st);

@@ -322,59 +322,101 @@ __global__ void __launch_bounds__(256) k_set_vel_ghosts(const Lev L, Fab vel, Fa
     }
 }
 
-// IncfloVelFill (src/prob/prob_bc.H:8-351), the mass-inflow (BCType::ext_dir) part, evaluated on the device:
-// fills the FIRST ghost layer of the velocity at inflow faces (:138-163 of incflo_apply_nodal_projection.cpp
-// call it with nghost = 1) from the face's boundary velocity bcv_vel and the probtype-specific profile of
-// the normal component.  The face blocks are applied in the reference's order (x-lo, x-hi, y-lo, y-hi, z-lo,
-// z-hi), so a ghost cell outside the domain in two directions ends up with the later face's value, as there.
+// IncfloVelFill (src/prob/prob_bc.H:8-351) evaluated on the device: fills the FIRST ghost layer of the velocity
+// (:138-163 of incflo_apply_nodal_projection.cpp call it with nghost = 1) from the face's boundary velocity
+// bcv_vel and the probtype-specific profile of the normal component.  The face blocks are applied in the
+// reference's order (x-lo, x-hi, y-lo, y-hi, z-lo, z-hi), so a ghost cell outside the domain in two directions
+// ends up with the later face's value, as there.
 // bcv[o][c]: o = amrex::Orientation index (dir + 3 * side), c = velocity component (m_bc_velocity).
-// direction_dependent faces (copy of the interior value when the flow leaves) and the mixed-BC probtypes
-// 1101 / 1102 are not handled here (the host refuses them: B200NP_ERR_UNSUPPORTED).
+// face[o]: how ApplyNodalProjection's inflow_bcr sees the face (:141-153):
+//   FACE_MASS_INFLOW         BCType::ext_dir            -> boundary value
+//   FACE_DIRECTION_DEPENDENT BCType::direction_dependent -> boundary value where the profile points into the domain,
+//                            else a copy of the first interior cell (prob_bc.H:93-109 and the five sibling blocks;
+//                            the z-lo block tests norm_vel <= 0 for inflow, :300-301 -- kept as written there)
+//   anything else            untouched (BCRec default)
+// and the "special case" probtypes 1101 (x faces, :86-92, :140-146) / 1102 (y-hi face, :243-251), whose blocks do not
+// look at the BCRec at all.
+enum { FACE_PLAIN = 0, FACE_MASS_INFLOW = 1, FACE_DIRECTION_DEPENDENT = 2, FACE_MIXED = 3 };
 struct InflowProfile {
     int probtype;
     double time;
     double bcv[6][3];
+    int face[6];
 };
 __device__ __forceinline__ double parab6(int idx, int n) { const double s = (idx + 0.5) / n; return 6.0 * s * (1.0 - s); }
-// value of component nc in ghost cell (i,j,k); returns false if no inflow face claims the cell
-__device__ __forceinline__ bool incflo_vel_fill(const InflowProfile& P, const Lev& L, int i, int j, int k, int nc, double& out)
+// the profile of the normal velocity on face (dir, side) at ghost cell (i,j,k)
+__device__ __forceinline__ double inflow_norm_vel(const InflowProfile& P, const Lev& L, int dir, int side, int i, int j, int k)
 {
-    bool hit = false;
+    double norm_vel = P.bcv[dir + 3 * side][dir];
+    const int pt = P.probtype;
+    if (dir == 0 && side == 0) {          // prob_bc.H:57-84
+        if (pt == 42) norm_vel = P.time;
+        else if (pt == 31) norm_vel = parab6(j, L.n[1]);
+        else if (pt == 43) norm_vel = parab6(j, L.n[1]) - 1.0;
+        else if (pt == 311) norm_vel = parab6(k, L.n[2]);
+        else if (pt == 41) norm_vel = 0.5 * ((k + 0.5) / L.n[2]);
+    } else if (dir == 0 && side == 1) {   // :129-138
+        if (pt == 42) norm_vel = P.time;
+        else if (pt == 43) norm_vel = parab6(j, L.n[1]) - 1.0;
+    } else if (dir == 1 && side == 0) {   // :190-202
+        if (pt == 32) norm_vel *= parab6(k, L.n[2]);
+        if (pt == 322) norm_vel *= parab6(i, L.n[0]);
+    } else if (dir == 1 && side == 1) {   // :241-246
+        if (pt == 16) { const double x = (i + 0.5) / L.n[0]; norm_vel = 16.0 * (x * x * x * x - 2.0 * x * x * x + x * x); }
+    } else if (dir == 2 && side == 0) {   // :298-308
+        if (pt == 33) norm_vel *= parab6(i, L.n[0]);
+        else if (pt == 333) norm_vel *= parab6(j, L.n[1]);
+    }
+    return norm_vel;
+}
+// does the profile value count as inflow on a direction_dependent face?  (the sign tests of the six blocks)
+__device__ __forceinline__ bool dd_is_inflow(int dir, int side, double norm_vel)
+{
+    if (side == 0 && dir != 2) return norm_vel >= 0.0;   // x-lo :94, y-lo :201
+    return norm_vel <= 0.0;                               // x-hi :148, y-hi :254, z-lo :301 (sic), z-hi :333
+}
+// all components of ghost cell (i,j,k); only components some face block writes are stored
+__device__ __forceinline__ void incflo_vel_fill_cell(const InflowProfile& P, const Lev& L, Fab& vel, int i, int j, int k)
+{
     const int idx[3] = {i, j, k};
 #pragma unroll
-    for (int dir = 0; dir < 3; ++dir)
+    for (int nc = 0; nc < 3; ++nc) {
+        bool hit = false;
+        double out = 0.0;
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const bool outside = side == 0 ? idx[dir] < 0 : idx[dir] >= L.n[dir];
-            const int kind = side == 0 ? L.rlo[dir] : L.rhi[dir];   // 2 = inflow (np_level.h)
-            if (!outside || kind != 2 || L.per[dir]) continue;
-            const double* b = P.bcv[dir + 3 * side];
-            double norm_vel = b[dir];
-            const int pt = P.probtype;
-            if (dir == 0 && side == 0) {          // prob_bc.H:57-84
-                if (pt == 42) norm_vel = P.time;
-                else if (pt == 31) norm_vel = parab6(j, L.n[1]);
-                else if (pt == 43) norm_vel = parab6(j, L.n[1]) - 1.0;
-                else if (pt == 311) norm_vel = parab6(k, L.n[2]);
-                else if (pt == 41) norm_vel = 0.5 * ((k + 0.5) / L.n[2]);
-            } else if (dir == 0 && side == 1) {   // :129-138
-                if (pt == 42) norm_vel = P.time;
-                else if (pt == 43) norm_vel = parab6(j, L.n[1]) - 1.0;
-            } else if (dir == 1 && side == 0) {   // :190-202
-                if (pt == 32) norm_vel *= parab6(k, L.n[2]);
-                if (pt == 322) norm_vel *= parab6(i, L.n[0]);
-            } else if (dir == 1 && side == 1) {   // :241-246
-                if (pt == 16) { const double x = (i + 0.5) / L.n[0]; norm_vel = 16.0 * (x * x * x * x - 2.0 * x * x * x + x * x); }
-            } else if (dir == 2 && side == 0) {   // :298-308
-                if (pt == 33) norm_vel *= parab6(i, L.n[0]);
-                else if (pt == 333) norm_vel *= parab6(j, L.n[1]);
+        for (int dir = 0; dir < 3; ++dir)
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const bool outside = side == 0 ? idx[dir] < 0 : idx[dir] >= L.n[dir];
+                if (!outside || L.per[dir]) continue;
+                const int o = dir + 3 * side;
+                const int pt = P.probtype;
+                if (pt == 1101 && dir == 0) {            // :86-92 / :140-146: all the logic of the x faces is here
+                    const int half = L.n[1] / 2;
+                    if (side == 0 && j > half) { out = P.bcv[0][nc]; hit = true; }
+                    if (side == 1 && j <= half) { out = -P.bcv[3][nc]; hit = true; }
+                    continue;
+                }
+                if (pt == 1102 && dir == 1 && side == 1) {   // :243-251, and :251 skips the generic part
+                    if (k <= L.n[2] / 2) { out = -P.bcv[4][nc]; hit = true; }
+                    continue;
+                }
+                const int ft = P.face[o];
+                if (ft != FACE_MASS_INFLOW && ft != FACE_DIRECTION_DEPENDENT) continue;
+                const double norm_vel = inflow_norm_vel(P, L, dir, side, i, j, k);
+                if (ft == FACE_MASS_INFLOW || dd_is_inflow(dir, side, norm_vel)) {
+                    out = nc == dir ? norm_vel : P.bcv[o][nc];   // normal component: the profile; tangential: bcv_vel
+                } else {   // the flow leaves: first interior cell (a ghost cell of another face for edge / corner cells)
+                    int q[3] = {i, j, k};
+                    q[dir] += side == 0 ? 1 : -1;
+                    out = vel.has(q[0], q[1], q[2]) ? vel.p[vel.idx(q[0], q[1], q[2], nc)] : 0.0;
+                }
+                hit = true;
             }
-            out = nc == dir ? norm_vel : b[nc];   // normal component: the profile; tangential: bcv_vel
-            hit = true;
-        }
-    return hit;
+        if (hit) vel.p[vel.idx(i, j, k, nc)] = out;
+    }
 }
-// one thread per cell of the domain grown by one; only ghost cells at inflow faces are written
+// one thread per cell of the domain grown by one; only ghost cells are written
 __global__ void __launch_bounds__(256) k_incflo_vel_fill(const Lev L, Fab vel, const InflowProfile P)
 {
     const int nx = L.n[0] + 2, ny = L.n[1] + 2;
@@ -383,12 +425,85 @@ __global__ void __launch_bounds__(256) k_incflo_vel_fill(const Lev L, Fab vel, c
         const int i = (int)(t % nx) - 1, j = (int)((t / nx) % ny) - 1, k = (int)(t / ((long long)nx * ny)) - 1 + L.ck0;
         const bool out = i < 0 || i >= L.n[0] || j < 0 || j >= L.n[1] || k < 0 || k >= L.n[2];
         if (!out || !vel.has(i, j, k)) continue;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            double v;
-            if (incflo_vel_fill(P, L, i, j, k, c, v)) vel.p[vel.idx(i, j, k, c)] = v;
+        incflo_vel_fill_cell(P, L, vel, i, j, k);
+    }
+}
+
+// HydroUtils::enforceInOutSolvability (AMReX-Hydro, un-vendored; call site incflo_apply_nodal_projection.cpp:166-179):
+// over the direction_dependent faces, influx = sum |u_n| dS over the boundary cells where the normal ghost velocity
+// points into the domain, outflux = the same over those where it points out; the outflow values are then scaled by
+// influx / outflux so that the net flux vanishes (the nodal solve has no Dirichlet node to absorb a net flux).
+// face cells: the first ghost layer over the face's own extent (edge / corner ghost cells excluded).
+// Pass 1: per-block partial sums {influx, outflux} (fixed order -> deterministic), this rank's cell planes only.
+__global__ void __launch_bounds__(256) k_inout_flux(const Lev L, Fab vel, const InflowProfile P, double* __restrict__ partial)
+{
+    __shared__ double sh[34];
+    double fin = 0.0, fout = 0.0;
+    const int klo = L.ck0, khi = L.ck0 + L.cnzl;   // owned cell planes [klo, khi)
+    for (int o = 0; o < 6; ++o) {
+        if (P.face[o] != FACE_DIRECTION_DEPENDENT) continue;
+        const int dir = o % 3, side = o / 3;
+        const int d1 = (dir + 1) % 3, d2 = (dir + 2) % 3;
+        const double ds = 1.0 / (L.dxinv[d1] * L.dxinv[d2]);
+        const long long total = (long long)L.n[d1] * L.n[d2];
+        for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+            int q[3];
+            q[dir] = side == 0 ? -1 : L.n[dir];
+            q[d1] = (int)(t % L.n[d1]); q[d2] = (int)(t / L.n[d1]);
+            if (dir == 2) { if (side == 0 ? klo != 0 : khi != L.n[2]) continue; }   // the rank at that end of the domain
+            else if (q[2] < klo || q[2] >= khi) continue;
+            if (!vel.has(q[0], q[1], q[2])) continue;
+            const double v = vel.p[vel.idx(q[0], q[1], q[2], dir)];
+            const bool in = side == 0 ? v >= 0.0 : v <= 0.0;
+            if (in) fin += fabs(v) * ds; else fout += fabs(v) * ds;
         }
     }
+    fin = block_reduce<false>(fin, sh);
+    fout = block_reduce<false>(fout, sh);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = fin; partial[2 * blockIdx.x + 1] = fout; }
+}
+// Pass 2: outflow cells *= sums[0] / sums[1] (both above small_vel, else nothing to do / the host reports the error)
+__global__ void __launch_bounds__(256) k_inout_correct(const Lev L, Fab vel, const InflowProfile P, const double* __restrict__ sums, double small_vel)
+{
+    const double influx = sums[0], outflux = sums[1];
+    if (!(influx > small_vel && outflux > small_vel)) return;
+    const double alpha = influx / outflux;
+    const int klo = L.ck0, khi = L.ck0 + L.cnzl;
+    for (int o = 0; o < 6; ++o) {
+        if (P.face[o] != FACE_DIRECTION_DEPENDENT) continue;
+        const int dir = o % 3, side = o / 3;
+        const int d1 = (dir + 1) % 3, d2 = (dir + 2) % 3;
+        const long long total = (long long)L.n[d1] * L.n[d2];
+        for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+            int q[3];
+            q[dir] = side == 0 ? -1 : L.n[dir];
+            q[d1] = (int)(t % L.n[d1]); q[d2] = (int)(t / L.n[d1]);
+            if (dir == 2) { if (side == 0 ? klo != 0 : khi != L.n[2]) continue; }
+            else if (q[2] < klo || q[2] >= khi) continue;
+            if (!vel.has(q[0], q[1], q[2])) continue;
+            const long long id = vel.idx(q[0], q[1], q[2], dir);
+            const double v = vel.p[id];
+            const bool in = side == 0 ? v >= 0.0 : v <= 0.0;
+            if (!in) vel.p[id] = v * alpha;
+        }
+    }
+}
+
+// MLNodeLaplacian::setOversetMask argument check: count the nodes of the caller's mask (1 = solve, 0 = Dirichlet) that
+// differ from the mixed-face mask in effect.  Lm: the level-0 descriptor with the domain's own Dirichlet faces cleared
+// (make_nodalBC_mask leaves those at 1).  One thread per node of the box.
+__global__ void __launch_bounds__(256) k_check_overset(const Lev Lm, const int* __restrict__ mask, int lox, int loy, int loz, int nx, int ny,
+                                                       int nz, int* __restrict__ mismatches)
+{
+    const long long total = (long long)nx * ny * nz;
+    int bad = 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx) + lox, j = (int)((t / nx) % ny) + loy, k = (int)(t / ((long long)nx * ny)) + loz;
+        if (i < 0 || i > Lm.n[0] || j < 0 || j > Lm.n[1] || k < 0 || k > Lm.n[2]) continue;
+        const bool dir = node_masked(Lm, nmap(i, Lm.n[0], Lm.per[0]), nmap(j, Lm.n[1], Lm.per[1]), nmap(k, Lm.n[2], Lm.per[2]));
+        if ((mask[t] == 0) != dir) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // K2: rhs = D u with the Neumann/inflow treatment of A.2.  One thread per owned node.

@@ -34,6 +34,12 @@ struct Lev {
     double fxyz, fmx2y2z, f2xmy2z, f2x2ymz, f4xm2ym2z, fm2x4ym2z, fm2xm2y4z;
     double csig;          // constant sigma (used when sigma == nullptr)
     const double* sigma;  // cell array, plane 0 of the owned range (ghost slot at -1)
+    // incflo BC::mixed faces: the outflow part of the face is Dirichlet through the overset mask of
+    // incflo::make_nodalBC_mask (src/boundary_conditions/incflo_set_bcs.cpp:10-53, prob_set_BC_MF src/prob/prob_bc.cpp:9-101):
+    // bit (dir + 3 side) of mixm marks a mixed face; on a low-side face the nodes with idx[mixdir] <= mixhalf are
+    // masked, on a high-side face those with idx[mixdir] > mixhalf.  mixhalf = (domain.length(mixdir) / 2) >> level:
+    // a coarser multigrid level takes the mask of its nodes from the finer level by injection (node 2i).
+    int mixm, mixdir, mixhalf;
 };
 
 // Programmatic dependent launch (PDL).  pdl_wait(): block until the predecessor kernel has completed
@@ -95,10 +101,23 @@ __host__ __device__ __forceinline__ int czplane(const Lev& L, int kl)
 {
     return L.dist ? kl : cmap(kl, L.n[2], L.per[2]);
 }
+// does the level have any Dirichlet (masked) node at all?
+__host__ __device__ __forceinline__ bool lev_any_masked(const Lev& L)
+{
+    return (L.dlo[0] | L.dhi[0] | L.dlo[1] | L.dhi[1] | L.dlo[2] | L.dhi[2] | L.mixm) != 0;
+}
 __host__ __device__ __forceinline__ bool node_masked(const Lev& L, int i, int j, int kg)
 {
-    return (L.dlo[0] && i == 0) || (L.dhi[0] && i == L.n[0]) || (L.dlo[1] && j == 0) || (L.dhi[1] && j == L.n[1]) ||
-           (L.dlo[2] && kg == 0) || (L.dhi[2] && kg == L.n[2]);
+    bool m = (L.dlo[0] && i == 0) || (L.dhi[0] && i == L.n[0]) || (L.dlo[1] && j == 0) || (L.dhi[1] && j == L.n[1]) ||
+             (L.dlo[2] && kg == 0) || (L.dhi[2] && kg == L.n[2]);
+    if (L.mixm) {
+        const int t = L.mixdir == 0 ? i : L.mixdir == 1 ? j : kg;
+        const bool lo = t <= L.mixhalf;
+        m = m || ((L.mixm & 1) && i == 0 && lo) || ((L.mixm & 8) && i == L.n[0] && !lo) ||
+            ((L.mixm & 2) && j == 0 && lo) || ((L.mixm & 16) && j == L.n[1] && !lo) ||
+            ((L.mixm & 4) && kg == 0 && lo) || ((L.mixm & 32) && kg == L.n[2] && !lo);
+    }
+    return m;
 }
 // dot-product / solvability weight: 1/2 per reflecting boundary direction
 __host__ __device__ __forceinline__ double node_weight(const Lev& L, int i, int j, int kg)

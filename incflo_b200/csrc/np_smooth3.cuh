@@ -91,7 +91,7 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     const int ztop = DIST ? L.nzl - H->tztop : L.nzl;
     const int kc0 = DIST ? (blockIdx.z == 0 ? ztop : ((int)blockIdx.z - 1) * TZ) : (int)blockIdx.z * TZ;
     const int kc1 = DIST ? (blockIdx.z == 0 ? L.nzl : min(kc0 + TZ, ztop)) : min(kc0 + TZ, L.nzl);
-    const bool anyD = L.dlo[0] | L.dhi[0] | L.dlo[1] | L.dhi[1] | L.dlo[2] | L.dhi[2];
+    const bool anyD = lev_any_masked(L);
     // shared-memory slot of node plane p / sigma layer c
     auto pslot = [&](int p) { return RES ? p - kc0 + 1 : (p + 1) & 3; };
     auto sslot = [&](int c) { return RES ? c - kc0 + 1 : (c + 1) % 3; };
@@ -504,7 +504,7 @@ __device__ __forceinline__ double resid_iso_body(const Lev& L, const double* __r
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
     const int i0 = blockIdx.x * SM_TX, j0 = blockIdx.y * SM_TY;
     const int kc0 = blockIdx.z * TZ, kc1 = min(kc0 + TZ, L.nzl);
-    const bool anyD = L.dlo[0] | L.dhi[0] | L.dlo[1] | L.dhi[1] | L.dlo[2] | L.dhi[2];
+    const bool anyD = lev_any_masked(L);
 
     int psrc[5], csrc[5];
     unsigned pdst[5], cdst[5];
@@ -718,7 +718,7 @@ __device__ __forceinline__ double resid_iso_body(const Lev& L, const double* __r
                 if (anyD && node_masked(L, gi0 + a, gj0 + b, kg)) out[b][a] = 0.0;
                 if (FULL || (colok[a] && rowok[b])) amax = fmax(amax, fabs(out[b][a]));
             }
-        {
+        if (res) {   // nullptr: the caller only wants the norm
             double* q0 = res + kl * L.ps + roff;
             asm volatile("" : "+l"(q0));
 #pragma unroll

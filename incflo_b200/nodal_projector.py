@@ -23,6 +23,7 @@ from ._lib import FabBox, Geom, Opts, Stats
 BC_PERIODIC, BC_NEUMANN, BC_DIRICHLET, BC_INFLOW = 0, 1, 2, 3
 A_SOL, A_RHS, A_RES, A_COR, A_RESCOR, A_SIGMA = range(6)
 OP_SMOOTH, OP_RESIDUAL, OP_RESTRICT, OP_INTERP, OP_BOTTOM, OP_VCYCLE, OP_COARSEN_SIGMA = range(7)
+FACE_DEFAULT, FACE_DIRECTION_DEPENDENT, FACE_MIXED = 0, 1, 2   # enum b200np_face_type
 SMOOTH_ZERO_START = 0x10000   # B200NP_SMOOTH_ZERO_START: OP_SMOOTH as the V-cycle's "cor = 0" pre-smooth
 
 # incflo BC names (src/boundary_conditions/boundary_conditions.cpp:30-222) -> LinOpBCType
@@ -119,9 +120,18 @@ class NodalProjector:
         self._h = None
         self._phi = None
         self._gphi = None
+        self._faces = None
         self.stats = Stats()
 
     # -- reference API ----------------------------------------------------------------
+    def setOversetMask(self, face_type, mixed_split_dir, mixed_half_num_cells, mask=None):
+        """getLinOp().setOversetMask(lev, incflo::make_nodalBC_mask(lev)) for the masks incflo can build: the mixed faces
+        (FACE_MIXED per Orientation), the split direction and domain.length(dir) / 2.  `mask` (optional, the caller's
+        nodal int32 array) is checked against it; a different mask raises B200NP_ERR_UNSUPPORTED."""
+        self._faces = (tuple(int(x) for x in face_type), int(mixed_split_dir), int(mixed_half_num_cells))
+        self._mask = mask
+        self._destroy()
+
     def setDomainBC(self, lo, hi):
         self.bclo, self.bchi = tuple(int(x) for x in lo), tuple(int(x) for x in hi)
         self._destroy()
@@ -158,6 +168,21 @@ class NodalProjector:
             if rc != 0:
                 raise ProjectionError(rc)
             self._h = h
+            if self._faces is not None:
+                arr = (C.c_int * 6)(*self._faces[0])
+                rc = self._L.b200np_set_face_types(h, C.byref(arr), self._faces[1], self._faces[2])
+                if rc != 0:
+                    raise ProjectionError(rc)
+                if self._mask is not None:
+                    m = self._mask
+                    ptr = C.c_void_p(m.data_ptr()) if hasattr(m, "data_ptr") else C.c_void_p(m.ctypes.data)
+                    b = FabBox()
+                    for d in range(3):
+                        b.lo[d] = 0; b.hi[d] = tuple(m.shape)[2 - d] - 1
+                    b.ncomp = 1
+                    rc = self._L.b200np_check_overset_mask(h, ptr, C.byref(b))
+                    if rc != 0:
+                        raise ProjectionError(rc)
         return self._h
 
     def _destroy(self):
@@ -302,6 +327,39 @@ class IncfloProjection:
         if rc != 0:
             raise ProjectionError(rc)
 
+    def set_face_types(self, face_type, mixed_split_dir=0, mixed_half_num_cells=0):
+        """incflo's face kinds beyond LinOpBCType (FACE_DEFAULT / FACE_DIRECTION_DEPENDENT / FACE_MIXED per Orientation
+        x-lo, y-lo, z-lo, x-hi, y-hi, z-hi): direction_dependent faces get IncfloVelFill's copy-out branch and
+        enforceInOutSolvability, mixed faces the overset mask of incflo::make_nodalBC_mask"""
+        arr = (C.c_int * 6)(*[int(x) for x in face_type])
+        rc = self._L.b200np_set_face_types(self._h, C.byref(arr), int(mixed_split_dir), int(mixed_half_num_cells))
+        if rc != 0:
+            raise ProjectionError(rc)
+
+    def check_overset_mask(self, mask):
+        """MLNodeLaplacian::setOversetMask argument check: True iff the int32 nodal mask (nz+1, ny+1, nx+1) -- numpy or
+        torch cuda -- equals the mask set_face_types put in effect"""
+        if hasattr(mask, "data_ptr"):
+            ptr, shape = C.c_void_p(mask.data_ptr()), tuple(mask.shape)
+        else:
+            assert mask.dtype == np.int32 and mask.flags["C_CONTIGUOUS"]
+            ptr, shape = C.c_void_p(mask.ctypes.data), mask.shape
+        b = FabBox()
+        for d in range(3):
+            b.lo[d] = 0 if d < 2 else self.zlo
+            b.hi[d] = b.lo[d] + shape[2 - d] - 1
+        b.ncomp = 1
+        rc = self._L.b200np_check_overset_mask(self._h, ptr, C.byref(b))
+        if rc not in (0, 7):
+            raise ProjectionError(rc)
+        return rc == 0
+
+    def inout_flux(self):
+        """(influx, outflux) found by the last projection's enforceInOutSolvability"""
+        a, b = C.c_double(), C.c_double()
+        self._L.b200np_inout_flux(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
     def set_stream(self, cuda_stream):
         """run on the caller's stream (int handle of a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)"""
         self._L.b200np_set_stream(self._h, C.c_void_p(cuda_stream))
@@ -309,6 +367,10 @@ class IncfloProjection:
     def halo_transport(self):
         """0: one GPU; 1: NVLink peer memory (CUDA IPC); 2: ncclSend/ncclRecv fallback"""
         return self._L.b200np_halo_transport(self._h)
+
+    def peer_map(self):
+        """how the neighbours' arenas are mapped: 0 not mapped, 1 cuMem* allocation over a POSIX fd, 2 legacy CUDA IPC"""
+        return self._L.b200np_peer_map(self._h)
 
     def time_op(self, lev, op, arg=1, reps=10):
         ms = C.c_double()

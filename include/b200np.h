@@ -39,7 +39,9 @@ enum b200np_status {
     B200NP_ERR_BAD_ARG = 4,
     B200NP_ERR_CUDA = 5,          /* no device / CUDA runtime error                            */
     B200NP_ERR_NCCL = 6,
-    B200NP_ERR_UNSUPPORTED = 7    /* EB, overset mask, AMR beyond one fine box at ratio 2      */
+    B200NP_ERR_UNSUPPORTED = 7,   /* EB, general overset masks, AMR beyond one fine box at ratio 2 */
+    B200NP_ERR_INOUT_FLUX = 8     /* enforceInOutSolvability: inflow without outflow through the direction_dependent
+                                     faces, or the reverse (AMReX-Hydro aborts)                 */
 };
 
 /* amrex::Geometry + domain BCs of one level (NodalProjector ctor + setDomainBC, :187-194) */
@@ -214,9 +216,35 @@ int  b200np_composite_apply_nodal_projection(b200np_composite_t* c, double* cons
  *   bcv_vel[6][3]  m_bc_velocity: boundary velocity per amrex::Orientation (x-lo, y-lo, z-lo, x-hi, y-hi, z-hi),
  *   probtype       the profile of the normal component (16, 31, 311, 32, 322, 33, 333, 41, 42, 43; else bcv_vel),
  *   time           probtype 42.
- * Mass-inflow (ext_dir) faces only: direction_dependent faces need the caller's inflow_vel array, probtypes
- * 1101 / 1102 (mixed BCs) return B200NP_ERR_UNSUPPORTED.  bcv_vel == NULL switches the profile off again. */
+ * Face kinds come from b200np_set_face_types (default: mass inflow); the special-case blocks of probtypes 1101 / 1102
+ * (prob_bc.H:86-92, :140-146, :243-251) are evaluated as written there.  bcv_vel == NULL switches the profile off again. */
 int b200np_set_inflow_profile(b200np_t* h, int probtype, const double* bcv_vel, double time);
+
+/* incflo's own face types where they matter beyond the LinOpBCType of get_projection_bc (BC enum, src/incflo.H:662-665;
+ * parsed in src/boundary_conditions/boundary_conditions.cpp:20-135).  face_type[6] in amrex::Orientation order
+ * (x-lo, y-lo, z-lo, x-hi, y-hi, z-hi); only B200NP_BC_INFLOW faces may carry a non-default type.
+ *   DEFAULT              mass inflow ("mi"): IncfloVelFill imposes the boundary velocity (BCType::ext_dir)
+ *   DIRECTION_DEPENDENT  "dd": IncfloVelFill imposes the boundary velocity where the profile points into the domain and
+ *                        copies the first interior cell where it points out (prob_bc.H:93-109 ...), and
+ *                        HydroUtils::enforceInOutSolvability rescales the outflow so that the net flux through these faces
+ *                        vanishes (incflo_apply_nodal_projection.cpp:166-179; has_inout_bndry).  Returns
+ *                        B200NP_ERR_INOUT_FLUX from the projection where AMReX-Hydro aborts.
+ *   MIXED                "mixed" (probtypes 1100/1101/1102): inflow on one half of the face, outflow on the other.  The
+ *                        outflow half is imposed as Dirichlet nodes through the solver's overset mask
+ *                        (incflo::make_nodalBC_mask, src/boundary_conditions/incflo_set_bcs.cpp:10-53 with
+ *                        prob_set_BC_MF, src/prob/prob_bc.cpp:9-101): on a low-side face the nodes with
+ *                        idx[mixed_split_dir] <= mixed_half_num_cells, on a high-side face those with idx > half;
+ *                        mixed_half_num_cells = domain.length(mixed_split_dir) / 2 in incflo.
+ * Replaces nodal_projector->getLinOp().setOversetMask(lev, make_nodalBC_mask(lev)) (:204-213) for the masks incflo can
+ * produce; b200np_check_overset_mask verifies a caller-built mask against it. */
+enum b200np_face_type { B200NP_FACE_DEFAULT = 0, B200NP_FACE_DIRECTION_DEPENDENT = 1, B200NP_FACE_MIXED = 2 };
+int b200np_set_face_types(b200np_t* h, const int face_type[6], int mixed_split_dir, int mixed_half_num_cells);
+/* MLNodeLaplacian::setOversetMask(lev, mask): mask is the caller's nodal int array (1 = solve, 0 = known / Dirichlet) on
+ * mask_box (nodal box covering this rank's nodes).  Supported masks are exactly those b200np_set_face_types describes;
+ * returns B200NP_OK when `mask` equals the mask in effect, B200NP_ERR_UNSUPPORTED otherwise. */
+int b200np_check_overset_mask(b200np_t* h, const int* mask, const b200np_fab* mask_box);
+/* influx / outflux (sum |u_n| dS) found by the last projection's enforceInOutSolvability */
+int b200np_inout_flux(const b200np_t* h, double* influx, double* outflux);
 
 const char* b200np_strerror(int status);
 int b200np_version(void);
@@ -241,6 +269,9 @@ int b200np_nlevels(const b200np_t* h);
 /* how the slab halos travel: 0 = single GPU (none), 1 = NVLink peer memory (CUDA IPC mapped neighbour arenas, stores /
  * loads issued by the solver kernels), 2 = grouped ncclSend/ncclRecv (fallback when a rank cannot map its neighbours) */
 int b200np_halo_transport(const b200np_t* h);
+/* how the neighbours' memory was mapped when the transport is 1: 1 = cuMemCreate allocation shared as a POSIX file
+ * descriptor over a UNIX socket (the default; what NCCL itself does), 2 = legacy cudaIpc handles; 0 = not mapped */
+int b200np_peer_map(const b200np_t* h);
 int b200np_level_dims(const b200np_t* h, int lev, int n_cell[3], int n_node[3]);
 int b200np_set_sigma(b200np_t* h, const double* sigma, const b200np_fab* sigma_box, double const_sigma);
 int b200np_level_set(b200np_t* h, int lev, int which, const double* host);

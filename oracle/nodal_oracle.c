@@ -97,6 +97,12 @@ static inline int masked(const orc_mg* mg, const level* L, int i, int j, int k)
         if (is_per(mg, d)) continue;
         if (idx[d] == 0 && mg->p.bclo[d] == ORC_BC_DIRICHLET) return 1;
         if (idx[d] == L->n[d] && mg->p.bchi[d] == ORC_BC_DIRICHLET) return 1;
+        /* mixed face: the outflow part of the overset mask (make_nodalBC_mask), injected to this level */
+        if (mg->p.mixed_lo[d] || mg->p.mixed_hi[d]) {
+            const int half = mg->p.mix_half / (mg->p.n[mg->p.mix_dir] / L->n[mg->p.mix_dir]);
+            if (idx[d] == 0 && mg->p.mixed_lo[d] && idx[mg->p.mix_dir] <= half) return 1;
+            if (idx[d] == L->n[d] && mg->p.mixed_hi[d] && idx[mg->p.mix_dir] > half) return 1;
+        }
     }
     return 0;
 }
@@ -189,8 +195,10 @@ orc_mg* orc_mg_create(const orc_params* p, const double* sigma, double const_sig
     orc_mg* mg = (orc_mg*)calloc(1, sizeof(orc_mg));
     mg->p = *p;
     mg->singular = 1;
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < 3; ++d) {
         if (p->bclo[d] == ORC_BC_DIRICHLET || p->bchi[d] == ORC_BC_DIRICHLET) mg->singular = 0;
+        if (p->mixed_lo[d] || p->mixed_hi[d]) mg->singular = 0;
+    }
     int n[3] = {p->n[0], p->n[1], p->n[2]};
     double dx[3] = {p->dx[0], p->dx[1], p->dx[2]};
     int lev = 0;

@@ -65,6 +65,13 @@ typedef struct {
                                       multigrid level (never below 2 cells), the top node plane of a non-periodic
                                       direction belongs to the last box, and the GPU smoother's z-chunk rule is NOT
                                       applied.  Use with box_order = ORC_SM_LEX, box_stale_per_call = 1.            */
+    /* incflo BC::mixed faces (src/boundary_conditions/incflo_set_bcs.cpp:10-53 make_nodalBC_mask +
+     * src/prob/prob_bc.cpp:9-101 prob_set_BC_MF, probtypes 1100/1101/1102): the projection sees LinOpBCType::inflow on
+     * the face (incflo_projection_bc.cpp:23-27) plus an overset mask whose zeros are Dirichlet nodes -- on a low-side
+     * face the nodes with idx[mix_dir] <= mix_half, on a high-side face those with idx[mix_dir] > mix_half
+     * (mix_half = domain.length(mix_dir) / 2).  Coarser multigrid levels take the mask by injection (node 2i). */
+    int    mixed_lo[3], mixed_hi[3];
+    int    mix_dir, mix_half;
 } orc_params;
 
 typedef struct {

@@ -26,6 +26,7 @@ class Params(C.Structure):
         ("nu1", C.c_int), ("nu2", C.c_int), ("nsweeps", C.c_int), ("smoother", C.c_int),
         ("box", C.c_int * 3), ("box_order", C.c_int), ("box_stale_per_call", C.c_int), ("verbose", C.c_int),
         ("box_amrex", C.c_int),
+        ("mixed_lo", C.c_int * 3), ("mixed_hi", C.c_int * 3), ("mix_dir", C.c_int), ("mix_half", C.c_int),
     ]
 
 
@@ -105,9 +106,9 @@ def make_params(n, dx, bclo=(0, 0, 0), bchi=(0, 0, 0), **kw):
     for d in range(3):
         p.n[d] = int(n[d]); p.dx[d] = float(dx[d]); p.bclo[d] = int(bclo[d]); p.bchi[d] = int(bchi[d])
     for k, v in kw.items():
-        if k == "box":
+        if k in ("box", "mixed_lo", "mixed_hi"):
             for d in range(3):
-                p.box[d] = int(v[d])
+                getattr(p, k)[d] = int(v[d])
         else:
             setattr(p, k, v)
     return p

@@ -150,12 +150,16 @@ def divergence(vel, ng, n, dx, bclo, bchi):
     return rhs, w
 
 
-def project(n, dx, bclo, bchi, vel, ng, sigma):
+def project(n, dx, bclo, bchi, vel, ng, sigma, dmask=None):
+    """dmask: optional boolean unique-node array of extra Dirichlet nodes (the zeros of an overset mask)"""
     sig = sigma if isinstance(sigma, np.ndarray) else np.full((n[2], n[1], n[0]), float(sigma))
     A, nn = fe_operator(n, dx, bclo, bchi, sig)
     rhs, w = divergence(vel, ng, n, dx, bclo, bchi)
+    if dmask is not None:
+        w = np.where(dmask, 0.0, w)
+        rhs = np.where(dmask, 0.0, rhs)
     m = (w > 0).ravel()
-    singular = all(b != DIR for b in tuple(bclo) + tuple(bchi))
+    singular = all(b != DIR for b in tuple(bclo) + tuple(bchi)) and (dmask is None or not dmask.any())
     Wi = sp.diags(1.0 / np.where(m, w.ravel(), 1.0))
     Ar = (Wi @ A)[m][:, m].tocsc()
     b = rhs.ravel()[m].copy()
@@ -214,17 +218,29 @@ def cases():
     bclo = bchi = (NEU, NEU, NEU)
     out.append(dict(name="box_neumann_aniso_const", n=n, dx=dx, bclo=bclo, bchi=bchi,
                     vel=smooth_random_velocity(n, 1, bclo, bchi, 41), ng=1, sigma=0.37))
+    # 5. mixed BC (incflo probtype 1101-like): x faces are "mixed" = LinOpBCType::inflow + overset mask, split along y;
+    #    x-lo: nodes j <= ny/2 are outflow (Dirichlet), x-hi: nodes j > ny/2 (make_nodalBC_mask / prob_set_BC_MF)
+    n, dx = (16, 12, 8), (1 / 16,) * 3
+    bclo, bchi = (INF, NEU, NEU), (INF, NEU, NEU)
+    half = n[1] // 2
+    kk, jj, ii = np.meshgrid(np.arange(n[2] + 1), np.arange(n[1] + 1), np.arange(n[0] + 1), indexing="ij")
+    dmask = ((ii == 0) & (jj <= half)) | ((ii == n[0]) & (jj > half))
+    rng = np.random.default_rng(5)
+    out.append(dict(name="mixed_x_split_y_var", n=n, dx=dx, bclo=bclo, bchi=bchi, vel=smooth_random_velocity(n, 1, bclo, bchi, 51), ng=1,
+                    sigma=rng.uniform(0.5, 2.0, size=(n[2], n[1], n[0])), dmask=dmask, mixed=dict(lo=(1, 0, 0), hi=(1, 0, 0), dir=1, half=half)))
     return out
 
 
 def main():
     for c in cases():
-        r = project(c["n"], c["dx"], c["bclo"], c["bchi"], c["vel"], c["ng"], c["sigma"])
+        r = project(c["n"], c["dx"], c["bclo"], c["bchi"], c["vel"], c["ng"], c["sigma"], c.get("dmask"))
         var = isinstance(c["sigma"], np.ndarray)
         path = os.path.join(HERE, c["name"] + ".npz")
         np.savez_compressed(path, n=np.array(c["n"]), dx=np.array(c["dx"]), bclo=np.array(c["bclo"]), bchi=np.array(c["bchi"]),
                             ng=c["ng"], vel_in=c["vel"], sigma=c["sigma"] if var else np.array(c["sigma"]), var=var,
-                            phi=r["phi"], gphi=r["gphi"], vel_out=r["vel_out"], rhs=r["rhs"])
+                            phi=r["phi"], gphi=r["gphi"], vel_out=r["vel_out"], rhs=r["rhs"],
+                            **({} if "mixed" not in c else dict(mixed_lo=np.array(c["mixed"]["lo"]), mixed_hi=np.array(c["mixed"]["hi"]),
+                                                                mix_dir=c["mixed"]["dir"], mix_half=c["mixed"]["half"])))
         print(f"{c['name']}: n={c['n']} |phi|max={np.abs(r['phi']).max():.4e} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 

@@ -213,14 +213,12 @@ def test_smoother_zero_start_resident_kernel(var, zero_start, oracle):
         _close(proj.level_get(lev, A_COR), mg.smooth(lev, start, rhs, 4), 1e-11)
 
 
-@pytest.mark.parametrize("env", [{}, {"B200NP_RES_CTAS": "0"}, {"B200NP_ZERO_START": "0"}, {"B200NP_RES_CTAS": "0", "B200NP_ZERO_START": "0"},
-                                 {"B200NP_TAIL": "0"}],
-                         ids=["default", "nonresident", "no_zero_start", "nonresident_no_zero_start", "no_coarse_tail"])
+@pytest.mark.parametrize("env", [{}, {"B200NP_RES_CTAS": "0"}, {"B200NP_ZERO_START": "0"}, {"B200NP_RES_CTAS": "0", "B200NP_ZERO_START": "0"}],
+                         ids=["default", "nonresident", "no_zero_start", "nonresident_no_zero_start"])
 @pytest.mark.parametrize("var", [False, True])
 @pytest.mark.parametrize("case", BC_CASES, ids=[c[0] for c in BC_CASES])
 def test_vcycle_kernel_routing(case, var, env, oracle, monkeypatch):
-    """one whole V-cycle with every kernel routing: resident / ring-slot smoother, zero-start on / off, and the coarse
-    levels either in the single-CTA tail kernel k_coarse_tail (default) or in the per-level kernels"""
+    """one whole V-cycle with every kernel routing: resident / ring-slot smoother, zero-start on / off"""
     from incflo_b200.nodal_projector import A_COR, A_RES, OP_VCYCLE
     for k, v in env.items():
         monkeypatch.setenv(k, v)

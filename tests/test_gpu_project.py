@@ -84,12 +84,15 @@ def test_project_parity(config, N, host, oracle):
     assert rel_l2(remove_mean(gphi), remove_mean(rl["phi"])) < 1e-7  # different smoother, same discrete solution
 
 
+@pytest.mark.parametrize("top", ["direct", "correction"])
 @pytest.mark.parametrize("case", BC_CASES, ids=[c[0] for c in BC_CASES])
 @pytest.mark.parametrize("var", [False, True])
-def test_project_bc_cases(case, var, oracle):
+def test_project_bc_cases(case, var, top, oracle, monkeypatch):
     """random velocity + every BC combination (walls, inflow with non-zero ghost velocity,
-    Dirichlet outflow, anisotropic dx), against the mirrored oracle."""
+    Dirichlet outflow, anisotropic dx), against the mirrored oracle.  `top`: the finest level of the V-cycle relaxes
+    (sol, rhs) directly (default) or MLMG's (cor, res) followed by sol += cor -- the same iterates up to rounding."""
     import torch
+    monkeypatch.setenv("B200NP_TOP_DIRECT", "1" if top == "direct" else "0")
     name, n, dx, bclo, bchi = case
     rng = np.random.default_rng(7)
     vel = rng.standard_normal((3, n[2] + 2, n[1] + 2, n[0] + 2))
