@@ -13,7 +13,7 @@ ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
 LIBDIR = os.path.join(_PKG, "lib")
 SO = os.path.join(LIBDIR, "libb200np.so")
-SOURCES = ["b200np.cu"]
+SOURCES = ["b200np.cu", "b200mac.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -59,6 +59,11 @@ class FabBox(C.Structure):
     _fields_ = [("lo", C.c_int * 3), ("hi", C.c_int * 3), ("ncomp", C.c_int)]
 
 
+class MFab(C.Structure):
+    """b200np_mfab: the local FArrayBoxes of an amrex::MultiFab"""
+    _fields_ = [("nfabs", C.c_int), ("ngrow", C.c_int), ("ncomp", C.c_int), ("box", C.POINTER(FabBox)), ("data", C.POINTER(C.c_void_p))]
+
+
 class Stats(C.Structure):
     _fields_ = [("iters", C.c_int), ("nlevels", C.c_int), ("bottom_iters", C.c_int), ("status", C.c_int),
                 ("rhsnorm", C.c_double), ("resnorm0", C.c_double), ("resnorm", C.c_double),
@@ -70,10 +75,11 @@ class Stats(C.Structure):
 # every symbol include/b200np.h declares
 EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np_nccl_unique_id", "b200np_slab_range", "b200np_dist_plan",
            "b200np_destroy", "b200np_set_stream", "b200np_project",
-           "b200np_apply_nodal_projection", "b200np_set_inflow_profile", "b200np_set_face_types", "b200np_check_overset_mask", "b200np_inout_flux", "b200np_strerror", "b200np_version", "b200np_nlevels",
+           "b200np_apply_nodal_projection", "b200np_project_mf", "b200np_apply_nodal_projection_mf", "b200np_set_inflow_profile", "b200np_set_face_types", "b200np_check_overset_mask", "b200np_inout_flux", "b200np_strerror", "b200np_version", "b200np_nlevels",
            "b200np_level_dims", "b200np_halo_transport", "b200np_peer_map", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
            "b200np_time_op", "b200np_composite_create", "b200np_composite_destroy", "b200np_composite_set_stream",
-           "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection"]
+           "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection",
+           "b200mac_create", "b200mac_destroy", "b200mac_nlevels", "b200mac_set_coeffs", "b200mac_project", "b200mac_level_op", "b200mac_level_dims"]
 
 _lib = None
 
@@ -100,6 +106,10 @@ def lib():
     L.b200np_project.argtypes = [vp, dp, fb, dp, fb, C.c_double, dp, fb, dp, fb, C.c_double, C.c_double, C.POINTER(Stats)]
     L.b200np_apply_nodal_projection.argtypes = [vp, dp, fb, dp, dp, fb, C.c_double, dp, fb, dp, fb, dp, C.c_double,
                                                 C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
+    mf = C.POINTER(MFab)
+    L.b200np_project_mf.argtypes = [vp, mf, mf, C.c_double, mf, mf, C.c_double, C.c_double, C.POINTER(Stats)]
+    L.b200np_apply_nodal_projection_mf.argtypes = [vp, mf, mf, mf, C.c_double, mf, mf, mf, C.c_double, C.c_int, C.c_int, C.c_double,
+                                                   C.c_double, C.POINTER(Stats)]
     L.b200np_set_inflow_profile.argtypes = [vp, C.c_int, C.POINTER(C.c_double * 18), C.c_double]
     L.b200np_set_face_types.argtypes = [vp, C.POINTER(C.c_int * 6), C.c_int, C.c_int]
     L.b200np_check_overset_mask.argtypes = [vp, C.c_void_p, fb]
@@ -128,5 +138,13 @@ def lib():
     p2, f2 = C.POINTER(C.c_void_p * 2), C.POINTER(fb * 2)
     L.b200np_composite_apply_nodal_projection.argtypes = [vp, p2, f2, p2, p2, f2, C.c_double, p2, f2, p2, f2, dp, C.c_double,
                                                           C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
+    L.b200mac_create.argtypes = [C.POINTER(vp), C.POINTER(Geom), C.POINTER(Opts), C.c_int]
+    L.b200mac_destroy.argtypes = [vp]
+    L.b200mac_destroy.restype = None
+    L.b200mac_nlevels.argtypes = [vp]
+    L.b200mac_set_coeffs.argtypes = [vp, dp, fb, dp, fb, dp, fb, C.c_double]
+    L.b200mac_project.argtypes = [vp, dp, fb, dp, fb, dp, fb, dp, fb, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
+    L.b200mac_level_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    L.b200mac_level_dims.argtypes = [vp, C.c_int, ip]
     _lib = L
     return L

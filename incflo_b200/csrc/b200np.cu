@@ -14,6 +14,7 @@
 #include "np_smooth.cuh"
 #include "np_smooth3.cuh"
 #include "np_composite.cuh"
+#include "np_multibox.cuh"
 #include "np_peer.h"
 
 #include <dlfcn.h>
@@ -161,6 +162,11 @@ struct b200np {
     long long launches = 0, launches_per_vcycle = 0, exchanges = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; };
     Stage stage[8];  // staging buffers for host-pointer callers
+    // multi-box callers (b200np_*_mf): per field the slab array the boxes are gathered into, the device table of fab
+    // descriptors and, for host pointers, the staging area of the fabs
+    struct MfSlot { double* slab = nullptr; size_t slab_bytes = 0; MfFab* tab = nullptr; size_t tab_cap = 0; double* stage = nullptr; size_t stage_bytes = 0; };
+    MfSlot mf[6];
+    cudaEvent_t mf_ev[2] = {nullptr, nullptr};
     int TZ = 64;
     int dist_graph = 1;       // capture the slab-decomposed V-cycle (NCCL send/recv included) into a CUDA graph (B200NP_DIST_GRAPH)
     int dist_min_planes = 64; // a level stays slab-distributed while every rank keeps at least this many cell planes (B200NP_DIST_MIN_PLANES;
@@ -393,7 +399,12 @@ void build_hierarchy(b200np* h)
         cudaGetLastError();
     }
     if (!base) CK(cudaMalloc(&base, h->arena.size));
+    // The memset runs on the legacy default stream, which the handle's non-blocking stream does not wait for: without the
+    // synchronisation the first small copies on h->stream (the records / IPC handles setup_p2p gathers through this very
+    // arena) can land BEFORE a large arena has been cleared and are then wiped -- the "invalid argument" from
+    // cudaIpcOpenMemHandle seen on 4-GPU boxes in round 1 was a zeroed handle, not an IPC limitation.
     CK(cudaMemset(base, 0, h->arena.size));
+    CK(cudaDeviceSynchronize());
     h->arena.base = static_cast<char*>(base);
     h->arena.off = 0; h->arena.measure = false;
     build_levels(h);                       // pass 2: pointers
@@ -1483,6 +1494,8 @@ void b200np_destroy(b200np_t* h)
     if (h->hscal) cudaFreeHost(h->hscal);
     if (h->hinfo) cudaFreeHost(h->hinfo);
     for (auto& s : h->stage) if (s.d) cudaFree(s.d);
+    for (auto& m : h->mf) { if (m.slab) cudaFree(m.slab); if (m.tab) cudaFree(m.tab); if (m.stage) cudaFree(m.stage); }
+    for (auto& e : h->mf_ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1763,6 +1776,257 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
         CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4])); st->ms_h2d = ms;
         CK(cudaEventElapsedTime(&ms, h->ev[5], h->ev[1])); st->ms_d2h = ms;
         return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+
+// ---- multi-box MultiFabs (b200np_*_mf): gather into the slab arrays, run the single-box path, scatter back ----
+namespace {
+struct MfField {
+    const b200np_mfab* mf = nullptr;
+    MfFab* tab = nullptr;            // device table of the fabs (device pointers)
+    std::vector<MfFab> host;
+    std::vector<size_t> off;         // staged: offset of fab f in the staging area (doubles)
+    bool staged = false;
+};
+size_t mf_fab_doubles(const b200np_fab& b, int ncomp)
+{
+    return (size_t)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1) * ncomp;
+}
+// the valid boxes must lie inside [lo, hi] (cell or nodal index space of the rank) and, for cell-centred MultiFabs,
+// tile it (the volumes add up; amrex::BoxArray boxes never overlap)
+bool mf_boxes_ok(const b200np_mfab* m, const int lo[3], const int hi[3], int ncomp, bool tile)
+{
+    if (!m || m->nfabs < 1 || m->ngrow < 0 || m->ncomp < ncomp || !m->box || !m->data) return false;
+    long long vol = 0;
+    for (int f = 0; f < m->nfabs; ++f) {
+        if (!m->data[f]) return false;
+        long long v = 1;
+        for (int d = 0; d < 3; ++d) {
+            const int vlo = m->box[f].lo[d] + m->ngrow, vhi = m->box[f].hi[d] - m->ngrow;
+            if (vhi < vlo || vlo < lo[d] || vhi > hi[d]) return false;
+            v *= vhi - vlo + 1;
+        }
+        vol += v;
+    }
+    if (tile) {
+        long long want = 1;
+        for (int d = 0; d < 3; ++d) want *= hi[d] - lo[d] + 1;
+        if (vol != want) return false;
+    }
+    return true;
+}
+void mf_map(b200np* h, int slot, const b200np_mfab* m, int ncomp, bool copy_in, b200np_stats* st, MfField& F)
+{
+    F = MfField{};
+    if (!m) return;
+    F.mf = m;
+    auto& S = h->mf[slot];
+    const int nf = m->nfabs;
+    F.staged = !is_device_ptr(m->data[0]);
+    F.host.resize(nf); F.off.assign(nf, 0);
+    size_t total = 0;
+    for (int f = 0; f < nf; ++f) { F.off[f] = total; total += mf_fab_doubles(m->box[f], m->ncomp); }
+    if (F.staged) {
+        if (S.stage_bytes < total * sizeof(double)) {
+            if (S.stage) CK(cudaFree(S.stage));
+            CK(cudaMalloc(&S.stage, total * sizeof(double)));
+            S.stage_bytes = total * sizeof(double);
+        }
+        if (copy_in) {
+            for (int f = 0; f < nf; ++f)
+                CK(cudaMemcpyAsync(S.stage + F.off[f], m->data[f], mf_fab_doubles(m->box[f], m->ncomp) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            st->h2d_bytes += (long long)(total * sizeof(double));
+        }
+    }
+    for (int f = 0; f < nf; ++f) {
+        MfFab& d = F.host[f];
+        const b200np_fab& b = m->box[f];
+        d.p = F.staged ? S.stage + F.off[f] : m->data[f];
+        for (int q = 0; q < 3; ++q) d.lo[q] = b.lo[q];
+        d.nx = b.hi[0] - b.lo[0] + 1; d.ny = b.hi[1] - b.lo[1] + 1; d.nz = b.hi[2] - b.lo[2] + 1;
+        d.cstride = (long long)d.nx * d.ny * d.nz;
+    }
+    if (S.tab_cap < (size_t)nf) {
+        if (S.tab) CK(cudaFree(S.tab));
+        CK(cudaMalloc(&S.tab, (size_t)nf * sizeof(MfFab)));
+        S.tab_cap = nf;
+    }
+    CK(cudaMemcpyAsync(S.tab, F.host.data(), (size_t)nf * sizeof(MfFab), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // F.host is about to go out of the caller's sight; tables are tiny
+    F.tab = S.tab;
+    (void)ncomp;
+}
+void mf_copy_back(b200np* h, int slot, MfField& F, b200np_stats* st)
+{
+    if (!F.mf || !F.staged) return;
+    auto& S = h->mf[slot];
+    size_t total = 0;
+    for (int f = 0; f < F.mf->nfabs; ++f) {
+        const size_t nd = mf_fab_doubles(F.mf->box[f], F.mf->ncomp);
+        CK(cudaMemcpyAsync(F.mf->data[f], S.stage + F.off[f], nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        total += nd;
+    }
+    st->d2h_bytes += (long long)(total * sizeof(double));
+}
+double* mf_slab(b200np* h, int slot, const b200np_fab& box)
+{
+    auto& S = h->mf[slot];
+    const size_t bytes = fab_bytes(&box);
+    if (S.slab_bytes < bytes) {
+        if (S.slab) CK(cudaFree(S.slab));
+        CK(cudaMalloc(&S.slab, bytes));
+        S.slab_bytes = bytes;
+    }
+    return S.slab;
+}
+dim3 mf_grid(const MfField& F)
+{
+    long long mx = 1;
+    for (const MfFab& f : F.host) mx = std::max(mx, (long long)f.nx * f.ny * f.nz);
+    return dim3((unsigned)std::min<long long>((mx + 255) / 256, 64), (unsigned)F.host.size());
+}
+void mf_gather(b200np* h, const MfField& F, int ncomp, double* slab, const b200np_fab& box, int mode)
+{
+    if (!F.mf) return;
+    const Lev& g = h->lv[0].g;
+    LAUNCH(h, k_mf_gather, mf_grid(F), 256, F.tab, F.mf->ngrow, ncomp, make_fab(slab, &box), mode, g.n[0], g.n[1], g.n[2]);
+}
+void mf_scatter(b200np* h, const MfField& F, int ncomp, double* slab, const b200np_fab& box, int mode)
+{
+    if (!F.mf) return;
+    LAUNCH(h, k_mf_scatter, mf_grid(F), 256, F.tab, F.mf->ngrow, ncomp, make_fab(slab, &box), mode);
+}
+// the slab boxes of this rank: cells, cells grown by one (velocity), nodes
+void mf_slab_boxes(const b200np* h, b200np_fab& cells, b200np_fab& grown, b200np_fab& nodes)
+{
+    const Lev& g = h->lv[0].g;
+    const int lo[3] = {0, 0, g.ck0}, hi[3] = {g.n[0] - 1, g.n[1] - 1, g.ck0 + g.cnzl - 1};
+    for (int d = 0; d < 3; ++d) {
+        cells.lo[d] = lo[d]; cells.hi[d] = hi[d];
+        grown.lo[d] = lo[d] - 1; grown.hi[d] = hi[d] + 1;
+        nodes.lo[d] = lo[d]; nodes.hi[d] = hi[d] + 1;
+    }
+    cells.ncomp = 1; grown.ncomp = 3; nodes.ncomp = 1;
+}
+void mf_events(b200np* h)
+{
+    for (auto& e : h->mf_ev) if (!e) CK(cudaEventCreate(&e));
+}
+}  // namespace
+
+int b200np_project_mf(b200np_t* h, const b200np_mfab* vel, const b200np_mfab* sigma, double const_sigma, const b200np_mfab* phi,
+                      const b200np_mfab* gphi, double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h) return st->status = B200NP_ERR_BAD_ARG;
+    try {
+        CK(cudaSetDevice(h->device));
+        b200np_fab cells{}, grown{}, nodes{};
+        mf_slab_boxes(h, cells, grown, nodes);
+        if (!mf_boxes_ok(vel, cells.lo, cells.hi, 3, true) || vel->ngrow < 1) return st->status = B200NP_ERR_BAD_ARG;
+        if (sigma && !mf_boxes_ok(sigma, cells.lo, cells.hi, 1, true)) return st->status = B200NP_ERR_BAD_ARG;
+        if (gphi && !mf_boxes_ok(gphi, cells.lo, cells.hi, 3, true)) return st->status = B200NP_ERR_BAD_ARG;
+        if (phi && !mf_boxes_ok(phi, nodes.lo, nodes.hi, 1, false)) return st->status = B200NP_ERR_BAD_ARG;
+        mf_events(h);
+        b200np_stats outer{};
+        CK(cudaEventRecord(h->mf_ev[0], h->stream));
+        MfField Fv, Fs, Fp, Fg;
+        mf_map(h, 0, vel, 3, true, &outer, Fv);
+        mf_map(h, 2, sigma, 1, true, &outer, Fs);
+        mf_map(h, 4, phi, 1, false, &outer, Fp);
+        mf_map(h, 3, gphi, 3, false, &outer, Fg);
+        b200np_fab gbox = cells; gbox.ncomp = 3;
+        double* svel = mf_slab(h, 0, grown);
+        double* ssig = sigma ? mf_slab(h, 2, cells) : nullptr;
+        double* sphi = phi ? mf_slab(h, 4, nodes) : nullptr;
+        double* sg = gphi ? mf_slab(h, 3, gbox) : nullptr;
+        long long extra = h->launches;
+        h->launches = 0;
+        CK(cudaMemsetAsync(svel, 0, fab_bytes(&grown), h->stream));
+        mf_gather(h, Fv, 3, svel, grown, MF_VALID_BC);
+        mf_gather(h, Fs, 1, ssig, cells, MF_VALID);
+        extra = h->launches;
+        int rc = b200np_project(h, svel, &grown, ssig, sigma ? &cells : nullptr, const_sigma, sphi, phi ? &nodes : nullptr, sg,
+                                gphi ? &gbox : nullptr, rtol, atol, st);
+        if (rc != B200NP_OK && rc != B200NP_ERR_NOT_CONVERGED && rc != B200NP_ERR_DIVERGED) return rc;
+        h->launches = 0;
+        mf_scatter(h, Fv, 3, svel, grown, MF_VALID);
+        mf_scatter(h, Fp, 1, sphi, nodes, MF_VALID);
+        mf_scatter(h, Fg, 3, sg, gbox, MF_VALID);
+        extra += h->launches;
+        mf_copy_back(h, 0, Fv, &outer); mf_copy_back(h, 4, Fp, &outer); mf_copy_back(h, 3, Fg, &outer);
+        CK(cudaEventRecord(h->mf_ev[1], h->stream));
+        CK(cudaEventSynchronize(h->mf_ev[1]));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, h->mf_ev[0], h->mf_ev[1])); st->ms_total = ms;
+        st->launches += extra; st->h2d_bytes += outer.h2d_bytes; st->d2h_bytes += outer.d2h_bytes;
+        return st->status = rc;
+    } catch (int e) { return st->status = e; }
+}
+
+int b200np_apply_nodal_projection_mf(b200np_t* h, const b200np_mfab* velocity, const b200np_mfab* velocity_o,
+                                     const b200np_mfab* density, double ro_0, const b200np_mfab* gp, const b200np_mfab* p_nd,
+                                     const b200np_mfab* inflow_vel, double scaling_factor, int incremental, int proj_for_small_dt,
+                                     double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h) return st->status = B200NP_ERR_BAD_ARG;
+    const int use_old = (incremental || proj_for_small_dt);
+    try {
+        CK(cudaSetDevice(h->device));
+        b200np_fab cells{}, grown{}, nodes{};
+        mf_slab_boxes(h, cells, grown, nodes);
+        if (!mf_boxes_ok(velocity, cells.lo, cells.hi, 3, true) || velocity->ngrow < 1) return st->status = B200NP_ERR_BAD_ARG;
+        if (use_old && !mf_boxes_ok(velocity_o, cells.lo, cells.hi, 3, true)) return st->status = B200NP_ERR_BAD_ARG;
+        if (density && !mf_boxes_ok(density, cells.lo, cells.hi, 1, true)) return st->status = B200NP_ERR_BAD_ARG;
+        if (!mf_boxes_ok(gp, cells.lo, cells.hi, 3, true) || !mf_boxes_ok(p_nd, nodes.lo, nodes.hi, 1, false)) return st->status = B200NP_ERR_BAD_ARG;
+        const int set_inflow = (!proj_for_small_dt && !incremental);
+        if (inflow_vel && set_inflow && (!mf_boxes_ok(inflow_vel, cells.lo, cells.hi, 3, true) || inflow_vel->ngrow < 1)) return st->status = B200NP_ERR_BAD_ARG;
+        mf_events(h);
+        b200np_stats outer{};
+        CK(cudaEventRecord(h->mf_ev[0], h->stream));
+        MfField Fv, Fo, Fr, Fg, Fp, Fi;
+        mf_map(h, 0, velocity, 3, true, &outer, Fv);
+        mf_map(h, 1, use_old ? velocity_o : nullptr, 3, true, &outer, Fo);
+        mf_map(h, 2, density, 1, true, &outer, Fr);
+        mf_map(h, 3, gp, 3, true, &outer, Fg);
+        mf_map(h, 4, p_nd, 1, incremental != 0, &outer, Fp);
+        mf_map(h, 5, (inflow_vel && set_inflow) ? inflow_vel : nullptr, 3, true, &outer, Fi);
+        b200np_fab gbox = cells; gbox.ncomp = 3;
+        double* svel = mf_slab(h, 0, grown);
+        double* svelo = Fo.mf ? mf_slab(h, 1, grown) : nullptr;
+        double* srho = Fr.mf ? mf_slab(h, 2, cells) : nullptr;
+        double* sgp = mf_slab(h, 3, gbox);
+        double* sp = mf_slab(h, 4, nodes);
+        double* sin = Fi.mf ? mf_slab(h, 5, grown) : nullptr;
+        h->launches = 0;
+        mf_gather(h, Fv, 3, svel, grown, MF_VALID);      // every ghost cell is set by setBndry(0) / the inflow fill below
+        mf_gather(h, Fo, 3, svelo, grown, MF_VALID);
+        mf_gather(h, Fr, 1, srho, cells, MF_VALID);
+        mf_gather(h, Fg, 3, sgp, gbox, MF_VALID);
+        if (incremental) mf_gather(h, Fp, 1, sp, nodes, MF_VALID);
+        if (Fi.mf) { CK(cudaMemsetAsync(sin, 0, fab_bytes(&grown), h->stream)); mf_gather(h, Fi, 3, sin, grown, MF_VALID_BC); }
+        long long extra = h->launches;
+        int rc = b200np_apply_nodal_projection(h, svel, &grown, svelo, srho, Fr.mf ? &cells : nullptr, ro_0, sgp, &gbox, sp, &nodes, sin,
+                                               scaling_factor, incremental, proj_for_small_dt, rtol, atol, st);
+        if (rc != B200NP_OK && rc != B200NP_ERR_NOT_CONVERGED && rc != B200NP_ERR_DIVERGED) return rc;
+        h->launches = 0;
+        mf_scatter(h, Fv, 3, svel, grown, MF_VALID_BC);
+        mf_scatter(h, Fg, 3, sgp, gbox, MF_VALID);
+        mf_scatter(h, Fp, 1, sp, nodes, MF_VALID);
+        extra += h->launches;
+        mf_copy_back(h, 0, Fv, &outer); mf_copy_back(h, 3, Fg, &outer); mf_copy_back(h, 4, Fp, &outer);
+        CK(cudaEventRecord(h->mf_ev[1], h->stream));
+        CK(cudaEventSynchronize(h->mf_ev[1]));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, h->mf_ev[0], h->mf_ev[1])); st->ms_total = ms;
+        st->launches += extra; st->h2d_bytes += outer.h2d_bytes; st->d2h_bytes += outer.d2h_bytes;
+        return st->status = rc;
     } catch (int e) { return st->status = e; }
 }
 

@@ -6,9 +6,9 @@
 //       descriptor; the descriptor travels to the neighbour over an abstract-namespace UNIX datagram socket
 //       (SCM_RIGHTS) and is mapped there with cuMemImportFromShareableHandle + cuMemMap + cuMemSetAccess.
 //       This is what NCCL itself does for its peer buffers (NCCL_CUMEM_ENABLE).
-//   (2) legacy CUDA IPC (cudaIpcGetMemHandle / cudaIpcOpenMemHandle) on a cudaMalloc arena.  Measured on this
-//       pool: opening a >= 1 GB arena fails with "invalid argument" on the 4-GPU boxes while 2- and 8-GPU boxes
-//       accept it (profiles/r2_ipc_probe.txt), hence (1) first.
+//   (2) legacy CUDA IPC (cudaIpcGetMemHandle / cudaIpcOpenMemHandle) on a cudaMalloc arena.
+// Both work on this pool's 2-, 4- and 8-GPU boxes for 128 MB .. 2.5 GB allocations (tools/ipc_probe.cu,
+// profiles/r2_ipc_probe_4gpu.txt); (1) is the default, (2) the fallback when cuMem* is unavailable.
 // Driver entry points are taken from the runtime (cudaGetDriverEntryPoint): no link dependency on libcuda.
 #pragma once
 #include <cuda.h>

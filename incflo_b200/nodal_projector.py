@@ -18,7 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import FabBox, Geom, Opts, Stats
+from ._lib import FabBox, Geom, MFab, Opts, Stats
 
 BC_PERIODIC, BC_NEUMANN, BC_DIRICHLET, BC_INFLOW = 0, 1, 2, 3
 A_SOL, A_RHS, A_RES, A_COR, A_RESCOR, A_SIGMA = range(6)
@@ -242,6 +242,71 @@ class NodalProjector:
         return ms.value
 
 
+class MultiFab:
+    """amrex::MultiFab as one rank sees it: a list of (valid_lo, valid_hi) boxes (cell index space; `nodal` adds the
+    high-end nodes) and one array per box, shaped (ncomp, nz, ny, nx) over the box grown by `ngrow` -- numpy (host) or
+    torch CUDA tensors.  Mirrors what the C++ side reads off MFIter / fab.box() / fab.dataPtr()."""
+
+    def __init__(self, boxes, arrays, ngrow, ncomp, nodal=False):
+        assert len(boxes) == len(arrays) and len(boxes) > 0
+        self.boxes, self.arrays, self.ngrow, self.ncomp, self.nodal = list(boxes), list(arrays), int(ngrow), int(ncomp), bool(nodal)
+        n = len(boxes)
+        self._box = (FabBox * n)()
+        self._ptr = (C.c_void_p * n)()
+        for f, ((lo, hi), a) in enumerate(zip(boxes, arrays)):
+            shape = tuple(a.shape)[-3:]
+            for d in range(3):
+                self._box[f].lo[d] = int(lo[d]) - self.ngrow
+                self._box[f].hi[d] = int(hi[d]) + self.ngrow + (1 if nodal else 0)
+                assert shape[2 - d] == self._box[f].hi[d] - self._box[f].lo[d] + 1, (shape, lo, hi)
+            self._box[f].ncomp = self.ncomp
+            if hasattr(a, "data_ptr"):
+                assert a.is_contiguous()
+                self._ptr[f] = a.data_ptr()
+            else:
+                assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+                self._ptr[f] = a.ctypes.data
+        self.c = MFab(n, self.ngrow, self.ncomp, C.cast(self._box, C.POINTER(FabBox)), C.cast(self._ptr, C.POINTER(C.c_void_p)))
+
+    def ref(self):
+        return C.byref(self.c)
+
+    @staticmethod
+    def split(full, n_cell, max_grid, ngrow, ncomp, nodal=False, zlo=0, to=None):
+        """chop a single-box array (ncomp, nz+2ng(+1), ny+.., nx+..) over cells [0,n) x [0,n) x [zlo, zlo+nz) into boxes of
+        at most max_grid cells per direction, each with its own ghost frame copied from `full` (zeros where `full` has
+        nothing); `to`: callable applied to each box array (e.g. lambda a: torch.from_numpy(a).cuda())"""
+        nx, ny, nz = n_cell
+        a4 = full.reshape((ncomp,) + tuple(full.shape)[-3:])
+        boxes, arrs = [], []
+        e = 1 if nodal else 0
+        for k0 in range(0, nz, max_grid):
+            for j0 in range(0, ny, max_grid):
+                for i0 in range(0, nx, max_grid):
+                    lo = (i0, j0, k0 + zlo)
+                    hi = (min(i0 + max_grid, nx) - 1, min(j0 + max_grid, ny) - 1, min(k0 + max_grid, nz) - 1 + zlo)
+                    sh = (ncomp, hi[2] - lo[2] + 1 + 2 * ngrow + e, hi[1] - lo[1] + 1 + 2 * ngrow + e, hi[0] - lo[0] + 1 + 2 * ngrow + e)
+                    b = np.zeros(sh)
+                    # the part of the grown box that `full` (cells [-ng, n+ng) around the same origin) holds
+                    src = a4[:, k0:k0 + sh[1], j0:j0 + sh[2], i0:i0 + sh[3]]
+                    b[:, :src.shape[1], :src.shape[2], :src.shape[3]] = src
+                    boxes.append((lo, hi)); arrs.append(np.ascontiguousarray(b) if to is None else to(np.ascontiguousarray(b)))
+        return MultiFab(boxes, arrs, ngrow, ncomp, nodal)
+
+    def assemble(self, n_cell, zlo=0):
+        """the valid regions put back together: (ncomp, nz(+1), ny(+1), nx(+1))"""
+        nx, ny, nz = n_cell
+        e = 1 if self.nodal else 0
+        out = np.zeros((self.ncomp, nz + e, ny + e, nx + e))
+        g = self.ngrow
+        for (lo, hi), a in zip(self.boxes, self.arrays):
+            a = a.detach().cpu().numpy() if hasattr(a, "detach") else a
+            a = a.reshape((self.ncomp,) + tuple(a.shape)[-3:])
+            v = a[:, g:a.shape[1] - g, g:a.shape[2] - g, g:a.shape[3] - g]
+            out[:, lo[2] - zlo:hi[2] - zlo + 1 + e, lo[1]:hi[1] + 1 + e, lo[0]:hi[0] + 1 + e] = v
+        return out
+
+
 def _empty_like(like, shape):
     if isinstance(like, np.ndarray):
         return np.zeros(shape)
@@ -311,6 +376,26 @@ class IncfloProjection:
                                                    float(ro_0), pg, C.byref(bg), pp, C.byref(bp), pi,
                                                    float(scaling_factor), int(incremental), int(proj_for_small_dt),
                                                    float(mg_rtol), float(mg_atol), C.byref(self.stats))
+        if rc != 0:
+            raise ProjectionError(rc)
+        return self.stats
+
+    def apply_nodal_projection_mf(self, velocity, gp, p_nd, density=None, ro_0=1.0, velocity_o=None, inflow_vel=None,
+                                  scaling_factor=1.0, incremental=False, proj_for_small_dt=False, mg_rtol=1e-11, mg_atol=1e-14):
+        """incflo::ApplyNodalProjection over multi-box MultiFabs (class MultiFab)"""
+        r = lambda m: m.ref() if m is not None else None
+        rc = self._L.b200np_apply_nodal_projection_mf(self._h, r(velocity), r(velocity_o), r(density), float(ro_0), r(gp), r(p_nd),
+                                                      r(inflow_vel), float(scaling_factor), int(incremental), int(proj_for_small_dt),
+                                                      float(mg_rtol), float(mg_atol), C.byref(self.stats))
+        if rc != 0:
+            raise ProjectionError(rc)
+        return self.stats
+
+    def project_mf(self, vel, sigma=None, const_sigma=1.0, phi=None, gphi=None, rtol=1e-11, atol=1e-14):
+        """Hydro::NodalProjector::project + getPhi / getGradPhi over multi-box MultiFabs"""
+        r = lambda m: m.ref() if m is not None else None
+        rc = self._L.b200np_project_mf(self._h, r(vel), r(sigma), float(const_sigma), r(phi), r(gphi), float(rtol), float(atol),
+                                       C.byref(self.stats))
         if rc != 0:
             raise ProjectionError(rc)
         return self.stats

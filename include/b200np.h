@@ -170,6 +170,33 @@ int b200np_apply_nodal_projection(b200np_t* h, double* velocity, const b200np_fa
                                   int incremental, int proj_for_small_dt, double rtol, double atol,
                                   b200np_stats* stats);
 
+/* ---- multi-box MultiFabs (amr.max_grid_size < domain: every reference deck, e.g. test_no_eb_3d/benchmark.rayleigh_taylor:16) ----
+ * amrex::MultiFab as this rank sees it: the FArrayBoxes of its local MFIter.  box[f] is the ALLOCATED box of fab f
+ * (fab.box(): the valid box grown by ngrow, in the MultiFab's own index space -- cell-centred, or nodal for p_nd / phi),
+ * data[f] its dataPtr().  All pointers of one MultiFab are of the same kind (device, or host => staged inside the call).
+ * The valid boxes must tile this rank's part of the domain (the whole domain on one GPU, the rank's z slab otherwise) --
+ * what an amrex::BoxArray guarantees.  The solver gathers the boxes into its slab arrays with one fused pass per
+ * field and scatters the results back the same way; results are bit-identical to the single-box calls. */
+typedef struct {
+    int nfabs;                 /* MultiFab::local_size()                                  */
+    int ngrow;                 /* MultiFab::nGrow()                                       */
+    int ncomp;                 /* MultiFab::nComp()                                       */
+    const b200np_fab* box;     /* [nfabs] allocated box of each fab (ncomp field ignored)  */
+    double* const* data;       /* [nfabs] fab.dataPtr()                                   */
+} b200np_mfab;
+/* b200np_project over MultiFabs.  After the call every cell of vel's fabs that lies inside the domain grown by one cell
+ * holds the projected velocity / the BC ghost value (interior ghost cells as after FillBoundary), sigma may be NULL. */
+int b200np_project_mf(b200np_t* h, const b200np_mfab* vel, const b200np_mfab* sigma, double const_sigma, const b200np_mfab* phi,
+                      const b200np_mfab* gphi, double rtol, double atol, b200np_stats* stats);
+/* b200np_apply_nodal_projection over incflo::LevelData's MultiFabs (velocity, velocity_o, density, gp, p_nd).  On
+ * return the ghost cells of velocity that lie inside the domain hold the neighbour boxes' projected values (as after
+ * FillBoundary; not across periodic faces beyond the first layer), the first layer outside the domain the BC value (0,
+ * or the inflow fill) and everything further out 0 (vel.setBndry(0.0), :137). */
+int b200np_apply_nodal_projection_mf(b200np_t* h, const b200np_mfab* velocity, const b200np_mfab* velocity_o,
+                                     const b200np_mfab* density, double ro_0, const b200np_mfab* gp, const b200np_mfab* p_nd,
+                                     const b200np_mfab* inflow_vel, double scaling_factor, int incremental, int proj_for_small_dt,
+                                     double rtol, double atol, b200np_stats* stats);
+
 /* ---- composite (two AMR level) projection: BASELINE configs[3], amr.max_level = 1 -------------------
  * incflo::ApplyNodalProjection loops over lev = 0..finest_level (:101-121, :130-164, :221-266) and hands
  * Hydro::NodalProjector the vectors vel[], sigma[], Geom(0,finest_level) (:181-192); AMReX's MLMG then
@@ -209,6 +236,36 @@ int  b200np_composite_apply_nodal_projection(b200np_composite_t* c, double* cons
                                              const b200np_fab* const gp_box[2], double* const p_nd[2],
                                              const b200np_fab* const p_box[2], const double* inflow_vel0, double scaling_factor,
                                              int incremental, int proj_for_small_dt, double rtol, double atol, b200np_stats* stats);
+
+/* ---- MAC projection: Hydro::MacProjector over amrex::MLMG / MLABecLaplacian --------------------------------------
+ * Call sites: src/convection/incflo_compute_MAC_projected_velocities.cpp:69-129 (inv_rho on faces = dt / rho,
+ * macproj->initProjector(lp_info, inv_rho) | initProjector(ba, dm, lp_info, dt / ro_0), setDomainBC(get_mac_projection_bc),
+ * updateCoeffs / updateBeta) and :280-299 (project(mac_phi, rtol, atol) | project(rtol, atol)); keys mac_proj.mg_rtol,
+ * mg_atol, mg_max_coarsening_level (src/setup/init.cpp:165-170).  One AMR level, one box, one GPU.
+ * geom.bc_lo / bc_hi: the LinOpBCType of incflo::get_mac_projection_bc (src/projection/incflo_projection_bc.cpp:43-79):
+ * PERIODIC, NEUMANN (walls, mass inflow, direction_dependent; B200NP_BC_INFLOW is accepted and means NEUMANN), DIRICHLET
+ * (pressure in/outflow).  Robin (mixed faces) returns B200NP_ERR_UNSUPPORTED from the C++ mirror.
+ * opts: maxiter, bottom_maxiter (MLMG defaults 200), bottom_rtol / bottom_atol, mg_max_coarsening_level, num_pre_smooth,
+ * num_post_smooth, verbose are used; opts == NULL takes these MLMG defaults. */
+typedef struct b200mac b200mac_t;
+int  b200mac_create(b200mac_t** out, const b200np_geom* geom, const b200np_opts* opts, int device);
+void b200mac_destroy(b200mac_t* h);
+int  b200mac_nlevels(const b200mac_t* h);
+/* initProjector / updateCoeffs (bx, by, bz: face-centred dt / rho, boxes in face index space: x faces [0,nx] x [0,ny) x
+ * [0,nz) ...) or, with all three NULL, initProjector(..., const_beta) / updateBeta(const_beta). */
+int  b200mac_set_coeffs(b200mac_t* h, const double* bx, const b200np_fab* bx_box, const double* by, const b200np_fab* by_box,
+                        const double* bz, const b200np_fab* bz_box, double const_beta);
+/* project: rhs = -div(u_mac); MLMG solve of -div(b grad phi) = rhs to max(atol, rtol * max(|rhs|, |res0|)); u_mac -= b grad phi
+ * on every face (boundary faces with the BC ghost cell: nothing at Neumann faces).  mac_phi (optional cell array): the
+ * initial guess when phi_is_initial_guess (project(mac_phi, ...), :287-292, incflo passes zeros), and phi on return. */
+int  b200mac_project(b200mac_t* h, double* umac, const b200np_fab* u_box, double* vmac, const b200np_fab* v_box, double* wmac,
+                     const b200np_fab* w_box, double* mac_phi, const b200np_fab* phi_box, int phi_is_initial_guess, double rtol,
+                     double atol, b200np_stats* stats);
+/* test hooks: op 0 smooth (arg MLMG smooth calls: cor = in_a, res = in_b), 1 residual (in_b - A in_a), 2 restriction of in_a to
+ * level lev + 1, 3 in_a + interpolation of in_b (level lev + 1), 4 bottom solve of in_b on the coarsest level.  Host arrays,
+ * dense cell layout (nz, ny, nx). */
+int  b200mac_level_op(b200mac_t* h, int lev, int op, int arg, const double* in_a, const double* in_b, double* out);
+int  b200mac_level_dims(const b200mac_t* h, int lev, int n_cell[3]);
 
 /* IncfloVelFill (src/prob/prob_bc.H:8-351) evaluated by the library: after this call,
  * b200np_apply_nodal_projection with inflow_vel == NULL fills the first ghost layer of the velocity at INFLOW

@@ -6,6 +6,8 @@
 //   shim_check composite in.bin out.bin nx ny nz dx bclo(3) bchi(3) flo(3) fhi(3)
 //       two AMR levels, constant sigma 0.37, fine box = coarse cells [flo, fhi] refined by 2, 1 ghost cell per level;
 //       in.bin: vel0, vel1; out.bin: vel0, vel1, phi0, phi1, gphi0, gphi1, iters
+//   shim_check multibox n max_grid        : incflo::ApplyNodalProjection over a MultiFab of max_grid^3 boxes (ng = 2) against
+//       the same call on one box -- must agree bit for bit (periodic x/y, walls z, variable density)
 #include "../../include/B200NodalProjector.H"
 
 #include <cstring>
@@ -82,7 +84,81 @@ static int host_checks()
     EXPECT(f.box.lo[0] == -3 && f.box.hi[2] == 10 && f.size() == (size_t)3 * 14 * 14 * 14);
     Fab pn = Fab::make(nullptr, n, 0, 1, true);
     EXPECT(pn.box.lo[1] == 0 && pn.box.hi[1] == 8 && pn.size() == (size_t)9 * 9 * 9);
+    // MultiFab view: what mfab_of(amrex::MultiFab&) builds
+    {
+        std::vector<double> a(1000), b(1000);
+        const int lo0[3] = {0, 0, 0}, hi0[3] = {3, 7, 7}, lo1[3] = {4, 0, 0}, hi1[3] = {7, 7, 7};
+        MultiFab mf({Fab::make_box(a.data(), lo0, hi0, 1, 1), Fab::make_box(b.data(), lo1, hi1, 1, 1)}, 1, 1);
+        const b200np_mfab* c = mf.c();
+        EXPECT(c && c->nfabs == 2 && c->ngrow == 1 && c->ncomp == 1 && c->data[1] == b.data());
+        EXPECT(c->box[1].lo[0] == 3 && c->box[1].hi[0] == 8 && c->box[0].lo[2] == -1);
+        EXPECT(MultiFab().c() == nullptr);
+    }
     std::printf("shim host checks OK\n");
+    return 0;
+}
+
+// incflo::ApplyNodalProjection on a multi-box LevelData against the single-box call
+static int multibox(int argc, char** argv)
+{
+    if (argc < 4) { std::printf("usage: shim_check multibox n max_grid\n"); return 2; }
+    abort_handler() = throwing_abort;
+    const int N = std::atoi(argv[2]), mg = std::atoi(argv[3]), ng = 2;
+    const int n[3] = {N, N, N};
+    Geometry g{{N, N, N}, {1.0 / N, 1.0 / N, 1.0 / N}, {true, true, false}};
+    std::array<LinOpBCType, 3> lo{LinOpBCType::Periodic, LinOpBCType::Periodic, LinOpBCType::Neumann}, hi = lo;
+    const int S = N + 2 * ng;
+    std::vector<double> vel((size_t)3 * S * S * S), rho((size_t)S * S * S), gp((size_t)3 * N * N * N, 0.0), p((size_t)(N + 1) * (N + 1) * (N + 1), 0.0);
+    unsigned long long seed = 88172645463325252ull;
+    auto rnd = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return (double)(seed % 2000001ull) / 1.0e6 - 1.0; };
+    for (auto& x : vel) x = rnd();
+    for (auto& x : rho) x = 1.0 + 0.5 * (rnd() + 1.0);
+    for (auto& x : gp) x = 0.1 * rnd();
+    try {
+        IncfloNodalProjection proj(g, lo, hi);
+        // (a) one box
+        std::vector<double> v1 = vel, g1 = gp, p1 = p;
+        Fab fv = Fab::make(v1.data(), n, ng, 3), fr = Fab::make(rho.data(), n, ng, 1), fg = Fab::make(g1.data(), n, 0, 3), fp = Fab::make(p1.data(), n, 0, 1, true);
+        proj.ApplyNodalProjection(&fr, 1.0, fv, nullptr, fg, fp, nullptr, 0.01, false);
+        const int it1 = proj.stats().iters;
+        // (b) boxes of mg^3 cells, each fab with its own ghost frame (what MFIter hands out)
+        struct Store { std::vector<std::vector<double>> d; };
+        Store sv, sr, sg, sp;
+        auto chop = [&](const std::vector<double>& full, int ncomp, int ngr, bool nodal, Store& st) {
+            std::vector<Fab> fabs;
+            const int e = nodal ? 1 : 0, FS = N + 2 * ngr + e;
+            for (int k0 = 0; k0 < N; k0 += mg) for (int j0 = 0; j0 < N; j0 += mg) for (int i0 = 0; i0 < N; i0 += mg) {
+                const int vlo[3] = {i0, j0, k0}, vhi[3] = {std::min(i0 + mg, N) - 1, std::min(j0 + mg, N) - 1, std::min(k0 + mg, N) - 1};
+                const int bx = vhi[0] - vlo[0] + 1 + 2 * ngr + e, by = vhi[1] - vlo[1] + 1 + 2 * ngr + e, bz = vhi[2] - vlo[2] + 1 + 2 * ngr + e;
+                st.d.emplace_back((size_t)ncomp * bx * by * bz);
+                auto& b = st.d.back();
+                for (int c = 0; c < ncomp; ++c) for (int k = 0; k < bz; ++k) for (int j = 0; j < by; ++j) for (int i = 0; i < bx; ++i)
+                    b[(((size_t)c * bz + k) * by + j) * bx + i] = full[(((size_t)c * FS + (k0 + k)) * FS + (j0 + j)) * FS + (i0 + i)];
+                fabs.push_back(Fab::make_box(b.data(), vlo, vhi, ngr, ncomp, nodal));
+            }
+            return MultiFab(std::move(fabs), ngr, ncomp);
+        };
+        MultiFab mv = chop(vel, 3, ng, false, sv), mr = chop(rho, 1, ng, false, sr), mgp = chop(gp, 3, 0, false, sg), mp = chop(p, 1, 0, true, sp);
+        proj.ApplyNodalProjection(&mr, 1.0, mv, nullptr, mgp, mp, nullptr, 0.01, false);
+        if (proj.stats().iters != it1) { std::printf("iterations differ: %d vs %d\n", proj.stats().iters, it1); return 5; }
+        // compare the valid regions
+        size_t bad = 0, f = 0;
+        for (int k0 = 0; k0 < N; k0 += mg) for (int j0 = 0; j0 < N; j0 += mg) for (int i0 = 0; i0 < N; i0 += mg, ++f) {
+            const Fab& a = mv.fabs[f];
+            const int bx = a.box.hi[0] - a.box.lo[0] + 1, by = a.box.hi[1] - a.box.lo[1] + 1, bz = a.box.hi[2] - a.box.lo[2] + 1;
+            for (int c = 0; c < 3; ++c) for (int k = ng; k < bz - ng; ++k) for (int j = ng; j < by - ng; ++j) for (int i = ng; i < bx - ng; ++i)
+                if (a.p[(((size_t)c * bz + k) * by + j) * bx + i] != v1[(((size_t)c * S + (k0 + k)) * S + (j0 + j)) * S + (i0 + i)]) ++bad;
+            const Fab& q = mp.fabs[f];
+            const int qx = q.box.hi[0] - q.box.lo[0] + 1, qy = q.box.hi[1] - q.box.lo[1] + 1, qz = q.box.hi[2] - q.box.lo[2] + 1;
+            for (int k = 0; k < qz; ++k) for (int j = 0; j < qy; ++j) for (int i = 0; i < qx; ++i)
+                if (q.p[((size_t)k * qy + j) * qx + i] != p1[((size_t)(k0 + k) * (N + 1) + (j0 + j)) * (N + 1) + (i0 + i)]) ++bad;
+        }
+        if (bad) { std::printf("%zu values differ between the multi-box and the single-box call\n", bad); return 6; }
+        std::printf("shim multibox OK: %zu boxes, %d V-cycles\n", mv.fabs.size(), it1);
+    } catch (const std::runtime_error& e) {
+        std::printf("amrex::Abort::%s\n", e.what());
+        return 1;
+    }
     return 0;
 }
 
@@ -138,6 +214,7 @@ int main(int argc, char** argv)
 {
     if (argc >= 2 && !std::strcmp(argv[1], "host")) return host_checks();
     if (argc >= 2 && !std::strcmp(argv[1], "composite")) return composite(argc, argv);
+    if (argc >= 2 && !std::strcmp(argv[1], "multibox")) return multibox(argc, argv);
     if (argc < 15 || std::strcmp(argv[1], "project")) { std::printf("usage: see header comment\n"); return 2; }
     abort_handler() = throwing_abort;
     const int n[3] = {std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6])};

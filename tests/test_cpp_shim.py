@@ -67,6 +67,15 @@ def test_shim_project_matches_oracle(shim_exe, tmp_path, config, N, oracle):
 
 
 @pytest.mark.gpu
+def test_shim_multibox_apply_equals_single_box(shim_exe):
+    """incflo::ApplyNodalProjection through the C++ mirror on a MultiFab of 16^3 boxes (what mfab_of(amrex::MultiFab&) hands
+    over with amr.max_grid_size = 16) against the same call on one box: bit-identical"""
+    out = subprocess.run([shim_exe, "multibox", "48", "16"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "shim multibox OK: 27 boxes" in out.stdout
+
+
+@pytest.mark.gpu
 def test_shim_two_level_project_matches_oracle(shim_exe, tmp_path, oracle):
     """Hydro::NodalProjector with two-element vectors (finest_level = 1) through the C++ mirror, against the
     composite oracle: periodic x/y, walls z, central box (bouss_bubble-like, BASELINE configs[3] scaled down)"""
