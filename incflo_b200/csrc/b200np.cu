@@ -919,23 +919,30 @@ double norminf(b200np* h, LevelData& L, const double* x)
 }
 
 // MLMG::solve (A.9) on level-0 arrays sol (initial guess, in/out) and rhs
-int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st)
+// sol_is_zero: the initial guess is identically zero (NodalProjector::project always starts there), so the initial residual
+// IS rhs -- no kernel needed when the cycle never reads L0.res (direct form)
+int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st, bool sol_is_zero = false)
 {
     LevelData& L0 = h->lv[0];
     st->iters = 0; st->bottom_iters = 0; st->status = B200NP_OK; st->nlevels = (int)h->lv.size();
     CK(cudaMemsetAsync(h->dinfo, 0, 4 * sizeof(int), h->stream));
     if (!h->singular) {
-        LAUNCH(h, k_zero_masked, L0.gn, 256, L0.g, L0.sol);
+        if (!sol_is_zero) LAUNCH(h, k_zero_masked, L0.gn, 256, L0.g, L0.sol);
         LAUNCH(h, k_zero_masked, L0.gn, 256, L0.g, L0.rhs);
-    } else {  // makeSolvable: subtract the weighted mean of rhs (A.8)
+        st->rhsnorm = norminf(h, L0, L0.rhs);
+    } else {  // makeSolvable: subtract the weighted mean of rhs (A.8); the inf-norm of the result comes out of the same pass
         LAUNCH(h, k_wsum_partial, L0.gn, 256, L0.g, L0.rhs, h->partial);
         LAUNCH(h, k_sum2_final, 1, 1024, h->partial, L0.nblk_n, h->dscal);
         allreduce(h, h->dscal, 2, ncclSum);
-        LAUNCH(h, k_sub_mean, L0.gn, 256, L0.g, L0.rhs, h->dscal);
+        LAUNCH(h, k_sub_mean, L0.gn, 256, L0.g, L0.rhs, (const double*)h->dscal, h->partial);
+        st->rhsnorm = norm_from_partials(h, L0.nblk_n);
     }
-    st->rhsnorm = norminf(h, L0, L0.rhs);
-    residual(h, L0, L0.sol, L0.rhs, L0.res, h->partial);
-    st->resnorm0 = norm_from_partials(h, resid_nblk(h, L0));
+    const bool direct0 = sol_is_zero && h->top_direct && h->lv.size() > 1;
+    if (direct0) st->resnorm0 = st->rhsnorm;
+    else {
+        residual(h, L0, L0.sol, L0.rhs, L0.res, h->partial);
+        st->resnorm0 = norm_from_partials(h, resid_nblk(h, L0));
+    }
     const double maxnorm = std::max(st->rhsnorm, st->resnorm0);
     const double target = std::max(atol, std::max(rtol, 1e-16) * maxnorm);
     st->resnorm = st->resnorm0;
@@ -1065,7 +1072,7 @@ int project_core(b200np* h, Fab vel, Fab velo, int add_old, Fab gphi, int acc_g,
     prof_mark(h, "halo vel + divu");
     CK(cudaMemsetAsync(L0.sol - L0.g.ps, 0, (size_t)L0.g.ps * (L0.g.nzl + 2) * sizeof(double), h->stream));
     CK(cudaEventRecord(h->ev[2], h->stream));
-    int status = mlmg_solve(h, rtol, atol, st);
+    int status = mlmg_solve(h, rtol, atol, st, true);
     CK(cudaEventRecord(h->ev[3], h->stream));
     halo_nodes(h, L0, L0.sol);  // the gradient and the copy-out read the node plane above the slab
     LAUNCH(h, k_mknewu, L0.gc, 256, L0.g, L0.sol, vel, velo, add_old, gphi, acc_g);

@@ -517,6 +517,31 @@ __global__ void __launch_bounds__(256) k_divu(const Lev L, Fab vel, double* __re
     const int kg = kl + L.k0;
     long long id = kl * L.ps + (long long)j * L.px + i;
     if (node_masked(L, i, j, kg)) { rhs[id] = 0.0; return; }
+    // interior node (the 8 cells around it are domain cells, held by the caller's box): fixed strides, no index maps
+    if (i > 0 && i < L.n[0] && j > 0 && j < L.n[1] && kg > 0 && kg < L.n[2] && (!L.dist || (kg > L.ck0 && kg < L.ck0 + L.cnzl))) {
+        const double* p0 = vel.p + vel.idx(i - 1, j - 1, kg - 1, 0);
+        const long long sy = vel.nx, sz = (long long)vel.nx * vel.ny;
+        double dux = 0, dvy = 0, dwz = 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const double* q = p0 + c * sz + b * sy;
+                dux += q[1] - q[0];
+            }
+        const double* pv = p0 + vel.cstride;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) dvy += pv[c * sz + sy + a] - pv[c * sz + a];
+        const double* pw = p0 + 2 * vel.cstride;
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int a = 0; a < 2; ++a) dwz += pw[sz + b * sy + a] - pw[b * sy + a];
+        rhs[id] = 0.25 * (L.dxinv[0] * dux + L.dxinv[1] * dvy + L.dxinv[2] * dwz);
+        return;
+    }
     double zx[2] = {1.0, 1.0}, zy[2] = {1.0, 1.0}, zz[2] = {1.0, 1.0}, scale = 1.0;
     if (!L.per[0]) { if (i == 0 && L.rlo[0]) { zx[0] = 0; scale *= 2; } if (i == L.n[0] && L.rhi[0]) { zx[1] = 0; scale *= 2; } }
     if (!L.per[1]) { if (j == 0 && L.rlo[1]) { zy[0] = 0; scale *= 2; } if (j == L.n[1] && L.rhi[1]) { zy[1] = 0; scale *= 2; } }
@@ -668,12 +693,24 @@ __global__ void __launch_bounds__(1024) k_max_final(const double* __restrict__ p
     if (threadIdx.x == 0) out[0] = a;
 }
 // x -= sums[0]/sums[1] on unmasked owned nodes
-__global__ void __launch_bounds__(256) k_sub_mean(const Lev L, double* __restrict__ x, const double* __restrict__ sums)
+// partial (optional): per-block max |x| after the subtraction, laid out like k_norminf_partial's -- the inf-norm in the same pass
+__global__ void __launch_bounds__(256) k_sub_mean(const Lev L, double* __restrict__ x, const double* __restrict__ sums,
+                                                  double* __restrict__ partial = nullptr)
 {
+    __shared__ double sh[34];
     const int i = blockIdx.x * 64 + (threadIdx.x & 63);
     const int j = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (i >= L.nn[0] || j >= L.nn[1]) return;
-    x[blockIdx.z * L.ps + (long long)j * L.px + i] -= sums[0] / sums[1];
+    double a = 0.0;
+    if (i < L.nn[0] && j < L.nn[1]) {
+        const long long id = blockIdx.z * L.ps + (long long)j * L.px + i;
+        const double v = x[id] - sums[0] / sums[1];
+        x[id] = v;
+        a = fabs(v);
+    }
+    if (partial) {
+        a = block_reduce<true>(a, sh);
+        if (threadIdx.x == 0) partial[(blockIdx.z * gridDim.y + blockIdx.y) * (long long)gridDim.x + blockIdx.x] = a;
+    }
 }
 __global__ void __launch_bounds__(256) k_norminf_partial(const Lev L, const double* __restrict__ x, double* __restrict__ partial)
 {

@@ -6,10 +6,15 @@
 //   shim_check composite in.bin out.bin nx ny nz dx bclo(3) bchi(3) flo(3) fhi(3)
 //       two AMR levels, constant sigma 0.37, fine box = coarse cells [flo, fhi] refined by 2, 1 ghost cell per level;
 //       in.bin: vel0, vel1; out.bin: vel0, vel1, phi0, phi1, gphi0, gphi1, iters
+//   shim_check mac n                      : the MacProjector call sequence of incflo_compute_MAC_projected_velocities.cpp:96-132,
+//       :287-298 (constant beta, then face arrays, periodic x/y + walls z); checks that the projected face velocity is
+//       discretely divergence-free and that project(mac_phi, ..) started from the converged phi does nothing
 //   shim_check multibox n max_grid        : incflo::ApplyNodalProjection over a MultiFab of max_grid^3 boxes (ng = 2) against
 //       the same call on one box -- must agree bit for bit (periodic x/y, walls z, variable density)
 #include "../../include/B200NodalProjector.H"
+#include "../../include/B200MacProjector.H"
 
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -210,8 +215,73 @@ static int composite(int argc, char** argv)
     return 0;
 }
 
+static int mac(int argc, char** argv)
+{
+    if (argc < 3) { std::printf("usage: shim_check mac n\n"); return 2; }
+    abort_handler() = throwing_abort;
+    const int N = std::atoi(argv[2]);
+    const int n[3] = {N, N, N};
+    Geometry g{{N, N, N}, {1.0 / N, 1.0 / N, 1.0 / N}, {true, true, false}};
+    auto lo = get_mac_projection_bc(g.is_periodic, {BC::undefined, BC::undefined, BC::no_slip_wall});
+    auto hi = get_mac_projection_bc(g.is_periodic, {BC::undefined, BC::undefined, BC::slip_wall});
+    if (lo[2] != LinOpBCType::Neumann || hi[0] != LinOpBCType::Periodic) { std::printf("get_mac_projection_bc wrong\n"); return 3; }
+    const size_t nu = (size_t)N * N * (N + 1), nc = (size_t)N * N * N;
+    std::vector<double> u(nu), v(nu), w(nu), bx(nu), by(nu), bz(nu), phi(nc, 0.0);
+    unsigned long long seed = 1234567ull;
+    auto rnd = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return (double)(seed % 2000001ull) / 1.0e6 - 1.0; };
+    for (auto& x : u) x = rnd();
+    for (auto& x : v) x = rnd();
+    for (auto& x : w) x = rnd();
+    for (auto& x : bx) x = 0.75 + 0.25 * rnd();
+    for (auto& x : by) x = 0.75 + 0.25 * rnd();
+    for (auto& x : bz) x = 0.75 + 0.25 * rnd();
+    // periodic x / y: one value per physical face; walls in z: no flow through them
+    for (int k = 0; k < N; ++k) for (int j = 0; j < N; ++j) { u[((size_t)k * N + j) * (N + 1) + N] = u[((size_t)k * N + j) * (N + 1)]; bx[((size_t)k * N + j) * (N + 1) + N] = bx[((size_t)k * N + j) * (N + 1)]; }
+    for (int k = 0; k < N; ++k) for (int i = 0; i < N; ++i) { v[((size_t)k * (N + 1) + N) * N + i] = v[((size_t)k * (N + 1)) * N + i]; by[((size_t)k * (N + 1) + N) * N + i] = by[((size_t)k * (N + 1)) * N + i]; }
+    for (int j = 0; j < N; ++j) for (int i = 0; i < N; ++i) { w[(size_t)j * N + i] = 0.0; w[((size_t)N * N + j) * N + i] = 0.0; }
+    const int flo[3] = {0, 0, 0};
+    const int uhi[3] = {N, N - 1, N - 1}, vhi[3] = {N - 1, N, N - 1}, whi[3] = {N - 1, N - 1, N}, chi[3] = {N - 1, N - 1, N - 1};
+    Fab fu(u.data(), flo, uhi, 1), fv(v.data(), flo, vhi, 1), fw(w.data(), flo, whi, 1), fphi(phi.data(), flo, chi, 1);
+    Fab fbx(bx.data(), flo, uhi, 1), fby(by.data(), flo, vhi, 1), fbz(bz.data(), flo, whi, 1);
+    (void)n;
+    try {
+        auto macproj = std::make_unique<MacProjector>(g);
+        if (!macproj->needInitialization()) return 4;
+        LPInfo lp_info;
+        lp_info.setMaxCoarseningLevel(100);
+        macproj->initProjector(lp_info, 0.01 / 1.0);                 // incflo.constant_density branch (:106-109)
+        macproj->setDomainBC(lo, hi);
+        std::vector<double> u0 = u, v0 = v, w0 = w;
+        macproj->project(fu, fv, fw, 1e-11, 1e-14);
+        const int it_const = macproj->stats().iters;
+        u = u0; v = v0; w = w0;
+        macproj->updateCoeffs({&fbx, &fby, &fbz});                   // variable density (:128)
+        macproj->project(fphi, fu, fv, fw, 1e-11, 1e-14);            // m_use_mac_phi_in_godunov branch (:287-292)
+        const int it_var = macproj->stats().iters;
+        double dmax = 0.0, dsum = 0.0;
+        for (int k = 0; k < N; ++k) for (int j = 0; j < N; ++j) for (int i = 0; i < N; ++i) {
+            const double d = (u[((size_t)k * N + j) * (N + 1) + i + 1] - u[((size_t)k * N + j) * (N + 1) + i]) * N +
+                             (v[((size_t)k * (N + 1) + j + 1) * N + i] - v[((size_t)k * (N + 1) + j) * N + i]) * N +
+                             (w[((size_t)(k + 1) * N + j) * N + i] - w[((size_t)k * N + j) * N + i]) * N;
+            dmax = std::max(dmax, std::fabs(d)); dsum += d;
+        }
+        const double bnorm = std::max(macproj->stats().rhsnorm, macproj->stats().resnorm0);
+        if (!(dmax <= 2e-11 * bnorm + std::fabs(dsum) / nc)) { std::printf("divergence %g after the projection (bnorm %g)\n", dmax, bnorm); return 5; }
+        std::vector<double> u1 = u0, v1 = v0, w1 = w0;
+        Fab gu(u1.data(), flo, uhi, 1), gv(v1.data(), flo, vhi, 1), gw(w1.data(), flo, whi, 1);
+        macproj->project(fphi, gu, gv, gw, 1e-10, 1e-14);            // warm start from the converged phi
+        if (macproj->stats().iters != 0) { std::printf("warm start took %d iterations\n", macproj->stats().iters); return 6; }
+        std::printf("shim mac OK: %d / %d V-cycles (constant / variable beta), max |div u| %.2e\n", it_const, it_var, dmax);
+    } catch (const std::runtime_error& e) {
+        std::printf("amrex::Abort::%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 2 && !std::strcmp(argv[1], "mac")) return mac(argc, argv);
     if (argc >= 2 && !std::strcmp(argv[1], "host")) return host_checks();
     if (argc >= 2 && !std::strcmp(argv[1], "composite")) return composite(argc, argv);
     if (argc >= 2 && !std::strcmp(argv[1], "multibox")) return multibox(argc, argv);

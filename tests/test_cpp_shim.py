@@ -67,6 +67,15 @@ def test_shim_project_matches_oracle(shim_exe, tmp_path, config, N, oracle):
 
 
 @pytest.mark.gpu
+def test_shim_mac_projector_call_sequence(shim_exe):
+    """Hydro::MacProjector through the C++ mirror (include/B200MacProjector.H): initProjector(const beta) / setDomainBC /
+    project, updateCoeffs(face arrays) / project(mac_phi, ...), warm start"""
+    out = subprocess.run([shim_exe, "mac", "32"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "shim mac OK" in out.stdout
+
+
+@pytest.mark.gpu
 def test_shim_multibox_apply_equals_single_box(shim_exe):
     """incflo::ApplyNodalProjection through the C++ mirror on a MultiFab of 16^3 boxes (what mfab_of(amrex::MultiFab&) hands
     over with amr.max_grid_size = 16) against the same call on one box: bit-identical"""
