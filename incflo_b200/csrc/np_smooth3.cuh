@@ -28,18 +28,23 @@ constexpr int SM_RES_TZ = 8;
 constexpr int SM_RES_DOUBLES = (SM_RES_TZ + 2) * SM_PHI_SLOT + (SM_RES_TZ + 1) * SM_SIG_SLOT;
 
 // DIST: slab-decomposed level with the FillBoundary fused into the sweep (NVLink peer memory, flags of
-// np_kernels.cuh K10).  Push protocol: the CTAs that finish the slab's first / last plane also store it
-// into the lower / upper neighbour's ghost plane slot of the output array (remote stores), and the
-// last of them raises the neighbour's flag for the next exchange; the neighbour's next sweep reads its
-// LOCAL ghost slots.  Only the bottom / top chunk CTAs wait for a flag (not in the first sweep of a
-// smooth call, whose input halo was filled by a standalone exchange or is zero); every other CTA starts
-// at once, and the boundary chunks are scheduled first (blockIdx.z = 0 is the top chunk, 1 the bottom
-// chunk), so on a large level the flags arrive long before the neighbour's next sweep needs them.
-// The plane march itself is the single-GPU code, untouched: the pushes happen after the march (top
-// plane from registers, bottom plane re-read from this CTA's own output) -- in-loop pushes cost 10 %
-// of the sweep in extra shared-memory reloads (register pressure).  A deliberately short top chunk
-// hides more latency on small levels but was measured to cost a V-cycle.
-// A flag also tells the neighbour that its previous boundary plane is no longer being read (WAR).
+// np_kernels.cuh K10).  Push protocol: the CTAs of the slab's bottom chunk store plane 0 into the lower neighbour's
+// upper ghost slot of the output array right after their FIRST plane (in-loop, from registers), the CTAs of the top
+// chunk store the slab's last plane into the upper neighbour's lower ghost slot after their march (remote stores);
+// the last CTA of a side raises the neighbour's flag for the next exchange, and the neighbour's next sweep reads its
+// LOCAL ghost slots.  Who waits, and when (not in the first sweep of a smooth call, whose input halo was filled by a
+// standalone exchange or is zero):
+//   * bottom chunk: before its first plane, for the lower neighbour's last plane of the previous sweep -- the one
+//     dependency that cannot be hidden (planes ascend), one chunk march + NVLink latency per sweep on small levels;
+//   * top chunk: only right before it stages the ghost plane for its LAST plane -- by then the upper neighbour's bottom
+//     chunk has long pushed (it does so after one plane), so the top chunk starts with everybody else and never stalls.
+// Measured before this split (both waits at kernel start, both pushes after the march): 30 us per sweep on a 128^3 slab
+// level against 18 us on one GPU (profiles/r2_8gpu_phase_profile_rank0.txt).
+// Every other CTA starts at once, and the boundary chunks are scheduled first (blockIdx.z = 0 is the top chunk, 1 the
+// bottom chunk).  A deliberately short top chunk hides more latency on small levels but was measured to cost a V-cycle.
+// A flag also tells the neighbour that its previous boundary plane is no longer being read (WAR): the bottom chunk of
+// sweep s+1 starts after the lower neighbour's top chunk finished sweep s (its last read of that ghost slot), and the
+// top chunk of sweep s+1 cannot finish before the upper neighbour's bottom chunk has begun sweep s+1.
 struct HaloFused {
     HaloFlags f;           // my: [4], [5] count bottom / top chunk CTAs that have pushed their plane; f.k: this sweep's exchange
     const double* pin_lo;  // plane -1 of pin: my ghost slot, or the reflection plane at a physical end
@@ -176,18 +181,32 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
 
     if (pdl_small_grid()) pdl_trigger();
     pdl_wait();   // everything above only touched kernel parameters and shared memory
-    if (DIST && !H->first) {
+    // DIST: the bottom chunk needs the lower neighbour's plane (my ghost slot -1) for its very first plane: wait now.
+    // The top chunk needs the upper neighbour's plane (ghost slot nzl) only for its LAST plane: that wait is deferred
+    // to the moment the ghost plane is staged (wait_hi below), so the top chunk starts with everybody else and the flag --
+    // raised by the neighbour's bottom chunk right after ITS first plane -- has long arrived by then.
+    const bool dist_top = DIST && kc1 == L.nzl && H->f.hi_flag != nullptr && !H->first;
+    if (DIST && !H->first && kc0 == 0 && H->f.lo_flag) {
         if (tid == 0) {
             const unsigned long long ep = halo_epoch(H->f);
-            if (kc0 == 0 && H->f.lo_flag) while (ld_acquire_sys(H->f.my + 0) < ep) __nanosleep(20);
-            if (kc1 == L.nzl && H->f.hi_flag) while (ld_acquire_sys(H->f.my + 1) < ep) __nanosleep(20);
+            while (ld_acquire_sys(H->f.my + 0) < ep) __nanosleep(20);
         }
         __syncthreads();
     }
+    auto wait_hi = [&]() {   // called by all threads right before the ghost plane nzl is staged
+        if (tid == 0) {
+            const unsigned long long ep = halo_epoch(H->f);
+            while (ld_acquire_sys(H->f.my + 1) < ep) __nanosleep(20);
+        }
+        __syncthreads();
+    };
+    bool hi_waited = false;
     double rcur[2][2], rnext[2][2];
     if (RES) {
-        // the whole chunk: planes kc0-1 .. kc1, sigma layers kc0-1 .. kc1-1
-        for (int p = kc0 - 1; p <= kc1; ++p) issue_phi(p);
+        // the whole chunk: planes kc0-1 .. kc1, sigma layers kc0-1 .. kc1-1 (the upper ghost plane of a slab's top
+        // chunk is staged later, see the march)
+        if (dist_top && kc0 >= L.nzl - 1) { wait_hi(); hi_waited = true; }   // one-plane top chunk: no later point to wait at
+        for (int p = kc0 - 1; p <= kc1 - ((dist_top && !hi_waited) ? 1 : 0); ++p) issue_phi(p);
         for (int c = kc0 - 1; c < kc1; ++c) issue_sig(c);
         cp_async_commit();
         load_rhs(kc0, rcur);
@@ -196,6 +215,7 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
         // prologue: planes kc0-1, kc0 (+ sigma layer kc0-1), then plane kc0+1 (+ sigma layer kc0)
         issue_phi(kc0 - 1); issue_phi(kc0); issue_sig(kc0 - 1);
         cp_async_commit();
+        if (dist_top && kc0 + 2 >= L.nzl) { wait_hi(); hi_waited = true; }   // one- or two-plane top chunk: the ghost plane is staged right away
         issue_phi(kc0 + 1); issue_sig(kc0);
         cp_async_commit();
         load_rhs(kc0, rcur);
@@ -225,8 +245,20 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
         }
     }
 
+    // The march runs in up to three segments so that the slab protocol stays OUT of the plane loop (a barrier or a fence
+    // inside it, even when never executed, pins the instruction schedule: measured 152 instead of 119 us per 256^3-slab
+    // sweep): [first plane] -> the bottom chunk pushes plane 0 down -> [...] -> the top chunk waits for the upper
+    // neighbour and stages the ghost plane -> [the planes that need it].  One GPU: a single segment.
+    const bool botpush = DIST && kc0 == 0 && H->out_lo != nullptr;
+    const int khi = RES ? L.nzl - 1 : L.nzl - 2;   // first plane whose iteration needs the upper ghost plane staged
+    int kl = kc0;
 #pragma unroll 1
-    for (int kl = kc0; kl < kc1; ++kl) {
+    for (int seg = DIST ? 0 : 2; seg < 3; ++seg) {
+    int kend = kc1;
+    if (DIST && seg == 0) kend = botpush ? min(kc0 + 1, kc1) : kc0;
+    if (DIST && seg == 1) kend = (dist_top && !hi_waited) ? min(max(kl, khi), kc1) : kl;
+#pragma unroll 1
+    for (; kl < kend; ++kl) {
         if (!RES) {
             if (kl + 2 <= kc1) { issue_phi(kl + 2); issue_sig(kl + 1); }
             cp_async_commit();
@@ -409,38 +441,46 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
         for (int c = 0; c < 4; ++c) { Wn[0][c] = Wp02[0][c]; Wn[1][c] = Wp02[1][c]; }
         if (kl + 2 == kc1) pdl_trigger();   // tail of the march (no-op if already triggered)
     }
-    pdl_trigger();
-    cp_async_wait<0>();
     if (DIST) {
-        // push the slab's first / last plane into the neighbour's ghost plane slot of pout, then report
-        const bool bot = kc0 == 0 && H->out_lo, top = kc1 == L.nzl && H->out_hi;
-        if (bot || top) {
-            auto push = [&](double* r0, const double (&w)[2][2]) {
-                r0 += roff;
+        // ownp: this thread's values of the last finished plane
+        auto push = [&](double* r0) {
+            r0 += roff;
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    double* q = r0 + b * L.px;
-                    if (FULL) *reinterpret_cast<double2*>(q) = make_double2(w[b][0], w[b][1]);
-                    else if (rowok[b]) {
-                        if (colok[1]) *reinterpret_cast<double2*>(q) = make_double2(w[b][0], w[b][1]);
-                        else if (colok[0]) q[0] = w[b][0];
-                    }
+            for (int b = 0; b < 2; ++b) {
+                double* q = r0 + b * L.px;
+                if (FULL) *reinterpret_cast<double2*>(q) = make_double2(ownp[b][0], ownp[b][1]);
+                else if (rowok[b]) {
+                    if (colok[1]) *reinterpret_cast<double2*>(q) = make_double2(ownp[b][0], ownp[b][1]);
+                    else if (colok[0]) q[0] = ownp[b][0];
                 }
-            };
-            if (top) push(H->out_hi, ownp);            // ownp: this thread's values of the last plane of the chunk
-            if (bot) {
-                double w[2][2];
-                if (kc1 - kc0 == 1) { w[0][0] = ownp[0][0]; w[0][1] = ownp[0][1]; w[1][0] = ownp[1][0]; w[1][1] = ownp[1][1]; }
-                else load_rhs(0, w, pout);             // plane 0 of this CTA's own output (written by this very thread)
-                push(H->out_lo, w);
             }
+        };
+        if (seg == 0 && botpush && kl == kc0 + 1) {
+            // the slab's first plane goes to the lower neighbour's upper ghost slot of pout as soon as it exists (that
+            // neighbour's top chunk needs it for its last plane only, but the flag must be there by then)
+            push(H->out_lo);
             __syncthreads();   // every thread's remote stores have been issued
-            if (tid == 0) {
-                if (bot) halo_report<0>(*H);
-                if (top) halo_report<1>(*H);
+            if (tid == 0) halo_report<0>(*H);
+        }
+        if (seg == 1 && dist_top && !hi_waited && kl == khi && kl < kc1) {
+            wait_hi();
+            hi_waited = true;
+            if (RES) {   // resident chunk: the ghost plane above the slab is staged now, before the last plane
+                issue_phi(L.nzl);
+                cp_async_commit();
+                cp_async_wait<0>();
             }
         }
+        if (seg == 2 && kc1 == L.nzl && H->out_hi) {
+            // the slab's last plane goes into the upper neighbour's lower ghost slot of pout after the march
+            push(H->out_hi);
+            __syncthreads();
+            if (tid == 0) halo_report<1>(*H);
+        }
     }
+    }
+    pdl_trigger();
+    cp_async_wait<0>();
 }
 
 // slab-decomposed variants with the halo exchange fused in (see HaloFused)
