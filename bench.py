@@ -377,6 +377,49 @@ def timed_solves(ctx, proj, wl, K, W, n_glob, restore="clone"):
     return allmax(ctx, t_dev) / K, step_ms, st, launches
 
 
+def mac_block(ctx, n1):
+    """SURVEY 8(f) rank 3, reported next to the headline (not part of `value`): one MAC projection (Hydro::MacProjector
+    semantics, b200mac_*) of an n1^3 rayleigh_taylor-like field, device-resident, CUDA-event time of the call"""
+    import torch
+    from incflo_b200 import mac_projector as mp
+    dev = ctx.device
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    z = (torch.arange(n1, device=dev, dtype=torch.float64) + 0.5) / n1
+    rho = (1.0 + 1.5 * (1.0 + torch.tanh((z - 0.5) / 0.05)))[:, None, None].expand(n1, n1, n1).contiguous()
+    dt = 0.01
+    bx = dt / (0.5 * (rho + torch.roll(rho, 1, 2))); bx = torch.cat([bx, bx[:, :, :1]], 2).contiguous()
+    by = dt / (0.5 * (rho + torch.roll(rho, 1, 1))); by = torch.cat([by, by[:, :1]], 1).contiguous()
+    rz = torch.cat([rho[:1], rho, rho[-1:]], 0)
+    bz = (dt / (0.5 * (rz[:-1] + rz[1:]))).contiguous()
+
+    def smooth(a):
+        for ax in range(3):
+            a = 0.5 * a + 0.25 * (torch.roll(a, 1, ax) + torch.roll(a, -1, ax))
+        return a
+    u0 = smooth(torch.randn((n1, n1, n1 + 1), device=dev, dtype=torch.float64, generator=g)); u0[:, :, -1] = u0[:, :, 0]
+    v0 = smooth(torch.randn((n1, n1 + 1, n1), device=dev, dtype=torch.float64, generator=g)); v0[:, -1] = v0[:, 0]
+    w0 = smooth(torch.randn((n1 + 1, n1, n1), device=dev, dtype=torch.float64, generator=g)); w0[0] = 0; w0[-1] = 0
+    proj = mp.MacProjector((n1, n1, n1), (1.0 / n1,) * 3, (0, 0, 1), (0, 0, 1))
+    proj.updateCoeffs([bx, by, bz])
+    phi = torch.zeros((n1, n1, n1), device=dev, dtype=torch.float64)
+    times, st = [], None
+    for s_ in range(5):
+        u, v, w = u0.clone(), v0.clone(), w0.clone()
+        torch.cuda.synchronize()
+        st = proj.project(u, v, w, RTOL, ATOL, mac_phi=phi)
+        if s_ >= 2:
+            times.append(st.ms_total)
+    div = (u[:, :, 1:] - u[:, :, :-1]) * n1 + (v[:, 1:] - v[:, :-1]) * n1 + (w[1:] - w[:-1]) * n1
+    rec = {"n_cell": [n1] * 3, "ms_per_projection": sum(times) / len(times), "vcycles": int(st.iters),
+           "resid_over_bnorm": st.resnorm / max(st.rhsnorm, st.resnorm0), "max_div_over_bnorm": float((div - div.mean()).abs().max()) / max(st.rhsnorm, st.resnorm0),
+           "Mcell_updates_per_s": n1 ** 3 / (sum(times) / len(times)) / 1e3, "launches": int(st.launches),
+           "what": "Hydro::MacProjector / MLABecLaplacian semantics (b200mac_*), variable beta = dt/rho on faces, periodic x/y + walls z"}
+    proj.close()
+    del u0, v0, w0, bx, by, bz, rho, phi
+    torch.cuda.empty_cache()
+    return rec
+
+
 def strong_block(ctx, sizes):
     """strong scaling: the n^3 problem on all N GPUs vs the SAME solve measured on one GPU (rank 0) in this run"""
     import torch
@@ -521,6 +564,14 @@ def run_ours(args):
     del wl, hv, hg, hp, hr
     torch.cuda.empty_cache()
 
+    # ---------------- MAC projection record (N = 1): the next operator of SURVEY 8(f), same size ----------------
+    mac_rec = None
+    if nranks == 1 and not args.no_mac and N <= 256:
+        try:
+            mac_rec = mac_block(ctx, N)
+        except Exception as e:   # never let the extra record take the headline down
+            mac_rec = {"error": repr(e)[:200]}
+
     # ---------------- strong-scaling record (N > 1): 512^3 / 1024^3 in total vs one GPU, measured here ----------------
     strong_rec = None
     if nranks > 1 and not args.no_strong and not strong:
@@ -549,6 +600,8 @@ def run_ours(args):
                 "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "wall_s_timed_region": wall}
         if strong_rec is not None:
             line["strong"] = strong_rec
+        if mac_rec is not None:
+            line["mac_projection"] = mac_rec
         if nranks == 1 and not args.no_cpu:
             times, it_cpu, _ = cpu_port_run((N, N, N), 1, 0, "reference")
             tcpu = min(times)
@@ -584,6 +637,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer arm (the line is then not a valid bench line)")
     ap.add_argument("--no-parity", action="store_true", help="tuning sweeps only: skip the oracle check before timing")
+    ap.add_argument("--no-mac", action="store_true", help="N = 1: skip the MAC projection record")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the 512^3 / 1024^3 strong-scaling record")
     args = ap.parse_args()
     real_stdout = _json_only_stdout()
