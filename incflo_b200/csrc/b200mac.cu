@@ -66,7 +66,7 @@ __device__ __forceinline__ double bface(const MacLev& L, int d, int i, int j, in
     return L.b[2][((long long)k * L.n[1] + j) * L.n[0] + i];
 }
 // phi of the neighbour of cell (i,j,k) one step s = -1 / +1 along d, BC ghost cells included
-__device__ __forceinline__ double nb(const MacLev& L, const double* __restrict__ phi, int i, int j, int k, int d, int s, double pc)
+__device__ __forceinline__ double nb(const MacLev& L, const double* phi, int i, int j, int k, int d, int s, double pc)
 {
     int q[3] = {i, j, k};
     const int c = q[d] + s, n = L.n[d];
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_mac_residual(const MacLev L, const doub
 // one red-black half-sweep in place (abec_gsrb).  old: the values the neighbours are read from -- phi itself (the six
 // neighbours of a cell have the other colour), or a snapshot on a level with an odd periodic extent, where the wrap
 // joins two cells of the same colour (AMReX reads those from ghost cells filled before the half-sweep).
-__global__ void __launch_bounds__(256) k_mac_gsrb(const MacLev L, double* __restrict__ phi, const double* __restrict__ old,
+__global__ void __launch_bounds__(256) k_mac_gsrb(const MacLev L, double* phi, const double* old /* may alias phi */,
                                                   const double* __restrict__ rhs, int redblack)
 {
     const int nxh = (L.n[0] + 1) / 2;
@@ -436,6 +436,9 @@ struct b200mac {
     long long launches = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[8];
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaGraph_t graph = nullptr;          // one V-cycle, captured once (every pointer in it belongs to the handle)
+    cudaGraphExec_t graph_exec = nullptr;
+    long long launches_per_vcycle = 0;
 };
 
 namespace {
@@ -542,6 +545,30 @@ void mac_vcycle(b200mac* h)
     }
 }
 
+// the V-cycle as a CUDA graph: ~80 small launches per cycle, most of them on levels that are pure launch latency
+void mac_vcycle_run(b200mac* h)
+{
+    if (!h->opts.use_graph) { mac_vcycle(h); return; }
+    if (!h->graph_exec) {
+        const long long before = h->launches;
+        MCK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        try { mac_vcycle(h); }
+        catch (int) {
+            cudaGraph_t broken = nullptr;
+            cudaStreamEndCapture(h->stream, &broken);
+            if (broken) cudaGraphDestroy(broken);
+            cudaGetLastError();
+            throw;
+        }
+        MCK(cudaStreamEndCapture(h->stream, &h->graph));
+        MCK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+        h->launches_per_vcycle = h->launches - before;
+        h->launches = before;
+    }
+    MCK(cudaGraphLaunch(h->graph_exec, h->stream));
+    h->launches += h->launches_per_vcycle;
+}
+
 double mac_read_norm(b200mac* h, int nb_)
 {
     MLAUNCH(h, k_mac_max_final, 1, 1024, (const double*)h->partial, nb_, h->dscal + 2);
@@ -573,7 +600,7 @@ int mac_solve(b200mac* h, double rtol, double atol, b200np_stats* st)
     if (st->resnorm0 <= target) return B200NP_OK;
     bool converged = false;
     for (int it = 0; it < h->opts.maxiter; ++it) {
-        mac_vcycle(h);
+        mac_vcycle_run(h);
         MLAUNCH(h, k_mac_axpy, nb_, 256, L0.sol, (const double*)L0.cor, L0.ncell);
         MLAUNCH(h, k_mac_residual, nb_, 256, L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
         st->resnorm = mac_read_norm(h, nb_);
@@ -657,6 +684,8 @@ void b200mac_destroy(b200mac_t* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& s : h->stage) if (s.d) cudaFree(s.d);
     if (h->hscal) cudaFreeHost(h->hscal);

@@ -969,8 +969,13 @@ int mlmg_solve(b200np* h, double rtol, double atol, b200np_stats* st, bool sol_i
     }
     if (!converged && st->status == B200NP_OK) st->status = B200NP_ERR_NOT_CONVERGED;
     CK(cudaMemcpyAsync(h->hinfo, h->dinfo, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (h->p2p) CK(cudaMemcpyAsync(h->hscal + 8, h->flags + 6, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     st->bottom_iters = h->hinfo[0];
+    if (h->p2p && reinterpret_cast<unsigned long long*>(h->hscal + 8)[0] != 0ull) {   // halo_spin gave up on a neighbour
+        CK(cudaMemsetAsync(h->flags + 6, 0, sizeof(unsigned long long), h->stream));
+        st->status = B200NP_ERR_PEER_TIMEOUT;
+    }
     if (talk && h->opts.verbose >= 1)
         printf("MLMG: Final Iter. %d resid, resid/bnorm = %.12g, %.12g\n", st->iters, st->resnorm, st->resnorm / maxnorm);
     return st->status;
@@ -1410,6 +1415,7 @@ const char* b200np_strerror(int s)
     case B200NP_ERR_CUDA: return "CUDA error / no usable sm_100 device (there is no CPU fallback)";
     case B200NP_ERR_NCCL: return "NCCL error";
     case B200NP_ERR_UNSUPPORTED: return "not supported by this build";
+    case B200NP_ERR_PEER_TIMEOUT: return "slab halo exchange timed out: a neighbour rank never raised its flag";
     case B200NP_ERR_INOUT_FLUX: return "cannot enforce solvability: inflow without outflow through the direction_dependent faces, or the reverse";
     default: return "unknown status";
     }

@@ -909,8 +909,8 @@ __device__ __forceinline__ void halo_handshake(const HaloFlags& f)
             if (f.lo_flag) st_release_sys(f.lo_flag, e);
             if (f.hi_flag) st_release_sys(f.hi_flag, e);
         }
-        if (f.lo_flag) while (ld_acquire_sys(f.my + 0) < e) __nanosleep(20);
-        if (f.hi_flag) while (ld_acquire_sys(f.my + 1) < e) __nanosleep(20);
+        if (f.lo_flag) halo_spin(f.my, 0, e);
+        if (f.hi_flag) halo_spin(f.my, 1, e);
     }
     __syncthreads();
 }

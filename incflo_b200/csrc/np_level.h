@@ -54,7 +54,7 @@ __device__ __forceinline__ bool pdl_small_grid() { return gridDim.x * gridDim.y 
 // ---- NVLink peer-memory halo flags (slab-decomposed path; protocol in np_kernels.cuh K10) ----
 struct HaloFlags {
     unsigned long long* my;       // [0] written by my lower neighbour, [1] by my upper neighbour, [2] epoch base,
-                                  // [4], [5] counters of the fused sweeps (np_smooth3.cuh)
+                                  // [4], [5] counters of the fused sweeps (np_smooth3.cuh), [6] a wait timed out (halo_spin)
     unsigned long long* lo_flag;  // lower neighbour's word [1] (peer pointer) or nullptr
     unsigned long long* hi_flag;  // upper neighbour's word [0] (peer pointer) or nullptr
     unsigned long long k;         // this exchange is number k since the base was last advanced: epoch = my[2] + 1 + k
@@ -76,6 +76,18 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+
+// Bounded wait for a neighbour's flag word my[which] to reach epoch e.  A rank that died, or left the call early with an
+// error of its own, must not hang this GPU for ever: after 2^33 cycles (about 4 s) the wait gives up and raises my[6]; the
+// host turns that into B200NP_ERR_PEER_TIMEOUT at the end of the solve (the numbers of such a solve are garbage).
+__device__ __forceinline__ void halo_spin(unsigned long long* my, int which, unsigned long long e)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(my + which) < e) {
+        __nanosleep(20);
+        if (clock64() - t0 > (1ll << 33)) { atomicExch(my + 6, 1ull); break; }
+    }
 }
 
 // node index in [-1, n+1] -> unique storage index

@@ -189,14 +189,14 @@ __device__ __forceinline__ void smooth_iso_body(const Lev& L, const double* __re
     if (DIST && !H->first && kc0 == 0 && H->f.lo_flag) {
         if (tid == 0) {
             const unsigned long long ep = halo_epoch(H->f);
-            while (ld_acquire_sys(H->f.my + 0) < ep) __nanosleep(20);
+            halo_spin(H->f.my, 0, ep);
         }
         __syncthreads();
     }
     auto wait_hi = [&]() {   // called by all threads right before the ghost plane nzl is staged
         if (tid == 0) {
             const unsigned long long ep = halo_epoch(H->f);
-            while (ld_acquire_sys(H->f.my + 1) < ep) __nanosleep(20);
+            halo_spin(H->f.my, 1, ep);
         }
         __syncthreads();
     };

@@ -40,6 +40,7 @@ enum b200np_status {
     B200NP_ERR_CUDA = 5,          /* no device / CUDA runtime error                            */
     B200NP_ERR_NCCL = 6,
     B200NP_ERR_UNSUPPORTED = 7,   /* EB, general overset masks, AMR beyond one fine box at ratio 2 */
+    B200NP_ERR_PEER_TIMEOUT = 9,  /* slab path: a neighbour rank never raised its halo flag (it died or left the call early) */
     B200NP_ERR_INOUT_FLUX = 8     /* enforceInOutSolvability: inflow without outflow through the direction_dependent
                                      faces, or the reverse (AMReX-Hydro aborts)                 */
 };
