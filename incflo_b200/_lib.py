@@ -13,7 +13,7 @@ ROOT = os.path.dirname(_PKG)
 CSRC = os.path.join(_PKG, "csrc")
 LIBDIR = os.path.join(_PKG, "lib")
 SO = os.path.join(LIBDIR, "libb200np.so")
-SOURCES = ["b200np.cu", "b200mac.cu"]
+SOURCES = ["b200np.cu", "b200mac.cu", "b200eb.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -64,6 +64,12 @@ class MFab(C.Structure):
     _fields_ = [("nfabs", C.c_int), ("ngrow", C.c_int), ("ncomp", C.c_int), ("box", C.POINTER(FabBox)), ("data", C.POINTER(C.c_void_p))]
 
 
+class EBFlow(C.Structure):
+    """b200eb_flow: the eb_flow.* inputs of set_eb_velocity / density / tracer"""
+    _fields_ = [("has_normal", C.c_int), ("normal", C.c_double * 3), ("normal_tol", C.c_double), ("is_mag", C.c_int), ("vel_mag", C.c_double),
+                ("velocity", C.c_double * 3), ("density", C.c_double), ("ntrac", C.c_int), ("tracer", C.c_double * 8)]
+
+
 class Stats(C.Structure):
     _fields_ = [("iters", C.c_int), ("nlevels", C.c_int), ("bottom_iters", C.c_int), ("status", C.c_int),
                 ("rhsnorm", C.c_double), ("resnorm0", C.c_double), ("resnorm", C.c_double),
@@ -79,7 +85,10 @@ EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np
            "b200np_level_dims", "b200np_halo_transport", "b200np_peer_map", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
            "b200np_time_op", "b200np_composite_create", "b200np_composite_destroy", "b200np_composite_set_stream",
            "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection",
-           "b200mac_create", "b200mac_destroy", "b200mac_nlevels", "b200mac_set_coeffs", "b200mac_project", "b200mac_level_op", "b200mac_level_dims"]
+           "b200mac_create", "b200mac_destroy", "b200mac_nlevels", "b200mac_set_coeffs", "b200mac_project", "b200mac_level_op", "b200mac_level_dims",
+           "b200eb_create", "b200eb_destroy", "b200eb_nlevels", "b200eb_set_geometry", "b200eb_set_eb_inflow_velocity", "b200eb_set_eb_flow",
+           "b200eb_project", "b200eb_apply_nodal_projection", "b200eb_build_stencils", "b200eb_level_stencil", "b200eb_level_op", "b200eb_level_dims",
+           "b200eb_compute_rhs"]
 
 _lib = None
 
@@ -146,5 +155,20 @@ def lib():
     L.b200mac_project.argtypes = [vp, dp, fb, dp, fb, dp, fb, dp, fb, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
     L.b200mac_level_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
     L.b200mac_level_dims.argtypes = [vp, C.c_int, ip]
+    L.b200eb_create.argtypes = [C.POINTER(vp), C.POINTER(Geom), C.POINTER(Opts), C.c_int]
+    L.b200eb_destroy.argtypes = [vp]
+    L.b200eb_destroy.restype = None
+    L.b200eb_nlevels.argtypes = [vp]
+    L.b200eb_set_geometry.argtypes = [vp, dp, fb, dp, fb]
+    L.b200eb_set_eb_inflow_velocity.argtypes = [vp, dp, fb, dp, fb, dp, fb]
+    L.b200eb_set_eb_flow.argtypes = [vp, C.POINTER(EBFlow), C.c_int, dp, fb, dp, fb, dp, fb, dp, fb]
+    L.b200eb_project.argtypes = [vp, dp, fb, dp, fb, C.c_double, dp, fb, dp, fb, C.c_double, C.c_double, C.POINTER(Stats)]
+    L.b200eb_apply_nodal_projection.argtypes = [vp, dp, fb, dp, dp, fb, C.c_double, dp, fb, dp, fb, dp, C.c_double,
+                                                C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
+    L.b200eb_build_stencils.argtypes = [vp, dp, fb, C.c_double]
+    L.b200eb_level_stencil.argtypes = [vp, C.c_int, dp]
+    L.b200eb_level_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    L.b200eb_level_dims.argtypes = [vp, C.c_int, ip, ip]
+    L.b200eb_compute_rhs.argtypes = [vp, dp, fb, dp]
     _lib = L
     return L

@@ -1,0 +1,1637 @@
+// b200eb.cu -- the EB (embedded boundary, cut cell) nodal projection behind the C ABI b200eb_* (include/b200np.h):
+// Hydro::NodalProjector over amrex::MLMG / MLNodeLaplacian built with an EBFArrayBoxFactory, as incflo drives it under
+// AMREX_USE_EB (src/projection/incflo_apply_nodal_projection.cpp:130-136 set_eb_*, :181-201 projector + setEBInflowVelocity,
+// :215-266 project / copy-out), BASELINE configs[4] (test_3d/benchmark.channel_cylinder-x).
+//
+// Discretisation (restated in oracle/eb_oracle.py, which tests/ compare this file with; derivation in its header):
+//   L(a, b) = - sum_cells sigma_c sum_d dxinv_d^2 int_{fluid part of c} d_d N_a d_d N_b     (Q1 stiffness over the fluid only;
+//             the integrals are combinations of the volume fraction and the 18 monomial integrals MLNodeLaplacian::buildIntegral
+//             stores -- mlndlap_set_connection / mlndlap_set_stencil_eb)
+//   rhs(a)  = - sum_cells u_c . int_fluid grad N_a  (+ sum_cells (u_eb . n)_c int_{EB face} N_a dA)            (mlndlap_divu_eb)
+//   u_c    -= sigma_c (1/V_c) int_fluid grad phi;  grad phi = that average; covered cells: 0                   (mlndlap_mknewu_eb)
+// Multigrid = AMReX's "RAP" strategy (what MLNodeLaplacian switches to with EB): every level is a symmetric 27-point stencil,
+// coarse levels are Galerkin products (1/8) P^T A P with trilinear P; smoother = Gauss-Seidel in 8 colours
+// (mlndlap_gscolor_sten), nodes with a zero diagonal (covered, Dirichlet) hold 0; MLMG V-cycle, BiCGStab bottom solve in one CTA.
+//
+// Layout: every nodal array of a level is stored COLOUR-MAJOR -- the 8 colours c = (i&1) + 2(j&1) + 4(k&1) one after the other, each a
+// dense (k/2, j/2, i/2) block -- so that a colour sweep reads its own 27 coefficients and writes its nodes with unit stride, and
+// the neighbours it reads (always other colours) are unit-stride runs of other blocks.  A row is stored completely (27 arrays per
+// level, t = (di+1) + 3(dj+1) + 9(dk+1)): 216 B of coefficients per node and sweep is the traffic that bounds the smoother.
+// One AMR level, one box, one GPU: the first correct path of this operator.
+#include "../../include/b200np.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+#define ECK(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            fprintf(stderr, "b200eb: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw int(B200NP_ERR_CUDA);                                                             \
+        }                                                                                           \
+    } while (0)
+
+struct EbLev {
+    int n[3], nn[3], per[3];
+    int dirlo[3], dirhi[3];   // Dirichlet faces: their nodes are masked
+    int nc[3][2];             // number of nodes of parity 0 / 1 per direction
+    long long cbase[9];       // start of colour c; cbase[8] = nnode
+    long long nnode;
+    double* st;               // 27 coefficient arrays, st + t * nnode; t = 13: diagonal
+    const unsigned char* flag;   // 1: the row of this node is the canonical row of an uncut neighbourhood with constant sigma (faces 0, edges
+    const double* canon;         // canon[0], corners canon[1], diagonal canon[2]): the kernels do not read its 27 coefficients.  All 0 with
+};                               // variable sigma.  canon lives in device memory: a captured V-cycle graph must see the current sigma.
+
+// caller array with its own box, component stride
+struct EFab {
+    double* p;
+    int lo[3];
+    int nx, ny;
+    long long cs;
+    __host__ __device__ __forceinline__ long long idx(int i, int j, int k) const
+    {
+        return (i - lo[0]) + (long long)nx * ((j - lo[1]) + (long long)ny * (k - lo[2]));
+    }
+};
+
+__device__ __forceinline__ long long nidx(const EbLev& L, int i, int j, int k)
+{
+    const int pi = i & 1, pj = j & 1, pk = k & 1;
+    return L.cbase[pi + 2 * pj + 4 * pk] + ((long long)(k >> 1) * L.nc[1][pj] + (j >> 1)) * L.nc[0][pi] + (i >> 1);
+}
+// colour-major position t -> node (i, j, k)
+__device__ __forceinline__ void ndecode(const EbLev& L, long long t, int& i, int& j, int& k)
+{
+    int c = 0;
+#pragma unroll
+    for (int q = 1; q < 8; ++q) c += (t >= L.cbase[q]) ? 1 : 0;
+    const long long l = t - L.cbase[c];
+    const int ncx = L.nc[0][c & 1], ncy = L.nc[1][(c >> 1) & 1];
+    i = 2 * (int)(l % ncx) + (c & 1);
+    j = 2 * (int)((l / ncx) % ncy) + ((c >> 1) & 1);
+    k = 2 * (int)(l / ((long long)ncx * ncy)) + (c >> 2);
+}
+// coordinates of q - 1, q, q + 1 per direction: periodic wrap; outside a non-periodic domain the coordinate is clamped (the
+// coefficient towards it is exactly zero by construction) and flagged
+struct Nb {
+    int c[3][3];
+    bool ok[3][3];
+};
+__device__ __forceinline__ void nb_coords(const EbLev& L, int i, int j, int k, Nb& q)
+{
+    const int p[3] = {i, j, k};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        q.c[d][1] = p[d]; q.ok[d][1] = true;
+        int lo = p[d] - 1, hi = p[d] + 1;
+        bool oklo = true, okhi = true;
+        if (lo < 0) { if (L.per[d]) lo = L.nn[d] - 1; else { lo = p[d]; oklo = false; } }
+        if (hi >= L.nn[d]) { if (L.per[d]) hi = 0; else { hi = p[d]; okhi = false; } }
+        q.c[d][0] = lo; q.ok[d][0] = oklo;
+        q.c[d][2] = hi; q.ok[d][2] = okhi;
+    }
+}
+__device__ __forceinline__ bool node_dirichlet(const EbLev& L, int i, int j, int k)
+{
+    const int p[3] = {i, j, k};
+    bool m = false;
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        if (!L.per[d]) m = m || (L.dirlo[d] && p[d] == 0) || (L.dirhi[d] && p[d] == L.nn[d] - 1);
+    return m;
+}
+
+__device__ __forceinline__ double canonical_entry(const EbLev& L, int tt)
+{
+    const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+    return nz == 0 ? L.canon[2] : nz == 1 ? 0.0 : nz == 2 ? L.canon[0] : L.canon[1];
+}
+
+template <bool MAXR>
+__device__ __forceinline__ double eb_block_reduce(double v, double* sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = MAXR ? fmax(v, w) : v + w;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        v = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = MAXR ? fmax(v, w) : v + w;
+        }
+        if (lane == 0) sh[32] = v;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// ---- cut-cell integrals --------------------------------------------------------------------------------------------------
+// geo: 19 cell arrays (natural cell order): 0 = volume fraction, 1 + m = the m-th monomial integral (amrex i_S_* order:
+// x y z x2 y2 z2 xy xz yz x2y x2z xy2 y2z xz2 yz2 x2y2 x2z2 y2z2)
+__device__ __forceinline__ int mom_index(int px, int py, int pz)
+{
+    // -1: the volume itself
+    constexpr int T[3][3][3] = {   // [px][py][pz]
+        {{-1, 2, 5}, {1, 8, 14}, {4, 12, 17}},
+        {{0, 7, 13}, {6, -2, -2}, {11, -2, -2}},
+        {{3, 10, 16}, {9, -2, -2}, {15, -2, -2}}};
+    return T[px][py][pz];
+}
+// M[d][p][q] = int x_e^p x_f^q over the fluid part, (e, f) = the two directions other than d
+__device__ __forceinline__ void load_moments(const double* __restrict__ geo, long long ncell, long long c, double M[3][3][3])
+{
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int px = d == 0 ? 0 : p, py = d == 0 ? p : (d == 1 ? 0 : q), pz = d == 2 ? 0 : q;
+                const int m = mom_index(px, py, pz);
+                M[d][p][q] = geo[(long long)(m + 1) * ncell + c];
+            }
+}
+// int_F d_d N_a,  N_a = prod (1/2 + s x)
+__device__ __forceinline__ double grad_integral(const double M[3][3][3], int d, int a)
+{
+    const int e = d == 0 ? 1 : 0, f = d == 2 ? 1 : 2;
+    const double sd = ((a >> d) & 1) ? 1.0 : -1.0, se = ((a >> e) & 1) ? 1.0 : -1.0, sf = ((a >> f) & 1) ? 1.0 : -1.0;
+    return sd * (0.25 * M[d][0][0] + 0.5 * se * M[d][1][0] + 0.5 * sf * M[d][0][1] + se * sf * M[d][1][1]);
+}
+// - sum_d dxinv_d^2 int_F d_d N_a d_d N_b
+__device__ __forceinline__ double stiff_entry(const double M[3][3][3], const double dh[3], int a, int b)
+{
+    double tot = 0.0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int e = d == 0 ? 1 : 0, f = d == 2 ? 1 : 2;
+        const double sad = ((a >> d) & 1) ? 1.0 : -1.0, sbd = ((b >> d) & 1) ? 1.0 : -1.0;
+        const double sae = ((a >> e) & 1) ? 1.0 : -1.0, sbe = ((b >> e) & 1) ? 1.0 : -1.0;
+        const double saf = ((a >> f) & 1) ? 1.0 : -1.0, sbf = ((b >> f) & 1) ? 1.0 : -1.0;
+        const double ce[3] = {0.25, 0.5 * (sae + sbe), sae * sbe};
+        const double cf[3] = {0.25, 0.5 * (saf + sbf), saf * sbf};
+        double acc = 0.0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) acc += ce[p] * cf[q] * M[d][p][q];
+        tot += dh[d] * sad * sbd * acc;
+    }
+    return -tot;
+}
+
+// ---- set-up kernels ---------------------------------------------------------------------------------------------------------
+// caller's vfrac / intg arrays (own boxes) -> geo
+__global__ void __launch_bounds__(256) k_eb_copy_geo(int nx, int ny, int nz, EFab vf, EFab ig, double* __restrict__ geo)
+{
+    const long long N = (long long)nx * ny * nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx), j = (int)((t / nx) % ny), k = (int)(t / ((long long)nx * ny));
+        geo[t] = vf.p[vf.idx(i, j, k)];
+        const long long q = ig.idx(i, j, k);
+#pragma unroll
+        for (int m = 0; m < 18; ++m) geo[(long long)(m + 1) * N + t] = ig.p[m * ig.cs + q];
+    }
+}
+// optional EB-inflow data: vn = u_eb . n and the 8 surface integrals (B_1 B_x B_y B_z B_xy B_xz B_yz B_xyz) -> ebf (9 cell arrays)
+__global__ void __launch_bounds__(256) k_eb_copy_flow(int nx, int ny, int nz, EFab ev, EFab bn, EFab bi, double* __restrict__ ebf)
+{
+    const long long N = (long long)nx * ny * nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx), j = (int)((t / nx) % ny), k = (int)(t / ((long long)nx * ny));
+        const long long qe = ev.idx(i, j, k), qn = bn.idx(i, j, k), qb = bi.idx(i, j, k);
+        ebf[t] = ev.p[qe] * bn.p[qn] + ev.p[ev.cs + qe] * bn.p[bn.cs + qn] + ev.p[2 * ev.cs + qe] * bn.p[2 * bn.cs + qn];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) ebf[(long long)(m + 1) * N + t] = bi.p[m * bi.cs + qb];
+    }
+}
+// sigma: caller array or constant -> dense cell array
+__global__ void __launch_bounds__(256) k_eb_copy_sigma(int nx, int ny, int nz, EFab sg, double cs, double* __restrict__ out)
+{
+    const long long N = (long long)nx * ny * nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx), j = (int)((t / nx) % ny), k = (int)(t / ((long long)nx * ny));
+        out[t] = sg.p ? sg.p[sg.idx(i, j, k)] : cs;
+    }
+}
+
+// level-0 stencil: the complete row of every node from sigma and the cut-cell integrals of its (up to) 8 cells
+__global__ void __launch_bounds__(128) k_eb_stencil0(const EbLev L, const double* __restrict__ geo, const double* __restrict__ sigma,
+                                                     double dhx, double dhy, double dhz)
+{
+    const long long ncell = (long long)L.n[0] * L.n[1] * L.n[2];
+    const double dh[3] = {dhx, dhy, dhz};
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
+        int i, j, k;
+        ndecode(L, t, i, j, k);
+        if (L.flag[t]) {
+#pragma unroll
+            for (int tt = 0; tt < 27; ++tt) L.st[(long long)tt * L.nnode + t] = canonical_entry(L, tt);
+            continue;
+        }
+        double row[27];
+#pragma unroll
+        for (int q = 0; q < 27; ++q) row[q] = 0.0;
+        const int p[3] = {i, j, k};
+        if (!node_dirichlet(L, i, j, k)) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {   // the node is corner a of cell c = node - a
+                int c[3];
+                bool ok = true;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    c[d] = p[d] - ((a >> d) & 1);
+                    if (c[d] < 0) { if (L.per[d]) c[d] = L.n[d] - 1; else ok = false; }
+                    if (c[d] >= L.n[d]) ok = false;   // only a non-periodic top node (periodic nodes end at n - 1)
+                }
+                if (!ok) continue;
+                const long long cc = ((long long)c[2] * L.n[1] + c[1]) * L.n[0] + c[0];
+                if (geo[cc] == 0.0) continue;   // covered cell
+                double M[3][3][3];
+                load_moments(geo, ncell, cc, M);
+                const double sg = sigma[cc];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const int tt = (((b & 1) - (a & 1)) + 1) + 3 * ((((b >> 1) & 1) - ((a >> 1) & 1)) + 1) + 9 * (((b >> 2) - (a >> 2)) + 1);
+                    row[tt] += sg * stiff_entry(M, dh, a, b);
+                }
+            }
+            Nb q;
+            nb_coords(L, i, j, k, q);
+#pragma unroll
+            for (int tt = 0; tt < 27; ++tt) {
+                const int di = tt % 3, dj = (tt / 3) % 3, dk = tt / 9;
+                if (tt == 13) continue;
+                if (!(q.ok[0][di] && q.ok[1][dj] && q.ok[2][dk]) || node_dirichlet(L, q.c[0][di], q.c[1][dj], q.c[2][dk])) row[tt] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) L.st[(long long)tt * L.nnode + t] = row[tt];
+    }
+}
+
+// level 0: a node has the canonical row iff its 8 cells exist and are uncut and neither it nor a neighbour is a Dirichlet node
+__global__ void __launch_bounds__(256) k_eb_flag0(const EbLev L, const double* __restrict__ geo, unsigned char* __restrict__ flag)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
+        int i, j, k;
+        ndecode(L, t, i, j, k);
+        const int p[3] = {i, j, k};
+        bool reg = true;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            int c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                c[d] = p[d] - ((a >> d) & 1);
+                if (c[d] < 0) { if (L.per[d]) c[d] = L.n[d] - 1; else reg = false; }
+                if (c[d] >= L.n[d]) reg = false;
+            }
+            if (reg) reg = geo[((long long)c[2] * L.n[1] + c[1]) * L.n[0] + c[0]] == 1.0;
+        }
+        if (reg) {
+            Nb q;
+            nb_coords(L, i, j, k, q);
+#pragma unroll
+            for (int tt = 0; tt < 27; ++tt) reg = reg && !node_dirichlet(L, q.c[0][tt % 3], q.c[1][(tt / 3) % 3], q.c[2][tt / 9]);
+        }
+        flag[t] = reg ? 1 : 0;
+    }
+}
+// coarser level: canonical iff the 27 fine nodes under it are, and no neighbour is a Dirichlet node
+__global__ void __launch_bounds__(256) k_eb_flag_coarse(const EbLev C, const EbLev F, unsigned char* __restrict__ flag)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < C.nnode; t += (long long)gridDim.x * blockDim.x) {
+        int I, J, K;
+        ndecode(C, t, I, J, K);
+        Nb q;
+        nb_coords(F, 2 * I, 2 * J, 2 * K, q);
+        bool reg = true;
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) {
+            const int di = tt % 3, dj = (tt / 3) % 3, dk = tt / 9;
+            reg = reg && q.ok[0][di] && q.ok[1][dj] && q.ok[2][dk] && F.flag[nidx(F, q.c[0][di], q.c[1][dj], q.c[2][dk])];
+        }
+        if (reg) {
+            Nb qc;
+            nb_coords(C, I, J, K, qc);
+#pragma unroll
+            for (int tt = 0; tt < 27; ++tt) {
+                const int di = tt % 3, dj = (tt / 3) % 3, dk = tt / 9;
+                reg = reg && qc.ok[0][di] && qc.ok[1][dj] && qc.ok[2][dk] && !node_dirichlet(C, qc.c[0][di], qc.c[1][dj], qc.c[2][dk]);
+            }
+        }
+        flag[t] = reg ? 1 : 0;
+    }
+}
+// canonical row of every level for a constant sigma: level l has cell size h 2^l
+__global__ void k_eb_set_canon(double* canon, int nlev, double sigma, double hinv2)
+{
+    const int l = threadIdx.x;
+    if (l >= nlev) return;
+    double s = sigma * hinv2;
+    for (int q = 0; q < l; ++q) s *= 0.25;
+    canon[3 * l + 0] = s / 6.0;
+    canon[3 * l + 1] = s / 12.0;
+    canon[3 * l + 2] = -8.0 * s / 3.0;
+}
+
+__device__ __forceinline__ double w1(int t) { return t == 0 ? 1.0 : 0.5; }
+
+// Galerkin coarse operator: A_c(I, I + D) = (1/8) sum_{a, o} w(a) A_f(2I + a, 2I + a + o) w(a + o - 2D), complete rows
+__global__ void __launch_bounds__(128) k_eb_rap(const EbLev C, const EbLev F)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < C.nnode; t += (long long)gridDim.x * blockDim.x) {
+        if (C.flag[t]) {
+            for (int tt = 0; tt < 27; ++tt) C.st[(long long)tt * C.nnode + t] = canonical_entry(C, tt);
+            continue;
+        }
+        int I, J, K;
+        ndecode(C, t, I, J, K);
+        double acc[27];
+#pragma unroll
+        for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+        const bool masked = node_dirichlet(C, I, J, K);
+        if (!masked) {
+            for (int az = -1; az <= 1; ++az)
+                for (int ay = -1; ay <= 1; ++ay)
+                    for (int ax = -1; ax <= 1; ++ax) {
+                        int f[3] = {2 * I + ax, 2 * J + ay, 2 * K + az};
+                        bool ok = true;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            if (f[d] < 0) { if (F.per[d]) f[d] += F.nn[d]; else ok = false; }
+                            if (f[d] >= F.nn[d]) { if (F.per[d]) f[d] -= F.nn[d]; else ok = false; }
+                        }
+                        if (!ok) continue;
+                        const long long pf = nidx(F, f[0], f[1], f[2]);
+                        const double wa = 0.125 * w1(ax) * w1(ay) * w1(az);
+                        for (int o = 0; o < 27; ++o) {
+                            const double A = F.st[(long long)o * F.nnode + pf];
+                            if (A == 0.0) continue;
+                            const int gx = ax + o % 3 - 1, gy = ay + (o / 3) % 3 - 1, gz = az + o / 9 - 1;   // g - 2I
+                            // coarse targets D with |g - 2D| <= 1: g even -> D = g / 2 (weight 1), g odd -> (g - 1) / 2 and (g + 1) / 2 (weight 1/2)
+                            const int x0 = (gx - 1 + 4) / 2 - 2 + ((gx & 1) ? 0 : 1), nxo = (gx & 1) ? 2 : 1;
+                            const int y0 = (gy - 1 + 4) / 2 - 2 + ((gy & 1) ? 0 : 1), nyo = (gy & 1) ? 2 : 1;
+                            const int z0 = (gz - 1 + 4) / 2 - 2 + ((gz & 1) ? 0 : 1), nzo = (gz & 1) ? 2 : 1;
+                            const double wo = wa * A * ((gx & 1) ? 0.5 : 1.0) * ((gy & 1) ? 0.5 : 1.0) * ((gz & 1) ? 0.5 : 1.0);
+                            for (int dz = 0; dz < nzo; ++dz)
+                                for (int dy = 0; dy < nyo; ++dy)
+                                    for (int dx = 0; dx < nxo; ++dx) acc[(x0 + dx + 1) + 3 * (y0 + dy + 1) + 9 * (z0 + dz + 1)] += wo;
+                        }
+                    }
+            Nb q;
+            nb_coords(C, I, J, K, q);
+            for (int tt = 0; tt < 27; ++tt) {
+                const int di = tt % 3, dj = (tt / 3) % 3, dk = tt / 9;
+                if (tt == 13) continue;
+                if (!(q.ok[0][di] && q.ok[1][dj] && q.ok[2][dk]) || node_dirichlet(C, q.c[0][di], q.c[1][dj], q.c[2][dk])) acc[tt] = 0.0;
+            }
+        }
+        for (int tt = 0; tt < 27; ++tt) C.st[(long long)tt * C.nnode + t] = acc[tt];
+    }
+}
+
+// ---- multigrid kernels ------------------------------------------------------------------------------------------------------
+// sum over the 26 neighbours of A(p, q) x(q)
+__device__ __forceinline__ double offdiag_sum(const EbLev& L, long long p, int i, int j, int k, const double* x)
+{
+    Nb q;
+    nb_coords(L, i, j, k, q);
+    double ax = 0.0;
+#pragma unroll
+    for (int dk = 0; dk < 3; ++dk)
+#pragma unroll
+        for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+            for (int di = 0; di < 3; ++di) {
+                const int tt = di + 3 * dj + 9 * dk;
+                if (tt == 13) continue;
+                ax += __ldg(L.st + (long long)tt * L.nnode + p) * x[nidx(L, q.c[0][di], q.c[1][dj], q.c[2][dk])];
+            }
+    return ax;
+}
+
+// the same sum for a node with the canonical row: 12 edge and 8 corner neighbours, no coefficient loads
+__device__ __forceinline__ double offdiag_sum_regular(const EbLev& L, int i, int j, int k, const double* x)
+{
+    Nb q;
+    nb_coords(L, i, j, k, q);
+    double se = 0.0, sc = 0.0;
+#pragma unroll
+    for (int dk = 0; dk < 3; ++dk)
+#pragma unroll
+        for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+            for (int di = 0; di < 3; ++di) {
+                const int nz = (di != 1) + (dj != 1) + (dk != 1);
+                if (nz < 2) continue;
+                const double v = x[nidx(L, q.c[0][di], q.c[1][dj], q.c[2][dk])];
+                if (nz == 2) se += v; else sc += v;
+            }
+    return L.canon[0] * se + L.canon[1] * sc;
+}
+
+// one colour of a Gauss-Seidel sweep (mlndlap_gscolor_sten).  old == x except on levels where a periodic wrap joins two nodes of
+// one colour (odd periodic extent): there old is a snapshot taken before the launch.
+__global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const double* old, const double* __restrict__ rhs, int color)
+{
+    const long long base = L.cbase[color], cnt = L.cbase[color + 1] - base;
+    const int ncx = L.nc[0][color & 1], ncy = L.nc[1][(color >> 1) & 1];
+    for (long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x; l < cnt; l += (long long)gridDim.x * blockDim.x) {
+        const long long p = base + l;
+        const int i = 2 * (int)(l % ncx) + (color & 1), j = 2 * (int)((l / ncx) % ncy) + ((color >> 1) & 1), k = 2 * (int)(l / ((long long)ncx * ncy)) + (color >> 2);
+        if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular(L, i, j, k, old)) / L.canon[2]; continue; }
+        const double d = __ldg(L.st + 13 * L.nnode + p);
+        if (d == 0.0) { x[p] = 0.0; continue; }
+        x[p] = (rhs[p] - offdiag_sum(L, p, i, j, k, old)) / d;
+    }
+}
+// all sweeps of a smooth call on a level small enough for ONE CTA: colours separated by __syncthreads instead of kernel boundaries
+// (a level of a few thousand nodes is pure launch latency otherwise: 8 launches per sweep).  snap != nullptr: odd periodic extent.
+__global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, double* snap, const double* __restrict__ rhs, int nsweeps)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int s = 0; s < nsweeps; ++s)
+        for (int c = 0; c < 8; ++c) {
+            const double* old = x;
+            if (snap) {
+                for (int t = tid; t < (int)L.nnode; t += nt) snap[t] = x[t];
+                __syncthreads();
+                old = snap;
+            }
+            const int lo = (int)L.cbase[c], hi = (int)L.cbase[c + 1];
+            for (int p = lo + tid; p < hi; p += nt) {
+                int i, j, k;
+                ndecode(L, p, i, j, k);
+                if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular(L, i, j, k, old)) / L.canon[2]; continue; }
+                const double d = L.st[13 * L.nnode + p];
+                x[p] = d == 0.0 ? 0.0 : (rhs[p] - offdiag_sum(L, p, i, j, k, old)) / d;
+            }
+            __syncthreads();
+        }
+}
+// out = rhs - A x on the active nodes, 0 elsewhere; optional inf-norm partials
+__global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double* __restrict__ x, const double* __restrict__ rhs, double* __restrict__ out,
+                                                     double* __restrict__ norm_partial)
+{
+    __shared__ double sh[34];
+    double amax = 0.0;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < L.nnode; p += (long long)gridDim.x * blockDim.x) {
+        double r = 0.0;
+        if (L.flag[p]) {
+            int i, j, k;
+            ndecode(L, p, i, j, k);
+            r = rhs[p] - (L.canon[2] * x[p] + offdiag_sum_regular(L, i, j, k, x));
+        } else {
+            const double d = __ldg(L.st + 13 * L.nnode + p);
+            if (d != 0.0) {
+                int i, j, k;
+                ndecode(L, p, i, j, k);
+                r = rhs[p] - (d * x[p] + offdiag_sum(L, p, i, j, k, x));
+            }
+        }
+        if (out) out[p] = r;
+        amax = fmax(amax, fabs(r));
+    }
+    if (norm_partial) {
+        amax = eb_block_reduce<true>(amax, sh);
+        if (threadIdx.x == 0) norm_partial[blockIdx.x] = amax;
+    }
+}
+// crse = (1/8) sum_a w(a) fine(2I + a): full weighting = P^T / 8; 0 on inactive coarse nodes
+__global__ void __launch_bounds__(256) k_eb_restrict(const EbLev C, const EbLev F, const double* __restrict__ fine, double* __restrict__ crse)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < C.nnode; t += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        if (C.st[13 * C.nnode + t] != 0.0) {
+            int I, J, K;
+            ndecode(C, t, I, J, K);
+            Nb q;
+            nb_coords(F, 2 * I, 2 * J, 2 * K, q);
+#pragma unroll
+            for (int dk = 0; dk < 3; ++dk)
+#pragma unroll
+                for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+                    for (int di = 0; di < 3; ++di) {
+                        if (!(q.ok[0][di] && q.ok[1][dj] && q.ok[2][dk])) continue;
+                        s += w1(di - 1) * w1(dj - 1) * w1(dk - 1) * fine[nidx(F, q.c[0][di], q.c[1][dj], q.c[2][dk])];
+                    }
+            s *= 0.125;
+        }
+        crse[t] = s;
+    }
+}
+// fine += P crse (trilinear) on the active fine nodes
+__global__ void __launch_bounds__(256) k_eb_interp_add(const EbLev F, const EbLev C, double* __restrict__ fine, const double* __restrict__ crse)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < F.nnode; t += (long long)gridDim.x * blockDim.x) {
+        if (F.st[13 * F.nnode + t] == 0.0) continue;
+        int i, j, k;
+        ndecode(F, t, i, j, k);
+        const int p[3] = {i, j, k};
+        int lo[3], hi[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            lo[d] = p[d] >> 1;
+            hi[d] = (p[d] + 1) >> 1;
+            if (hi[d] >= C.nn[d]) hi[d] = C.per[d] ? 0 : lo[d];
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            s += crse[nidx(C, (c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2])];
+        fine[t] += 0.125 * s;
+    }
+}
+
+// sums over the active nodes (solvability offset): partial[b] = sum, partial[nb + b] = count
+__global__ void __launch_bounds__(256) k_eb_sum_active(const EbLev L, const double* __restrict__ x, double* __restrict__ partial)
+{
+    __shared__ double sh[34];
+    double s = 0.0, c = 0.0;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < L.nnode; p += (long long)gridDim.x * blockDim.x)
+        if (L.st[13 * L.nnode + p] != 0.0) { s += x[p]; c += 1.0; }
+    s = eb_block_reduce<false>(s, sh);
+    c = eb_block_reduce<false>(c, sh);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = s; partial[gridDim.x + blockIdx.x] = c; }
+}
+__global__ void __launch_bounds__(1024) k_eb_mean_final(const double* __restrict__ partial, int nb_, double* __restrict__ out)
+{
+    __shared__ double sh[34];
+    double s = 0.0, c = 0.0;
+    for (int t = threadIdx.x; t < nb_; t += blockDim.x) { s += partial[t]; c += partial[nb_ + t]; }
+    s = eb_block_reduce<false>(s, sh);
+    c = eb_block_reduce<false>(c, sh);
+    if (threadIdx.x == 0) out[0] = c > 0.0 ? s / c : 0.0;
+}
+// x = active ? x - mean : 0, optional inf-norm partials of the result
+__global__ void __launch_bounds__(256) k_eb_sub_active(const EbLev L, double* __restrict__ x, const double* __restrict__ mean, double* __restrict__ norm_partial)
+{
+    __shared__ double sh[34];
+    const double m = mean ? mean[0] : 0.0;
+    double amax = 0.0;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < L.nnode; p += (long long)gridDim.x * blockDim.x) {
+        const double v = L.st[13 * L.nnode + p] != 0.0 ? x[p] - m : 0.0;
+        x[p] = v;
+        amax = fmax(amax, fabs(v));
+    }
+    if (norm_partial) {
+        amax = eb_block_reduce<true>(amax, sh);
+        if (threadIdx.x == 0) norm_partial[blockIdx.x] = amax;
+    }
+}
+__global__ void __launch_bounds__(1024) k_eb_max_final(const double* __restrict__ partial, int nb_, double* __restrict__ out)
+{
+    __shared__ double sh[34];
+    double a = 0.0;
+    for (int t = threadIdx.x; t < nb_; t += blockDim.x) a = fmax(a, partial[t]);
+    a = eb_block_reduce<true>(a, sh);
+    if (threadIdx.x == 0) out[0] = a;
+}
+__global__ void __launch_bounds__(256) k_eb_axpy(double* __restrict__ y, const double* __restrict__ x, long long n)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) y[t] += x[t];
+}
+
+// Bottom solve in ONE CTA: MLCGSolver::solve_bicgstab (x0 = 0, plain dot products, reductions in a fixed order), solvability offset
+// over the active nodes first when the operator is singular; on failure 8 smooth calls (MLMG::bottomSolve).
+// work: 7 vectors of N doubles.  info[0] += iterations, info[1] = return code.
+__global__ void __launch_bounds__(1024) k_eb_bottom(const EbLev L, double* __restrict__ x, double* __restrict__ b, double* __restrict__ work, int maxiter,
+                                                    double eps_rel, double eps_abs, int singular, int nsweeps, int* __restrict__ info)
+{
+    __shared__ double sh[34];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int N = (int)L.nnode;
+    double *r = work, *rh = work + N, *pp = work + 2 * (long long)N, *v = work + 3 * (long long)N, *s = work + 4 * (long long)N, *tt = work + 5 * (long long)N,
+           *snap = work + 6 * (long long)N;
+    const double* dg = L.st + 13 * L.nnode;
+    auto apply = [&](const double* in, double* out) {
+        __syncthreads();
+        for (int t = tid; t < N; t += nt) {
+            double y = 0.0;
+            if (dg[t] != 0.0) { int i, j, k; ndecode(L, t, i, j, k); y = dg[t] * in[t] + offdiag_sum(L, t, i, j, k, in); }
+            out[t] = y;
+        }
+        __syncthreads();
+    };
+    auto dot = [&](const double* a, const double* c) { double q = 0.0; for (int t = tid; t < N; t += nt) q += a[t] * c[t]; return eb_block_reduce<false>(q, sh); };
+    auto ninf = [&](const double* a) { double q = 0.0; for (int t = tid; t < N; t += nt) q = fmax(q, fabs(a[t])); return eb_block_reduce<true>(q, sh); };
+    {
+        double q = 0.0, c = 0.0;
+        if (singular) {
+            for (int t = tid; t < N; t += nt) if (dg[t] != 0.0) { q += b[t]; c += 1.0; }
+            q = eb_block_reduce<false>(q, sh);
+            c = eb_block_reduce<false>(c, sh);
+        }
+        const double mean = c > 0.0 ? q / c : 0.0;
+        for (int t = tid; t < N; t += nt) b[t] = dg[t] != 0.0 ? b[t] - mean : 0.0;
+        __syncthreads();
+    }
+    for (int t = tid; t < N; t += nt) { r[t] = b[t]; rh[t] = b[t]; x[t] = 0.0; }
+    __syncthreads();
+    double rnorm = ninf(r);
+    const double rnorm0 = rnorm;
+    int ret = 0, it = 0;
+    if (!(rnorm0 == 0.0 || rnorm0 < eps_abs)) {
+        double rho_1 = 0.0, alpha = 0.0, omega = 0.0;
+        for (it = 1; it <= maxiter; ++it) {
+            const double rho = dot(rh, r);
+            if (rho == 0.0) { ret = 1; break; }
+            if (it == 1) { for (int t = tid; t < N; t += nt) pp[t] = r[t]; }
+            else {
+                const double beta = (rho / rho_1) * (alpha / omega);
+                for (int t = tid; t < N; t += nt) pp[t] = r[t] + beta * (pp[t] - omega * v[t]);
+            }
+            apply(pp, v);
+            const double rhTv = dot(rh, v);
+            if (rhTv == 0.0) { ret = 2; break; }
+            alpha = rho / rhTv;
+            for (int t = tid; t < N; t += nt) { x[t] += alpha * pp[t]; s[t] = r[t] - alpha * v[t]; }
+            __syncthreads();
+            rnorm = ninf(s);
+            if (rnorm < eps_rel * rnorm0 || rnorm < eps_abs) break;
+            apply(s, tt);
+            const double t2 = dot(tt, tt);
+            if (t2 == 0.0) { ret = 3; break; }
+            omega = dot(tt, s) / t2;
+            for (int t = tid; t < N; t += nt) { x[t] += omega * s[t]; r[t] = s[t] - omega * tt[t]; }
+            __syncthreads();
+            rnorm = ninf(r);
+            if (rnorm < eps_rel * rnorm0 || rnorm < eps_abs) break;
+            if (omega == 0.0) { ret = 4; break; }
+            rho_1 = rho;
+        }
+        if (ret == 0 && !(rnorm < eps_rel * rnorm0 || rnorm < eps_abs)) ret = 8;
+        if (it > maxiter) it = maxiter;
+    }
+    __syncthreads();
+    if (ret != 0) {   // start over with 8 smooth calls; every colour reads a snapshot (one CTA: cheap and always safe)
+        for (int t = tid; t < N; t += nt) x[t] = 0.0;
+        __syncthreads();
+        for (int call = 0; call < 8 * nsweeps; ++call)
+            for (int c = 0; c < 8; ++c) {
+                for (int t = tid; t < N; t += nt) snap[t] = x[t];
+                __syncthreads();
+                const int lo = (int)L.cbase[c], hi = (int)L.cbase[c + 1];
+                for (int t = lo + tid; t < hi; t += nt) {
+                    if (dg[t] == 0.0) { x[t] = 0.0; continue; }
+                    int i, j, k;
+                    ndecode(L, t, i, j, k);
+                    x[t] = (b[t] - offdiag_sum(L, t, i, j, k, snap)) / dg[t];
+                }
+                __syncthreads();
+            }
+    }
+    if (tid == 0) { atomicAdd(info, it); info[1] = ret; }
+}
+
+// ---- right-hand side, update, copies ------------------------------------------------------------------------------------------
+// rhs = D u: natural finite-element rows.  Cells beyond ONE non-periodic face contribute the normal velocity of the first ghost layer
+// (0 at walls, the inflow value at inflow faces) with the geometry of the adjacent interior cell; cells beyond two or three faces
+// nothing.  ebf != nullptr: + EB inflow, dxinv * (u_eb . n) * int_{EB face} N_a dA.
+__global__ void __launch_bounds__(128) k_eb_divu(const EbLev L, const double* __restrict__ geo, EFab vel, const double* __restrict__ ebf, double dxi, double dyi,
+                                                 double dzi, double* __restrict__ rhs)
+{
+    const long long ncell = (long long)L.n[0] * L.n[1] * L.n[2];
+    const double dxinv[3] = {dxi, dyi, dzi};
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
+        double r = 0.0;
+        if (L.flag[t]) {   // 8 uncut cells, none of them a ghost cell: int_F d_d N_a = s_d / 4
+            int i, j, k;
+            ndecode(L, t, i, j, k);
+            const int p[3] = {i, j, k};
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                int g[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { g[d] = p[d] - ((a >> d) & 1); if (g[d] < 0) g[d] = L.n[d] - 1; }
+                const long long qv = vel.idx(g[0], g[1], g[2]);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) r -= dxinv[d] * vel.p[d * vel.cs + qv] * (((a >> d) & 1) ? 0.25 : -0.25);
+            }
+        } else if (L.st[13 * L.nnode + t] != 0.0) {
+            int i, j, k;
+            ndecode(L, t, i, j, k);
+            const int p[3] = {i, j, k};
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                int c[3], g[3];      // cell used for the geometry, cell used for the velocity
+                int nout = 0, dout = 0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    c[d] = g[d] = p[d] - ((a >> d) & 1);
+                    if (c[d] < 0) { if (L.per[d]) c[d] = g[d] = L.n[d] - 1; else { c[d] = 0; ++nout; dout = d; } }
+                    else if (c[d] >= L.n[d]) { c[d] = L.n[d] - 1; ++nout; dout = d; }   // non-periodic top node only
+                }
+                if (nout >= 2) continue;
+                const long long cc = ((long long)c[2] * L.n[1] + c[1]) * L.n[0] + c[0];
+                if (geo[cc] == 0.0) continue;
+                double M[3][3][3];
+                load_moments(geo, ncell, cc, M);
+                const long long qv = vel.idx(g[0], g[1], g[2]);
+                if (nout == 1) {
+                    r -= dxinv[dout] * vel.p[dout * vel.cs + qv] * grad_integral(M, dout, a);
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) r -= dxinv[d] * vel.p[d * vel.cs + qv] * grad_integral(M, d, a);
+                    if (ebf) {
+                        const double vn = ebf[cc];
+                        if (vn != 0.0) {
+                            const double sx = (a & 1) ? 1.0 : -1.0, sy = (a & 2) ? 1.0 : -1.0, sz = (a & 4) ? 1.0 : -1.0;
+                            const double* B = ebf + ncell + cc;
+                            const double bn = 0.125 * B[0] + 0.25 * (sx * B[ncell] + sy * B[2 * ncell] + sz * B[3 * ncell]) +
+                                              0.5 * (sx * sy * B[4 * ncell] + sx * sz * B[5 * ncell] + sy * sz * B[6 * ncell]) + sx * sy * sz * B[7 * ncell];
+                            r += dxinv[0] * vn * bn;
+                        }
+                    }
+                }
+            }
+        }
+        rhs[t] = r;
+    }
+}
+// u -= sigma * (1/V) int_F grad phi; gphi = that average (optionally accumulated); covered cells: u = 0, gphi = 0.
+// velo: add velocity_o back afterwards (ApplyNodalProjection :85-91).
+__global__ void __launch_bounds__(256) k_eb_mknewu(const EbLev L, const double* __restrict__ geo, const double* __restrict__ sigma, const double* __restrict__ phi,
+                                                   EFab vel, EFab velo, EFab gphi, int acc_g, double dxi, double dyi, double dzi)
+{
+    const long long ncell = (long long)L.n[0] * L.n[1] * L.n[2];
+    const double dxinv[3] = {dxi, dyi, dzi};
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ncell; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % L.n[0]), j = (int)((t / L.n[0]) % L.n[1]), k = (int)(t / ((long long)L.n[0] * L.n[1]));
+        const double V = geo[t];
+        double g[3] = {0.0, 0.0, 0.0};
+        if (V != 0.0) {
+            double M[3][3][3];
+            if (V != 1.0) load_moments(geo, ncell, t, M);   // an uncut cell has the integrals of the cube: int_F d_d N_a = s_d / 4
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                int q[3] = {i + (a & 1), j + ((a >> 1) & 1), k + (a >> 2)};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) if (q[d] >= L.nn[d]) q[d] = 0;   // periodic wrap
+                const double pa = phi[nidx(L, q[0], q[1], q[2])];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) g[d] += pa * (V != 1.0 ? grad_integral(M, d, a) : (((a >> d) & 1) ? 0.25 : -0.25));
+            }
+            const double vinv = 1.0 / V;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) g[d] *= dxinv[d] * vinv;
+        }
+        const long long qv = vel.idx(i, j, k);
+        const double sg = sigma[t];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double u = V != 0.0 ? vel.p[d * vel.cs + qv] - sg * g[d] : 0.0;
+            if (velo.p) u += velo.p[d * velo.cs + velo.idx(i, j, k)];
+            vel.p[d * vel.cs + qv] = u;
+        }
+        if (gphi.p) {
+            const long long qg = gphi.idx(i, j, k);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (acc_g) gphi.p[d * gphi.cs + qg] += g[d]; else gphi.p[d * gphi.cs + qg] = g[d];
+            }
+        }
+    }
+}
+// colour-major node array <-> the caller's nodal fab (natural order): to_fab = 1: fab (=|+=) x; 0: x = fab
+__global__ void __launch_bounds__(256) k_eb_copy_nodes(const EbLev L, double* __restrict__ x, EFab f, int to_fab, int accumulate)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
+        int i, j, k;
+        ndecode(L, t, i, j, k);
+        const long long q = f.idx(i, j, k);
+        if (!to_fab) x[t] = f.p[q];
+        else if (accumulate) f.p[q] += x[t];
+        else f.p[q] = x[t];
+    }
+}
+// a periodic nodal fab of the caller also holds the duplicate node n (= node 0): fill it after the copy-out
+__global__ void __launch_bounds__(256) k_eb_fill_dup(const EbLev L, const double* __restrict__ x, EFab f, int hx, int hy, int hz, int accumulate)
+{
+    const long long N = (long long)(hx + 1) * (hy + 1) * (hz + 1);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % (hx + 1)), j = (int)((t / (hx + 1)) % (hy + 1)), k = (int)(t / ((long long)(hx + 1) * (hy + 1)));
+        if (i < L.nn[0] && j < L.nn[1] && k < L.nn[2]) continue;
+        const double v = x[nidx(L, i % L.nn[0], j % L.nn[1], k % L.nn[2])];
+        const long long q = f.idx(i, j, k);
+        if (accumulate) f.p[q] += v; else f.p[q] = v;
+    }
+}
+// the 13 forward entries + the diagonal of a level in natural node order (test hook)
+__global__ void __launch_bounds__(256) k_eb_export_stencil(const EbLev L, double* __restrict__ out)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
+        int i, j, k;
+        ndecode(L, t, i, j, k);
+        const long long q = ((long long)k * L.nn[1] + j) * L.nn[0] + i;
+        for (int m = 0; m < 13; ++m) out[(long long)m * L.nnode + q] = L.st[(long long)(14 + m) * L.nnode + t];
+        out[13 * L.nnode + q] = L.st[13 * L.nnode + t];
+    }
+}
+
+// ---- incflo-level kernels (ApplyNodalProjection around the projector) --------------------------------------------------------
+// :53-59 u += s * gp / rho (unless incremental); :68 u -= u_old (incremental || proj_for_small_dt); sigma = s / rho (:115-118)
+__global__ void __launch_bounds__(256) k_eb_pre_add_sigma(int nx, int ny, int nz, EFab vel, EFab gp, EFab rho, EFab velo, double s, double ro_0, int add_gp,
+                                                          int sub_old, double* __restrict__ sigma)
+{
+    const long long N = (long long)nx * ny * nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % nx), j = (int)((t / nx) % ny), k = (int)(t / ((long long)nx * ny));
+        const double sor = s / (rho.p ? rho.p[rho.idx(i, j, k)] : ro_0);
+        sigma[t] = sor;
+        const long long qv = vel.idx(i, j, k);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double u = vel.p[d * vel.cs + qv];
+            if (add_gp) u += gp.p[d * gp.cs + gp.idx(i, j, k)] * sor;
+            if (sub_old) u -= velo.p[d * velo.cs + velo.idx(i, j, k)];
+            vel.p[d * vel.cs + qv] = u;
+        }
+    }
+}
+// vel.setBndry(0) (:137) over every ghost cell of the caller's box, then the first ghost layer of the INFLOW faces from `inflow`
+// (same box as vel; :138-163)
+__global__ void __launch_bounds__(256) k_eb_set_vel_ghosts(int nx, int ny, int nz, int bx0, int bx1, int by0, int by1, int bz0, int bz1, EFab vel, EFab inflow,
+                                                           int inflo0, int inflo1, int inflo2, int infhi0, int infhi1, int infhi2)
+{
+    const int ex = bx1 - bx0 + 1, ey = by1 - by0 + 1, ez = bz1 - bz0 + 1;
+    const long long N = (long long)ex * ey * ez;
+    const int n[3] = {nx, ny, nz};
+    const int inflo[3] = {inflo0, inflo1, inflo2}, infhi[3] = {infhi0, infhi1, infhi2};
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+        const int q[3] = {bx0 + (int)(t % ex), by0 + (int)((t / ex) % ey), bz0 + (int)(t / ((long long)ex * ey))};
+        int nout = 0, dout = 0, side = 0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (q[d] < 0) { ++nout; dout = d; side = 0; }
+            if (q[d] >= n[d]) { ++nout; dout = d; side = 1; }
+        }
+        if (nout == 0) continue;
+        const long long qv = vel.idx(q[0], q[1], q[2]);
+        const bool first = nout == 1 && (side == 0 ? q[dout] == -1 : q[dout] == n[dout]);
+        const bool fill = first && inflow.p && (side == 0 ? inflo[dout] : infhi[dout]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) vel.p[d * vel.cs + qv] = fill ? inflow.p[d * inflow.cs + qv] : 0.0;
+    }
+}
+// set_eb_velocity / set_eb_density / set_eb_tracer (src/boundary_conditions/incflo_set_bcs.cpp:195-431): 0 everywhere; in cut cells
+// (EBCellFlag::isSingleValued) the eb_flow value, masked by the direction test against eb_flow.normal; then FillBoundary of nghost
+// layers across periodic faces.  One launch per output array: out has ncomp components; mode 0: velocity (from magnitude: -n * mag,
+// "the EB normal points out of the domain"), 1: constant components val[0..ncomp)
+__global__ void __launch_bounds__(256) k_eb_set_flow(int nx, int ny, int nz, int per0, int per1, int per2, int nghost, const double* __restrict__ geo, EFab bn,
+                                                     EFab out, int bx0, int bx1, int by0, int by1, int bz0, int bz1, int ncomp, int mode, int has_normal,
+                                                     double n0, double n1, double n2, double tol_lo, double tol_hi, double mag, const double* __restrict__ val)
+{
+    const int ex = bx1 - bx0 + 1, ey = by1 - by0 + 1, ez = bz1 - bz0 + 1;
+    const long long N = (long long)ex * ey * ez;
+    const int n[3] = {nx, ny, nz}, per[3] = {per0, per1, per2};
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+        const int q[3] = {bx0 + (int)(t % ex), by0 + (int)((t / ex) % ey), bz0 + (int)(t / ((long long)ex * ey))};
+        int c[3];
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            c[d] = q[d];
+            if (q[d] < 0 || q[d] >= n[d]) {
+                const int dist = q[d] < 0 ? -q[d] : q[d] - n[d] + 1;
+                if (per[d] && dist <= nghost) c[d] = (q[d] % n[d] + n[d]) % n[d]; else ok = false;
+            }
+        }
+        const long long qo = out.idx(q[0], q[1], q[2]);
+        double mask = 0.0, nv[3] = {0.0, 0.0, 0.0};
+        if (ok) {
+            const double V = geo[((long long)c[2] * ny + c[1]) * nx + c[0]];
+            if (V > 0.0 && V < 1.0) {
+                const long long qn = bn.idx(c[0], c[1], c[2]);
+                nv[0] = bn.p[qn]; nv[1] = bn.p[bn.cs + qn]; nv[2] = bn.p[2 * bn.cs + qn];
+                mask = 1.0;
+                if (has_normal) {
+                    const double dp = nv[0] * n0 + nv[1] * n1 + nv[2] * n2;
+                    mask = (tol_lo <= dp && dp <= tol_hi) ? 1.0 : 0.0;
+                }
+            }
+        }
+        for (int m = 0; m < ncomp; ++m) {
+            double v = 0.0;
+            if (mask != 0.0) v = mode == 0 ? -mask * nv[m] * mag : mask * val[m];
+            out.p[m * out.cs + qo] = v;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_eb_permute(const EbLev L, const double* __restrict__ in, double* __restrict__ out, int to_natural)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
+        int i, j, k;
+        ndecode(L, t, i, j, k);
+        const long long q = ((long long)k * L.nn[1] + j) * L.nn[0] + i;
+        if (to_natural) out[q] = in[t]; else out[t] = in[q];
+    }
+}
+
+struct EbLevel {
+    EbLev g{};
+    unsigned char* flag = nullptr;
+    double *cor = nullptr, *res = nullptr, *rescor = nullptr, *sol = nullptr, *rhs = nullptr;
+    bool odd_periodic = false;
+};
+
+bool eb_is_dev_ptr(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+size_t eb_box_doubles(const b200np_fab* b)
+{
+    return (size_t)(b->hi[0] - b->lo[0] + 1) * (b->hi[1] - b->lo[1] + 1) * (b->hi[2] - b->lo[2] + 1) * (size_t)std::max(b->ncomp, 1);
+}
+EFab efab(double* p, const b200np_fab* b)
+{
+    EFab f{};
+    f.p = p;
+    if (!b || !p) { f.p = nullptr; return f; }
+    for (int d = 0; d < 3; ++d) f.lo[d] = b->lo[d];
+    f.nx = b->hi[0] - b->lo[0] + 1; f.ny = b->hi[1] - b->lo[1] + 1;
+    f.cs = (long long)f.nx * f.ny * (b->hi[2] - b->lo[2] + 1);
+    return f;
+}
+int eb_grid(long long n, int per_block = 256) { return (int)std::max<long long>(1, std::min<long long>((n + per_block - 1) / per_block, 148 * 16)); }
+// the box must hold [lo, hi] per direction
+bool eb_box_covers(const b200np_fab* b, const int lo[3], const int hi[3], int ncomp)
+{
+    if (!b || b->ncomp < ncomp) return false;
+    for (int d = 0; d < 3; ++d) if (b->lo[d] > lo[d] || b->hi[d] < hi[d]) return false;
+    return true;
+}
+
+}  // namespace
+
+struct b200eb {
+    b200np_geom geom{};
+    b200np_opts opts{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<EbLevel> lv;
+    std::vector<void*> allocs;
+    double *geo = nullptr, *ebf = nullptr, *sigma = nullptr;
+    double *partial = nullptr, *dscal = nullptr, *work = nullptr, *snap = nullptr, *tmp_nat = nullptr;
+    int* dinfo = nullptr;
+    double* hscal = nullptr;
+    int* hinfo = nullptr;
+    bool singular = true, have_geometry = false, have_ebflow = false, have_stencil = false;
+    int flags_state = 0;      // 0: unknown, 1: all zero (variable sigma), 2: computed for a constant sigma and the current geometry
+    double* canon = nullptr;  // 3 doubles per level
+    int small_nodes = 20000;  // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
+    long long launches = 0, ncell = 0;
+    struct Stage { double* d = nullptr; size_t bytes = 0; } stage[12];
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    long long launches_per_vcycle = 0;
+};
+
+namespace {
+
+#define ELAUNCH(h, kern, grid, block, ...)                  \
+    do {                                                    \
+        kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); \
+        (h)->launches++;                                    \
+    } while (0)
+
+double* eb_alloc(b200eb* h, size_t doubles)
+{
+    void* p = nullptr;
+    ECK(cudaMalloc(&p, std::max<size_t>(doubles, 1) * sizeof(double)));
+    ECK(cudaMemsetAsync(p, 0, std::max<size_t>(doubles, 1) * sizeof(double), h->stream));
+    h->allocs.push_back(p);
+    return static_cast<double*>(p);
+}
+
+void eb_build(b200eb* h)
+{
+    const b200np_geom& G = h->geom;
+    int n[3] = {G.n_cell[0], G.n_cell[1], G.n_cell[2]};
+    h->singular = true;
+    for (int d = 0; d < 3; ++d)
+        if (G.bc_lo[d] == B200NP_BC_DIRICHLET || G.bc_hi[d] == B200NP_BC_DIRICHLET) h->singular = false;
+    h->ncell = (long long)n[0] * n[1] * n[2];
+    for (int lev = 0;; ++lev) {
+        EbLevel L;
+        EbLev& g = L.g;
+        for (int d = 0; d < 3; ++d) {
+            g.n[d] = n[d];
+            g.per[d] = G.bc_lo[d] == B200NP_BC_PERIODIC;
+            g.nn[d] = g.per[d] ? n[d] : n[d] + 1;
+            g.dirlo[d] = G.bc_lo[d] == B200NP_BC_DIRICHLET;
+            g.dirhi[d] = G.bc_hi[d] == B200NP_BC_DIRICHLET;
+            g.nc[d][0] = (g.nn[d] + 1) / 2;
+            g.nc[d][1] = g.nn[d] / 2;
+            if (g.per[d] && (g.nn[d] & 1)) L.odd_periodic = true;
+        }
+        long long off = 0;
+        for (int c = 0; c < 8; ++c) {
+            g.cbase[c] = off;
+            off += (long long)g.nc[0][c & 1] * g.nc[1][(c >> 1) & 1] * g.nc[2][c >> 2];
+        }
+        g.cbase[8] = g.nnode = off;
+        g.st = eb_alloc(h, (size_t)27 * g.nnode);
+        L.flag = reinterpret_cast<unsigned char*>(eb_alloc(h, (size_t)(g.nnode + 7) / 8 + 1));
+        g.flag = L.flag;
+        L.cor = eb_alloc(h, g.nnode); L.res = eb_alloc(h, g.nnode); L.rescor = eb_alloc(h, g.nnode);
+        if (lev == 0) { L.sol = eb_alloc(h, g.nnode); L.rhs = eb_alloc(h, g.nnode); }
+        h->lv.push_back(L);
+        bool can = lev + 1 <= h->opts.mg_max_coarsening_level && lev + 1 < 30;
+        for (int d = 0; d < 3; ++d) if (n[d] % 2 != 0 || n[d] / 2 < 2) can = false;
+        if (!can) break;
+        for (int d = 0; d < 3; ++d) n[d] /= 2;
+    }
+    h->canon = eb_alloc(h, 3 * h->lv.size());
+    for (size_t l = 0; l < h->lv.size(); ++l) h->lv[l].g.canon = h->canon + 3 * l;
+    if (const char* e = getenv("B200EB_SMALL_NODES")) h->small_nodes = atoi(e);
+    h->geo = eb_alloc(h, (size_t)19 * h->ncell);
+    h->sigma = eb_alloc(h, (size_t)h->ncell);
+    h->work = eb_alloc(h, (size_t)7 * h->lv.back().g.nnode);
+    h->snap = eb_alloc(h, (size_t)h->lv[0].g.nnode);
+    h->tmp_nat = eb_alloc(h, (size_t)14 * h->lv[0].g.nnode);
+    h->partial = eb_alloc(h, 2 * 148 * 16 + 8);
+    h->dscal = eb_alloc(h, 16);
+    h->dinfo = reinterpret_cast<int*>(eb_alloc(h, 4));
+    ECK(cudaMallocHost(&h->hscal, 16 * sizeof(double)));
+    ECK(cudaMallocHost(&h->hinfo, 8 * sizeof(int)));
+}
+
+// MLNodeLaplacian::buildStencil: level 0 from sigma and the integrals, then the Galerkin products.
+// const_sigma > 0: sigma is that constant -- nodes away from the body and the domain faces then share one row per level, which is
+// flagged instead of stored (B200EB_FLAGS=0 disables it).
+void eb_build_stencils(b200eb* h, double const_sigma)
+{
+    const b200np_geom& G = h->geom;
+    EbLevel& L0 = h->lv[0];
+    static const bool use_flags = !(getenv("B200EB_FLAGS") && atoi(getenv("B200EB_FLAGS")) == 0);
+    const int want = (const_sigma > 0 && use_flags) ? 2 : 1;
+    if (h->flags_state != want) {
+        if (want == 1) {
+            for (auto& L : h->lv) ECK(cudaMemsetAsync(L.flag, 0, (size_t)L.g.nnode, h->stream));
+        } else {
+            ELAUNCH(h, k_eb_flag0, eb_grid(L0.g.nnode), 256, L0.g, (const double*)h->geo, L0.flag);
+            for (size_t l = 0; l + 1 < h->lv.size(); ++l)
+                ELAUNCH(h, k_eb_flag_coarse, eb_grid(h->lv[l + 1].g.nnode), 256, h->lv[l + 1].g, h->lv[l].g, h->lv[l + 1].flag);
+        }
+        h->flags_state = want;
+    }
+    if (want == 2) ELAUNCH(h, k_eb_set_canon, 1, 32, h->canon, (int)h->lv.size(), const_sigma, 1.0 / (G.dx[0] * G.dx[0]));
+    ELAUNCH(h, k_eb_stencil0, eb_grid(L0.g.nnode, 128), 128, L0.g, (const double*)h->geo, (const double*)h->sigma, 1.0 / (G.dx[0] * G.dx[0]),
+            1.0 / (G.dx[1] * G.dx[1]), 1.0 / (G.dx[2] * G.dx[2]));
+    for (size_t l = 0; l + 1 < h->lv.size(); ++l)
+        ELAUNCH(h, k_eb_rap, eb_grid(h->lv[l + 1].g.nnode, 128), 128, h->lv[l + 1].g, h->lv[l].g);
+    h->have_stencil = true;
+}
+
+// one MLMG smooth call = smooth_num_sweeps sweeps of 8 colours
+void eb_smooth(b200eb* h, EbLevel& L, double* x, const double* rhs, int ncalls)
+{
+    const int nsw = std::max(1, h->opts.smooth_num_sweeps);
+    if (L.g.nnode <= h->small_nodes) {
+        ELAUNCH(h, k_eb_gs_small, 1, 1024, L.g, x, L.odd_periodic ? h->snap : (double*)nullptr, rhs, ncalls * nsw);
+        return;
+    }
+    for (int s = 0; s < ncalls * nsw; ++s)
+        for (int c = 0; c < 8; ++c) {
+            const long long cnt = L.g.cbase[c + 1] - L.g.cbase[c];
+            if (cnt == 0) continue;
+            const double* old = x;
+            if (L.odd_periodic) {
+                ECK(cudaMemcpyAsync(h->snap, x, L.g.nnode * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                old = h->snap;
+            }
+            ELAUNCH(h, k_eb_gs, eb_grid(cnt), 256, L.g, x, old, rhs, c);
+        }
+}
+
+void eb_bottom(b200eb* h)
+{
+    EbLevel& B = h->lv.back();
+    ELAUNCH(h, k_eb_bottom, 1, 1024, B.g, B.cor, B.res, h->work, h->opts.bottom_maxiter, h->opts.bottom_rtol, h->opts.bottom_atol, h->singular ? 1 : 0,
+            std::max(1, h->opts.smooth_num_sweeps), h->dinfo);
+}
+
+void eb_vcycle(b200eb* h)
+{
+    const int nl = (int)h->lv.size();
+    const int nu1 = h->opts.num_pre_smooth, nu2 = h->opts.num_post_smooth;
+    for (int l = 0; l < nl - 1; ++l) {
+        EbLevel &L = h->lv[l], &C = h->lv[l + 1];
+        ECK(cudaMemsetAsync(L.cor, 0, L.g.nnode * sizeof(double), h->stream));
+        eb_smooth(h, L, L.cor, L.res, nu1);
+        ELAUNCH(h, k_eb_residual, eb_grid(L.g.nnode), 256, L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        ELAUNCH(h, k_eb_restrict, eb_grid(C.g.nnode), 256, C.g, L.g, (const double*)L.rescor, C.res);
+    }
+    eb_bottom(h);
+    for (int l = nl - 2; l >= 0; --l) {
+        EbLevel &L = h->lv[l], &C = h->lv[l + 1];
+        ELAUNCH(h, k_eb_interp_add, eb_grid(L.g.nnode), 256, L.g, C.g, L.cor, (const double*)C.cor);
+        eb_smooth(h, L, L.cor, L.res, nu2);
+    }
+}
+
+void eb_vcycle_run(b200eb* h)
+{
+    if (!h->opts.use_graph) { eb_vcycle(h); return; }
+    if (!h->graph_exec) {
+        const long long before = h->launches;
+        ECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        try { eb_vcycle(h); }
+        catch (int) {
+            cudaGraph_t broken = nullptr;
+            cudaStreamEndCapture(h->stream, &broken);
+            if (broken) cudaGraphDestroy(broken);
+            cudaGetLastError();
+            throw;
+        }
+        ECK(cudaStreamEndCapture(h->stream, &h->graph));
+        ECK(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+        h->launches_per_vcycle = h->launches - before;
+        h->launches = before;
+    }
+    ECK(cudaGraphLaunch(h->graph_exec, h->stream));
+    h->launches += h->launches_per_vcycle;
+}
+
+double eb_read_norm(b200eb* h, int nb_)
+{
+    ELAUNCH(h, k_eb_max_final, 1, 1024, (const double*)h->partial, nb_, h->dscal + 2);
+    ECK(cudaMemcpyAsync(h->hscal + 2, h->dscal + 2, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    ECK(cudaStreamSynchronize(h->stream));
+    return h->hscal[2];
+}
+
+// MLMG::solve on (sol = 0, rhs) of level 0
+int eb_solve(b200eb* h, double rtol, double atol, b200np_stats* st)
+{
+    EbLevel& L0 = h->lv[0];
+    st->iters = 0; st->bottom_iters = 0; st->status = B200NP_OK; st->nlevels = (int)h->lv.size();
+    ECK(cudaMemsetAsync(h->dinfo, 0, 4 * sizeof(int), h->stream));
+    const int nb_ = eb_grid(L0.g.nnode);
+    if (h->singular) {   // makeSolvable: remove the mean over the active nodes
+        ELAUNCH(h, k_eb_sum_active, nb_, 256, L0.g, (const double*)L0.rhs, h->partial);
+        ELAUNCH(h, k_eb_mean_final, 1, 1024, (const double*)h->partial, nb_, h->dscal);
+        ELAUNCH(h, k_eb_sub_active, nb_, 256, L0.g, L0.rhs, (const double*)h->dscal, h->partial);
+    } else {
+        ELAUNCH(h, k_eb_sub_active, nb_, 256, L0.g, L0.rhs, (const double*)nullptr, h->partial);
+    }
+    st->rhsnorm = eb_read_norm(h, nb_);
+    // zero initial guess: the initial residual is rhs itself
+    ECK(cudaMemsetAsync(L0.sol, 0, L0.g.nnode * sizeof(double), h->stream));
+    ECK(cudaMemcpyAsync(L0.res, L0.rhs, L0.g.nnode * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    st->resnorm0 = st->rhsnorm;
+    const double maxnorm = std::max(st->rhsnorm, st->resnorm0);
+    const double target = std::max(atol, std::max(rtol, 1e-16) * maxnorm);
+    st->resnorm = st->resnorm0;
+    st->resnorm_hist[0] = st->resnorm0;
+    if (h->opts.verbose >= 1) printf("MLMG: Initial rhs               = %.12g\nMLMG: Initial residual (resid0) = %.12g\n", st->rhsnorm, st->resnorm0);
+    if (st->resnorm0 <= target) return B200NP_OK;
+    bool converged = false;
+    for (int it = 0; it < h->opts.maxiter; ++it) {
+        if (h->lv.size() == 1) { eb_bottom(h); }
+        else eb_vcycle_run(h);
+        ELAUNCH(h, k_eb_axpy, nb_, 256, L0.sol, (const double*)L0.cor, L0.g.nnode);
+        ELAUNCH(h, k_eb_residual, nb_, 256, L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+        st->resnorm = eb_read_norm(h, nb_);
+        st->iters = it + 1;
+        if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
+        if (h->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
+        if (st->resnorm <= target) { converged = true; break; }
+        if (!(st->resnorm <= 1e20 * maxnorm)) { st->status = B200NP_ERR_DIVERGED; break; }
+    }
+    if (!converged && st->status == B200NP_OK) st->status = B200NP_ERR_NOT_CONVERGED;
+    ECK(cudaMemcpyAsync(h->hinfo, h->dinfo, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    ECK(cudaStreamSynchronize(h->stream));
+    st->bottom_iters = h->hinfo[0];
+    if (h->opts.verbose >= 1) printf("MLMG: Final Iter. %d resid, resid/bnorm = %.12g, %.12g\n", st->iters, st->resnorm, st->resnorm / maxnorm);
+    return st->status;
+}
+
+double* eb_stage_in(b200eb* h, int slot, const double* p, const b200np_fab* box, bool copy, bool* staged, b200np_stats* st)
+{
+    *staged = false;
+    if (!p) return nullptr;
+    if (eb_is_dev_ptr(p)) return const_cast<double*>(p);
+    const size_t bytes = eb_box_doubles(box) * sizeof(double);
+    auto& S = h->stage[slot];
+    if (S.bytes < bytes) {
+        if (S.d) ECK(cudaFree(S.d));
+        ECK(cudaMalloc(&S.d, bytes));
+        S.bytes = bytes;
+    }
+    if (copy) { ECK(cudaMemcpyAsync(S.d, p, bytes, cudaMemcpyHostToDevice, h->stream)); if (st) st->h2d_bytes += (long long)bytes; }
+    *staged = true;
+    return S.d;
+}
+void eb_stage_out(b200eb* h, int slot, double* p, const b200np_fab* box, bool staged, b200np_stats* st)
+{
+    if (!staged || !p) return;
+    const size_t bytes = eb_box_doubles(box) * sizeof(double);
+    ECK(cudaMemcpyAsync(p, h->stage[slot].d, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (st) st->d2h_bytes += (long long)bytes;
+}
+
+// NodalProjector::project on device arrays: sigma already in h->sigma
+int eb_project_dev(b200eb* h, double const_sigma, EFab fvel, EFab fvelo, EFab fphi, const b200np_fab* phi_box, int acc_p, EFab fgphi, int acc_g, double rtol,
+                   double atol, b200np_stats* st)
+{
+    const b200np_geom& G = h->geom;
+    EbLevel& L0 = h->lv[0];
+    const double dxi = 1.0 / G.dx[0], dyi = 1.0 / G.dx[1], dzi = 1.0 / G.dx[2];
+    eb_build_stencils(h, const_sigma);
+    ELAUNCH(h, k_eb_divu, eb_grid(L0.g.nnode, 128), 128, L0.g, (const double*)h->geo, fvel, (const double*)(h->have_ebflow ? h->ebf : nullptr), dxi, dyi, dzi, L0.rhs);
+    ECK(cudaEventRecord(h->ev[2], h->stream));
+    const int status = eb_solve(h, rtol, atol, st);
+    ECK(cudaEventRecord(h->ev[3], h->stream));
+    ELAUNCH(h, k_eb_mknewu, eb_grid(h->ncell), 256, L0.g, (const double*)h->geo, (const double*)h->sigma, (const double*)L0.sol, fvel, fvelo, fgphi, acc_g, dxi, dyi,
+            dzi);
+    if (fphi.p) {
+        ELAUNCH(h, k_eb_copy_nodes, eb_grid(L0.g.nnode), 256, L0.g, L0.sol, fphi, 1, acc_p);
+        if (L0.g.per[0] || L0.g.per[1] || L0.g.per[2]) {
+            const int hx = std::min(phi_box->hi[0], G.n_cell[0]), hy = std::min(phi_box->hi[1], G.n_cell[1]), hz = std::min(phi_box->hi[2], G.n_cell[2]);
+            if (hx >= L0.g.nn[0] || hy >= L0.g.nn[1] || hz >= L0.g.nn[2])
+                ELAUNCH(h, k_eb_fill_dup, eb_grid((long long)(hx + 1) * (hy + 1) * (hz + 1)), 256, L0.g, (const double*)L0.sol, fphi, hx, hy, hz, acc_p);
+        }
+    }
+    return status;
+}
+
+bool eb_cell_box_ok(const b200eb* h, const b200np_fab* b, int ng, int ncomp)
+{
+    const int lo[3] = {-ng, -ng, -ng};
+    const int hi[3] = {h->geom.n_cell[0] - 1 + ng, h->geom.n_cell[1] - 1 + ng, h->geom.n_cell[2] - 1 + ng};
+    return eb_box_covers(b, lo, hi, ncomp);
+}
+bool eb_node_box_ok(const b200eb* h, const b200np_fab* b)
+{
+    const int lo[3] = {0, 0, 0};
+    const int hi[3] = {h->lv[0].g.nn[0] - 1, h->lv[0].g.nn[1] - 1, h->lv[0].g.nn[2] - 1};
+    return eb_box_covers(b, lo, hi, 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200eb_create(b200eb_t** out, const b200np_geom* geom, const b200np_opts* opts, int device)
+{
+    if (!out || !geom) return B200NP_ERR_BAD_ARG;
+    *out = nullptr;
+    for (int d = 0; d < 3; ++d) {
+        if (geom->n_cell[d] < 2 || !(geom->dx[d] > 0)) return B200NP_ERR_BAD_ARG;
+        if (geom->bc_lo[d] < 0 || geom->bc_lo[d] > 3 || geom->bc_hi[d] < 0 || geom->bc_hi[d] > 3) return B200NP_ERR_BAD_BC;
+        if ((geom->bc_lo[d] == B200NP_BC_PERIODIC) != (geom->bc_hi[d] == B200NP_BC_PERIODIC)) return B200NP_ERR_BAD_BC;
+    }
+    // AMReX's EB support asserts dx == dy == dz
+    if (std::fabs(geom->dx[0] - geom->dx[1]) > 1e-12 * geom->dx[0] || std::fabs(geom->dx[0] - geom->dx[2]) > 1e-12 * geom->dx[0]) return B200NP_ERR_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return B200NP_ERR_CUDA; }
+    b200eb* h = new b200eb();
+    try {
+        ECK(cudaSetDevice(device));
+        h->device = device;
+        h->geom = *geom;
+        if (opts) h->opts = *opts; else b200np_default_opts(&h->opts);
+        ECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (auto& e : h->ev) ECK(cudaEventCreate(&e));
+        eb_build(h);
+        ECK(cudaStreamSynchronize(h->stream));
+    } catch (int e) { b200eb_destroy(h); return e; }
+    *out = h;
+    return B200NP_OK;
+}
+
+void b200eb_destroy(b200eb_t* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    for (void* p : h->allocs) cudaFree(p);
+    for (auto& s : h->stage) if (s.d) cudaFree(s.d);
+    if (h->hscal) cudaFreeHost(h->hscal);
+    if (h->hinfo) cudaFreeHost(h->hinfo);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int b200eb_nlevels(const b200eb_t* h) { return h ? (int)h->lv.size() : 0; }
+
+int b200eb_set_geometry(b200eb_t* h, const double* vfrac, const b200np_fab* vfrac_box, const double* intg, const b200np_fab* intg_box)
+{
+    if (!h || !vfrac || !intg) return B200NP_ERR_BAD_ARG;
+    if (!eb_cell_box_ok(h, vfrac_box, 0, 1) || !eb_cell_box_ok(h, intg_box, 0, 18)) return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        bool s0, s1;
+        double* dv = eb_stage_in(h, 0, vfrac, vfrac_box, true, &s0, nullptr);
+        double* di = eb_stage_in(h, 1, intg, intg_box, true, &s1, nullptr);
+        const int* n = h->geom.n_cell;
+        ELAUNCH(h, k_eb_copy_geo, eb_grid(h->ncell), 256, n[0], n[1], n[2], efab(dv, vfrac_box), efab(di, intg_box), h->geo);
+        ECK(cudaStreamSynchronize(h->stream));
+        h->have_geometry = true;
+        h->flags_state = 0;
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+int b200eb_set_eb_inflow_velocity(b200eb_t* h, const double* eb_vel, const b200np_fab* vel_box, const double* bnorm, const b200np_fab* bnorm_box,
+                                  const double* bintg, const b200np_fab* bintg_box)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    if (!eb_vel) { h->have_ebflow = false; return B200NP_OK; }
+    if (!bnorm || !bintg) return B200NP_ERR_BAD_ARG;
+    if (!eb_cell_box_ok(h, vel_box, 0, 3) || !eb_cell_box_ok(h, bnorm_box, 0, 3) || !eb_cell_box_ok(h, bintg_box, 0, 8)) return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        if (!h->ebf) h->ebf = eb_alloc(h, (size_t)9 * h->ncell);
+        bool s0, s1, s2;
+        double* dv = eb_stage_in(h, 0, eb_vel, vel_box, true, &s0, nullptr);
+        double* dn = eb_stage_in(h, 1, bnorm, bnorm_box, true, &s1, nullptr);
+        double* db = eb_stage_in(h, 2, bintg, bintg_box, true, &s2, nullptr);
+        const int* n = h->geom.n_cell;
+        ELAUNCH(h, k_eb_copy_flow, eb_grid(h->ncell), 256, n[0], n[1], n[2], efab(dv, vel_box), efab(dn, bnorm_box), efab(db, bintg_box), h->ebf);
+        ECK(cudaStreamSynchronize(h->stream));
+        h->have_ebflow = true;
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+int b200eb_set_eb_flow(b200eb_t* h, const b200eb_flow* f, int nghost, const double* bnorm, const b200np_fab* bnorm_box, double* eb_vel,
+                       const b200np_fab* vel_box, double* eb_density, const b200np_fab* density_box, double* eb_tracer, const b200np_fab* tracer_box)
+{
+    if (!h || !f || !bnorm || !h->have_geometry || nghost < 0) return B200NP_ERR_BAD_ARG;
+    if (!eb_cell_box_ok(h, bnorm_box, 0, 3)) return B200NP_ERR_BAD_ARG;
+    if (f->ntrac < 0 || f->ntrac > 8) return B200NP_ERR_BAD_ARG;
+    if ((eb_vel && !eb_cell_box_ok(h, vel_box, 0, 3)) || (eb_density && !eb_cell_box_ok(h, density_box, 0, 1)) ||
+        (eb_tracer && !eb_cell_box_ok(h, tracer_box, 0, std::max(f->ntrac, 1))))
+        return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        bool sn;
+        double* dn = eb_stage_in(h, 0, bnorm, bnorm_box, true, &sn, nullptr);
+        const EFab fn = efab(dn, bnorm_box);
+        const int* n = h->geom.n_cell;
+        const int per[3] = {h->lv[0].g.per[0], h->lv[0].g.per[1], h->lv[0].g.per[2]};
+        // Real pad = std::numeric_limits<float>::epsilon(); norm_tol_lo / hi = -1 -/+ (normal_tol + pad)   (:218-221)
+        const double pad = 1.1920928955078125e-07;
+        const double tol_lo = -1.0 - (f->normal_tol + pad), tol_hi = -1.0 + (f->normal_tol + pad);
+        double* dval = h->dscal + 4;   // up to 8 constants
+        struct Out { double* p; const b200np_fab* box; int ncomp; int mode; double val[8]; } outs[3] = {
+            {eb_vel, vel_box, 3, f->is_mag ? 0 : 1, {f->velocity[0], f->velocity[1], f->velocity[2]}},
+            {eb_density, density_box, 1, 1, {f->density}},
+            {eb_tracer, tracer_box, f->ntrac, 1, {}}};
+        for (int m = 0; m < f->ntrac; ++m) outs[2].val[m] = f->tracer[m];
+        for (int o = 0; o < 3; ++o) {
+            if (!outs[o].p || outs[o].ncomp == 0) continue;
+            bool so;
+            double* dp = eb_stage_in(h, 1 + o, outs[o].p, outs[o].box, false, &so, nullptr);
+            ECK(cudaMemcpyAsync(dval, outs[o].val, 8 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            ECK(cudaStreamSynchronize(h->stream));   // outs[o].val is a stack array
+            const b200np_fab* b = outs[o].box;
+            const long long N = (long long)(b->hi[0] - b->lo[0] + 1) * (b->hi[1] - b->lo[1] + 1) * (b->hi[2] - b->lo[2] + 1);
+            ELAUNCH(h, k_eb_set_flow, eb_grid(N), 256, n[0], n[1], n[2], per[0], per[1], per[2], nghost, (const double*)h->geo, fn, efab(dp, b), b->lo[0], b->hi[0],
+                    b->lo[1], b->hi[1], b->lo[2], b->hi[2], outs[o].ncomp, outs[o].mode, f->has_normal, f->normal[0], f->normal[1], f->normal[2], tol_lo, tol_hi,
+                    f->vel_mag, (const double*)dval);
+            eb_stage_out(h, 1 + o, outs[o].p, b, so, nullptr);
+            ECK(cudaStreamSynchronize(h->stream));
+        }
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+int b200eb_project(b200eb_t* h, double* vel, const b200np_fab* vel_box, const double* sigma, const b200np_fab* sigma_box, double const_sigma, double* phi,
+                   const b200np_fab* phi_box, double* gphi, const b200np_fab* gphi_box, double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h || !vel || !h->have_geometry) return st->status = B200NP_ERR_BAD_ARG;
+    if (!eb_cell_box_ok(h, vel_box, 1, 3)) return st->status = B200NP_ERR_BAD_ARG;
+    if (sigma ? !eb_cell_box_ok(h, sigma_box, 0, 1) : !(const_sigma > 0)) return st->status = B200NP_ERR_BAD_ARG;
+    if (phi && !eb_node_box_ok(h, phi_box)) return st->status = B200NP_ERR_BAD_ARG;
+    if (gphi && !eb_cell_box_ok(h, gphi_box, 0, 3)) return st->status = B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        h->launches = 0;
+        ECK(cudaEventRecord(h->ev[0], h->stream));
+        bool sv, ss, sp, sg;
+        double* dv = eb_stage_in(h, 3, vel, vel_box, true, &sv, st);
+        double* ds = eb_stage_in(h, 4, sigma, sigma_box, true, &ss, st);
+        double* dp = eb_stage_in(h, 5, phi, phi_box, false, &sp, st);
+        double* dg = eb_stage_in(h, 6, gphi, gphi_box, false, &sg, st);
+        const int* n = h->geom.n_cell;
+        ELAUNCH(h, k_eb_copy_sigma, eb_grid(h->ncell), 256, n[0], n[1], n[2], efab(ds, sigma_box), const_sigma, h->sigma);
+        const int status = eb_project_dev(h, sigma ? 0.0 : const_sigma, efab(dv, vel_box), EFab{}, efab(dp, phi_box), phi_box, 0, efab(dg, gphi_box), 0, rtol, atol, st);
+        eb_stage_out(h, 3, vel, vel_box, sv, st); eb_stage_out(h, 5, phi, phi_box, sp, st); eb_stage_out(h, 6, gphi, gphi_box, sg, st);
+        ECK(cudaEventRecord(h->ev[1], h->stream));
+        ECK(cudaEventSynchronize(h->ev[1]));
+        float ms = 0;
+        ECK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); st->ms_total = ms;
+        ECK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); st->ms_solve = ms;
+        st->launches = h->launches;
+        return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+int b200eb_apply_nodal_projection(b200eb_t* h, double* velocity, const b200np_fab* vel_box, const double* velocity_o, const double* density,
+                                  const b200np_fab* rho_box, double ro_0, double* gp, const b200np_fab* gp_box, double* p_nd, const b200np_fab* p_box,
+                                  const double* inflow_vel, double scaling_factor, int incremental, int proj_for_small_dt, double rtol, double atol,
+                                  b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h || !velocity || !gp || !p_nd || !h->have_geometry) return st->status = B200NP_ERR_BAD_ARG;
+    const bool use_old = incremental || proj_for_small_dt;
+    if (use_old && !velocity_o) return st->status = B200NP_ERR_BAD_ARG;
+    if (!eb_cell_box_ok(h, vel_box, 1, 3) || !eb_cell_box_ok(h, gp_box, 0, 3) || !eb_node_box_ok(h, p_box)) return st->status = B200NP_ERR_BAD_ARG;
+    if (density ? !eb_cell_box_ok(h, rho_box, 0, 1) : !(ro_0 > 0)) return st->status = B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        h->launches = 0;
+        ECK(cudaEventRecord(h->ev[0], h->stream));
+        bool sv, so, sr, sg, sp, si;
+        double* dv = eb_stage_in(h, 3, velocity, vel_box, true, &sv, st);
+        double* dvo = eb_stage_in(h, 4, velocity_o, vel_box, use_old, &so, st);
+        double* dr = eb_stage_in(h, 5, density, rho_box, true, &sr, st);
+        double* dgp = eb_stage_in(h, 6, gp, gp_box, true, &sg, st);
+        double* dp = eb_stage_in(h, 7, p_nd, p_box, incremental != 0, &sp, st);
+        const bool set_inflow = !proj_for_small_dt && !incremental;   // :81
+        double* din = eb_stage_in(h, 8, set_inflow ? inflow_vel : nullptr, vel_box, true, &si, st);
+        const EFab fvel = efab(dv, vel_box), fvelo = efab(use_old ? dvo : nullptr, vel_box), frho = efab(dr, rho_box), fgp = efab(dgp, gp_box),
+                   fp = efab(dp, p_box), fin = efab(din, vel_box);
+        const int* n = h->geom.n_cell;
+        const b200np_geom& G = h->geom;
+        ELAUNCH(h, k_eb_pre_add_sigma, eb_grid(h->ncell), 256, n[0], n[1], n[2], fvel, fgp, frho, fvelo, scaling_factor, ro_0, incremental ? 0 : 1, use_old ? 1 : 0,
+                h->sigma);
+        const long long nb = eb_box_doubles(vel_box) / std::max(vel_box->ncomp, 1);
+        ELAUNCH(h, k_eb_set_vel_ghosts, eb_grid(nb), 256, n[0], n[1], n[2], vel_box->lo[0], vel_box->hi[0], vel_box->lo[1], vel_box->hi[1], vel_box->lo[2],
+                vel_box->hi[2], fvel, fin, G.bc_lo[0] == B200NP_BC_INFLOW, G.bc_lo[1] == B200NP_BC_INFLOW, G.bc_lo[2] == B200NP_BC_INFLOW,
+                G.bc_hi[0] == B200NP_BC_INFLOW, G.bc_hi[1] == B200NP_BC_INFLOW, G.bc_hi[2] == B200NP_BC_INFLOW);
+        const int status = eb_project_dev(h, density ? 0.0 : scaling_factor / ro_0, fvel, fvelo, fp, p_box, incremental ? 1 : 0, fgp, incremental ? 1 : 0, rtol, atol, st);
+        eb_stage_out(h, 3, velocity, vel_box, sv, st); eb_stage_out(h, 6, gp, gp_box, sg, st); eb_stage_out(h, 7, p_nd, p_box, sp, st);
+        ECK(cudaEventRecord(h->ev[1], h->stream));
+        ECK(cudaEventSynchronize(h->ev[1]));
+        float ms = 0;
+        ECK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1])); st->ms_total = ms;
+        ECK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); st->ms_solve = ms;
+        st->launches = h->launches;
+        return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+int b200eb_level_dims(const b200eb_t* h, int lev, int n_cell[3], int n_node[3])
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size()) return B200NP_ERR_BAD_ARG;
+    for (int d = 0; d < 3; ++d) { n_cell[d] = h->lv[lev].g.n[d]; n_node[d] = h->lv[lev].g.nn[d]; }
+    return B200NP_OK;
+}
+
+// test hook: build the stencil hierarchy from sigma (host or device cell array, or NULL + const_sigma) without projecting
+int b200eb_build_stencils(b200eb_t* h, const double* sigma, const b200np_fab* sigma_box, double const_sigma)
+{
+    if (!h || !h->have_geometry) return B200NP_ERR_BAD_ARG;
+    if (sigma ? !eb_cell_box_ok(h, sigma_box, 0, 1) : !(const_sigma > 0)) return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        bool ss;
+        double* ds = eb_stage_in(h, 4, sigma, sigma_box, true, &ss, nullptr);
+        const int* n = h->geom.n_cell;
+        ELAUNCH(h, k_eb_copy_sigma, eb_grid(h->ncell), 256, n[0], n[1], n[2], efab(ds, sigma_box), const_sigma, h->sigma);
+        eb_build_stencils(h, sigma ? 0.0 : const_sigma);
+        ECK(cudaStreamSynchronize(h->stream));
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+// test hook: the 13 forward entries + diagonal of level lev, host array (14, nnz, nny, nnx)
+int b200eb_level_stencil(b200eb_t* h, int lev, double* out)
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size() || !out || !h->have_stencil) return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        EbLevel& L = h->lv[lev];
+        ELAUNCH(h, k_eb_export_stencil, eb_grid(L.g.nnode), 256, L.g, h->tmp_nat);
+        ECK(cudaMemcpyAsync(out, h->tmp_nat, (size_t)14 * L.g.nnode * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        ECK(cudaStreamSynchronize(h->stream));
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+// test hooks on level arrays; host arrays in natural node order (nnz, nny, nnx):
+// op 0 smooth (arg MLMG smooth calls: x = in_a, rhs = in_b), 1 residual (in_b - A in_a), 2 restriction of in_a to level lev + 1,
+// 3 in_a + interpolation of in_b (level lev + 1), 4 bottom solve of in_b on the coarsest level, 5 A in_a
+int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, const double* in_b, double* out)
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size() || !h->have_stencil || !out) return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        EbLevel& L = h->lv[lev];
+        auto up = [&](EbLevel& T, double* d, const double* src) {
+            if (!src) return;
+            ECK(cudaMemcpyAsync(h->tmp_nat, src, T.g.nnode * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            ELAUNCH(h, k_eb_permute, eb_grid(T.g.nnode), 256, T.g, (const double*)h->tmp_nat, d, 0);
+        };
+        auto down = [&](EbLevel& T, const double* d) {
+            ELAUNCH(h, k_eb_permute, eb_grid(T.g.nnode), 256, T.g, d, h->tmp_nat, 1);
+            ECK(cudaMemcpyAsync(out, h->tmp_nat, T.g.nnode * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        };
+        switch (op) {
+        case 0:
+            up(L, L.cor, in_a); up(L, L.res, in_b);
+            eb_smooth(h, L, L.cor, L.res, arg);
+            down(L, L.cor);
+            break;
+        case 1:
+            up(L, L.cor, in_a); up(L, L.res, in_b);
+            ELAUNCH(h, k_eb_residual, eb_grid(L.g.nnode), 256, L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            down(L, L.rescor);
+            break;
+        case 2: {
+            if (lev + 1 >= (int)h->lv.size()) return B200NP_ERR_BAD_ARG;
+            EbLevel& C = h->lv[lev + 1];
+            up(L, L.rescor, in_a);
+            ELAUNCH(h, k_eb_restrict, eb_grid(C.g.nnode), 256, C.g, L.g, (const double*)L.rescor, C.res);
+            down(C, C.res);
+            break;
+        }
+        case 3: {
+            if (lev + 1 >= (int)h->lv.size()) return B200NP_ERR_BAD_ARG;
+            EbLevel& C = h->lv[lev + 1];
+            up(L, L.cor, in_a); up(C, C.cor, in_b);
+            ELAUNCH(h, k_eb_interp_add, eb_grid(L.g.nnode), 256, L.g, C.g, L.cor, (const double*)C.cor);
+            down(L, L.cor);
+            break;
+        }
+        case 4: {
+            EbLevel& B = h->lv.back();
+            up(B, B.res, in_b);
+            ECK(cudaMemsetAsync(h->dinfo, 0, 4 * sizeof(int), h->stream));
+            eb_bottom(h);
+            down(B, B.cor);
+            break;
+        }
+        case 5: {   // A x = -(0 - A x)
+            up(L, L.cor, in_a);
+            ECK(cudaMemsetAsync(L.res, 0, L.g.nnode * sizeof(double), h->stream));
+            ELAUNCH(h, k_eb_residual, eb_grid(L.g.nnode), 256, L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            ELAUNCH(h, k_eb_permute, eb_grid(L.g.nnode), 256, L.g, (const double*)L.rescor, h->tmp_nat, 1);
+            ECK(cudaMemcpyAsync(out, h->tmp_nat, L.g.nnode * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            ECK(cudaStreamSynchronize(h->stream));
+            for (long long t = 0; t < L.g.nnode; ++t) out[t] = -out[t];
+            return B200NP_OK;
+        }
+        default: return B200NP_ERR_BAD_ARG;
+        }
+        ECK(cudaStreamSynchronize(h->stream));
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+// test hook: rhs = D u (+ EB inflow) of the caller's velocity (one ghost layer), natural node order; needs built stencils (active set)
+int b200eb_compute_rhs(b200eb_t* h, const double* vel, const b200np_fab* vel_box, double* out)
+{
+    if (!h || !vel || !out || !h->have_stencil || !eb_cell_box_ok(h, vel_box, 1, 3)) return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        bool sv;
+        double* dv = eb_stage_in(h, 3, vel, vel_box, true, &sv, nullptr);
+        EbLevel& L0 = h->lv[0];
+        const b200np_geom& G = h->geom;
+        ELAUNCH(h, k_eb_divu, eb_grid(L0.g.nnode, 128), 128, L0.g, (const double*)h->geo, efab(dv, vel_box), (const double*)(h->have_ebflow ? h->ebf : nullptr),
+                1.0 / G.dx[0], 1.0 / G.dx[1], 1.0 / G.dx[2], L0.rhs);
+        ELAUNCH(h, k_eb_permute, eb_grid(L0.g.nnode), 256, L0.g, (const double*)L0.rhs, h->tmp_nat, 1);
+        ECK(cudaMemcpyAsync(out, h->tmp_nat, L0.g.nnode * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        ECK(cudaStreamSynchronize(h->stream));
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+}  // extern "C"

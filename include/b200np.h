@@ -268,6 +268,69 @@ int  b200mac_project(b200mac_t* h, double* umac, const b200np_fab* u_box, double
 int  b200mac_level_op(b200mac_t* h, int lev, int op, int arg, const double* in_a, const double* in_b, double* out);
 int  b200mac_level_dims(const b200mac_t* h, int lev, int n_cell[3]);
 
+/* ---- EB (cut cell) nodal projection: Hydro::NodalProjector over MLMG / MLNodeLaplacian built with an EBFArrayBoxFactory ------
+ * What incflo runs under AMREX_USE_EB (BASELINE configs[4], test_3d/benchmark.channel_cylinder-x): call sites
+ * src/projection/incflo_apply_nodal_projection.cpp:130-136 (set_eb_velocity / density / tracer), :181-194 (projector, whose ctor takes
+ * the EB factory from vel[lev]->Factory()), :196-201 (getLinOp().setEBInflowVelocity), :215-266 (project, copy-out).
+ * One AMR level, one box, one GPU.  geom.dx must be isotropic (AMReX's EB support asserts dx == dy == dz).
+ * The operator is the Q1 stiffness matrix integrated over the fluid part of every cell; the multigrid is AMReX's "RAP" strategy
+ * (Galerkin coarse stencils); see csrc/b200eb.cu and oracle/eb_oracle.py. */
+typedef struct b200eb b200eb_t;
+int  b200eb_create(b200eb_t** out, const b200np_geom* geom, const b200np_opts* opts, int device);
+void b200eb_destroy(b200eb_t* h);
+int  b200eb_nlevels(const b200eb_t* h);
+/* The EB data the linear operator takes from the factory, per cell of the level (cell-centred boxes that cover the domain):
+ *   vfrac  EBFArrayBoxFactory::getVolFrac()            1 comp
+ *   intg   MLNodeLaplacian::m_integral (buildIntegral) 18 comps, integrals of x y z x2 y2 z2 xy xz yz x2y x2z xy2 y2z xz2 yz2 x2y2
+ *          x2z2 y2z2 over the fluid part of the cell, cell-local coordinates in [-1/2, 1/2] (amrex i_S_* order)
+ * Uncut cells: vfrac = 1, int x2 = 1/12, int x2y2 = 1/144, odd ones 0; covered cells: all 0. */
+int  b200eb_set_geometry(b200eb_t* h, const double* vfrac, const b200np_fab* vfrac_box, const double* intg, const b200np_fab* intg_box);
+/* nodal_projector->getLinOp().setEBInflowVelocity(lev, eb_vel) (:196-201): adds dxinv * (u_eb . n) * int_{EB face} N_a dA to the rhs.
+ *   eb_vel 3 comps (get_velocity_eb), bnorm 3 comps (getBndryNormal, pointing out of the fluid), bintg 8 comps: integrals of
+ *   1 x y z xy xz yz xyz over the EB face inside the cell (comp 0 = getBndryArea; amrex i_B_* order).  eb_vel == NULL clears it. */
+int  b200eb_set_eb_inflow_velocity(b200eb_t* h, const double* eb_vel, const b200np_fab* vel_box, const double* bnorm,
+                                   const b200np_fab* bnorm_box, const double* bintg, const b200np_fab* bintg_box);
+/* incflo::set_eb_velocity / set_eb_density / set_eb_tracer (src/boundary_conditions/incflo_set_bcs.cpp:195-285, :287-358, :360-431):
+ * the eb_flow.* inputs; every output array is zeroed, cut cells (EBCellFlag::isSingleValued, 0 < vfrac < 1) get the value -- for
+ * the velocity either eb_flow.velocity or -normal * eb_flow.vel_mag -- masked by the direction test
+ * -1 - (normal_tol + eps_float) <= bnorm . eb_flow.normal <= -1 + (normal_tol + eps_float), and nghost layers are filled across periodic
+ * faces (FillBoundary).  Any of the three outputs may be NULL. */
+typedef struct {
+    int    has_normal;     /* eb_flow.normal given        */
+    double normal[3];
+    double normal_tol;     /* eb_flow.normal_tol          */
+    int    is_mag;         /* velocity given as magnitude */
+    double vel_mag;
+    double velocity[3];
+    double density;
+    int    ntrac;          /* <= 8                        */
+    double tracer[8];
+} b200eb_flow;
+int  b200eb_set_eb_flow(b200eb_t* h, const b200eb_flow* f, int nghost, const double* bnorm, const b200np_fab* bnorm_box, double* eb_vel,
+                        const b200np_fab* vel_box, double* eb_density, const b200np_fab* density_box, double* eb_tracer,
+                        const b200np_fab* tracer_box);
+/* NodalProjector::project(rtol, atol) + getPhi() / getGradPhi(): same arguments as b200np_project.  vel: valid cells become
+ * u - sigma * (cell average of grad phi over the fluid), 0 in covered cells; one ghost layer is an input at non-periodic faces.
+ * phi: nodal box [0, n_cell] (0 on nodes inside the body), gphi: cell average of grad phi over the fluid part. */
+int  b200eb_project(b200eb_t* h, double* vel, const b200np_fab* vel_box, const double* sigma, const b200np_fab* sigma_box,
+                    double const_sigma, double* phi, const b200np_fab* phi_box, double* gphi, const b200np_fab* gphi_box, double rtol,
+                    double atol, b200np_stats* stats);
+/* incflo::ApplyNodalProjection under AMREX_USE_EB: same arguments and semantics as b200np_apply_nodal_projection */
+int  b200eb_apply_nodal_projection(b200eb_t* h, double* velocity, const b200np_fab* vel_box, const double* velocity_o,
+                                   const double* density, const b200np_fab* rho_box, double ro_0, double* gp, const b200np_fab* gp_box,
+                                   double* p_nd, const b200np_fab* p_box, const double* inflow_vel, double scaling_factor,
+                                   int incremental, int proj_for_small_dt, double rtol, double atol, b200np_stats* stats);
+/* test hooks (host arrays, natural node order (nnz, nny, nnx), nn = n_cell in a periodic direction, n_cell + 1 otherwise):
+ * build_stencils: MLNodeLaplacian::buildStencil for a sigma without projecting; level_stencil: the 13 forward entries
+ * (offset t = (di+1) + 3(dj+1) + 9(dk+1), t = 14..26) + the diagonal of a level, (14, nnz, nny, nnx);
+ * level_op: 0 smooth (arg MLMG smooth calls: x = in_a, rhs = in_b), 1 residual in_b - A in_a, 2 restriction of in_a to level lev + 1,
+ * 3 in_a + interpolation of in_b (level lev + 1), 4 bottom solve of in_b on the coarsest level, 5 A in_a; compute_rhs: D u (+ EB inflow). */
+int  b200eb_build_stencils(b200eb_t* h, const double* sigma, const b200np_fab* sigma_box, double const_sigma);
+int  b200eb_level_stencil(b200eb_t* h, int lev, double* out);
+int  b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, const double* in_b, double* out);
+int  b200eb_level_dims(const b200eb_t* h, int lev, int n_cell[3], int n_node[3]);
+int  b200eb_compute_rhs(b200eb_t* h, const double* vel, const b200np_fab* vel_box, double* out);
+
 /* IncfloVelFill (src/prob/prob_bc.H:8-351) evaluated by the library: after this call,
  * b200np_apply_nodal_projection with inflow_vel == NULL fills the first ghost layer of the velocity at INFLOW
  * faces itself (:138-163, PhysBCFunct<GpuBndryFuncFab<IncfloVelFill>> with nghost = 1) from
