@@ -43,9 +43,9 @@ namespace {
 struct EbLev {
     int n[3], nn[3], per[3];
     int dirlo[3], dirhi[3];   // Dirichlet faces: their nodes are masked
-    int nc[3][2];             // number of nodes of parity 0 / 1 per direction
-    long long cbase[9];       // start of colour c; cbase[8] = nnode
-    long long nnode;
+    int H[3];                 // extent of a colour block per direction: (nn + 1) / 2 (the odd-parity block of an odd extent has one
+    int CS;                   // unused slot per row: a hole; holes hold zeros everywhere and are never written); CS = H[0] H[1] H[2]
+    long long nnode;          // allocated length of a nodal array = 8 CS (< 2^31)
     double* st;               // 27 coefficient arrays, st + t * nnode; t = 13: diagonal
     const unsigned char* flag;   // 1: the row of this node is the canonical row of an uncut neighbourhood with constant sigma (faces 0, edges
     const double* canon;         // canon[0], corners canon[1], diagonal canon[2]): the kernels do not read its 27 coefficients.  All 0 with
@@ -63,22 +63,46 @@ struct EFab {
     }
 };
 
-__device__ __forceinline__ long long nidx(const EbLev& L, int i, int j, int k)
+// position of node (i, j, k): colour block ((k&1) 4 + (j&1) 2 + (i&1)), then (k/2, j/2, i/2) -- a sum of one term per direction
+__device__ __forceinline__ int nidx(const EbLev& L, int i, int j, int k)
 {
-    const int pi = i & 1, pj = j & 1, pk = k & 1;
-    return L.cbase[pi + 2 * pj + 4 * pk] + ((long long)(k >> 1) * L.nc[1][pj] + (j >> 1)) * L.nc[0][pi] + (i >> 1);
+    return ((k & 1) * 4 + (j & 1) * 2 + (i & 1)) * L.CS + ((k >> 1) * L.H[1] + (j >> 1)) * L.H[0] + (i >> 1);
 }
-// colour-major position t -> node (i, j, k)
-__device__ __forceinline__ void ndecode(const EbLev& L, long long t, int& i, int& j, int& k)
+// position t -> node (i, j, k); false: t is a hole
+__device__ __forceinline__ bool ndecode(const EbLev& L, long long tt, int& i, int& j, int& k)
 {
-    int c = 0;
+    const int t = (int)tt;
+    const int c = t / L.CS, l = t - c * L.CS;
+    const int r = l / L.H[0];
+    i = 2 * (l - r * L.H[0]) + (c & 1);
+    const int k2 = r / L.H[1];
+    j = 2 * (r - k2 * L.H[1]) + ((c >> 1) & 1);
+    k = 2 * k2 + (c >> 2);
+    return i < L.nn[0] && j < L.nn[1] && k < L.nn[2];
+}
+// the same for the 26 neighbours: index = X[di] + Y[dj] + Z[dk] (periodic wrap; clamped where the neighbour does not exist -- its
+// coefficient is exactly zero)
+struct NbIdx {
+    int X[3], Y[3], Z[3];
+};
+__device__ __forceinline__ void nb_index(const EbLev& L, int i, int j, int k, NbIdx& q)
+{
+    const int p[3] = {i, j, k};
+    int c[3][3];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) c += (t >= L.cbase[q]) ? 1 : 0;
-    const long long l = t - L.cbase[c];
-    const int ncx = L.nc[0][c & 1], ncy = L.nc[1][(c >> 1) & 1];
-    i = 2 * (int)(l % ncx) + (c & 1);
-    j = 2 * (int)((l / ncx) % ncy) + ((c >> 1) & 1);
-    k = 2 * (int)(l / ((long long)ncx * ncy)) + (c >> 2);
+    for (int d = 0; d < 3; ++d) {
+        int lo = p[d] - 1, hi = p[d] + 1;
+        if (lo < 0) lo = L.per[d] ? L.nn[d] - 1 : p[d];
+        if (hi >= L.nn[d]) hi = L.per[d] ? 0 : p[d];
+        c[d][0] = lo; c[d][1] = p[d]; c[d][2] = hi;
+    }
+    const int sy = L.H[0], sz = L.H[0] * L.H[1];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        q.X[t] = (c[0][t] & 1) * L.CS + (c[0][t] >> 1);
+        q.Y[t] = (c[1][t] & 1) * 2 * L.CS + (c[1][t] >> 1) * sy;
+        q.Z[t] = (c[2][t] & 1) * 4 * L.CS + (c[2][t] >> 1) * sz;
+    }
 }
 // coordinates of q - 1, q, q + 1 per direction: periodic wrap; outside a non-periodic domain the coordinate is clamped (the
 // coefficient towards it is exactly zero by construction) and flagged
@@ -124,7 +148,8 @@ __device__ __forceinline__ double eb_block_reduce(double v, double* sh)
         const double w = __shfl_xor_sync(0xffffffffu, v, o);
         v = MAXR ? fmax(v, w) : v + w;
     }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = (blockDim.x * blockDim.y + 31) >> 5;
     __syncthreads();
     if (lane == 0) sh[wid] = v;
     __syncthreads();
@@ -239,7 +264,7 @@ __global__ void __launch_bounds__(128) k_eb_stencil0(const EbLev L, const double
     const double dh[3] = {dhx, dhy, dhz};
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
         int i, j, k;
-        ndecode(L, t, i, j, k);
+        if (!ndecode(L, t, i, j, k)) continue;
         if (L.flag[t]) {
 #pragma unroll
             for (int tt = 0; tt < 27; ++tt) L.st[(long long)tt * L.nnode + t] = canonical_entry(L, tt);
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(256) k_eb_flag0(const EbLev L, const double* _
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
         int i, j, k;
-        ndecode(L, t, i, j, k);
+        if (!ndecode(L, t, i, j, k)) continue;
         const int p[3] = {i, j, k};
         bool reg = true;
 #pragma unroll
@@ -319,7 +344,7 @@ __global__ void __launch_bounds__(256) k_eb_flag_coarse(const EbLev C, const EbL
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < C.nnode; t += (long long)gridDim.x * blockDim.x) {
         int I, J, K;
-        ndecode(C, t, I, J, K);
+        if (!ndecode(C, t, I, J, K)) continue;
         Nb q;
         nb_coords(F, 2 * I, 2 * J, 2 * K, q);
         bool reg = true;
@@ -363,7 +388,7 @@ __global__ void __launch_bounds__(128) k_eb_rap(const EbLev C, const EbLev F)
             continue;
         }
         int I, J, K;
-        ndecode(C, t, I, J, K);
+        if (!ndecode(C, t, I, J, K)) continue;
         double acc[27];
 #pragma unroll
         for (int q = 0; q < 27; ++q) acc[q] = 0.0;
@@ -409,42 +434,59 @@ __global__ void __launch_bounds__(128) k_eb_rap(const EbLev C, const EbLev F)
 }
 
 // ---- multigrid kernels ------------------------------------------------------------------------------------------------------
-// sum over the 26 neighbours of A(p, q) x(q)
+// loads the compiler may not sink towards their use: with one node per thread the kernels below are pure latency unless every load
+// of a node is in flight before the first multiply (nvcc otherwise pairs each load with its FMA: 26 dependent round trips per node)
+__device__ __forceinline__ double ld_early(const double* p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_early_nc(const double* p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// sum over the 26 neighbours of A(p, q) x(q).  All loads are issued before the first multiply (the kernels around this are latency
+// bound: one node per thread, nothing else to overlap with).
 __device__ __forceinline__ double offdiag_sum(const EbLev& L, long long p, int i, int j, int k, const double* x)
 {
-    Nb q;
-    nb_coords(L, i, j, k, q);
+    NbIdx q;
+    nb_index(L, i, j, k, q);
+    double c[27], v[27];
+#pragma unroll
+    for (int tt = 0; tt < 27; ++tt) {
+        if (tt == 13) continue;
+        c[tt] = ld_early_nc(L.st + (long long)tt * L.nnode + p);
+        v[tt] = ld_early(x + (q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]));
+    }
     double ax = 0.0;
 #pragma unroll
-    for (int dk = 0; dk < 3; ++dk)
-#pragma unroll
-        for (int dj = 0; dj < 3; ++dj)
-#pragma unroll
-            for (int di = 0; di < 3; ++di) {
-                const int tt = di + 3 * dj + 9 * dk;
-                if (tt == 13) continue;
-                ax += __ldg(L.st + (long long)tt * L.nnode + p) * x[nidx(L, q.c[0][di], q.c[1][dj], q.c[2][dk])];
-            }
+    for (int tt = 26; tt >= 0; --tt) {   // the first product needs the LAST loads: nothing can stall before all of them are issued
+        if (tt == 13) continue;
+        ax += c[tt] * v[tt];
+    }
     return ax;
 }
-
 // the same sum for a node with the canonical row: 12 edge and 8 corner neighbours, no coefficient loads
 __device__ __forceinline__ double offdiag_sum_regular(const EbLev& L, int i, int j, int k, const double* x)
 {
-    Nb q;
-    nb_coords(L, i, j, k, q);
+    NbIdx q;
+    nb_index(L, i, j, k, q);
+    double v[27];
+#pragma unroll
+    for (int tt = 0; tt < 27; ++tt) {
+        const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+        if (nz >= 2) v[tt] = ld_early(x + (q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]));
+    }
     double se = 0.0, sc = 0.0;
 #pragma unroll
-    for (int dk = 0; dk < 3; ++dk)
-#pragma unroll
-        for (int dj = 0; dj < 3; ++dj)
-#pragma unroll
-            for (int di = 0; di < 3; ++di) {
-                const int nz = (di != 1) + (dj != 1) + (dk != 1);
-                if (nz < 2) continue;
-                const double v = x[nidx(L, q.c[0][di], q.c[1][dj], q.c[2][dk])];
-                if (nz == 2) se += v; else sc += v;
-            }
+    for (int tt = 26; tt >= 0; --tt) {
+        const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+        if (nz == 2) se += v[tt];
+        if (nz == 3) sc += v[tt];
+    }
     return L.canon[0] * se + L.canon[1] * sc;
 }
 
@@ -452,16 +494,15 @@ __device__ __forceinline__ double offdiag_sum_regular(const EbLev& L, int i, int
 // one colour (odd periodic extent): there old is a snapshot taken before the launch.
 __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const double* old, const double* __restrict__ rhs, int color)
 {
-    const long long base = L.cbase[color], cnt = L.cbase[color + 1] - base;
-    const int ncx = L.nc[0][color & 1], ncy = L.nc[1][(color >> 1) & 1];
-    for (long long l = blockIdx.x * (long long)blockDim.x + threadIdx.x; l < cnt; l += (long long)gridDim.x * blockDim.x) {
-        const long long p = base + l;
-        const int i = 2 * (int)(l % ncx) + (color & 1), j = 2 * (int)((l / ncx) % ncy) + ((color >> 1) & 1), k = 2 * (int)(l / ((long long)ncx * ncy)) + (color >> 2);
-        if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular(L, i, j, k, old)) / L.canon[2]; continue; }
-        const double d = __ldg(L.st + 13 * L.nnode + p);
-        if (d == 0.0) { x[p] = 0.0; continue; }
-        x[p] = (rhs[p] - offdiag_sum(L, p, i, j, k, old)) / d;
-    }
+    // block (64, 4): 64 consecutive i/2 of 4 rows j/2; blockIdx.z = k/2
+    const int i2 = blockIdx.x * 64 + threadIdx.x, j2 = blockIdx.y * 4 + threadIdx.y, k2 = blockIdx.z;
+    const int i = 2 * i2 + (color & 1), j = 2 * j2 + ((color >> 1) & 1), k = 2 * k2 + (color >> 2);
+    if (i >= L.nn[0] || j >= L.nn[1] || k >= L.nn[2]) return;
+    const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
+    if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular(L, i, j, k, old)) / L.canon[2]; return; }
+    const double d = __ldg(L.st + 13 * L.nnode + p);
+    if (d == 0.0) { x[p] = 0.0; return; }
+    x[p] = (rhs[p] - offdiag_sum(L, p, i, j, k, old)) / d;
 }
 // all sweeps of a smooth call on a level small enough for ONE CTA: colours separated by __syncthreads instead of kernel boundaries
 // (a level of a few thousand nodes is pure launch latency otherwise: 8 launches per sweep).  snap != nullptr: odd periodic extent.
@@ -476,10 +517,10 @@ __global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, 
                 __syncthreads();
                 old = snap;
             }
-            const int lo = (int)L.cbase[c], hi = (int)L.cbase[c + 1];
+            const int lo = c * L.CS, hi = lo + L.CS;
             for (int p = lo + tid; p < hi; p += nt) {
                 int i, j, k;
-                ndecode(L, p, i, j, k);
+                if (!ndecode(L, p, i, j, k)) continue;
                 if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular(L, i, j, k, old)) / L.canon[2]; continue; }
                 const double d = L.st[13 * L.nnode + p];
                 x[p] = d == 0.0 ? 0.0 : (rhs[p] - offdiag_sum(L, p, i, j, k, old)) / d;
@@ -491,28 +532,25 @@ __global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, 
 __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double* __restrict__ x, const double* __restrict__ rhs, double* __restrict__ out,
                                                      double* __restrict__ norm_partial)
 {
+    // block (64, 4) as in k_eb_gs; blockIdx.z = colour * H[2] + k/2.  norm_partial: one entry per block
     __shared__ double sh[34];
-    double amax = 0.0;
-    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < L.nnode; p += (long long)gridDim.x * blockDim.x) {
-        double r = 0.0;
+    const int color = blockIdx.z / L.H[2], k2 = blockIdx.z - color * L.H[2];
+    const int i2 = blockIdx.x * 64 + threadIdx.x, j2 = blockIdx.y * 4 + threadIdx.y;
+    const int i = 2 * i2 + (color & 1), j = 2 * j2 + ((color >> 1) & 1), k = 2 * k2 + (color >> 2);
+    double r = 0.0;
+    if (i < L.nn[0] && j < L.nn[1] && k < L.nn[2]) {
+        const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
         if (L.flag[p]) {
-            int i, j, k;
-            ndecode(L, p, i, j, k);
             r = rhs[p] - (L.canon[2] * x[p] + offdiag_sum_regular(L, i, j, k, x));
         } else {
             const double d = __ldg(L.st + 13 * L.nnode + p);
-            if (d != 0.0) {
-                int i, j, k;
-                ndecode(L, p, i, j, k);
-                r = rhs[p] - (d * x[p] + offdiag_sum(L, p, i, j, k, x));
-            }
+            if (d != 0.0) r = rhs[p] - (d * x[p] + offdiag_sum(L, p, i, j, k, x));
         }
         if (out) out[p] = r;
-        amax = fmax(amax, fabs(r));
     }
     if (norm_partial) {
-        amax = eb_block_reduce<true>(amax, sh);
-        if (threadIdx.x == 0) norm_partial[blockIdx.x] = amax;
+        const double amax = eb_block_reduce<true>(fabs(r), sh);
+        if (threadIdx.x == 0 && threadIdx.y == 0) norm_partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = amax;
     }
 }
 // crse = (1/8) sum_a w(a) fine(2I + a): full weighting = P^T / 8; 0 on inactive coarse nodes
@@ -690,7 +728,7 @@ __global__ void __launch_bounds__(1024) k_eb_bottom(const EbLev L, double* __res
             for (int c = 0; c < 8; ++c) {
                 for (int t = tid; t < N; t += nt) snap[t] = x[t];
                 __syncthreads();
-                const int lo = (int)L.cbase[c], hi = (int)L.cbase[c + 1];
+                const int lo = c * L.CS, hi = lo + L.CS;
                 for (int t = lo + tid; t < hi; t += nt) {
                     if (dg[t] == 0.0) { x[t] = 0.0; continue; }
                     int i, j, k;
@@ -817,7 +855,7 @@ __global__ void __launch_bounds__(256) k_eb_copy_nodes(const EbLev L, double* __
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
         int i, j, k;
-        ndecode(L, t, i, j, k);
+        if (!ndecode(L, t, i, j, k)) continue;
         const long long q = f.idx(i, j, k);
         if (!to_fab) x[t] = f.p[q];
         else if (accumulate) f.p[q] += x[t];
@@ -841,10 +879,11 @@ __global__ void __launch_bounds__(256) k_eb_export_stencil(const EbLev L, double
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
         int i, j, k;
-        ndecode(L, t, i, j, k);
+        if (!ndecode(L, t, i, j, k)) continue;
         const long long q = ((long long)k * L.nn[1] + j) * L.nn[0] + i;
-        for (int m = 0; m < 13; ++m) out[(long long)m * L.nnode + q] = L.st[(long long)(14 + m) * L.nnode + t];
-        out[13 * L.nnode + q] = L.st[13 * L.nnode + t];
+        const long long nr = (long long)L.nn[0] * L.nn[1] * L.nn[2];
+        for (int m = 0; m < 13; ++m) out[(long long)m * nr + q] = L.st[(long long)(14 + m) * L.nnode + t];
+        out[13 * nr + q] = L.st[13 * L.nnode + t];
     }
 }
 
@@ -941,7 +980,7 @@ __global__ void __launch_bounds__(256) k_eb_permute(const EbLev L, const double*
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
         int i, j, k;
-        ndecode(L, t, i, j, k);
+        if (!ndecode(L, t, i, j, k)) continue;
         const long long q = ((long long)k * L.nn[1] + j) * L.nn[0] + i;
         if (to_natural) out[q] = in[t]; else out[t] = in[q];
     }
@@ -961,6 +1000,7 @@ bool eb_is_dev_ptr(const void* p)
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
+size_t eb_nreal(const EbLev& g) { return (size_t)g.nn[0] * g.nn[1] * g.nn[2]; }   // nodes without the holes: length of a natural-order array
 size_t eb_box_doubles(const b200np_fab* b)
 {
     return (size_t)(b->hi[0] - b->lo[0] + 1) * (b->hi[1] - b->lo[1] + 1) * (b->hi[2] - b->lo[2] + 1) * (size_t)std::max(b->ncomp, 1);
@@ -1001,7 +1041,7 @@ struct b200eb {
     bool singular = true, have_geometry = false, have_ebflow = false, have_stencil = false;
     int flags_state = 0;      // 0: unknown, 1: all zero (variable sigma), 2: computed for a constant sigma and the current geometry
     double* canon = nullptr;  // 3 doubles per level
-    int small_nodes = 20000;  // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
+    int small_nodes = 4096;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
     long long launches = 0, ncell = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[12];
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1017,6 +1057,9 @@ namespace {
         kern<<<grid, block, 0, (h)->stream>>>(__VA_ARGS__); \
         (h)->launches++;                                    \
     } while (0)
+
+dim3 eb_grid3(const EbLev& g, int ncolors) { return dim3((g.H[0] + 63) / 64, (g.H[1] + 3) / 4, g.H[2] * ncolors); }
+int eb_blocks3(const EbLev& g, int ncolors) { const dim3 d = eb_grid3(g, ncolors); return (int)(d.x * d.y * d.z); }
 
 double* eb_alloc(b200eb* h, size_t doubles)
 {
@@ -1044,16 +1087,12 @@ void eb_build(b200eb* h)
             g.nn[d] = g.per[d] ? n[d] : n[d] + 1;
             g.dirlo[d] = G.bc_lo[d] == B200NP_BC_DIRICHLET;
             g.dirhi[d] = G.bc_hi[d] == B200NP_BC_DIRICHLET;
-            g.nc[d][0] = (g.nn[d] + 1) / 2;
-            g.nc[d][1] = g.nn[d] / 2;
+            g.H[d] = (g.nn[d] + 1) / 2;
             if (g.per[d] && (g.nn[d] & 1)) L.odd_periodic = true;
         }
-        long long off = 0;
-        for (int c = 0; c < 8; ++c) {
-            g.cbase[c] = off;
-            off += (long long)g.nc[0][c & 1] * g.nc[1][(c >> 1) & 1] * g.nc[2][c >> 2];
-        }
-        g.cbase[8] = g.nnode = off;
+        if ((long long)g.H[0] * g.H[1] * g.H[2] * 8 >= (1LL << 31)) throw int(B200NP_ERR_UNSUPPORTED);   // 32-bit node positions
+        g.CS = g.H[0] * g.H[1] * g.H[2];
+        g.nnode = 8LL * g.CS;
         g.st = eb_alloc(h, (size_t)27 * g.nnode);
         L.flag = reinterpret_cast<unsigned char*>(eb_alloc(h, (size_t)(g.nnode + 7) / 8 + 1));
         g.flag = L.flag;
@@ -1073,7 +1112,7 @@ void eb_build(b200eb* h)
     h->work = eb_alloc(h, (size_t)7 * h->lv.back().g.nnode);
     h->snap = eb_alloc(h, (size_t)h->lv[0].g.nnode);
     h->tmp_nat = eb_alloc(h, (size_t)14 * h->lv[0].g.nnode);
-    h->partial = eb_alloc(h, 2 * 148 * 16 + 8);
+    h->partial = eb_alloc(h, std::max(2 * 148 * 16, eb_blocks3(h->lv[0].g, 8)) + 8);
     h->dscal = eb_alloc(h, 16);
     h->dinfo = reinterpret_cast<int*>(eb_alloc(h, 4));
     ECK(cudaMallocHost(&h->hscal, 16 * sizeof(double)));
@@ -1117,14 +1156,12 @@ void eb_smooth(b200eb* h, EbLevel& L, double* x, const double* rhs, int ncalls)
     }
     for (int s = 0; s < ncalls * nsw; ++s)
         for (int c = 0; c < 8; ++c) {
-            const long long cnt = L.g.cbase[c + 1] - L.g.cbase[c];
-            if (cnt == 0) continue;
             const double* old = x;
             if (L.odd_periodic) {
                 ECK(cudaMemcpyAsync(h->snap, x, L.g.nnode * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
                 old = h->snap;
             }
-            ELAUNCH(h, k_eb_gs, eb_grid(cnt), 256, L.g, x, old, rhs, c);
+            ELAUNCH(h, k_eb_gs, eb_grid3(L.g, 1), dim3(64, 4), L.g, x, old, rhs, c);
         }
 }
 
@@ -1143,7 +1180,7 @@ void eb_vcycle(b200eb* h)
         EbLevel &L = h->lv[l], &C = h->lv[l + 1];
         ECK(cudaMemsetAsync(L.cor, 0, L.g.nnode * sizeof(double), h->stream));
         eb_smooth(h, L, L.cor, L.res, nu1);
-        ELAUNCH(h, k_eb_residual, eb_grid(L.g.nnode), 256, L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        ELAUNCH(h, k_eb_residual, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
         ELAUNCH(h, k_eb_restrict, eb_grid(C.g.nnode), 256, C.g, L.g, (const double*)L.rescor, C.res);
     }
     eb_bottom(h);
@@ -1215,8 +1252,8 @@ int eb_solve(b200eb* h, double rtol, double atol, b200np_stats* st)
         if (h->lv.size() == 1) { eb_bottom(h); }
         else eb_vcycle_run(h);
         ELAUNCH(h, k_eb_axpy, nb_, 256, L0.sol, (const double*)L0.cor, L0.g.nnode);
-        ELAUNCH(h, k_eb_residual, nb_, 256, L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
-        st->resnorm = eb_read_norm(h, nb_);
+        ELAUNCH(h, k_eb_residual, eb_grid3(L0.g, 8), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+        st->resnorm = eb_read_norm(h, eb_blocks3(L0.g, 8));
         st->iters = it + 1;
         if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
         if (h->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
@@ -1539,7 +1576,7 @@ int b200eb_level_stencil(b200eb_t* h, int lev, double* out)
         ECK(cudaSetDevice(h->device));
         EbLevel& L = h->lv[lev];
         ELAUNCH(h, k_eb_export_stencil, eb_grid(L.g.nnode), 256, L.g, h->tmp_nat);
-        ECK(cudaMemcpyAsync(out, h->tmp_nat, (size_t)14 * L.g.nnode * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        ECK(cudaMemcpyAsync(out, h->tmp_nat, 14 * eb_nreal(L.g) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         ECK(cudaStreamSynchronize(h->stream));
         return B200NP_OK;
     } catch (int e) { return e; }
@@ -1556,12 +1593,12 @@ int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, c
         EbLevel& L = h->lv[lev];
         auto up = [&](EbLevel& T, double* d, const double* src) {
             if (!src) return;
-            ECK(cudaMemcpyAsync(h->tmp_nat, src, T.g.nnode * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            ECK(cudaMemcpyAsync(h->tmp_nat, src, eb_nreal(T.g) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             ELAUNCH(h, k_eb_permute, eb_grid(T.g.nnode), 256, T.g, (const double*)h->tmp_nat, d, 0);
         };
         auto down = [&](EbLevel& T, const double* d) {
             ELAUNCH(h, k_eb_permute, eb_grid(T.g.nnode), 256, T.g, d, h->tmp_nat, 1);
-            ECK(cudaMemcpyAsync(out, h->tmp_nat, T.g.nnode * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            ECK(cudaMemcpyAsync(out, h->tmp_nat, eb_nreal(T.g) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         };
         switch (op) {
         case 0:
@@ -1571,7 +1608,7 @@ int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, c
             break;
         case 1:
             up(L, L.cor, in_a); up(L, L.res, in_b);
-            ELAUNCH(h, k_eb_residual, eb_grid(L.g.nnode), 256, L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            ELAUNCH(h, k_eb_residual, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
             down(L, L.rescor);
             break;
         case 2: {
@@ -1601,11 +1638,11 @@ int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, c
         case 5: {   // A x = -(0 - A x)
             up(L, L.cor, in_a);
             ECK(cudaMemsetAsync(L.res, 0, L.g.nnode * sizeof(double), h->stream));
-            ELAUNCH(h, k_eb_residual, eb_grid(L.g.nnode), 256, L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            ELAUNCH(h, k_eb_residual, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
             ELAUNCH(h, k_eb_permute, eb_grid(L.g.nnode), 256, L.g, (const double*)L.rescor, h->tmp_nat, 1);
-            ECK(cudaMemcpyAsync(out, h->tmp_nat, L.g.nnode * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            ECK(cudaMemcpyAsync(out, h->tmp_nat, eb_nreal(L.g) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             ECK(cudaStreamSynchronize(h->stream));
-            for (long long t = 0; t < L.g.nnode; ++t) out[t] = -out[t];
+            for (size_t t = 0; t < eb_nreal(L.g); ++t) out[t] = -out[t];
             return B200NP_OK;
         }
         default: return B200NP_ERR_BAD_ARG;
@@ -1628,7 +1665,7 @@ int b200eb_compute_rhs(b200eb_t* h, const double* vel, const b200np_fab* vel_box
         ELAUNCH(h, k_eb_divu, eb_grid(L0.g.nnode, 128), 128, L0.g, (const double*)h->geo, efab(dv, vel_box), (const double*)(h->have_ebflow ? h->ebf : nullptr),
                 1.0 / G.dx[0], 1.0 / G.dx[1], 1.0 / G.dx[2], L0.rhs);
         ELAUNCH(h, k_eb_permute, eb_grid(L0.g.nnode), 256, L0.g, (const double*)L0.rhs, h->tmp_nat, 1);
-        ECK(cudaMemcpyAsync(out, h->tmp_nat, L0.g.nnode * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        ECK(cudaMemcpyAsync(out, h->tmp_nat, eb_nreal(L0.g) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         ECK(cudaStreamSynchronize(h->stream));
         return B200NP_OK;
     } catch (int e) { return e; }

@@ -11,8 +11,13 @@
 //       discretely divergence-free and that project(mac_phi, ..) started from the converged phi does nothing
 //   shim_check multibox n max_grid        : incflo::ApplyNodalProjection over a MultiFab of max_grid^3 boxes (ng = 2) against
 //       the same call on one box -- must agree bit for bit (periodic x/y, walls z, variable density)
+//   shim_check eb in.bin out.bin nx ny nz dx bclo(3) bchi(3) sigma ebflow
+//       the AMREX_USE_EB call sequence of incflo_apply_nodal_projection.cpp:130-136, :181-219 through b200::EBNodalProjector:
+//       in.bin: vel (3, nz+2, ny+2, nx+2), vfrac, intg (18), bnorm (3), bintg (8); constant sigma; ebflow != 0: set_eb_velocity with
+//       eb_flow.vel_mag = ebflow, then getLinOp().setEBInflowVelocity; out.bin: vel, phi, gphi, eb_vel (3, with 1 ghost cell), iters
 #include "../../include/B200NodalProjector.H"
 #include "../../include/B200MacProjector.H"
+#include "../../include/B200EBNodalProjector.H"
 
 #include <cmath>
 #include <cstring>
@@ -279,8 +284,69 @@ static int mac(int argc, char** argv)
     return 0;
 }
 
+static int eb(int argc, char** argv)
+{
+    if (argc < 16) { std::printf("usage: shim_check eb in.bin out.bin nx ny nz dx bclo(3) bchi(3) sigma ebflow\n"); return 2; }
+    abort_handler() = throwing_abort;
+    const int n[3] = {std::atoi(argv[4]), std::atoi(argv[5]), std::atoi(argv[6])};
+    const double dx = std::atof(argv[7]);
+    std::array<LinOpBCType, 3> lo, hi;
+    Geometry g{{n[0], n[1], n[2]}, {dx, dx, dx}, {false, false, false}};
+    for (int d = 0; d < 3; ++d) {
+        lo[d] = (LinOpBCType)std::atoi(argv[8 + d]); hi[d] = (LinOpBCType)std::atoi(argv[11 + d]);
+        g.is_periodic[d] = lo[d] == LinOpBCType::Periodic;
+    }
+    const double sigma = std::atof(argv[14]), ebflow = std::atof(argv[15]);
+    const size_t nc = (size_t)n[0] * n[1] * n[2], ng1 = (size_t)(n[0] + 2) * (n[1] + 2) * (n[2] + 2);
+    std::vector<double> vel(3 * ng1), vfrac(nc), intg(18 * nc), bnorm(3 * nc), bintg(8 * nc), ebvel(3 * ng1, -1.0);
+    std::ifstream in(argv[2], std::ios::binary);
+    in.read((char*)vel.data(), vel.size() * 8); in.read((char*)vfrac.data(), vfrac.size() * 8); in.read((char*)intg.data(), intg.size() * 8);
+    in.read((char*)bnorm.data(), bnorm.size() * 8); in.read((char*)bintg.data(), bintg.size() * 8);
+    if (!in) { std::printf("short input\n"); return 2; }
+    try {
+        EBFArrayBoxFactory factory{Fab::make(vfrac.data(), n, 0, 1), Fab::make(intg.data(), n, 0, 18), Fab::make(bnorm.data(), n, 0, 3),
+                                   Fab::make(bintg.data(), n, 0, 8)};
+        Fab fvel = Fab::make(vel.data(), n, 1, 3), feb = Fab::make(ebvel.data(), n, 1, 3);
+        EBFlow flow;
+        flow.enabled = ebflow != 0.0; flow.is_mag = true; flow.vel_mag = ebflow;
+        if (flow.enabled) {   // set_eb_velocity(lev, time, *get_velocity_eb()[lev], 1)   (:130-136)
+            IncfloEBNodalProjection inc(g, lo, hi, factory);
+            inc.set_eb_flow(flow, 1, &feb, nullptr, nullptr);
+        }
+        LPInfo info;
+        info.setMaxCoarseningLevel(100);
+        auto nodal_projector = std::make_unique<EBNodalProjector>(fvel, sigma, g, factory, info);      // :187-188
+        nodal_projector->setDomainBC(lo, hi);                                                            // :194
+        if (flow.enabled) {
+            // the linear operator takes eb_vel without ghost cells as well: pass the valid part through a ghost-free copy
+            std::vector<double> ev(3 * nc);
+            for (int c = 0; c < 3; ++c) for (int k = 0; k < n[2]; ++k) for (int j = 0; j < n[1]; ++j) for (int i = 0; i < n[0]; ++i)
+                ev[((size_t)(c * n[2] + k) * n[1] + j) * n[0] + i] = ebvel[((size_t)(c * (n[2] + 2) + k + 1) * (n[1] + 2) + j + 1) * (n[0] + 2) + i + 1];
+            Fab fev = Fab::make(ev.data(), n, 0, 3);
+            nodal_projector->getLinOp().setEBInflowVelocity(0, fev);                                     // :196-201
+            nodal_projector->project(1e-11, 1e-14);
+        } else {
+            nodal_projector->project(1e-11, 1e-14);                                                      // :215
+        }
+        auto phi = nodal_projector->getPhi();
+        auto gradphi = nodal_projector->getGradPhi();
+        const double iters = nodal_projector->stats().iters;
+        std::ofstream out(argv[3], std::ios::binary);
+        out.write((const char*)vel.data(), vel.size() * 8);
+        out.write((const char*)phi[0]->p, phi[0]->size() * 8);
+        out.write((const char*)gradphi[0]->p, gradphi[0]->size() * 8);
+        out.write((const char*)ebvel.data(), ebvel.size() * 8);
+        out.write((const char*)&iters, 8);
+    } catch (const std::runtime_error& e) {
+        std::printf("amrex::Abort::%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv)
 {
+    if (argc >= 2 && !std::strcmp(argv[1], "eb")) return eb(argc, argv);
     if (argc >= 2 && !std::strcmp(argv[1], "mac")) return mac(argc, argv);
     if (argc >= 2 && !std::strcmp(argv[1], "host")) return host_checks();
     if (argc >= 2 && !std::strcmp(argv[1], "composite")) return composite(argc, argv);

@@ -18,7 +18,7 @@ def _lib():
 def test_library_exports_every_declared_symbol():
     mod, L = _lib()
     header = open(os.path.join(ROOT, "include", "b200np.h")).read()
-    declared = set(re.findall(r"\b(b200(?:np|mac)_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(b200(?:np|mac|eb)_[a-z_]+)\s*\(", header))
     assert declared == set(mod.EXPORTS), declared ^ set(mod.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
@@ -120,3 +120,22 @@ def test_inflow_profile_argument_checks():
     mod, L = _lib()
     arr = (C.c_double * 18)()
     assert L.b200np_set_inflow_profile(None, 31, C.byref(arr), 0.0) == 4   # no handle
+
+
+def test_eb_argument_checks_need_no_gpu():
+    """b200eb_create validates geometry and BCs before touching CUDA (AMReX's EB support asserts dx == dy == dz)"""
+    mod, L = _lib()
+    g = mod.Geom()
+    for d in range(3):
+        g.n_cell[d] = 8; g.dx[d] = 0.125; g.bc_lo[d] = 0; g.bc_hi[d] = 0
+    h = C.c_void_p()
+    g.dx[2] = 0.25
+    assert L.b200eb_create(C.byref(h), C.byref(g), None, 0) == 4       # B200NP_ERR_BAD_ARG
+    g.dx[2] = 0.125
+    g.bc_lo[0] = 1                                                      # periodic on one side only
+    assert L.b200eb_create(C.byref(h), C.byref(g), None, 0) == 3       # B200NP_ERR_BAD_BC
+    g.bc_lo[0] = 0
+    if not has_gpu():
+        assert L.b200eb_create(C.byref(h), C.byref(g), None, 0) == 5   # B200NP_ERR_CUDA: no CPU fallback
+    assert L.b200eb_project(None, None, None, None, None, 1.0, None, None, None, None, 1e-11, 1e-14, None) == 4
+    assert L.b200eb_nlevels(None) == 0
