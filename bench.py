@@ -377,6 +377,50 @@ def timed_solves(ctx, proj, wl, K, W, n_glob, restore="clone"):
     return allmax(ctx, t_dev) / K, step_ms, st, launches
 
 
+def eb_block(ctx):
+    """SURVEY 8(f) rank 4 / BASELINE configs[4], reported next to the headline (not part of `value`): one EB nodal projection
+    (b200eb_*) of test_3d/benchmark.channel_cylinder-x scaled to 512 x 128 x 128, device-resident, CUDA-event time of the call;
+    `sweep`: the level-0 Gauss-Seidel sweep (8 colour launches) against the measured HBM peak"""
+    import numpy as np
+    import torch
+    from incflo_b200 import eb_geometry as eg, eb_projector as ebp
+    n = (512, 128, 128)
+    h = 0.4 / n[1]
+    geom = eg.cylinder(n, h, 0.05000001, (0.151, 0.2, 0.0), direction=2, small_vfrac=1e-6)
+    vel0 = np.zeros((3, n[2] + 2, n[1] + 2, n[0] + 2))
+    vel0[0, 1:-1, 1:-1, 1:-1] = (geom.vfrac > 0)
+    y = (np.arange(n[1]) + 0.5) / n[1]
+    vel0[0, 1:-1, 1:-1, 0] = (6.0 * y * (1.0 - y))[None, :]          # IncfloVelFill, probtype 31
+    proj = ebp.EBNodalProjector(n, (h,) * 3, (3, 1, 0), (2, 1, 0), geom.vfrac, geom.intg)
+    tv0 = torch.from_numpy(vel0).to(ctx.device)
+    phi = torch.zeros((n[2] + 1, n[1] + 1, n[0] + 1), device=ctx.device, dtype=torch.float64)
+    times, st = [], None
+    for s_ in range(5):
+        tv = tv0.clone()
+        torch.cuda.synchronize()
+        st = proj.project(tv, 1.0, RTOL, ATOL, phi=phi)
+        if s_ >= 2:
+            times.append(st.ms_total)
+    ms = sum(times) / len(times)
+    _, nn = proj.level_dims(0)
+    nnode = nn[0] * nn[1] * nn[2]
+    t_sweep = proj.time_op(0, 0, 1, 10) / 4.0                      # ms per sweep of level 0
+    peak = peaks()[0]
+    # algorithmic bytes of a sweep: phi of the 4 neighbour colours + rhs + flag in, phi out = 49 B per node with the canonical-row flag
+    # (constant sigma, away from the body); 27 coefficients more (265 B) where the row is stored -- here < 2 % of the nodes
+    rec = {"n_cell": list(n), "ms_per_projection": ms, "ms_solve": float(st.ms_solve), "vcycles": int(st.iters), "nlevels": int(st.nlevels),
+           "resid_over_bnorm": st.resnorm / max(st.rhsnorm, st.resnorm0), "Mcell_updates_per_s": n[0] * n[1] * n[2] / ms / 1e3,
+           "launches": int(st.launches), "cut_cells": int(geom.cut_mask().sum()), "covered_cells": int((geom.vfrac == 0).sum()),
+           "sweep": {"us": 1e3 * t_sweep, "algorithmic_bytes": 49.0 * nnode, "achieved_GBs": 49.0 * nnode / t_sweep / 1e6,
+                     "frac_of_measured_peak": 49.0 * nnode / t_sweep / 1e6 / peak},
+           "what": "Hydro::NodalProjector with an EB factory (b200eb_*): channel_cylinder-x, cylinder r = 0.05 along z, mass inflow x-lo (probtype 31), "
+                   "pressure outflow x-hi, walls y, periodic z, constant density; initial projection of u = (1, 0, 0)"}
+    proj.close()
+    del tv0, phi
+    torch.cuda.empty_cache()
+    return rec
+
+
 def mac_block(ctx, n1):
     """SURVEY 8(f) rank 3, reported next to the headline (not part of `value`): one MAC projection (Hydro::MacProjector
     semantics, b200mac_*) of an n1^3 rayleigh_taylor-like field, device-resident, CUDA-event time of the call"""
@@ -572,6 +616,14 @@ def run_ours(args):
         except Exception as e:   # never let the extra record take the headline down
             mac_rec = {"error": repr(e)[:200]}
 
+    # ---------------- EB nodal projection record (N = 1): BASELINE configs[4] ----------------
+    eb_rec = None
+    if nranks == 1 and not args.no_eb:
+        try:
+            eb_rec = eb_block(ctx)
+        except Exception as e:
+            eb_rec = {"error": repr(e)[:200]}
+
     # ---------------- strong-scaling record (N > 1): 512^3 / 1024^3 in total vs one GPU, measured here ----------------
     strong_rec = None
     if nranks > 1 and not args.no_strong and not strong:
@@ -602,6 +654,8 @@ def run_ours(args):
             line["strong"] = strong_rec
         if mac_rec is not None:
             line["mac_projection"] = mac_rec
+        if eb_rec is not None:
+            line["eb_projection"] = eb_rec
         if nranks == 1 and not args.no_cpu:
             times, it_cpu, _ = cpu_port_run((N, N, N), 1, 0, "reference")
             tcpu = min(times)
@@ -638,6 +692,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer arm (the line is then not a valid bench line)")
     ap.add_argument("--no-parity", action="store_true", help="tuning sweeps only: skip the oracle check before timing")
     ap.add_argument("--no-mac", action="store_true", help="N = 1: skip the MAC projection record")
+    ap.add_argument("--no-eb", action="store_true", help="N = 1: skip the EB nodal projection record (BASELINE configs[4])")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the 512^3 / 1024^3 strong-scaling record")
     args = ap.parse_args()
     real_stdout = _json_only_stdout()

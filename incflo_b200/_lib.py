@@ -88,7 +88,7 @@ EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np
            "b200mac_create", "b200mac_destroy", "b200mac_nlevels", "b200mac_set_coeffs", "b200mac_project", "b200mac_level_op", "b200mac_level_dims",
            "b200eb_create", "b200eb_destroy", "b200eb_nlevels", "b200eb_set_geometry", "b200eb_set_eb_inflow_velocity", "b200eb_set_eb_flow",
            "b200eb_project", "b200eb_apply_nodal_projection", "b200eb_build_stencils", "b200eb_level_stencil", "b200eb_level_op", "b200eb_level_dims",
-           "b200eb_compute_rhs"]
+           "b200eb_compute_rhs", "b200eb_time_op"]
 
 _lib = None
 
@@ -170,5 +170,6 @@ def lib():
     L.b200eb_level_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
     L.b200eb_level_dims.argtypes = [vp, C.c_int, ip, ip]
     L.b200eb_compute_rhs.argtypes = [vp, dp, fb, dp]
+    L.b200eb_time_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L

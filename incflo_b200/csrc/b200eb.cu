@@ -448,50 +448,167 @@ __device__ __forceinline__ double ld_early_nc(const double* p)
     asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-// sum over the 26 neighbours of A(p, q) x(q).  All loads are issued before the first multiply (the kernels around this are latency
-// bound: one node per thread, nothing else to overlap with).
+// BATCH = true: every load of a node is issued before the first multiply (~120 registers, few resident warps): right for the
+// coarser levels, whose launches are a handful of waves and pure latency.  BATCH = false: plain loads the compiler pairs with
+// their FMAs (~40 registers, full occupancy): measured faster on a level of millions of nodes, where many resident warps hide the latency.
+// sum over the 26 neighbours of A(p, q) x(q)
+template <bool BATCH>
 __device__ __forceinline__ double offdiag_sum(const EbLev& L, long long p, int i, int j, int k, const double* x)
 {
     NbIdx q;
     nb_index(L, i, j, k, q);
-    double c[27], v[27];
-#pragma unroll
-    for (int tt = 0; tt < 27; ++tt) {
-        if (tt == 13) continue;
-        c[tt] = ld_early_nc(L.st + (long long)tt * L.nnode + p);
-        v[tt] = ld_early(x + (q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]));
-    }
     double ax = 0.0;
+    if constexpr (!BATCH) {
 #pragma unroll
-    for (int tt = 26; tt >= 0; --tt) {   // the first product needs the LAST loads: nothing can stall before all of them are issued
-        if (tt == 13) continue;
-        ax += c[tt] * v[tt];
+        for (int tt = 0; tt < 27; ++tt) {
+            if (tt == 13) continue;
+            ax += __ldg(L.st + (long long)tt * L.nnode + p) * x[q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]];
+        }
+        return ax;
+    } else {
+        double c[27], v[27];
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) {
+            if (tt == 13) continue;
+            c[tt] = ld_early_nc(L.st + (long long)tt * L.nnode + p);
+            v[tt] = ld_early(x + (q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]));
+        }
+#pragma unroll
+        for (int tt = 26; tt >= 0; --tt) {   // the first product needs the LAST loads: nothing can stall before all of them are issued
+            if (tt == 13) continue;
+            ax += c[tt] * v[tt];
+        }
+        return ax;
     }
-    return ax;
 }
 // the same sum for a node with the canonical row: 12 edge and 8 corner neighbours, no coefficient loads
+template <bool BATCH>
 __device__ __forceinline__ double offdiag_sum_regular(const EbLev& L, int i, int j, int k, const double* x)
 {
     NbIdx q;
     nb_index(L, i, j, k, q);
-    double v[27];
-#pragma unroll
-    for (int tt = 0; tt < 27; ++tt) {
-        const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
-        if (nz >= 2) v[tt] = ld_early(x + (q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]));
-    }
     double se = 0.0, sc = 0.0;
+    if constexpr (!BATCH) {
 #pragma unroll
-    for (int tt = 26; tt >= 0; --tt) {
-        const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
-        if (nz == 2) se += v[tt];
-        if (nz == 3) sc += v[tt];
+        for (int tt = 0; tt < 27; ++tt) {
+            const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+            if (nz == 2) se += x[q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]];
+            if (nz == 3) sc += x[q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]];
+        }
+        return L.canon[0] * se + L.canon[1] * sc;
+    } else {
+        double v[27];
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) {
+            const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+            if (nz >= 2) v[tt] = ld_early(x + (q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]));
+        }
+#pragma unroll
+        for (int tt = 26; tt >= 0; --tt) {
+            const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+            if (nz == 2) se += v[tt];
+            if (nz == 3) sc += v[tt];
+        }
+        return L.canon[0] * se + L.canon[1] * sc;
     }
-    return L.canon[0] * se + L.canon[1] * sc;
+}
+
+// Interior nodes (no wrap, no clamp: 0 < i < nn - 1 in every direction): the 26 neighbours sit at p + a constant that depends on the
+// colour only -- stepping down from an even coordinate goes to the odd block one slot earlier, from an odd one to the even block at the
+// same slot, and so on.  D[d][0 / 2] = offset of the lower / upper neighbour in direction d; D[d][1] = 0.
+struct NbOff {
+    int D[3][3];
+};
+__device__ __forceinline__ NbOff nb_offsets(const EbLev& L, int color)
+{
+    NbOff o;
+    const int cs[3] = {L.CS, 2 * L.CS, 4 * L.CS}, st[3] = {1, L.H[0], L.H[0] * L.H[1]};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const bool odd = (color >> d) & 1;
+        o.D[d][0] = odd ? -cs[d] : cs[d] - st[d];
+        o.D[d][1] = 0;
+        o.D[d][2] = odd ? -cs[d] + st[d] : cs[d];
+    }
+    return o;
+}
+template <bool BATCH>
+__device__ __forceinline__ double offdiag_sum_inner(const EbLev& L, int p, const NbOff& o, const double* x)
+{
+    const double* xp = x + p;
+    const double* cp = L.st + p;
+    double ax = 0.0;
+    if constexpr (!BATCH) {
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) {
+            if (tt == 13) continue;
+            ax += __ldg(cp + (long long)tt * L.nnode) * xp[o.D[0][tt % 3] + o.D[1][(tt / 3) % 3] + o.D[2][tt / 9]];
+        }
+        return ax;
+    } else {
+        double c[27], v[27];
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) {
+            if (tt == 13) continue;
+            c[tt] = ld_early_nc(cp + (long long)tt * L.nnode);
+            v[tt] = ld_early(xp + (o.D[0][tt % 3] + o.D[1][(tt / 3) % 3] + o.D[2][tt / 9]));
+        }
+#pragma unroll
+        for (int tt = 26; tt >= 0; --tt) {
+            if (tt == 13) continue;
+            ax += c[tt] * v[tt];
+        }
+        return ax;
+    }
+}
+template <bool BATCH>
+__device__ __forceinline__ double offdiag_sum_regular_inner(const EbLev& L, int p, const NbOff& o, const double* x)
+{
+    const double* xp = x + p;
+    double se = 0.0, sc = 0.0;
+    if constexpr (!BATCH) {
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) {
+            const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+            if (nz == 2) se += xp[o.D[0][tt % 3] + o.D[1][(tt / 3) % 3] + o.D[2][tt / 9]];
+            if (nz == 3) sc += xp[o.D[0][tt % 3] + o.D[1][(tt / 3) % 3] + o.D[2][tt / 9]];
+        }
+        return L.canon[0] * se + L.canon[1] * sc;
+    } else {
+        double v[27];
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) {
+            const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+            if (nz >= 2) v[tt] = ld_early(xp + (o.D[0][tt % 3] + o.D[1][(tt / 3) % 3] + o.D[2][tt / 9]));
+        }
+#pragma unroll
+        for (int tt = 26; tt >= 0; --tt) {
+            const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+            if (nz == 2) se += v[tt];
+            if (nz == 3) sc += v[tt];
+        }
+        return L.canon[0] * se + L.canon[1] * sc;
+    }
+}
+// sum_q!=p A(p, q) x(q) and the diagonal of node p = (i, j, k) of colour `color`, by the cheapest applicable path; false: inactive node
+template <bool BATCH>
+__device__ __forceinline__ bool node_row(const EbLev& L, int p, int i, int j, int k, int color, const double* x, double& off, double& diag)
+{
+    const bool inner = i > 0 && i < L.nn[0] - 1 && j > 0 && j < L.nn[1] - 1 && k > 0 && k < L.nn[2] - 1;
+    if (L.flag[p]) {
+        diag = L.canon[2];
+        off = inner ? offdiag_sum_regular_inner<BATCH>(L, p, nb_offsets(L, color), x) : offdiag_sum_regular<BATCH>(L, i, j, k, x);
+        return true;
+    }
+    diag = __ldg(L.st + 13 * L.nnode + p);
+    if (diag == 0.0) return false;
+    off = inner ? offdiag_sum_inner<BATCH>(L, p, nb_offsets(L, color), x) : offdiag_sum<BATCH>(L, p, i, j, k, x);
+    return true;
 }
 
 // one colour of a Gauss-Seidel sweep (mlndlap_gscolor_sten).  old == x except on levels where a periodic wrap joins two nodes of
 // one colour (odd periodic extent): there old is a snapshot taken before the launch.
+template <bool BATCH>
 __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const double* old, const double* __restrict__ rhs, int color)
 {
     // block (64, 4): 64 consecutive i/2 of 4 rows j/2; blockIdx.z = k/2
@@ -499,10 +616,8 @@ __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const d
     const int i = 2 * i2 + (color & 1), j = 2 * j2 + ((color >> 1) & 1), k = 2 * k2 + (color >> 2);
     if (i >= L.nn[0] || j >= L.nn[1] || k >= L.nn[2]) return;
     const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
-    if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular(L, i, j, k, old)) / L.canon[2]; return; }
-    const double d = __ldg(L.st + 13 * L.nnode + p);
-    if (d == 0.0) { x[p] = 0.0; return; }
-    x[p] = (rhs[p] - offdiag_sum(L, p, i, j, k, old)) / d;
+    double off, d;
+    x[p] = node_row<BATCH>(L, p, i, j, k, color, old, off, d) ? (rhs[p] - off) / d : 0.0;
 }
 // all sweeps of a smooth call on a level small enough for ONE CTA: colours separated by __syncthreads instead of kernel boundaries
 // (a level of a few thousand nodes is pure launch latency otherwise: 8 launches per sweep).  snap != nullptr: odd periodic extent.
@@ -521,14 +636,15 @@ __global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, 
             for (int p = lo + tid; p < hi; p += nt) {
                 int i, j, k;
                 if (!ndecode(L, p, i, j, k)) continue;
-                if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular(L, i, j, k, old)) / L.canon[2]; continue; }
+                if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular<true>(L, i, j, k, old)) / L.canon[2]; continue; }
                 const double d = L.st[13 * L.nnode + p];
-                x[p] = d == 0.0 ? 0.0 : (rhs[p] - offdiag_sum(L, p, i, j, k, old)) / d;
+                x[p] = d == 0.0 ? 0.0 : (rhs[p] - offdiag_sum<true>(L, p, i, j, k, old)) / d;
             }
             __syncthreads();
         }
 }
 // out = rhs - A x on the active nodes, 0 elsewhere; optional inf-norm partials
+template <bool BATCH>
 __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double* __restrict__ x, const double* __restrict__ rhs, double* __restrict__ out,
                                                      double* __restrict__ norm_partial)
 {
@@ -540,12 +656,8 @@ __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double
     double r = 0.0;
     if (i < L.nn[0] && j < L.nn[1] && k < L.nn[2]) {
         const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
-        if (L.flag[p]) {
-            r = rhs[p] - (L.canon[2] * x[p] + offdiag_sum_regular(L, i, j, k, x));
-        } else {
-            const double d = __ldg(L.st + 13 * L.nnode + p);
-            if (d != 0.0) r = rhs[p] - (d * x[p] + offdiag_sum(L, p, i, j, k, x));
-        }
+        double off, d;
+        if (node_row<BATCH>(L, p, i, j, k, color, x, off, d)) r = rhs[p] - (d * x[p] + off);
         if (out) out[p] = r;
     }
     if (norm_partial) {
@@ -665,7 +777,7 @@ __global__ void __launch_bounds__(1024) k_eb_bottom(const EbLev L, double* __res
         __syncthreads();
         for (int t = tid; t < N; t += nt) {
             double y = 0.0;
-            if (dg[t] != 0.0) { int i, j, k; ndecode(L, t, i, j, k); y = dg[t] * in[t] + offdiag_sum(L, t, i, j, k, in); }
+            if (dg[t] != 0.0) { int i, j, k; ndecode(L, t, i, j, k); y = dg[t] * in[t] + offdiag_sum<true>(L, t, i, j, k, in); }
             out[t] = y;
         }
         __syncthreads();
@@ -733,7 +845,7 @@ __global__ void __launch_bounds__(1024) k_eb_bottom(const EbLev L, double* __res
                     if (dg[t] == 0.0) { x[t] = 0.0; continue; }
                     int i, j, k;
                     ndecode(L, t, i, j, k);
-                    x[t] = (b[t] - offdiag_sum(L, t, i, j, k, snap)) / dg[t];
+                    x[t] = (b[t] - offdiag_sum<true>(L, t, i, j, k, snap)) / dg[t];
                 }
                 __syncthreads();
             }
@@ -1041,6 +1153,7 @@ struct b200eb {
     bool singular = true, have_geometry = false, have_ebflow = false, have_stencil = false;
     int flags_state = 0;      // 0: unknown, 1: all zero (variable sigma), 2: computed for a constant sigma and the current geometry
     double* canon = nullptr;  // 3 doubles per level
+    long long batch_below = 4000000;   // levels with fewer nodes use the load-batching kernels (B200EB_BATCH_BELOW)
     int small_nodes = 4096;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
     long long launches = 0, ncell = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[12];
@@ -1107,6 +1220,7 @@ void eb_build(b200eb* h)
     h->canon = eb_alloc(h, 3 * h->lv.size());
     for (size_t l = 0; l < h->lv.size(); ++l) h->lv[l].g.canon = h->canon + 3 * l;
     if (const char* e = getenv("B200EB_SMALL_NODES")) h->small_nodes = atoi(e);
+    if (const char* e = getenv("B200EB_BATCH_BELOW")) h->batch_below = atoll(e);
     h->geo = eb_alloc(h, (size_t)19 * h->ncell);
     h->sigma = eb_alloc(h, (size_t)h->ncell);
     h->work = eb_alloc(h, (size_t)7 * h->lv.back().g.nnode);
@@ -1161,7 +1275,8 @@ void eb_smooth(b200eb* h, EbLevel& L, double* x, const double* rhs, int ncalls)
                 ECK(cudaMemcpyAsync(h->snap, x, L.g.nnode * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
                 old = h->snap;
             }
-            ELAUNCH(h, k_eb_gs, eb_grid3(L.g, 1), dim3(64, 4), L.g, x, old, rhs, c);
+            if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_gs<false>, eb_grid3(L.g, 1), dim3(64, 4), L.g, x, old, rhs, c);
+            else ELAUNCH(h, k_eb_gs<true>, eb_grid3(L.g, 1), dim3(64, 4), L.g, x, old, rhs, c);
         }
 }
 
@@ -1180,7 +1295,8 @@ void eb_vcycle(b200eb* h)
         EbLevel &L = h->lv[l], &C = h->lv[l + 1];
         ECK(cudaMemsetAsync(L.cor, 0, L.g.nnode * sizeof(double), h->stream));
         eb_smooth(h, L, L.cor, L.res, nu1);
-        ELAUNCH(h, k_eb_residual, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
         ELAUNCH(h, k_eb_restrict, eb_grid(C.g.nnode), 256, C.g, L.g, (const double*)L.rescor, C.res);
     }
     eb_bottom(h);
@@ -1252,7 +1368,8 @@ int eb_solve(b200eb* h, double rtol, double atol, b200np_stats* st)
         if (h->lv.size() == 1) { eb_bottom(h); }
         else eb_vcycle_run(h);
         ELAUNCH(h, k_eb_axpy, nb_, 256, L0.sol, (const double*)L0.cor, L0.g.nnode);
-        ELAUNCH(h, k_eb_residual, eb_grid3(L0.g, 8), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+        if (L0.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L0.g, 8), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+        else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L0.g, 8), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
         st->resnorm = eb_read_norm(h, eb_blocks3(L0.g, 8));
         st->iters = it + 1;
         if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
@@ -1608,7 +1725,8 @@ int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, c
             break;
         case 1:
             up(L, L.cor, in_a); up(L, L.res, in_b);
-            ELAUNCH(h, k_eb_residual, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
             down(L, L.rescor);
             break;
         case 2: {
@@ -1638,7 +1756,8 @@ int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, c
         case 5: {   // A x = -(0 - A x)
             up(L, L.cor, in_a);
             ECK(cudaMemsetAsync(L.res, 0, L.g.nnode * sizeof(double), h->stream));
-            ELAUNCH(h, k_eb_residual, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
             ELAUNCH(h, k_eb_permute, eb_grid(L.g.nnode), 256, L.g, (const double*)L.rescor, h->tmp_nat, 1);
             ECK(cudaMemcpyAsync(out, h->tmp_nat, eb_nreal(L.g) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             ECK(cudaStreamSynchronize(h->stream));
@@ -1648,6 +1767,33 @@ int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, c
         default: return B200NP_ERR_BAD_ARG;
         }
         ECK(cudaStreamSynchronize(h->stream));
+        return B200NP_OK;
+    } catch (int e) { return e; }
+}
+
+// measurement hook: `reps` times { arg smooth calls (op 0) | one residual (op 1) } on the device arrays of level lev, timed with CUDA
+// events on the handle's stream; ms = average per repetition.  Needs built stencils.
+int b200eb_time_op(b200eb_t* h, int lev, int op, int arg, int reps, double* ms)
+{
+    if (!h || lev < 0 || lev >= (int)h->lv.size() || !h->have_stencil || !ms || reps < 1) return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        EbLevel& L = h->lv[lev];
+        for (int pass = 0; pass < 2; ++pass) {   // pass 0: warm-up
+            ECK(cudaEventRecord(h->ev[0], h->stream));
+            for (int r = 0; r < (pass ? reps : 1); ++r) {
+                if (op == 0) eb_smooth(h, L, L.cor, L.res, arg);
+                else if (op == 1) {
+                    if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+                    else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+                } else return B200NP_ERR_BAD_ARG;
+            }
+            ECK(cudaEventRecord(h->ev[1], h->stream));
+            ECK(cudaEventSynchronize(h->ev[1]));
+        }
+        float t = 0;
+        ECK(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+        *ms = (double)t / reps;
         return B200NP_OK;
     } catch (int e) { return e; }
 }

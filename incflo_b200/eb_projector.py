@@ -148,6 +148,11 @@ class EBNodalProjector:
         self._chk(self._L.b200eb_compute_rhs(self._h, pv, C.byref(bv), C.c_void_p(out.ctypes.data)))
         return out
 
+    def time_op(self, lev, op, arg=1, reps=10):
+        ms = C.c_double()
+        self._chk(self._L.b200eb_time_op(self._h, lev, op, arg, reps, C.byref(ms)))
+        return ms.value
+
     def close(self):
         if self._h is not None:
             self._L.b200eb_destroy(self._h)

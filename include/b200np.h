@@ -39,7 +39,7 @@ enum b200np_status {
     B200NP_ERR_BAD_ARG = 4,
     B200NP_ERR_CUDA = 5,          /* no device / CUDA runtime error                            */
     B200NP_ERR_NCCL = 6,
-    B200NP_ERR_UNSUPPORTED = 7,   /* EB, general overset masks, AMR beyond one fine box at ratio 2 */
+    B200NP_ERR_UNSUPPORTED = 7,   /* general overset masks, AMR beyond one fine box at ratio 2, EB beyond one level / box */
     B200NP_ERR_PEER_TIMEOUT = 9,  /* slab path: a neighbour rank never raised its halo flag (it died or left the call early) */
     B200NP_ERR_INOUT_FLUX = 8     /* enforceInOutSolvability: inflow without outflow through the direction_dependent
                                      faces, or the reverse (AMReX-Hydro aborts)                 */
@@ -330,6 +330,8 @@ int  b200eb_level_stencil(b200eb_t* h, int lev, double* out);
 int  b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, const double* in_b, double* out);
 int  b200eb_level_dims(const b200eb_t* h, int lev, int n_cell[3], int n_node[3]);
 int  b200eb_compute_rhs(b200eb_t* h, const double* vel, const b200np_fab* vel_box, double* out);
+/* measurement hook: reps x { arg smooth calls (op 0) | one residual (op 1) } on level lev, CUDA events; ms per repetition */
+int  b200eb_time_op(b200eb_t* h, int lev, int op, int arg, int reps, double* ms);
 
 /* IncfloVelFill (src/prob/prob_bc.H:8-351) evaluated by the library: after this call,
  * b200np_apply_nodal_projection with inflow_vel == NULL fills the first ghost layer of the velocity at INFLOW

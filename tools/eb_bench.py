@@ -42,6 +42,15 @@ for s in range(K + 2):
     if s >= 2:
         times.append(st.ms_total); solve.append(st.ms_solve)
 ms, mss = sum(times) / len(times), sum(solve) / len(solve)
+# per-level smoother / residual times (one smooth call = smooth_num_sweeps sweeps of 8 colours)
+levels = []
+for lev in range(proj.nlevels()):
+    nc_, nn_ = proj.level_dims(lev)
+    nnod = nn_[0] * nn_[1] * nn_[2]
+    t_s = proj.time_op(lev, 0, 1, 10) / 4.0
+    t_r = proj.time_op(lev, 1, 1, 10)
+    levels.append({"lev": lev, "nodes": nnod, "us_per_sweep": 1e3 * t_s, "us_per_residual": 1e3 * t_r,
+                   "sweep_GBs_at_240B_per_node": 240.0 * nnod / t_s / 1e6, "sweep_GBs_at_49B_per_node": 49.0 * nnod / t_s / 1e6})
 ncell = n[0] * n[1] * n[2]
 nnode = (n[0] + 1) * (n[1] + 1) * n[2]
 # algorithmic bytes per node and V-cycle: 16 sweeps x (27 coefficients + rhs + phi in/out = 240 B) + residual 240 + restriction 9 + interpolation 17,
@@ -54,5 +63,5 @@ print(json.dumps({"metric": "eb_nodal_projection_Mcell_updates_per_s", "value": 
                   "ms_per_projection": ms, "ms_solve": mss, "ms_setup_and_update": ms - mss, "vcycles": st.iters, "nlevels": st.nlevels,
                   "bottom_iters": st.bottom_iters, "resid_over_bnorm": st.resnorm / max(st.rhsnorm, st.resnorm0), "launches": st.launches,
                   "cut_cells": int(geom.cut_mask().sum()), "covered_cells": int((geom.vfrac == 0).sum()), "geometry_s": t_geom,
-                  "max_u_after": float(u.abs().max()),
+                  "max_u_after": float(u.abs().max()), "levels": levels,
                   "whole_solve": {"algorithmic_bytes": total, "achieved_GBs": total / ms / 1e6, "frac_of_measured_peak": total / ms / 1e6 / peak}}))
