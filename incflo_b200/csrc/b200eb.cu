@@ -591,24 +591,25 @@ __device__ __forceinline__ double offdiag_sum_regular_inner(const EbLev& L, int 
     }
 }
 // sum_q!=p A(p, q) x(q) and the diagonal of node p = (i, j, k) of colour `color`, by the cheapest applicable path; false: inactive node
-template <bool BATCH>
+// BATCH: 0 plain loads; 1 batched loads on the canonical rows only (20 loads, ~56 registers); 2 batched everywhere (~120 registers)
+template <int BATCH>
 __device__ __forceinline__ bool node_row(const EbLev& L, int p, int i, int j, int k, int color, const double* x, double& off, double& diag)
 {
     const bool inner = i > 0 && i < L.nn[0] - 1 && j > 0 && j < L.nn[1] - 1 && k > 0 && k < L.nn[2] - 1;
     if (L.flag[p]) {
         diag = L.canon[2];
-        off = inner ? offdiag_sum_regular_inner<BATCH>(L, p, nb_offsets(L, color), x) : offdiag_sum_regular<BATCH>(L, i, j, k, x);
+        off = inner ? offdiag_sum_regular_inner<(BATCH >= 1)>(L, p, nb_offsets(L, color), x) : offdiag_sum_regular<(BATCH >= 1)>(L, i, j, k, x);
         return true;
     }
     diag = __ldg(L.st + 13 * L.nnode + p);
     if (diag == 0.0) return false;
-    off = inner ? offdiag_sum_inner<BATCH>(L, p, nb_offsets(L, color), x) : offdiag_sum<BATCH>(L, p, i, j, k, x);
+    off = inner ? offdiag_sum_inner<(BATCH >= 2)>(L, p, nb_offsets(L, color), x) : offdiag_sum<(BATCH >= 2)>(L, p, i, j, k, x);
     return true;
 }
 
 // one colour of a Gauss-Seidel sweep (mlndlap_gscolor_sten).  old == x except on levels where a periodic wrap joins two nodes of
 // one colour (odd periodic extent): there old is a snapshot taken before the launch.
-template <bool BATCH>
+template <int BATCH>
 __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const double* old, const double* __restrict__ rhs, int color)
 {
     // block (64, 4): 64 consecutive i/2 of 4 rows j/2; blockIdx.z = k/2
@@ -644,7 +645,7 @@ __global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, 
         }
 }
 // out = rhs - A x on the active nodes, 0 elsewhere; optional inf-norm partials
-template <bool BATCH>
+template <int BATCH>
 __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double* __restrict__ x, const double* __restrict__ rhs, double* __restrict__ out,
                                                      double* __restrict__ norm_partial)
 {
@@ -1154,6 +1155,7 @@ struct b200eb {
     int flags_state = 0;      // 0: unknown, 1: all zero (variable sigma), 2: computed for a constant sigma and the current geometry
     double* canon = nullptr;  // 3 doubles per level
     long long batch_below = 4000000;   // levels with fewer nodes use the load-batching kernels (B200EB_BATCH_BELOW)
+    int big_variant = 1;      // levels of >= batch_below nodes: 0 plain loads, 1 batched loads on the canonical rows (B200EB_BIG_VARIANT)
     int small_nodes = 4096;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
     long long launches = 0, ncell = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[12];
@@ -1221,6 +1223,7 @@ void eb_build(b200eb* h)
     for (size_t l = 0; l < h->lv.size(); ++l) h->lv[l].g.canon = h->canon + 3 * l;
     if (const char* e = getenv("B200EB_SMALL_NODES")) h->small_nodes = atoi(e);
     if (const char* e = getenv("B200EB_BATCH_BELOW")) h->batch_below = atoll(e);
+    if (const char* e = getenv("B200EB_BIG_VARIANT")) h->big_variant = atoi(e);
     h->geo = eb_alloc(h, (size_t)19 * h->ncell);
     h->sigma = eb_alloc(h, (size_t)h->ncell);
     h->work = eb_alloc(h, (size_t)7 * h->lv.back().g.nnode);
@@ -1260,6 +1263,22 @@ void eb_build_stencils(b200eb* h, double const_sigma)
     h->have_stencil = true;
 }
 
+// kernel variant by level size (struct b200eb: batch_below, big_variant)
+void eb_launch_gs(b200eb* h, EbLevel& L, double* x, const double* old, const double* rhs, int c)
+{
+    const dim3 grid = eb_grid3(L.g, 1), block(64, 4);
+    if (L.g.nnode < h->batch_below) ELAUNCH(h, k_eb_gs<2>, grid, block, L.g, x, old, rhs, c);
+    else if (h->big_variant == 1) ELAUNCH(h, k_eb_gs<1>, grid, block, L.g, x, old, rhs, c);
+    else ELAUNCH(h, k_eb_gs<0>, grid, block, L.g, x, old, rhs, c);
+}
+void eb_launch_residual(b200eb* h, EbLevel& L, const double* x, const double* rhs, double* out, double* partial)
+{
+    const dim3 grid = eb_grid3(L.g, 8), block(64, 4);
+    if (L.g.nnode < h->batch_below) ELAUNCH(h, k_eb_residual<2>, grid, block, L.g, x, rhs, out, partial);
+    else if (h->big_variant == 1) ELAUNCH(h, k_eb_residual<1>, grid, block, L.g, x, rhs, out, partial);
+    else ELAUNCH(h, k_eb_residual<0>, grid, block, L.g, x, rhs, out, partial);
+}
+
 // one MLMG smooth call = smooth_num_sweeps sweeps of 8 colours
 void eb_smooth(b200eb* h, EbLevel& L, double* x, const double* rhs, int ncalls)
 {
@@ -1275,8 +1294,7 @@ void eb_smooth(b200eb* h, EbLevel& L, double* x, const double* rhs, int ncalls)
                 ECK(cudaMemcpyAsync(h->snap, x, L.g.nnode * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
                 old = h->snap;
             }
-            if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_gs<false>, eb_grid3(L.g, 1), dim3(64, 4), L.g, x, old, rhs, c);
-            else ELAUNCH(h, k_eb_gs<true>, eb_grid3(L.g, 1), dim3(64, 4), L.g, x, old, rhs, c);
+            eb_launch_gs(h, L, x, old, rhs, c);
         }
 }
 
@@ -1295,8 +1313,7 @@ void eb_vcycle(b200eb* h)
         EbLevel &L = h->lv[l], &C = h->lv[l + 1];
         ECK(cudaMemsetAsync(L.cor, 0, L.g.nnode * sizeof(double), h->stream));
         eb_smooth(h, L, L.cor, L.res, nu1);
-        if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
-        else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        eb_launch_residual(h, L, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
         ELAUNCH(h, k_eb_restrict, eb_grid(C.g.nnode), 256, C.g, L.g, (const double*)L.rescor, C.res);
     }
     eb_bottom(h);
@@ -1368,8 +1385,7 @@ int eb_solve(b200eb* h, double rtol, double atol, b200np_stats* st)
         if (h->lv.size() == 1) { eb_bottom(h); }
         else eb_vcycle_run(h);
         ELAUNCH(h, k_eb_axpy, nb_, 256, L0.sol, (const double*)L0.cor, L0.g.nnode);
-        if (L0.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L0.g, 8), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
-        else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L0.g, 8), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+        eb_launch_residual(h, L0, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
         st->resnorm = eb_read_norm(h, eb_blocks3(L0.g, 8));
         st->iters = it + 1;
         if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
@@ -1725,8 +1741,7 @@ int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, c
             break;
         case 1:
             up(L, L.cor, in_a); up(L, L.res, in_b);
-            if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
-        else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            eb_launch_residual(h, L, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
             down(L, L.rescor);
             break;
         case 2: {
@@ -1756,8 +1771,7 @@ int b200eb_level_op(b200eb_t* h, int lev, int op, int arg, const double* in_a, c
         case 5: {   // A x = -(0 - A x)
             up(L, L.cor, in_a);
             ECK(cudaMemsetAsync(L.res, 0, L.g.nnode * sizeof(double), h->stream));
-            if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
-        else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            eb_launch_residual(h, L, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
             ELAUNCH(h, k_eb_permute, eb_grid(L.g.nnode), 256, L.g, (const double*)L.rescor, h->tmp_nat, 1);
             ECK(cudaMemcpyAsync(out, h->tmp_nat, eb_nreal(L.g) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
             ECK(cudaStreamSynchronize(h->stream));
@@ -1784,8 +1798,7 @@ int b200eb_time_op(b200eb_t* h, int lev, int op, int arg, int reps, double* ms)
             for (int r = 0; r < (pass ? reps : 1); ++r) {
                 if (op == 0) eb_smooth(h, L, L.cor, L.res, arg);
                 else if (op == 1) {
-                    if (L.g.nnode >= h->batch_below) ELAUNCH(h, k_eb_residual<false>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
-                    else ELAUNCH(h, k_eb_residual<true>, eb_grid3(L.g, 8), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+                    eb_launch_residual(h, L, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
                 } else return B200NP_ERR_BAD_ARG;
             }
             ECK(cudaEventRecord(h->ev[1], h->stream));

@@ -353,3 +353,36 @@ def test_bad_arguments():
     with pytest.raises(ProjectionError):      # constant sigma must be positive
         pr.project(np.zeros((3, 10, 10, 10)), 0.0, 1e-10, 1e-14)
     pr.close()
+
+
+@pytest.mark.parametrize("name", ["eb_channel_cylinder", "eb_cylinder_ebflow", "eb_sphere_periodic_var"])
+def test_finest_level_kernel_variants(name, monkeypatch):
+    """the kernels of the finest level of configs[4] (k_eb_gs<false> / k_eb_residual<false>: plain loads, full occupancy) are selected by
+    size; B200EB_BATCH_BELOW = 0 puts every level of the small fixtures on them (and B200EB_SMALL_NODES = 0 takes the one-CTA smoother out)"""
+    from incflo_b200 import eb_projector as ebp
+    from oracle import eb_oracle as eo
+    monkeypatch.setenv("B200EB_BATCH_BELOW", "0")
+    monkeypatch.setenv("B200EB_SMALL_NODES", "0")
+    g, p, sigma, ebv = load(name)
+    mg = eo.MG(p, sigma, g["vfrac"], g["intg"])
+    pr = make_projector(g, p, ebv)
+    pr.build_stencils(sigma)
+    rng = np.random.default_rng(5)
+    for l, L in enumerate(mg.lv):
+        x = np.where(L.active, rng.standard_normal(L.shape), 0.0)
+        b = np.where(L.active, rng.standard_normal(L.shape), 0.0) * np.abs(L.st[13]).max()
+        want = eo.gs_sweeps(L, x.copy(), b, p.nsweeps)
+        assert relmax(pr.level_op(l, ebp.OP_SMOOTH, 1, a=x, b=b), want) < 1e-11, (name, l)
+        assert relmax(pr.level_op(l, ebp.OP_RESIDUAL, a=x, b=b), eo.residual(L, x, b)) < 1e-12
+    ref = eo.project(p, g["vel"], sigma, g["vfrac"], g["intg"], 1e-11, 1e-14, ebv, g["bnorm"], g["bintg"])
+    vel = np.ascontiguousarray(g["vel"]).copy()
+    n = p.n
+    phi = np.zeros((n[2] + 1, n[1] + 1, n[0] + 1))
+    st = pr.project(vel, sigma, 1e-11, 1e-14, phi=phi)
+    assert st.status == 0 and st.iters == ref["info"]["iters"]
+    act = ref["mg"].lv[0].active
+    a, b = phi[:act.shape[0], :act.shape[1], :act.shape[2]].copy(), ref["phi"].copy()
+    if p.singular:
+        a[act] -= a[act].mean(); b[act] -= b[act].mean()
+    assert rel(a, b) < 1e-9 and rel(vel[:, 1:-1, 1:-1, 1:-1], ref["vel"]) < 1e-9
+    pr.close()
