@@ -377,7 +377,7 @@ def timed_solves(ctx, proj, wl, K, W, n_glob, restore="clone"):
     return allmax(ctx, t_dev) / K, step_ms, st, launches
 
 
-def eb_block(ctx):
+def eb_block(ctx, with_cpu=True):
     """SURVEY 8(f) rank 4 / BASELINE configs[4], reported next to the headline (not part of `value`): one EB nodal projection
     (b200eb_*) of test_3d/benchmark.channel_cylinder-x scaled to 512 x 128 x 128, device-resident, CUDA-event time of the call;
     `sweep`: the level-0 Gauss-Seidel sweep (8 colour launches) against the measured HBM peak"""
@@ -418,6 +418,32 @@ def eb_block(ctx):
     proj.close()
     del tv0, phi
     torch.cuda.empty_cache()
+    if with_cpu:
+        # the CPU restatement timed beside it on a bounded sample of the same workload (256 x 64 x 64), and parity at that size
+        import time as _t
+        from oracle import eb_oracle as eo
+        ns = (256, 64, 64)
+        hs = 0.4 / ns[1]
+        gs = eg.cylinder(ns, hs, 0.05000001, (0.151, 0.2, 0.0), direction=2, small_vfrac=1e-6)
+        vs = np.zeros((3, ns[2] + 2, ns[1] + 2, ns[0] + 2))
+        vs[0, 1:-1, 1:-1, 1:-1] = (gs.vfrac > 0)
+        ys = (np.arange(ns[1]) + 0.5) / ns[1]
+        vs[0, 1:-1, 1:-1, 0] = (6.0 * ys * (1.0 - ys))[None, :]
+        t0 = _t.perf_counter()
+        ref = eo.project(eo.Params(ns, (hs,) * 3, (3, 1, 0), (2, 1, 0)), vs, 1.0, gs.vfrac, gs.intg, RTOL, ATOL)
+        tcpu = _t.perf_counter() - t0
+        pr2 = ebp.EBNodalProjector(ns, (hs,) * 3, (3, 1, 0), (2, 1, 0), gs.vfrac, gs.intg)
+        vg = vs.copy()
+        pg = np.zeros((ns[2] + 1, ns[1] + 1, ns[0] + 1))
+        st2 = pr2.project(vg, 1.0, RTOL, ATOL, phi=pg)
+        pr2.close()
+        rl2 = lambda a, b: float(np.linalg.norm((a - b).ravel()) / np.linalg.norm(b.ravel()))
+        rec["cpu_port"] = {"n_cell": list(ns), "seconds": tcpu, "Mcell_updates_per_s": ns[0] * ns[1] * ns[2] / tcpu / 1e6, "cores": 1,
+                           "vcycles": int(ref["info"]["iters"]), "what": "oracle/eb_oracle.py (numpy + SciPy sparse, one thread): CPU restatement, not AMReX"}
+        rec["parity"] = {"n_cell": list(ns), "rel_l2_phi": rl2(pg[:ns[2]], ref["phi"]), "rel_l2_u": rl2(vg[:, 1:-1, 1:-1, 1:-1], ref["vel"]),
+                         "vcycles_gpu": int(st2.iters), "vcycles_oracle": int(ref["info"]["iters"]), "tolerance": 1e-9}
+        if not (rec["parity"]["rel_l2_phi"] < 1e-9 and rec["parity"]["rel_l2_u"] < 1e-9):
+            rec["parity"]["FAILED"] = True
     return rec
 
 
@@ -620,7 +646,7 @@ def run_ours(args):
     eb_rec = None
     if nranks == 1 and not args.no_eb:
         try:
-            eb_rec = eb_block(ctx)
+            eb_rec = eb_block(ctx, with_cpu=not args.no_cpu)
         except Exception as e:
             eb_rec = {"error": repr(e)[:200]}
 
