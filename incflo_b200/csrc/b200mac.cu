@@ -86,7 +86,8 @@ __device__ __forceinline__ double block_reduce(double v, double* sh)
         const double w = __shfl_xor_sync(0xffffffffu, v, o);
         v = MAXR ? fmax(v, w) : v + w;
     }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const int tid_ = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lane = tid_ & 31, wid = tid_ >> 5, nw = (blockDim.x * blockDim.y + 31) >> 5;
     __syncthreads();
     if (lane == 0) sh[wid] = v;
     __syncthreads();
@@ -116,23 +117,22 @@ __device__ __forceinline__ double adotx_cell(const MacLev& L, const double* __re
     return y;
 }
 
-// out = rhs - A phi (rhs may be nullptr: out = -A phi ... used as +A phi by the bottom solver with sign = -1)
+// out = rhs - A phi; optional inf-norm partials (one entry per block).  Launch: block (64, 4), grid (ceil(nx / 64), ceil(ny / 4), nz).
 __global__ void __launch_bounds__(256) k_mac_residual(const MacLev L, const double* __restrict__ phi, const double* __restrict__ rhs,
                                                       double* __restrict__ out, double* __restrict__ norm_partial)
 {
     __shared__ double sh[34];
-    const long long N = (long long)L.n[0] * L.n[1] * L.n[2];
-    double amax = 0.0;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(t % L.n[0]), j = (int)((t / L.n[0]) % L.n[1]), k = (int)(t / ((long long)L.n[0] * L.n[1]));
+    const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    double r = 0.0;
+    if (i < L.n[0] && j < L.n[1]) {
+        const long long t = cidx(L, i, j, k);
         const double pc = phi[t];
-        const double r = rhs[t] - adotx_cell(L, phi, i, j, k, pc);
+        r = rhs[t] - adotx_cell(L, phi, i, j, k, pc);
         if (out) out[t] = r;
-        amax = fmax(amax, fabs(r));
     }
     if (norm_partial) {
-        amax = block_reduce<true>(amax, sh);
-        if (threadIdx.x == 0) norm_partial[blockIdx.x] = amax;
+        const double amax = block_reduce<true>(fabs(r), sh);
+        if (threadIdx.x == 0 && threadIdx.y == 0) norm_partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = amax;
     }
 }
 
@@ -142,28 +142,25 @@ __global__ void __launch_bounds__(256) k_mac_residual(const MacLev L, const doub
 __global__ void __launch_bounds__(256) k_mac_gsrb(const MacLev L, double* phi, const double* old /* may alias phi */,
                                                   const double* __restrict__ rhs, int redblack)
 {
-    const int nxh = (L.n[0] + 1) / 2;
-    const long long N = (long long)nxh * L.n[1] * L.n[2];
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
-        const int ih = (int)(t % nxh), j = (int)((t / nxh) % L.n[1]), k = (int)(t / ((long long)nxh * L.n[1]));
-        const int i = 2 * ih + ((j + k + redblack) & 1);
-        if (i >= L.n[0]) continue;
-        const long long c = cidx(L, i, j, k);
-        const double pc = old[c];
-        double gamma = 0.0, delta = 0.0, rho = 0.0;
+    // block (64, 4) over (i / 2, j), blockIdx.z = k
+    const int ih = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
+    const int i = 2 * ih + ((j + k + redblack) & 1);
+    if (i >= L.n[0] || j >= L.n[1]) return;
+    const long long c = cidx(L, i, j, k);
+    const double pc = old[c];
+    double gamma = 0.0, delta = 0.0, rho = 0.0;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int q = d == 0 ? i : d == 1 ? j : k;
-            const double bl = bface(L, d, i, j, k), bh = bface(L, d, i + (d == 0), j + (d == 1), k + (d == 2));
-            const double lo = nb(L, old, i, j, k, d, -1, pc), hi = nb(L, old, i, j, k, d, +1, pc);
-            gamma += L.dh[d] * (bl + bh);
-            rho += L.dh[d] * (bl * lo + bh * hi);
-            if (q == 0) delta += L.dh[d] * bl * L.cflo[d];
-            if (q == L.n[d] - 1) delta += L.dh[d] * bh * L.cfhi[d];
-        }
-        const double res = rhs[c] - (gamma * pc - rho);
-        phi[c] = pc + MAC_OMEGA / (gamma - delta) * res;
+    for (int d = 0; d < 3; ++d) {
+        const int q = d == 0 ? i : d == 1 ? j : k;
+        const double bl = bface(L, d, i, j, k), bh = bface(L, d, i + (d == 0), j + (d == 1), k + (d == 2));
+        const double lo = nb(L, old, i, j, k, d, -1, pc), hi = nb(L, old, i, j, k, d, +1, pc);
+        gamma += L.dh[d] * (bl + bh);
+        rho += L.dh[d] * (bl * lo + bh * hi);
+        if (q == 0) delta += L.dh[d] * bl * L.cflo[d];
+        if (q == L.n[d] - 1) delta += L.dh[d] * bh * L.cfhi[d];
     }
+    const double res = rhs[c] - (gamma * pc - rho);
+    phi[c] = pc + MAC_OMEGA / (gamma - delta) * res;
 }
 
 // crse = mean of the 8 fine cells (MLCellLinOp::restriction)
@@ -278,12 +275,21 @@ __global__ void __launch_bounds__(256) k_mac_absmax_partial(const double* __rest
     a = block_reduce<true>(a, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = a;
 }
-// x -= mean(x): one CTA sums in a fixed order (solvability offset of all-Neumann / periodic problems)
-__global__ void __launch_bounds__(1024) k_mac_sum(const double* __restrict__ x, long long n, double* __restrict__ out)
+// x -= mean(x): partial sums per block, then one CTA adds them -- a fixed order for a given size (solvability offset of all-Neumann /
+// periodic problems)
+__global__ void __launch_bounds__(256) k_mac_sum_partial(const double* __restrict__ x, long long n, double* __restrict__ partial)
 {
     __shared__ double sh[34];
     double a = 0.0;
-    for (long long t = threadIdx.x; t < n; t += blockDim.x) a += x[t];
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) a += x[t];
+    a = block_reduce<false>(a, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = a;
+}
+__global__ void __launch_bounds__(1024) k_mac_sum(const double* __restrict__ partial, int nb_, long long n, double* __restrict__ out)
+{
+    __shared__ double sh[34];
+    double a = 0.0;
+    for (int t = threadIdx.x; t < nb_; t += blockDim.x) a += partial[t];
     a = block_reduce<false>(a, sh);
     if (threadIdx.x == 0) out[0] = a / (double)n;
 }
@@ -417,6 +423,8 @@ MFab mfab(double* p, const b200np_fab* b)
     f.nx = b->hi[0] - b->lo[0] + 1; f.ny = b->hi[1] - b->lo[1] + 1;
     return f;
 }
+dim3 mac_grid3(const MacLev& g, int xdiv = 1) { return dim3(((g.n[0] + xdiv - 1) / xdiv + 63) / 64, (g.n[1] + 3) / 4, g.n[2]); }
+int mac_blocks3(const MacLev& g) { const dim3 d = mac_grid3(g); return (int)(d.x * d.y * d.z); }
 int grid_for(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148 * 8)); }
 
 }  // namespace
@@ -491,7 +499,7 @@ void mac_build(b200mac* h)
     const MacLevel& B = h->lv.back();
     h->work = mac_alloc(h, (size_t)8 * B.ncell);
     h->snap = mac_alloc(h, (size_t)h->lv[0].ncell);
-    h->partial = mac_alloc(h, 148 * 8 + 8);
+    h->partial = mac_alloc(h, std::max(148 * 8, mac_blocks3(h->lv[0].g)) + 8);
     h->dscal = mac_alloc(h, 16);
     h->dinfo = reinterpret_cast<int*>(mac_alloc(h, 4));
     MCK(cudaMallocHost(&h->hscal, 16 * sizeof(double)));
@@ -512,7 +520,6 @@ void mac_coarsen_coeffs(b200mac* h)
 // one MLMG smooth call: red half-sweep, black half-sweep
 void mac_smooth(b200mac* h, MacLevel& L, double* phi, const double* rhs, int ncalls)
 {
-    const long long nh = (long long)((L.g.n[0] + 1) / 2) * L.g.n[1] * L.g.n[2];
     for (int c = 0; c < ncalls; ++c)
         for (int rb = 0; rb < 2; ++rb) {
             const double* old = phi;
@@ -520,7 +527,7 @@ void mac_smooth(b200mac* h, MacLevel& L, double* phi, const double* rhs, int nca
                 MCK(cudaMemcpyAsync(h->snap, phi, L.ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
                 old = h->snap;
             }
-            MLAUNCH(h, k_mac_gsrb, grid_for(nh), 256, L.g, phi, old, rhs, rb);
+            MLAUNCH(h, k_mac_gsrb, mac_grid3(L.g, 2), dim3(64, 4), L.g, phi, old, rhs, rb);
         }
 }
 
@@ -532,7 +539,7 @@ void mac_vcycle(b200mac* h)
         MacLevel &L = h->lv[l], &C = h->lv[l + 1];
         MCK(cudaMemsetAsync(L.cor, 0, L.ncell * sizeof(double), h->stream));
         mac_smooth(h, L, L.cor, L.res, nu1);
-        MLAUNCH(h, k_mac_residual, grid_for(L.ncell), 256, L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        MLAUNCH(h, k_mac_residual, mac_grid3(L.g), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
         MLAUNCH(h, k_mac_restrict, grid_for(C.ncell), 256, C.g, L.g.n[0], L.g.n[1], (const double*)L.rescor, C.res);
     }
     MacLevel& B = h->lv.back();
@@ -584,14 +591,15 @@ int mac_solve(b200mac* h, double rtol, double atol, b200np_stats* st)
     st->iters = 0; st->bottom_iters = 0; st->status = B200NP_OK; st->nlevels = (int)h->lv.size();
     MCK(cudaMemsetAsync(h->dinfo, 0, 4 * sizeof(int), h->stream));
     if (h->singular) {   // makeSolvable: remove the mean of rhs
-        MLAUNCH(h, k_mac_sum, 1, 1024, (const double*)L0.rhs, L0.ncell, h->dscal);
+        MLAUNCH(h, k_mac_sum_partial, grid_for(L0.ncell), 256, (const double*)L0.rhs, L0.ncell, h->partial);
+        MLAUNCH(h, k_mac_sum, 1, 1024, (const double*)h->partial, grid_for(L0.ncell), L0.ncell, h->dscal);
         MLAUNCH(h, k_mac_sub, grid_for(L0.ncell), 256, L0.rhs, L0.ncell, (const double*)h->dscal);
     }
     const int nb_ = grid_for(L0.ncell);
     MLAUNCH(h, k_mac_absmax_partial, nb_, 256, (const double*)L0.rhs, L0.ncell, h->partial);
     st->rhsnorm = mac_read_norm(h, nb_);
-    MLAUNCH(h, k_mac_residual, nb_, 256, L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
-    st->resnorm0 = mac_read_norm(h, nb_);
+    MLAUNCH(h, k_mac_residual, mac_grid3(L0.g), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+    st->resnorm0 = mac_read_norm(h, mac_blocks3(L0.g));
     const double maxnorm = std::max(st->rhsnorm, st->resnorm0);
     const double target = std::max(atol, std::max(rtol, 1e-16) * maxnorm);
     st->resnorm = st->resnorm0;
@@ -602,8 +610,8 @@ int mac_solve(b200mac* h, double rtol, double atol, b200np_stats* st)
     for (int it = 0; it < h->opts.maxiter; ++it) {
         mac_vcycle_run(h);
         MLAUNCH(h, k_mac_axpy, nb_, 256, L0.sol, (const double*)L0.cor, L0.ncell);
-        MLAUNCH(h, k_mac_residual, nb_, 256, L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
-        st->resnorm = mac_read_norm(h, nb_);
+        MLAUNCH(h, k_mac_residual, mac_grid3(L0.g), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+        st->resnorm = mac_read_norm(h, mac_blocks3(L0.g));
         st->iters = it + 1;
         if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
         if (h->opts.verbose >= 2) printf("MLMG: Iteration %3d Fine resid/bnorm = %.12g\n", it + 1, st->resnorm / maxnorm);
@@ -797,7 +805,7 @@ int b200mac_level_op(b200mac_t* h, int lev, int op, int arg, const double* in_a,
             break;
         case 1:   // residual: out = in_b - A in_a
             up(L.cor, in_a); up(L.res, in_b);
-            MLAUNCH(h, k_mac_residual, grid_for(L.ncell), 256, L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+            MLAUNCH(h, k_mac_residual, mac_grid3(L.g), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
             MCK(cudaMemcpyAsync(out, L.rescor, bytes, cudaMemcpyDeviceToHost, h->stream));
             break;
         case 2: { // restrict: out (level lev+1) = R in_a
