@@ -51,6 +51,11 @@ struct EbLev {
     const double* canon;         // canon[0], corners canon[1], diagonal canon[2]): the kernels do not read its 27 coefficients.  All 0 with
 };                               // variable sigma.  canon lives in device memory: a captured V-cycle graph must see the current sigma.
 
+// Programmatic dependent launch: pdl_wait() blocks until the predecessor kernel has completed and its writes are visible (must precede
+// the first access to data it produced); pdl_trigger() lets the successor become resident early (it waits in its own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // caller array with its own box, component stride
 struct EFab {
     double* p;
@@ -615,6 +620,8 @@ __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const d
     // block (64, 4): 64 consecutive i/2 of 4 rows j/2; blockIdx.z = k/2
     const int i2 = blockIdx.x * 64 + threadIdx.x, j2 = blockIdx.y * 4 + threadIdx.y, k2 = blockIdx.z;
     const int i = 2 * i2 + (color & 1), j = 2 * j2 + ((color >> 1) & 1), k = 2 * k2 + (color >> 2);
+    if (gridDim.x * gridDim.y * gridDim.z <= 1184u) pdl_trigger();   // a single wave: let the next colour's blocks in right away
+    pdl_wait();
     if (i >= L.nn[0] || j >= L.nn[1] || k >= L.nn[2]) return;
     const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
     double off, d;
@@ -624,6 +631,7 @@ __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const d
 // (a level of a few thousand nodes is pure launch latency otherwise: 8 launches per sweep).  snap != nullptr: odd periodic extent.
 __global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, double* snap, const double* __restrict__ rhs, int nsweeps)
 {
+    pdl_wait();
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int s = 0; s < nsweeps; ++s)
         for (int c = 0; c < 8; ++c) {
@@ -655,6 +663,7 @@ __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double
     const int i2 = blockIdx.x * 64 + threadIdx.x, j2 = blockIdx.y * 4 + threadIdx.y;
     const int i = 2 * i2 + (color & 1), j = 2 * j2 + ((color >> 1) & 1), k = 2 * k2 + (color >> 2);
     double r = 0.0;
+    pdl_wait();
     if (i < L.nn[0] && j < L.nn[1] && k < L.nn[2]) {
         const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
         double off, d;
@@ -669,6 +678,7 @@ __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double
 // crse = (1/8) sum_a w(a) fine(2I + a): full weighting = P^T / 8; 0 on inactive coarse nodes
 __global__ void __launch_bounds__(256) k_eb_restrict(const EbLev C, const EbLev F, const double* __restrict__ fine, double* __restrict__ crse)
 {
+    pdl_wait();
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < C.nnode; t += (long long)gridDim.x * blockDim.x) {
         double s = 0.0;
         if (C.st[13 * C.nnode + t] != 0.0) {
@@ -693,6 +703,7 @@ __global__ void __launch_bounds__(256) k_eb_restrict(const EbLev C, const EbLev 
 // fine += P crse (trilinear) on the active fine nodes
 __global__ void __launch_bounds__(256) k_eb_interp_add(const EbLev F, const EbLev C, double* __restrict__ fine, const double* __restrict__ crse)
 {
+    pdl_wait();
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < F.nnode; t += (long long)gridDim.x * blockDim.x) {
         if (F.st[13 * F.nnode + t] == 0.0) continue;
         int i, j, k;
@@ -1155,6 +1166,7 @@ struct b200eb {
     int flags_state = 0;      // 0: unknown, 1: all zero (variable sigma), 2: computed for a constant sigma and the current geometry
     double* canon = nullptr;  // 3 doubles per level
     long long batch_below = 4000000;   // levels with fewer nodes use the load-batching kernels (B200EB_BATCH_BELOW)
+    int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200EB_PDL)
     int big_variant = 1;      // levels of >= batch_below nodes: 0 plain loads, 1 batched loads on the canonical rows (B200EB_BIG_VARIANT)
     int small_nodes = 4096;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
     long long launches = 0, ncell = 0;
@@ -1175,6 +1187,20 @@ namespace {
 
 dim3 eb_grid3(const EbLev& g, int ncolors) { return dim3((g.H[0] + 63) / 64, (g.H[1] + 3) / 4, g.H[2] * ncolors); }
 int eb_blocks3(const EbLev& g, int ncolors) { const dim3 d = eb_grid3(g, ncolors); return (int)(d.x * d.y * d.z); }
+
+// launch with the programmatic-stream-serialization attribute: ONLY for kernels that call pdl_wait() before touching data
+template <typename... KArgs, typename... Args>
+void eb_launch_pdl(b200eb* h, void (*kern)(KArgs...), dim3 grid, dim3 block, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->use_pdl ? 1 : 0;
+    ECK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+    h->launches++;
+}
 
 double* eb_alloc(b200eb* h, size_t doubles)
 {
@@ -1223,6 +1249,7 @@ void eb_build(b200eb* h)
     for (size_t l = 0; l < h->lv.size(); ++l) h->lv[l].g.canon = h->canon + 3 * l;
     if (const char* e = getenv("B200EB_SMALL_NODES")) h->small_nodes = atoi(e);
     if (const char* e = getenv("B200EB_BATCH_BELOW")) h->batch_below = atoll(e);
+    if (const char* e = getenv("B200EB_PDL")) h->use_pdl = atoi(e);
     if (const char* e = getenv("B200EB_BIG_VARIANT")) h->big_variant = atoi(e);
     h->geo = eb_alloc(h, (size_t)19 * h->ncell);
     h->sigma = eb_alloc(h, (size_t)h->ncell);
@@ -1267,16 +1294,16 @@ void eb_build_stencils(b200eb* h, double const_sigma)
 void eb_launch_gs(b200eb* h, EbLevel& L, double* x, const double* old, const double* rhs, int c)
 {
     const dim3 grid = eb_grid3(L.g, 1), block(64, 4);
-    if (L.g.nnode < h->batch_below) ELAUNCH(h, k_eb_gs<2>, grid, block, L.g, x, old, rhs, c);
-    else if (h->big_variant == 1) ELAUNCH(h, k_eb_gs<1>, grid, block, L.g, x, old, rhs, c);
-    else ELAUNCH(h, k_eb_gs<0>, grid, block, L.g, x, old, rhs, c);
+    if (L.g.nnode < h->batch_below) eb_launch_pdl(h, k_eb_gs<2>, grid, block, L.g, x, old, rhs, c);
+    else if (h->big_variant == 1) eb_launch_pdl(h, k_eb_gs<1>, grid, block, L.g, x, old, rhs, c);
+    else eb_launch_pdl(h, k_eb_gs<0>, grid, block, L.g, x, old, rhs, c);
 }
 void eb_launch_residual(b200eb* h, EbLevel& L, const double* x, const double* rhs, double* out, double* partial)
 {
     const dim3 grid = eb_grid3(L.g, 8), block(64, 4);
-    if (L.g.nnode < h->batch_below) ELAUNCH(h, k_eb_residual<2>, grid, block, L.g, x, rhs, out, partial);
-    else if (h->big_variant == 1) ELAUNCH(h, k_eb_residual<1>, grid, block, L.g, x, rhs, out, partial);
-    else ELAUNCH(h, k_eb_residual<0>, grid, block, L.g, x, rhs, out, partial);
+    if (L.g.nnode < h->batch_below) eb_launch_pdl(h, k_eb_residual<2>, grid, block, L.g, x, rhs, out, partial);
+    else if (h->big_variant == 1) eb_launch_pdl(h, k_eb_residual<1>, grid, block, L.g, x, rhs, out, partial);
+    else eb_launch_pdl(h, k_eb_residual<0>, grid, block, L.g, x, rhs, out, partial);
 }
 
 // one MLMG smooth call = smooth_num_sweeps sweeps of 8 colours
@@ -1284,7 +1311,7 @@ void eb_smooth(b200eb* h, EbLevel& L, double* x, const double* rhs, int ncalls)
 {
     const int nsw = std::max(1, h->opts.smooth_num_sweeps);
     if (L.g.nnode <= h->small_nodes) {
-        ELAUNCH(h, k_eb_gs_small, 1, 1024, L.g, x, L.odd_periodic ? h->snap : (double*)nullptr, rhs, ncalls * nsw);
+        eb_launch_pdl(h, k_eb_gs_small, dim3(1), dim3(1024), L.g, x, L.odd_periodic ? h->snap : (double*)nullptr, rhs, ncalls * nsw);
         return;
     }
     for (int s = 0; s < ncalls * nsw; ++s)
@@ -1314,12 +1341,12 @@ void eb_vcycle(b200eb* h)
         ECK(cudaMemsetAsync(L.cor, 0, L.g.nnode * sizeof(double), h->stream));
         eb_smooth(h, L, L.cor, L.res, nu1);
         eb_launch_residual(h, L, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
-        ELAUNCH(h, k_eb_restrict, eb_grid(C.g.nnode), 256, C.g, L.g, (const double*)L.rescor, C.res);
+        eb_launch_pdl(h, k_eb_restrict, dim3(eb_grid(C.g.nnode)), dim3(256), C.g, L.g, (const double*)L.rescor, C.res);
     }
     eb_bottom(h);
     for (int l = nl - 2; l >= 0; --l) {
         EbLevel &L = h->lv[l], &C = h->lv[l + 1];
-        ELAUNCH(h, k_eb_interp_add, eb_grid(L.g.nnode), 256, L.g, C.g, L.cor, (const double*)C.cor);
+        eb_launch_pdl(h, k_eb_interp_add, dim3(eb_grid(L.g.nnode)), dim3(256), L.g, C.g, L.cor, (const double*)C.cor);
         eb_smooth(h, L, L.cor, L.res, nu2);
     }
 }
