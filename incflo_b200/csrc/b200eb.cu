@@ -1168,7 +1168,7 @@ struct b200eb {
     long long batch_below = 4000000;   // levels with fewer nodes use the load-batching kernels (B200EB_BATCH_BELOW)
     int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200EB_PDL)
     int big_variant = 1;      // levels of >= batch_below nodes: 0 plain loads, 1 batched loads on the canonical rows (B200EB_BIG_VARIANT)
-    int small_nodes = 4096;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
+    int small_nodes = 1000;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
     long long launches = 0, ncell = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[12];
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
