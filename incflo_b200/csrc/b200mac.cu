@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -48,6 +49,11 @@ struct MFab {
         return (i - lo[0]) + (long long)nx * ((j - lo[1]) + (long long)ny * (k - lo[2]));
     }
 };
+
+// Programmatic dependent launch: pdl_wait() blocks until the predecessor kernel has completed and its writes are visible (must precede
+// the first access to data it produced); pdl_trigger() lets the successor become resident early (it waits in its own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 #define MCK(call)                                                                                   \
     do {                                                                                            \
@@ -124,6 +130,7 @@ __global__ void __launch_bounds__(256) k_mac_residual(const MacLev L, const doub
     __shared__ double sh[34];
     const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     double r = 0.0;
+    pdl_wait();
     if (i < L.n[0] && j < L.n[1]) {
         const long long t = cidx(L, i, j, k);
         const double pc = phi[t];
@@ -145,6 +152,8 @@ __global__ void __launch_bounds__(256) k_mac_gsrb(const MacLev L, double* phi, c
     // block (64, 4) over (i / 2, j), blockIdx.z = k
     const int ih = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y, k = blockIdx.z;
     const int i = 2 * ih + ((j + k + redblack) & 1);
+    if (gridDim.x * gridDim.y * gridDim.z <= 1184u) pdl_trigger();   // a single wave: let the next half-sweep's blocks in right away
+    pdl_wait();
     if (i >= L.n[0] || j >= L.n[1]) return;
     const long long c = cidx(L, i, j, k);
     const double pc = old[c];
@@ -166,6 +175,7 @@ __global__ void __launch_bounds__(256) k_mac_gsrb(const MacLev L, double* phi, c
 // crse = mean of the 8 fine cells (MLCellLinOp::restriction)
 __global__ void __launch_bounds__(256) k_mac_restrict(const MacLev C, int fnx, int fny, const double* __restrict__ fine, double* __restrict__ crse)
 {
+    pdl_wait();
     const long long N = (long long)C.n[0] * C.n[1] * C.n[2];
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t % C.n[0]), j = (int)((t / C.n[0]) % C.n[1]), k = (int)(t / ((long long)C.n[0] * C.n[1]));
@@ -183,6 +193,7 @@ __global__ void __launch_bounds__(256) k_mac_restrict(const MacLev C, int fnx, i
 // fine += crse(i/2, j/2, k/2) (MLCellLinOp::interpolation)
 __global__ void __launch_bounds__(256) k_mac_interp_add(const MacLev F, int cnx, int cny, double* __restrict__ fine, const double* __restrict__ crse)
 {
+    pdl_wait();
     const long long N = (long long)F.n[0] * F.n[1] * F.n[2];
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t % F.n[0]), j = (int)((t / F.n[0]) % F.n[1]), k = (int)(t / ((long long)F.n[0] * F.n[1]));
@@ -457,6 +468,21 @@ namespace {
         (h)->launches++;                                   \
     } while (0)
 
+// launch with the programmatic-stream-serialization attribute: ONLY for kernels that call pdl_wait() before touching data
+template <typename... KArgs, typename... Args>
+void mac_launch_pdl(b200mac* h, void (*kern)(KArgs...), dim3 grid, dim3 block, Args... args)
+{
+    static const int use_pdl = getenv("B200MAC_PDL") ? atoi(getenv("B200MAC_PDL")) : 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = use_pdl ? 1 : 0;
+    MCK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+    h->launches++;
+}
+
 double* mac_alloc(b200mac* h, size_t doubles)
 {
     void* p = nullptr;
@@ -527,7 +553,7 @@ void mac_smooth(b200mac* h, MacLevel& L, double* phi, const double* rhs, int nca
                 MCK(cudaMemcpyAsync(h->snap, phi, L.ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
                 old = h->snap;
             }
-            MLAUNCH(h, k_mac_gsrb, mac_grid3(L.g, 2), dim3(64, 4), L.g, phi, old, rhs, rb);
+            mac_launch_pdl(h, k_mac_gsrb, mac_grid3(L.g, 2), dim3(64, 4), L.g, phi, old, rhs, rb);
         }
 }
 
@@ -539,15 +565,15 @@ void mac_vcycle(b200mac* h)
         MacLevel &L = h->lv[l], &C = h->lv[l + 1];
         MCK(cudaMemsetAsync(L.cor, 0, L.ncell * sizeof(double), h->stream));
         mac_smooth(h, L, L.cor, L.res, nu1);
-        MLAUNCH(h, k_mac_residual, mac_grid3(L.g), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
-        MLAUNCH(h, k_mac_restrict, grid_for(C.ncell), 256, C.g, L.g.n[0], L.g.n[1], (const double*)L.rescor, C.res);
+        mac_launch_pdl(h, k_mac_residual, mac_grid3(L.g), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        mac_launch_pdl(h, k_mac_restrict, dim3(grid_for(C.ncell)), dim3(256), C.g, L.g.n[0], L.g.n[1], (const double*)L.rescor, C.res);
     }
     MacLevel& B = h->lv.back();
     MLAUNCH(h, k_mac_bottom, 1, 1024, B.g, B.cor, B.res, h->work, h->opts.bottom_maxiter, h->opts.bottom_rtol, h->opts.bottom_atol,
             h->singular ? 1 : 0, h->dinfo);
     for (int l = nl - 2; l >= 0; --l) {
         MacLevel &L = h->lv[l], &C = h->lv[l + 1];
-        MLAUNCH(h, k_mac_interp_add, grid_for(L.ncell), 256, L.g, C.g.n[0], C.g.n[1], L.cor, (const double*)C.cor);
+        mac_launch_pdl(h, k_mac_interp_add, dim3(grid_for(L.ncell)), dim3(256), L.g, C.g.n[0], C.g.n[1], L.cor, (const double*)C.cor);
         mac_smooth(h, L, L.cor, L.res, nu2);
     }
 }

@@ -386,3 +386,51 @@ def test_finest_level_kernel_variants(name, monkeypatch):
         a[act] -= a[act].mean(); b[act] -= b[act].mean()
     assert rel(a, b) < 1e-9 and rel(vel[:, 1:-1, 1:-1, 1:-1], ref["vel"]) < 1e-9
     pr.close()
+
+
+def test_properties_at_benchmark_class_size():
+    """channel_cylinder-x at 256 x 64 x 64 (half the linear size of the bench configuration; the oracle would need ~15 s): properties that
+    need no oracle -- convergence to rtol, linearity of the projection in u, phi ~ 1 / sigma at fixed u, zeros inside the body, idempotence
+    of the flags / no-flags kernels (constant sigma passed as an array takes the stored-coefficient path)"""
+    import torch
+    from incflo_b200 import eb_projector as ebp
+    n = (256, 64, 64)
+    h = 0.4 / n[1]
+    geom = eg.cylinder(n, h, 0.05000001, (0.151, 0.2, 0.0), direction=2, small_vfrac=1e-6)
+    bclo, bchi = (3, 1, 0), (2, 1, 0)
+    rng = np.random.default_rng(17)
+    vel0 = np.zeros((3, n[2] + 2, n[1] + 2, n[0] + 2))
+    vel0[:, 1:-1, 1:-1, 1:-1] = (1.0 + 0.2 * rng.standard_normal((3, n[2], n[1], n[0]))) * (geom.vfrac > 0)
+    y = (np.arange(n[1]) + 0.5) / n[1]
+    vel0[0, 1:-1, 1:-1, 0] = (6.0 * y * (1.0 - y))[None, :]
+    pr = ebp.EBNodalProjector(n, (h,) * 3, bclo, bchi, geom.vfrac, geom.intg)
+    dev = torch.device("cuda:0")
+
+    def run(vel, sigma):
+        tv = torch.from_numpy(vel).to(dev)
+        phi = torch.zeros((n[2] + 1, n[1] + 1, n[0] + 1), device=dev, dtype=torch.float64)
+        st = pr.project(tv, sigma, 1e-11, 1e-14, phi=phi)
+        assert st.status == 0 and st.resnorm <= 1e-11 * max(st.rhsnorm, st.resnorm0)
+        return tv.cpu().numpy()[:, 1:-1, 1:-1, 1:-1], phi.cpu().numpy(), st.iters
+
+    u1, p1, it1 = run(vel0, 1.0)
+    assert it1 <= 10
+    u2, p2, _ = run(2.5 * vel0, 1.0)                        # linear in u
+    assert rel(u2, 2.5 * u1) < 1e-9 and rel(p2, 2.5 * p1) < 1e-9
+    u3, p3, _ = run(vel0, 4.0)                              # sigma grad phi is what is fixed
+    assert rel(u3, u1) < 1e-9 and rel(4.0 * p3, p1) < 1e-9
+    sig = torch.full((n[2], n[1], n[0]), 4.0, device=dev, dtype=torch.float64)
+    u4, p4, _ = run(vel0, sig)                              # the same sigma as an array: no canonical-row flags, stored coefficients
+    assert rel(u4, u3) < 1e-9 and rel(p4, p3) < 1e-9
+    cov = geom.vfrac == 0
+    assert np.all(u1[:, cov] == 0)
+    inside = np.ones((n[2] + 1, n[1] + 1, n[0] + 1), dtype=bool)   # nodes all of whose cells are covered
+    pad = np.pad(cov, ((0, 0), (1, 1), (1, 1)), constant_values=False)
+    padz = np.concatenate([pad[-1:], pad, pad[:1]], axis=0)          # periodic z
+    for dk in (0, 1):
+        for dj in (0, 1):
+            for di in (0, 1):
+                inside &= padz[dk:dk + n[2] + 1, dj:dj + n[1] + 1, di:di + n[0] + 1]
+    assert inside.sum() > 0 and np.all(p1[inside] == 0)
+    assert np.all(p1[:, :, -1] == 0)                       # pressure outflow face: phi = 0
+    pr.close()
