@@ -490,6 +490,37 @@ def mac_block(ctx, n1):
     return rec
 
 
+def north_star_block(ctx):
+    """BASELINE north_star's single-GPU target, measured in the default run so that it is in the driver's record: the 512^3
+    variable-density projection to rtol 1e-11 on one B200, with the level-0 smoother / residual kernels against the HBM peak"""
+    import torch
+    from incflo_b200 import nodal_projector as npj
+    n = (512, 512, 512)
+    wl = workload(n, 1, 0, ctx.device)
+    proj = make_projection(ctx, n, nranks=1)
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    ms, _, st, _ = timed_solves(ctx, proj, wl, 3, 1, n, "clone")
+    _, nn = proj.level_dims(0)
+    nodes = nn[0] * nn[1] * nn[2]
+    ms_sm = proj.time_op(0, npj.OP_SMOOTH, 2, reps=20) / 2.0
+    ms_res = proj.time_op(0, npj.OP_RESIDUAL, 0, reps=20)
+    clocks = sampler.stop()
+    peak, _ = peaks()
+    gbs = lambda t: 32.0 * nodes / (t * 1e-3) / 1e9
+    solve_bytes = solve_roofline(nodes, n[0] * n[1] * n[2], st.iters, True)
+    rec = {"n_cell": list(n), "ms_per_solve": ms, "vcycles": int(st.iters), "resid_over_bnorm": st.resnorm / max(st.rhsnorm, st.resnorm0),
+           "Mcell_updates_per_s": n[0] * n[1] * n[2] / ms / 1e3, "steps": 3, "warmup": 1,
+           "smoother_sweep": {"us": ms_sm * 1e3, "GBs": gbs(ms_sm), "frac_of_measured_peak": gbs(ms_sm) / peak, "frac_of_nominal_8TBs": gbs(ms_sm) / 8000.0},
+           "residual": {"us": ms_res * 1e3, "GBs": gbs(ms_res), "frac_of_measured_peak": gbs(ms_res) / peak, "frac_of_nominal_8TBs": gbs(ms_res) / 8000.0},
+           "whole_solve_frac_of_measured_peak": solve_bytes / (ms * 1e-3) / 1e9 / peak, "clocks": clocks,
+           "target": "north_star: 512^3 variable density to rtol 1e-11 on one B200, smoother / residual kernels >= 60 % of HBM peak"}
+    proj.close()
+    del wl
+    torch.cuda.empty_cache()
+    return rec
+
+
 def strong_block(ctx, sizes):
     """strong scaling: the n^3 problem on all N GPUs vs the SAME solve measured on one GPU (rank 0) in this run"""
     import torch
@@ -642,6 +673,14 @@ def run_ours(args):
         except Exception as e:   # never let the extra record take the headline down
             mac_rec = {"error": repr(e)[:200]}
 
+    # ---------------- north_star's single-GPU target (N = 1): 512^3 ----------------
+    ns_rec = None
+    if nranks == 1 and not args.no_512 and N == 256:
+        try:
+            ns_rec = north_star_block(ctx)
+        except Exception as e:
+            ns_rec = {"error": repr(e)[:200]}
+
     # ---------------- EB nodal projection record (N = 1): BASELINE configs[4] ----------------
     eb_rec = None
     if nranks == 1 and not args.no_eb:
@@ -682,6 +721,8 @@ def run_ours(args):
             line["mac_projection"] = mac_rec
         if eb_rec is not None:
             line["eb_projection"] = eb_rec
+        if ns_rec is not None:
+            line["north_star_512"] = ns_rec
         if nranks == 1 and not args.no_cpu:
             times, it_cpu, _ = cpu_port_run((N, N, N), 1, 0, "reference")
             tcpu = min(times)
@@ -718,6 +759,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer arm (the line is then not a valid bench line)")
     ap.add_argument("--no-parity", action="store_true", help="tuning sweeps only: skip the oracle check before timing")
     ap.add_argument("--no-mac", action="store_true", help="N = 1: skip the MAC projection record")
+    ap.add_argument("--no-512", dest="no_512", action="store_true", help="N = 1: skip the 512^3 north_star record")
     ap.add_argument("--no-eb", action="store_true", help="N = 1: skip the EB nodal projection record (BASELINE configs[4])")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the 512^3 / 1024^3 strong-scaling record")
     args = ap.parse_args()
