@@ -596,19 +596,55 @@ __device__ __forceinline__ double offdiag_sum_regular_inner(const EbLev& L, int 
     }
 }
 // sum_q!=p A(p, q) x(q) and the diagonal of node p = (i, j, k) of colour `color`, by the cheapest applicable path; false: inactive node
-// BATCH: 0 plain loads; 1 batched loads on the canonical rows only (20 loads, ~56 registers); 2 batched everywhere (~120 registers)
+__device__ __forceinline__ unsigned ld_early_u8(const unsigned char* p)
+{
+    unsigned v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// BATCH: 0 plain loads; 1 batched loads on the canonical rows only (20 loads, ~56 registers); 2 batched everywhere (~120 registers);
+// 3 SPECULATIVE: an interior node issues its flag AND the 20 neighbour values of the canonical row together and decides afterwards
+// (one memory round trip instead of two on the path 98 % of the nodes of the finest level take; the rest reloads for the general row)
 template <int BATCH>
 __device__ __forceinline__ bool node_row(const EbLev& L, int p, int i, int j, int k, int color, const double* x, double& off, double& diag)
 {
     const bool inner = i > 0 && i < L.nn[0] - 1 && j > 0 && j < L.nn[1] - 1 && k > 0 && k < L.nn[2] - 1;
+    if (BATCH == 3 && inner) {
+        const NbOff o = nb_offsets(L, color);
+        const unsigned f = ld_early_u8(L.flag + p);
+        const double ce = ld_early_nc(L.canon), cc = ld_early_nc(L.canon + 1), cd = ld_early_nc(L.canon + 2);
+        const double* xp = x + p;
+        double v[27];
+#pragma unroll
+        for (int tt = 0; tt < 27; ++tt) {
+            const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+            if (nz >= 2) v[tt] = ld_early(xp + (o.D[0][tt % 3] + o.D[1][(tt / 3) % 3] + o.D[2][tt / 9]));
+        }
+        if (f) {
+            double se = 0.0, sc = 0.0;
+#pragma unroll
+            for (int tt = 26; tt >= 0; --tt) {
+                const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+                if (nz == 2) se += v[tt];
+                if (nz == 3) sc += v[tt];
+            }
+            diag = cd;
+            off = ce * se + cc * sc;
+            return true;
+        }
+        diag = __ldg(L.st + 13 * L.nnode + p);
+        if (diag == 0.0) return false;
+        off = offdiag_sum_inner<false>(L, p, o, x);
+        return true;
+    }
     if (L.flag[p]) {
         diag = L.canon[2];
-        off = inner ? offdiag_sum_regular_inner<(BATCH >= 1)>(L, p, nb_offsets(L, color), x) : offdiag_sum_regular<(BATCH >= 1)>(L, i, j, k, x);
+        off = inner ? offdiag_sum_regular_inner<(BATCH == 1 || BATCH == 2)>(L, p, nb_offsets(L, color), x) : offdiag_sum_regular<(BATCH == 1 || BATCH == 2)>(L, i, j, k, x);
         return true;
     }
     diag = __ldg(L.st + 13 * L.nnode + p);
     if (diag == 0.0) return false;
-    off = inner ? offdiag_sum_inner<(BATCH >= 2)>(L, p, nb_offsets(L, color), x) : offdiag_sum<(BATCH >= 2)>(L, p, i, j, k, x);
+    off = inner ? offdiag_sum_inner<(BATCH == 2)>(L, p, nb_offsets(L, color), x) : offdiag_sum<(BATCH == 2)>(L, p, i, j, k, x);
     return true;
 }
 
@@ -624,8 +660,9 @@ __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const d
     pdl_wait();
     if (i >= L.nn[0] || j >= L.nn[1] || k >= L.nn[2]) return;
     const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
+    const double r = BATCH >= 2 ? ld_early_nc(rhs + p) : rhs[p];   // in flight together with the row's loads
     double off, d;
-    x[p] = node_row<BATCH>(L, p, i, j, k, color, old, off, d) ? (rhs[p] - off) / d : 0.0;
+    x[p] = node_row<BATCH>(L, p, i, j, k, color, old, off, d) ? (r - off) / d : 0.0;
 }
 // all sweeps of a smooth call on a level small enough for ONE CTA: colours separated by __syncthreads instead of kernel boundaries
 // (a level of a few thousand nodes is pure launch latency otherwise: 8 launches per sweep).  snap != nullptr: odd periodic extent.
@@ -666,8 +703,9 @@ __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double
     pdl_wait();
     if (i < L.nn[0] && j < L.nn[1] && k < L.nn[2]) {
         const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
+        const double b = BATCH >= 2 ? ld_early_nc(rhs + p) : rhs[p], xc = BATCH >= 2 ? ld_early(x + p) : x[p];
         double off, d;
-        if (node_row<BATCH>(L, p, i, j, k, color, x, off, d)) r = rhs[p] - (d * x[p] + off);
+        if (node_row<BATCH>(L, p, i, j, k, color, x, off, d)) r = b - (d * xc + off);
         if (out) out[p] = r;
     }
     if (norm_partial) {
@@ -1165,9 +1203,9 @@ struct b200eb {
     bool singular = true, have_geometry = false, have_ebflow = false, have_stencil = false;
     int flags_state = 0;      // 0: unknown, 1: all zero (variable sigma), 2: computed for a constant sigma and the current geometry
     double* canon = nullptr;  // 3 doubles per level
-    long long batch_below = 4000000;   // levels with fewer nodes use the load-batching kernels (B200EB_BATCH_BELOW)
+    long long batch_below = 500000;    // levels with fewer nodes use the load-batching kernels (B200EB_BATCH_BELOW)
     int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200EB_PDL)
-    int big_variant = 1;      // levels of >= batch_below nodes: 0 plain loads, 1 batched loads on the canonical rows (B200EB_BIG_VARIANT)
+    int big_variant = 3;      // levels of >= batch_below nodes: 0 plain loads, 1 batched loads on the canonical rows, 3 speculative (B200EB_BIG_VARIANT)
     int small_nodes = 1000;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
     long long launches = 0, ncell = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[12];
@@ -1295,6 +1333,7 @@ void eb_launch_gs(b200eb* h, EbLevel& L, double* x, const double* old, const dou
 {
     const dim3 grid = eb_grid3(L.g, 1), block(64, 4);
     if (L.g.nnode < h->batch_below) eb_launch_pdl(h, k_eb_gs<2>, grid, block, L.g, x, old, rhs, c);
+    else if (h->big_variant == 3) eb_launch_pdl(h, k_eb_gs<3>, grid, block, L.g, x, old, rhs, c);
     else if (h->big_variant == 1) eb_launch_pdl(h, k_eb_gs<1>, grid, block, L.g, x, old, rhs, c);
     else eb_launch_pdl(h, k_eb_gs<0>, grid, block, L.g, x, old, rhs, c);
 }
@@ -1302,6 +1341,7 @@ void eb_launch_residual(b200eb* h, EbLevel& L, const double* x, const double* rh
 {
     const dim3 grid = eb_grid3(L.g, 8), block(64, 4);
     if (L.g.nnode < h->batch_below) eb_launch_pdl(h, k_eb_residual<2>, grid, block, L.g, x, rhs, out, partial);
+    else if (h->big_variant == 3) eb_launch_pdl(h, k_eb_residual<3>, grid, block, L.g, x, rhs, out, partial);
     else if (h->big_variant == 1) eb_launch_pdl(h, k_eb_residual<1>, grid, block, L.g, x, rhs, out, partial);
     else eb_launch_pdl(h, k_eb_residual<0>, grid, block, L.g, x, rhs, out, partial);
 }
