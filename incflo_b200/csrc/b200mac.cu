@@ -409,6 +409,39 @@ __global__ void __launch_bounds__(1024) k_mac_bottom(const MacLev L, double* __r
     if (tid == 0) { atomicAdd(info, it); info[1] = ret; }
 }
 
+// ---- multi-box MultiFabs (every reference deck: amr.max_grid_size = 16): gather into / scatter from one dense array per field ----
+struct MacMfFab {
+    double* p;
+    int lo[3];           // allocated box
+    int nx, ny, nz;
+};
+// dense (ex, ey, ez) <- the valid boxes of the fabs (allocated box shrunk by ngrow; for a face-centred MultiFab that is the cells' box
+// plus the far face, which adjacent boxes share: both hold the same value)
+__global__ void __launch_bounds__(256) k_mac_mf_gather(const MacMfFab* __restrict__ tab, int ngrow, double* __restrict__ dense, int ex, int ey, int ez)
+{
+    const MacMfFab f = tab[blockIdx.y];
+    const int vx = f.nx - 2 * ngrow, vy = f.ny - 2 * ngrow, vz = f.nz - 2 * ngrow;
+    const long long total = (long long)vx * vy * vz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int li = (int)(t % vx) + ngrow, lj = (int)((t / vx) % vy) + ngrow, lk = (int)(t / ((long long)vx * vy)) + ngrow;
+        const int i = li + f.lo[0], j = lj + f.lo[1], k = lk + f.lo[2];
+        if (i < 0 || i >= ex || j < 0 || j >= ey || k < 0 || k >= ez) continue;
+        dense[((long long)k * ey + j) * ex + i] = f.p[((long long)lk * f.ny + lj) * f.nx + li];
+    }
+}
+__global__ void __launch_bounds__(256) k_mac_mf_scatter(const MacMfFab* __restrict__ tab, int ngrow, const double* __restrict__ dense, int ex, int ey, int ez)
+{
+    const MacMfFab f = tab[blockIdx.y];
+    const int vx = f.nx - 2 * ngrow, vy = f.ny - 2 * ngrow, vz = f.nz - 2 * ngrow;
+    const long long total = (long long)vx * vy * vz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int li = (int)(t % vx) + ngrow, lj = (int)((t / vx) % vy) + ngrow, lk = (int)(t / ((long long)vx * vy)) + ngrow;
+        const int i = li + f.lo[0], j = lj + f.lo[1], k = lk + f.lo[2];
+        if (i < 0 || i >= ex || j < 0 || j >= ey || k < 0 || k >= ez) continue;
+        f.p[((long long)lk * f.ny + lj) * f.nx + li] = dense[((long long)k * ey + j) * ex + i];
+    }
+}
+
 struct MacLevel {
     MacLev g{};
     double* b[3] = {nullptr, nullptr, nullptr};
@@ -455,6 +488,7 @@ struct b200mac {
     long long launches = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[8];
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    struct Mf { double* dense = nullptr; size_t dense_doubles = 0; double* stage = nullptr; size_t stage_doubles = 0; MacMfFab* tab = nullptr; size_t tab_cap = 0; } mf[8];
     cudaGraph_t graph = nullptr;          // one V-cycle, captured once (every pointer in it belongs to the handle)
     cudaGraphExec_t graph_exec = nullptr;
     long long launches_per_vcycle = 0;
@@ -722,6 +756,7 @@ void b200mac_destroy(b200mac_t* h)
     if (h->graph) cudaGraphDestroy(h->graph);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& s : h->stage) if (s.d) cudaFree(s.d);
+    for (auto& m : h->mf) { if (m.dense) cudaFree(m.dense); if (m.stage) cudaFree(m.stage); if (m.tab) cudaFree(m.tab); }
     if (h->hscal) cudaFreeHost(h->hscal);
     if (h->hinfo) cudaFreeHost(h->hinfo);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -811,6 +846,156 @@ int b200mac_project(b200mac_t* h, double* umac, const b200np_fab* u_box, double*
         MCK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); st->ms_solve = ms;
         st->launches = h->launches;
         return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+}  // extern "C"
+
+namespace {
+// one MultiFab of the call: validated, its fabs on the device (staged if host pointers), gathered into a dense array
+struct MacMfView {
+    const b200np_mfab* m = nullptr;
+    int slot = 0, ext[3] = {0, 0, 0};
+    bool staged = false;
+    std::vector<size_t> off;
+    double* dense = nullptr;
+    b200np_fab dense_box{};
+};
+// the valid boxes (allocated box shrunk by ngrow) minus the far face in direction d must tile the domain's cells
+bool mac_mf_ok(const b200np_mfab* m, const int n[3], int d)
+{
+    if (!m || m->nfabs < 1 || m->ngrow < 0 || !m->box || !m->data) return false;
+    long long vol = 0;
+    for (int f = 0; f < m->nfabs; ++f) {
+        if (!m->data[f]) return false;
+        long long v = 1;
+        for (int q = 0; q < 3; ++q) {
+            const int vlo = m->box[f].lo[q] + m->ngrow, vhi = m->box[f].hi[q] - m->ngrow - (q == d ? 1 : 0);
+            if (vhi < vlo || vlo < 0 || vhi > n[q] - 1) return false;
+            v *= vhi - vlo + 1;
+        }
+        vol += v;
+    }
+    return vol == (long long)n[0] * n[1] * n[2];
+}
+void mac_mf_map(b200mac* h, MacMfView& V, int slot, const b200np_mfab* m, const int n[3], int d, bool copy_in, b200np_stats* st)
+{
+    V.m = m; V.slot = slot;
+    for (int q = 0; q < 3; ++q) V.ext[q] = n[q] + (q == d ? 1 : 0);
+    auto& S = h->mf[slot];
+    const int nf = m->nfabs;
+    V.staged = !is_dev_ptr(m->data[0]);
+    V.off.assign(nf, 0);
+    size_t total = 0;
+    std::vector<MacMfFab> host(nf);
+    for (int f = 0; f < nf; ++f) {
+        const b200np_fab& b = m->box[f];
+        host[f].nx = b.hi[0] - b.lo[0] + 1; host[f].ny = b.hi[1] - b.lo[1] + 1; host[f].nz = b.hi[2] - b.lo[2] + 1;
+        for (int q = 0; q < 3; ++q) host[f].lo[q] = b.lo[q];
+        V.off[f] = total;
+        total += (size_t)host[f].nx * host[f].ny * host[f].nz;
+    }
+    if (V.staged) {
+        if (S.stage_doubles < total) { if (S.stage) MCK(cudaFree(S.stage)); MCK(cudaMalloc(&S.stage, total * sizeof(double))); S.stage_doubles = total; }
+        if (copy_in) {
+            for (int f = 0; f < nf; ++f)
+                MCK(cudaMemcpyAsync(S.stage + V.off[f], m->data[f], (size_t)host[f].nx * host[f].ny * host[f].nz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            st->h2d_bytes += (long long)(total * sizeof(double));
+        }
+    }
+    for (int f = 0; f < nf; ++f) host[f].p = V.staged ? S.stage + V.off[f] : m->data[f];
+    if (S.tab_cap < (size_t)nf) { if (S.tab) MCK(cudaFree(S.tab)); MCK(cudaMalloc(&S.tab, (size_t)nf * sizeof(MacMfFab))); S.tab_cap = nf; }
+    MCK(cudaMemcpyAsync(S.tab, host.data(), (size_t)nf * sizeof(MacMfFab), cudaMemcpyHostToDevice, h->stream));
+    MCK(cudaStreamSynchronize(h->stream));   // `host` goes out of scope
+    const size_t nd = (size_t)V.ext[0] * V.ext[1] * V.ext[2];
+    if (S.dense_doubles < nd) { if (S.dense) MCK(cudaFree(S.dense)); MCK(cudaMalloc(&S.dense, nd * sizeof(double))); S.dense_doubles = nd; }
+    V.dense = S.dense;
+    for (int q = 0; q < 3; ++q) { V.dense_box.lo[q] = 0; V.dense_box.hi[q] = V.ext[q] - 1; }
+    V.dense_box.ncomp = 1;
+}
+dim3 mac_mf_grid(const b200np_mfab* m)
+{
+    long long mx = 1;
+    for (int f = 0; f < m->nfabs; ++f)
+        mx = std::max(mx, (long long)(m->box[f].hi[0] - m->box[f].lo[0] + 1) * (m->box[f].hi[1] - m->box[f].lo[1] + 1) * (m->box[f].hi[2] - m->box[f].lo[2] + 1));
+    return dim3((unsigned)std::min<long long>((mx + 255) / 256, 64), (unsigned)m->nfabs);
+}
+void mac_mf_gather(b200mac* h, MacMfView& V)
+{
+    MLAUNCH(h, k_mac_mf_gather, mac_mf_grid(V.m), 256, (const MacMfFab*)h->mf[V.slot].tab, V.m->ngrow, V.dense, V.ext[0], V.ext[1], V.ext[2]);
+}
+void mac_mf_scatter(b200mac* h, MacMfView& V, b200np_stats* st)
+{
+    MLAUNCH(h, k_mac_mf_scatter, mac_mf_grid(V.m), 256, (const MacMfFab*)h->mf[V.slot].tab, V.m->ngrow, (const double*)V.dense, V.ext[0], V.ext[1], V.ext[2]);
+    if (!V.staged) return;
+    size_t total = 0;
+    for (int f = 0; f < V.m->nfabs; ++f) {
+        const b200np_fab& b = V.m->box[f];
+        const size_t nd = (size_t)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1);
+        MCK(cudaMemcpyAsync(V.m->data[f], h->mf[V.slot].stage + V.off[f], nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        total += nd;
+    }
+    st->d2h_bytes += (long long)(total * sizeof(double));
+}
+}  // namespace
+
+extern "C" {
+
+// initProjector / updateCoeffs over face-centred MultiFabs (inv_rho[lev][d], :71-90)
+int b200mac_set_coeffs_mf(b200mac_t* h, const b200np_mfab* bx, const b200np_mfab* by, const b200np_mfab* bz)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    const int* n = h->lv[0].g.n;
+    const b200np_mfab* m[3] = {bx, by, bz};
+    for (int d = 0; d < 3; ++d) if (!mac_mf_ok(m[d], n, d)) return B200NP_ERR_BAD_ARG;
+    try {
+        MCK(cudaSetDevice(h->device));
+        b200np_stats st{};
+        MacMfView V[3];
+        for (int d = 0; d < 3; ++d) {
+            mac_mf_map(h, V[d], d, m[d], n, d, true, &st);
+            mac_mf_gather(h, V[d]);
+        }
+        MCK(cudaStreamSynchronize(h->stream));
+        return b200mac_set_coeffs(h, V[0].dense, &V[0].dense_box, V[1].dense, &V[1].dense_box, V[2].dense, &V[2].dense_box, 0.0);
+    } catch (int e) { return e; }
+}
+
+// project over multi-box MultiFabs: u_mac / v_mac / w_mac face-centred, mac_phi cell-centred (optional).  Results are bit-identical to
+// the single-box call; only the valid faces / cells of every fab are written.
+int b200mac_project_mf(b200mac_t* h, const b200np_mfab* umac, const b200np_mfab* vmac, const b200np_mfab* wmac, const b200np_mfab* mac_phi,
+                       int phi_is_initial_guess, double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h || !h->have_coeffs) return st->status = B200NP_ERR_BAD_ARG;
+    const int* n = h->lv[0].g.n;
+    const b200np_mfab* m[3] = {umac, vmac, wmac};
+    for (int d = 0; d < 3; ++d) if (!mac_mf_ok(m[d], n, d)) return st->status = B200NP_ERR_BAD_ARG;
+    if (mac_phi && !mac_mf_ok(mac_phi, n, -1)) return st->status = B200NP_ERR_BAD_ARG;
+    try {
+        MCK(cudaSetDevice(h->device));
+        MacMfView V[4];
+        for (int d = 0; d < 3; ++d) {
+            mac_mf_map(h, V[d], 3 + d, m[d], n, d, true, st);
+            mac_mf_gather(h, V[d]);
+        }
+        if (mac_phi) {
+            mac_mf_map(h, V[3], 6, mac_phi, n, -1, phi_is_initial_guess != 0, st);
+            if (phi_is_initial_guess) mac_mf_gather(h, V[3]);
+        }
+        MCK(cudaStreamSynchronize(h->stream));
+        b200np_stats inner{};
+        const int rc = b200mac_project(h, V[0].dense, &V[0].dense_box, V[1].dense, &V[1].dense_box, V[2].dense, &V[2].dense_box,
+                                       mac_phi ? V[3].dense : nullptr, mac_phi ? &V[3].dense_box : nullptr, phi_is_initial_guess, rtol, atol, &inner);
+        const long long h2d = st->h2d_bytes;
+        *st = inner;
+        st->h2d_bytes += h2d;
+        for (int d = 0; d < 3; ++d) mac_mf_scatter(h, V[d], st);
+        if (mac_phi) mac_mf_scatter(h, V[3], st);
+        MCK(cudaStreamSynchronize(h->stream));
+        return st->status = rc;
     } catch (int e) { return st->status = e; }
 }
 

@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import FabBox, Geom, Stats
+from ._lib import FabBox, Geom, MFab, Stats
 from .nodal_projector import ProjectionError, nodal_proj_opts
 
 OP_SMOOTH, OP_RESIDUAL, OP_RESTRICT, OP_INTERP, OP_BOTTOM = range(5)
@@ -34,6 +34,58 @@ def _ptr_box(a):
         b.lo[d] = 0; b.hi[d] = shape[2 - d] - 1
     b.ncomp = 1
     return ptr, b
+
+
+class FaceMultiFab:
+    """A face-centred (d = 0, 1, 2) or cell-centred (d = -1) one-component amrex::MultiFab as one rank sees it: boxes = valid CELL
+    boxes (lo, hi), arrays = one per box over the cell box grown by ngrow, plus the far face in direction d -- shaped (nz, ny, nx) of
+    that allocated box; numpy (host) or torch CUDA tensors."""
+
+    def __init__(self, boxes, arrays, ngrow, d):
+        self.boxes, self.arrays, self.ngrow, self.d = list(boxes), list(arrays), int(ngrow), int(d)
+        n = len(boxes)
+        self._box = (FabBox * n)()
+        self._ptr = (C.c_void_p * n)()
+        for f, ((lo, hi), a) in enumerate(zip(boxes, arrays)):
+            for q in range(3):
+                self._box[f].lo[q] = int(lo[q]) - self.ngrow
+                self._box[f].hi[q] = int(hi[q]) + self.ngrow + (1 if q == self.d else 0)
+                assert tuple(a.shape)[2 - q] == self._box[f].hi[q] - self._box[f].lo[q] + 1
+            self._box[f].ncomp = 1
+            self._ptr[f] = a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+        self.c = MFab(n, self.ngrow, 1, C.cast(self._box, C.POINTER(FabBox)), C.cast(self._ptr, C.POINTER(C.c_void_p)))
+
+    def ref(self):
+        return C.byref(self.c)
+
+    @staticmethod
+    def split(full, n_cell, max_grid, ngrow, d, to=None, fill=0.0):
+        """chop a dense array over the whole domain (faces of direction d: extent n + 1 there) into boxes of at most max_grid cells per
+        direction; ghost faces / cells hold `fill` (the projector must neither read nor write them)"""
+        nx, ny, nz = n_cell
+        boxes, arrs = [], []
+        for k0 in range(0, nz, max_grid):
+            for j0 in range(0, ny, max_grid):
+                for i0 in range(0, nx, max_grid):
+                    lo = (i0, j0, k0)
+                    hi = (min(i0 + max_grid, nx) - 1, min(j0 + max_grid, ny) - 1, min(k0 + max_grid, nz) - 1)
+                    ext = [hi[q] - lo[q] + 1 + (1 if q == d else 0) for q in range(3)]
+                    b = np.full((ext[2] + 2 * ngrow, ext[1] + 2 * ngrow, ext[0] + 2 * ngrow), fill)
+                    b[ngrow:ngrow + ext[2], ngrow:ngrow + ext[1], ngrow:ngrow + ext[0]] = full[k0:k0 + ext[2], j0:j0 + ext[1], i0:i0 + ext[0]]
+                    boxes.append((lo, hi))
+                    arrs.append(np.ascontiguousarray(b) if to is None else to(np.ascontiguousarray(b)))
+        return FaceMultiFab(boxes, arrs, ngrow, d)
+
+    def assemble(self, n_cell):
+        """the valid regions put back together (shared faces: the later box wins -- they agree)"""
+        ext = [n_cell[q] + (1 if q == self.d else 0) for q in range(3)]
+        out = np.zeros((ext[2], ext[1], ext[0]))
+        g = self.ngrow
+        for (lo, hi), a in zip(self.boxes, self.arrays):
+            a = a.detach().cpu().numpy() if hasattr(a, "detach") else a
+            e = [hi[q] - lo[q] + 1 + (1 if q == self.d else 0) for q in range(3)]
+            out[lo[2]:lo[2] + e[2], lo[1]:lo[1] + e[1], lo[0]:lo[0] + e[0]] = a[g:g + e[2], g:g + e[1], g:g + e[0]]
+        return out
 
 
 class MacProjector:
@@ -68,6 +120,19 @@ class MacProjector:
         pp, bp = _ptr_box(mac_phi)
         rc = self._L.b200mac_project(self._h, pu, C.byref(bu), pv, C.byref(bv), pw, C.byref(bw), pp, C.byref(bp) if bp is not None else None,
                                      int(use_phi_as_guess), float(rtol), float(atol), C.byref(self.stats))
+        if rc != 0:
+            raise ProjectionError(rc)
+        return self.stats
+
+    def updateCoeffs_mf(self, bx, by, bz):
+        """initProjector / updateCoeffs over multi-box face MultiFabs (FaceMultiFab)"""
+        rc = self._L.b200mac_set_coeffs_mf(self._h, bx.ref(), by.ref(), bz.ref())
+        if rc != 0:
+            raise ProjectionError(rc)
+
+    def project_mf(self, umac, vmac, wmac, rtol, atol, mac_phi=None, use_phi_as_guess=False):
+        rc = self._L.b200mac_project_mf(self._h, umac.ref(), vmac.ref(), wmac.ref(), mac_phi.ref() if mac_phi is not None else None,
+                                        int(use_phi_as_guess), float(rtol), float(atol), C.byref(self.stats))
         if rc != 0:
             raise ProjectionError(rc)
         return self.stats

@@ -262,6 +262,13 @@ int  b200mac_set_coeffs(b200mac_t* h, const double* bx, const b200np_fab* bx_box
 int  b200mac_project(b200mac_t* h, double* umac, const b200np_fab* u_box, double* vmac, const b200np_fab* v_box, double* wmac,
                      const b200np_fab* w_box, double* mac_phi, const b200np_fab* phi_box, int phi_is_initial_guess, double rtol,
                      double atol, b200np_stats* stats);
+/* The same two calls over multi-box MultiFabs (b200np_mfab below; every reference deck runs with amr.max_grid_size = 16): bx / by / bz and
+ * umac / vmac / wmac face-centred (the valid box of a fab = its cells' box + the far face of its direction, shared with the neighbour box),
+ * mac_phi cell-centred.  The fabs are gathered into one array per field, projected, and the valid faces / cells scattered back:
+ * bit-identical to the single-box call. */
+int  b200mac_set_coeffs_mf(b200mac_t* h, const b200np_mfab* bx, const b200np_mfab* by, const b200np_mfab* bz);
+int  b200mac_project_mf(b200mac_t* h, const b200np_mfab* umac, const b200np_mfab* vmac, const b200np_mfab* wmac,
+                        const b200np_mfab* mac_phi, int phi_is_initial_guess, double rtol, double atol, b200np_stats* stats);
 /* test hooks: op 0 smooth (arg MLMG smooth calls: cor = in_a, res = in_b), 1 residual (in_b - A in_a), 2 restriction of in_a to
  * level lev + 1, 3 in_a + interpolation of in_b (level lev + 1), 4 bottom solve of in_b on the coarsest level.  Host arrays,
  * dense cell layout (nz, ny, nx). */
