@@ -47,7 +47,11 @@ struct EbLev {
     int CS;                   // unused slot per row: a hole; holes hold zeros everywhere and are never written); CS = H[0] H[1] H[2]
     long long nnode;          // allocated length of a nodal array = 8 CS (< 2^31)
     double* st;               // 27 coefficient arrays, st + t * nnode; t = 13: diagonal
-    const unsigned char* flag;   // 1: the row of this node is the canonical row of an uncut neighbourhood with constant sigma (faces 0, edges
+    const double* sigma;         // level 0 with variable sigma: the cell array (natural order) the flag-2 rows are computed from; else nullptr
+    double hinv2_12;             // 1 / (12 h^2) of the level (isotropic cells)
+    const unsigned char* flag;   // 2: uncut neighbourhood with VARIABLE sigma (level 0 only): the row follows from the 8 sigmas around the node
+                                 // (corners sigma_c / 12h^2, edges (sigma_a + sigma_b) / 12h^2, faces 0, diagonal -sum / 3h^2), not read from st;
+                                 // 1: the row of this node is the canonical row of an uncut neighbourhood with constant sigma (faces 0, edges
     const double* canon;         // canon[0], corners canon[1], diagonal canon[2]): the kernels do not read its 27 coefficients.  All 0 with
 };                               // variable sigma.  canon lives in device memory: a captured V-cycle graph must see the current sigma.
 
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(128) k_eb_stencil0(const EbLev L, const double
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
         int i, j, k;
         if (!ndecode(L, t, i, j, k)) continue;
-        if (L.flag[t]) {
+        if (L.flag[t] == 1) {
 #pragma unroll
             for (int tt = 0; tt < 27; ++tt) L.st[(long long)tt * L.nnode + t] = canonical_entry(L, tt);
             continue;
@@ -317,7 +321,7 @@ __global__ void __launch_bounds__(128) k_eb_stencil0(const EbLev L, const double
 }
 
 // level 0: a node has the canonical row iff its 8 cells exist and are uncut and neither it nor a neighbour is a Dirichlet node
-__global__ void __launch_bounds__(256) k_eb_flag0(const EbLev L, const double* __restrict__ geo, unsigned char* __restrict__ flag)
+__global__ void __launch_bounds__(256) k_eb_flag0(const EbLev L, const double* __restrict__ geo, unsigned char* __restrict__ flag, int kind)
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L.nnode; t += (long long)gridDim.x * blockDim.x) {
         int i, j, k;
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(256) k_eb_flag0(const EbLev L, const double* _
 #pragma unroll
             for (int tt = 0; tt < 27; ++tt) reg = reg && !node_dirichlet(L, q.c[0][tt % 3], q.c[1][(tt / 3) % 3], q.c[2][tt / 9]);
         }
-        flag[t] = reg ? 1 : 0;
+        flag[t] = reg ? kind : 0;
     }
 }
 // coarser level: canonical iff the 27 fine nodes under it are, and no neighbour is a Dirichlet node
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(256) k_eb_flag_coarse(const EbLev C, const EbL
 #pragma unroll
         for (int tt = 0; tt < 27; ++tt) {
             const int di = tt % 3, dj = (tt / 3) % 3, dk = tt / 9;
-            reg = reg && q.ok[0][di] && q.ok[1][dj] && q.ok[2][dk] && F.flag[nidx(F, q.c[0][di], q.c[1][dj], q.c[2][dk])];
+            reg = reg && q.ok[0][di] && q.ok[1][dj] && q.ok[2][dk] && F.flag[nidx(F, q.c[0][di], q.c[1][dj], q.c[2][dk])] == 1;
         }
         if (reg) {
             Nb qc;
@@ -388,7 +392,7 @@ __device__ __forceinline__ double w1(int t) { return t == 0 ? 1.0 : 0.5; }
 __global__ void __launch_bounds__(128) k_eb_rap(const EbLev C, const EbLev F)
 {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < C.nnode; t += (long long)gridDim.x * blockDim.x) {
-        if (C.flag[t]) {
+        if (C.flag[t] == 1) {
             for (int tt = 0; tt < 27; ++tt) C.st[(long long)tt * C.nnode + t] = canonical_entry(C, tt);
             continue;
         }
@@ -596,6 +600,39 @@ __device__ __forceinline__ double offdiag_sum_regular_inner(const EbLev& L, int 
     }
 }
 // sum_q!=p A(p, q) x(q) and the diagonal of node p = (i, j, k) of colour `color`, by the cheapest applicable path; false: inactive node
+// row of an interior node with 8 uncut cells from their sigmas (SURVEY A.3 with isotropic cells); all loads before the first multiply
+__device__ __forceinline__ void sigma_row(const EbLev& L, int p, int i, int j, int k, const NbOff& o, const double* x, double& off, double& diag)
+{
+    double S[2][2][2], v[27];
+    const double* sg = L.sigma + ((long long)(k - 1) * L.n[1] + (j - 1)) * L.n[0] + (i - 1);
+    const long long sy = L.n[0], sz = (long long)L.n[0] * L.n[1];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) S[c >> 2][(c >> 1) & 1][c & 1] = ld_early_nc(sg + (c >> 2) * sz + ((c >> 1) & 1) * sy + (c & 1));
+#pragma unroll
+    for (int tt = 0; tt < 27; ++tt) {
+        const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+        if (nz >= 2) v[tt] = ld_early(x + p + (o.D[0][tt % 3] + o.D[1][(tt / 3) % 3] + o.D[2][tt / 9]));
+    }
+    double acc = 0.0, sum = 0.0;
+#pragma unroll
+    for (int tt = 26; tt >= 0; --tt) {
+        const int di = tt % 3, dj = (tt / 3) % 3, dk = tt / 9;
+        const int nz = (di != 1) + (dj != 1) + (dk != 1);
+        if (nz < 2) continue;
+        double w = 0.0;   // sum of sigma over the cells that touch both nodes
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int az = c >> 2, ay = (c >> 1) & 1, ax = c & 1;
+            const bool tx = di == 1 || (di == 0 ? ax == 0 : ax == 1), ty = dj == 1 || (dj == 0 ? ay == 0 : ay == 1), tz = dk == 1 || (dk == 0 ? az == 0 : az == 1);
+            if (tx && ty && tz) w += S[az][ay][ax];
+        }
+        acc += w * v[tt];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sum += S[c >> 2][(c >> 1) & 1][c & 1];
+    off = L.hinv2_12 * acc;
+    diag = -4.0 * L.hinv2_12 * sum;
+}
 __device__ __forceinline__ unsigned ld_early_u8(const unsigned char* p)
 {
     unsigned v;
@@ -605,7 +642,9 @@ __device__ __forceinline__ unsigned ld_early_u8(const unsigned char* p)
 // BATCH: 0 plain loads; 1 batched loads on the canonical rows only (20 loads, ~56 registers); 2 batched everywhere (~120 registers);
 // 3 SPECULATIVE: an interior node issues its flag AND the 20 neighbour values of the canonical row together and decides afterwards
 // (one memory round trip instead of two on the path 98 % of the nodes of the finest level take; the rest reloads for the general row)
-template <int BATCH>
+// SIG: the level may carry sigma-form rows (flag 2: level 0 with variable sigma); a separate instantiation, because the extra path costs
+// the constant-sigma kernel 10 registers and a fifth of its speed
+template <int BATCH, bool SIG = false>
 __device__ __forceinline__ bool node_row(const EbLev& L, int p, int i, int j, int k, int color, const double* x, double& off, double& diag)
 {
     const bool inner = i > 0 && i < L.nn[0] - 1 && j > 0 && j < L.nn[1] - 1 && k > 0 && k < L.nn[2] - 1;
@@ -620,7 +659,7 @@ __device__ __forceinline__ bool node_row(const EbLev& L, int p, int i, int j, in
             const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
             if (nz >= 2) v[tt] = ld_early(xp + (o.D[0][tt % 3] + o.D[1][(tt / 3) % 3] + o.D[2][tt / 9]));
         }
-        if (f) {
+        if (f == 1) {
             double se = 0.0, sc = 0.0;
 #pragma unroll
             for (int tt = 26; tt >= 0; --tt) {
@@ -632,12 +671,15 @@ __device__ __forceinline__ bool node_row(const EbLev& L, int p, int i, int j, in
             off = ce * se + cc * sc;
             return true;
         }
+        if (SIG && f == 2) { sigma_row(L, p, i, j, k, o, x, off, diag); return true; }
         diag = __ldg(L.st + 13 * L.nnode + p);
         if (diag == 0.0) return false;
         off = offdiag_sum_inner<false>(L, p, o, x);
         return true;
     }
-    if (L.flag[p]) {
+    const unsigned fl = L.flag[p];
+    if (SIG && fl == 2 && inner) { sigma_row(L, p, i, j, k, nb_offsets(L, color), x, off, diag); return true; }
+    if (fl == 1) {
         diag = L.canon[2];
         off = inner ? offdiag_sum_regular_inner<(BATCH == 1 || BATCH == 2)>(L, p, nb_offsets(L, color), x) : offdiag_sum_regular<(BATCH == 1 || BATCH == 2)>(L, i, j, k, x);
         return true;
@@ -650,7 +692,7 @@ __device__ __forceinline__ bool node_row(const EbLev& L, int p, int i, int j, in
 
 // one colour of a Gauss-Seidel sweep (mlndlap_gscolor_sten).  old == x except on levels where a periodic wrap joins two nodes of
 // one colour (odd periodic extent): there old is a snapshot taken before the launch.
-template <int BATCH>
+template <int BATCH, bool SIG>
 __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const double* old, const double* __restrict__ rhs, int color)
 {
     // block (64, 4): 64 consecutive i/2 of 4 rows j/2; blockIdx.z = k/2
@@ -662,7 +704,7 @@ __global__ void __launch_bounds__(256) k_eb_gs(const EbLev L, double* x, const d
     const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
     const double r = BATCH >= 2 ? ld_early_nc(rhs + p) : rhs[p];   // in flight together with the row's loads
     double off, d;
-    x[p] = node_row<BATCH>(L, p, i, j, k, color, old, off, d) ? (r - off) / d : 0.0;
+    x[p] = node_row<BATCH, SIG>(L, p, i, j, k, color, old, off, d) ? (r - off) / d : 0.0;
 }
 // all sweeps of a smooth call on a level small enough for ONE CTA: colours separated by __syncthreads instead of kernel boundaries
 // (a level of a few thousand nodes is pure launch latency otherwise: 8 launches per sweep).  snap != nullptr: odd periodic extent.
@@ -682,7 +724,7 @@ __global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, 
             for (int p = lo + tid; p < hi; p += nt) {
                 int i, j, k;
                 if (!ndecode(L, p, i, j, k)) continue;
-                if (L.flag[p]) { x[p] = (rhs[p] - offdiag_sum_regular<true>(L, i, j, k, old)) / L.canon[2]; continue; }
+                if (L.flag[p] == 1) { x[p] = (rhs[p] - offdiag_sum_regular<true>(L, i, j, k, old)) / L.canon[2]; continue; }
                 const double d = L.st[13 * L.nnode + p];
                 x[p] = d == 0.0 ? 0.0 : (rhs[p] - offdiag_sum<true>(L, p, i, j, k, old)) / d;
             }
@@ -690,7 +732,7 @@ __global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, 
         }
 }
 // out = rhs - A x on the active nodes, 0 elsewhere; optional inf-norm partials
-template <int BATCH>
+template <int BATCH, bool SIG>
 __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double* __restrict__ x, const double* __restrict__ rhs, double* __restrict__ out,
                                                      double* __restrict__ norm_partial)
 {
@@ -705,7 +747,7 @@ __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double
         const int p = color * L.CS + (k2 * L.H[1] + j2) * L.H[0] + i2;
         const double b = BATCH >= 2 ? ld_early_nc(rhs + p) : rhs[p], xc = BATCH >= 2 ? ld_early(x + p) : x[p];
         double off, d;
-        if (node_row<BATCH>(L, p, i, j, k, color, x, off, d)) r = b - (d * xc + off);
+        if (node_row<BATCH, SIG>(L, p, i, j, k, color, x, off, d)) r = b - (d * xc + off);
         if (out) out[p] = r;
     }
     if (norm_partial) {
@@ -1201,7 +1243,7 @@ struct b200eb {
     double* hscal = nullptr;
     int* hinfo = nullptr;
     bool singular = true, have_geometry = false, have_ebflow = false, have_stencil = false;
-    int flags_state = 0;      // 0: unknown, 1: all zero (variable sigma), 2: computed for a constant sigma and the current geometry
+    int flags_state = 0;      // 0: unknown; see eb_build_stencils
     double* canon = nullptr;  // 3 doubles per level
     long long batch_below = 500000;    // levels with fewer nodes use the load-batching kernels (B200EB_BATCH_BELOW)
     int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200EB_PDL)
@@ -1291,6 +1333,11 @@ void eb_build(b200eb* h)
     if (const char* e = getenv("B200EB_BIG_VARIANT")) h->big_variant = atoi(e);
     h->geo = eb_alloc(h, (size_t)19 * h->ncell);
     h->sigma = eb_alloc(h, (size_t)h->ncell);
+    for (size_t l = 0; l < h->lv.size(); ++l) {
+        const double hl = G.dx[0] * (double)(1 << l);
+        h->lv[l].g.sigma = l == 0 ? h->sigma : nullptr;
+        h->lv[l].g.hinv2_12 = 1.0 / (12.0 * hl * hl);
+    }
     h->work = eb_alloc(h, (size_t)7 * h->lv.back().g.nnode);
     h->snap = eb_alloc(h, (size_t)h->lv[0].g.nnode);
     h->tmp_nat = eb_alloc(h, (size_t)14 * h->lv[0].g.nnode);
@@ -1309,14 +1356,18 @@ void eb_build_stencils(b200eb* h, double const_sigma)
     const b200np_geom& G = h->geom;
     EbLevel& L0 = h->lv[0];
     static const bool use_flags = !(getenv("B200EB_FLAGS") && atoi(getenv("B200EB_FLAGS")) == 0);
-    const int want = (const_sigma > 0 && use_flags) ? 2 : 1;
+    // 2: constant sigma -- canonical rows on every level; 1: variable sigma -- sigma-form rows (flag 2) on level 0, stored rows below;
+    // 3: no flags at all
+    const int want = !use_flags ? 3 : (const_sigma > 0 ? 2 : 1);
     if (h->flags_state != want) {
-        if (want == 1) {
+        if (want == 3) {
             for (auto& L : h->lv) ECK(cudaMemsetAsync(L.flag, 0, (size_t)L.g.nnode, h->stream));
         } else {
-            ELAUNCH(h, k_eb_flag0, eb_grid(L0.g.nnode), 256, L0.g, (const double*)h->geo, L0.flag);
-            for (size_t l = 0; l + 1 < h->lv.size(); ++l)
-                ELAUNCH(h, k_eb_flag_coarse, eb_grid(h->lv[l + 1].g.nnode), 256, h->lv[l + 1].g, h->lv[l].g, h->lv[l + 1].flag);
+            ELAUNCH(h, k_eb_flag0, eb_grid(L0.g.nnode), 256, L0.g, (const double*)h->geo, L0.flag, want == 2 ? 1 : 2);
+            for (size_t l = 0; l + 1 < h->lv.size(); ++l) {
+                if (want == 2) ELAUNCH(h, k_eb_flag_coarse, eb_grid(h->lv[l + 1].g.nnode), 256, h->lv[l + 1].g, h->lv[l].g, h->lv[l + 1].flag);
+                else ECK(cudaMemsetAsync(h->lv[l + 1].flag, 0, (size_t)h->lv[l + 1].g.nnode, h->stream));
+            }
         }
         h->flags_state = want;
     }
@@ -1329,21 +1380,34 @@ void eb_build_stencils(b200eb* h, double const_sigma)
 }
 
 // kernel variant by level size (struct b200eb: batch_below, big_variant)
-void eb_launch_gs(b200eb* h, EbLevel& L, double* x, const double* old, const double* rhs, int c)
+template <bool SIG>
+void eb_launch_gs_t(b200eb* h, EbLevel& L, double* x, const double* old, const double* rhs, int c)
 {
     const dim3 grid = eb_grid3(L.g, 1), block(64, 4);
-    if (L.g.nnode < h->batch_below) eb_launch_pdl(h, k_eb_gs<2>, grid, block, L.g, x, old, rhs, c);
-    else if (h->big_variant == 3) eb_launch_pdl(h, k_eb_gs<3>, grid, block, L.g, x, old, rhs, c);
-    else if (h->big_variant == 1) eb_launch_pdl(h, k_eb_gs<1>, grid, block, L.g, x, old, rhs, c);
-    else eb_launch_pdl(h, k_eb_gs<0>, grid, block, L.g, x, old, rhs, c);
+    if (L.g.nnode < h->batch_below) eb_launch_pdl(h, k_eb_gs<2, SIG>, grid, block, L.g, x, old, rhs, c);
+    else if (h->big_variant == 3) eb_launch_pdl(h, k_eb_gs<3, SIG>, grid, block, L.g, x, old, rhs, c);
+    else if (h->big_variant == 1) eb_launch_pdl(h, k_eb_gs<1, SIG>, grid, block, L.g, x, old, rhs, c);
+    else eb_launch_pdl(h, k_eb_gs<0, SIG>, grid, block, L.g, x, old, rhs, c);
+}
+// sigma-form rows exist on level 0 when sigma is variable (flags_state 1)
+void eb_launch_gs(b200eb* h, EbLevel& L, double* x, const double* old, const double* rhs, int c)
+{
+    if (h->flags_state == 1 && &L == &h->lv[0]) eb_launch_gs_t<true>(h, L, x, old, rhs, c);
+    else eb_launch_gs_t<false>(h, L, x, old, rhs, c);
+}
+template <bool SIG>
+void eb_launch_residual_t(b200eb* h, EbLevel& L, const double* x, const double* rhs, double* out, double* partial)
+{
+    const dim3 grid = eb_grid3(L.g, 8), block(64, 4);
+    if (L.g.nnode < h->batch_below) eb_launch_pdl(h, k_eb_residual<2, SIG>, grid, block, L.g, x, rhs, out, partial);
+    else if (h->big_variant == 3) eb_launch_pdl(h, k_eb_residual<3, SIG>, grid, block, L.g, x, rhs, out, partial);
+    else if (h->big_variant == 1) eb_launch_pdl(h, k_eb_residual<1, SIG>, grid, block, L.g, x, rhs, out, partial);
+    else eb_launch_pdl(h, k_eb_residual<0, SIG>, grid, block, L.g, x, rhs, out, partial);
 }
 void eb_launch_residual(b200eb* h, EbLevel& L, const double* x, const double* rhs, double* out, double* partial)
 {
-    const dim3 grid = eb_grid3(L.g, 8), block(64, 4);
-    if (L.g.nnode < h->batch_below) eb_launch_pdl(h, k_eb_residual<2>, grid, block, L.g, x, rhs, out, partial);
-    else if (h->big_variant == 3) eb_launch_pdl(h, k_eb_residual<3>, grid, block, L.g, x, rhs, out, partial);
-    else if (h->big_variant == 1) eb_launch_pdl(h, k_eb_residual<1>, grid, block, L.g, x, rhs, out, partial);
-    else eb_launch_pdl(h, k_eb_residual<0>, grid, block, L.g, x, rhs, out, partial);
+    if (h->flags_state == 1 && &L == &h->lv[0]) eb_launch_residual_t<true>(h, L, x, rhs, out, partial);
+    else eb_launch_residual_t<false>(h, L, x, rhs, out, partial);
 }
 
 // one MLMG smooth call = smooth_num_sweeps sweeps of 8 colours

@@ -15,6 +15,7 @@ from incflo_b200 import eb_geometry as eg, eb_projector as ebp
 
 n = tuple(int(x) for x in sys.argv[1:4]) if len(sys.argv) > 3 else (512, 128, 128)
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+VAR = len(sys.argv) > 5 and sys.argv[5] == "var"      # variable density: sigma = dt / rho as a cell array (4:1), e.g. test_3d/benchmark.eb_flow_density
 h = 0.4 / n[1]
 peak = 6545.9
 try:
@@ -34,11 +35,15 @@ proj = ebp.EBNodalProjector(n, (h,) * 3, bclo, bchi, geom.vfrac, geom.intg)
 tv0 = torch.from_numpy(vel0).to(dev)
 phi = torch.zeros((n[2] + 1, n[1] + 1, n[0] + 1), device=dev, dtype=torch.float64)
 gphi = torch.zeros((3, n[2], n[1], n[0]), device=dev, dtype=torch.float64)
+sigma = 1.0
+if VAR:
+    zz = (torch.arange(n[1], device=dev, dtype=torch.float64) + 0.5) / n[1]
+    sigma = (1.0 / (1.0 + 1.5 * (1.0 + torch.tanh((zz - 0.5) / 0.1))))[None, :, None].expand(n[2], n[1], n[0]).contiguous()
 times, solve = [], []
 for s in range(K + 2):
     tv = tv0.clone()
     torch.cuda.synchronize()
-    st = proj.project(tv, 1.0, 1e-11, 1e-14, phi=phi, gphi=gphi)
+    st = proj.project(tv, sigma, 1e-11, 1e-14, phi=phi, gphi=gphi)
     if s >= 2:
         times.append(st.ms_total); solve.append(st.ms_solve)
 ms, mss = sum(times) / len(times), sum(solve) / len(solve)
@@ -59,7 +64,7 @@ per_node = (16 * 240 + 240 + 9 + 17) * 8.0 / 7.0 + 24 + 240
 total = per_node * nnode * st.iters + (19 * 8 + 27 * 8 + 27 * 8 * 2.0 / 7.0) * nnode
 u = tv[:, 1:-1, 1:-1, 1:-1]
 print(json.dumps({"metric": "eb_nodal_projection_Mcell_updates_per_s", "value": ncell / ms / 1e3, "unit": "Mcell-updates/s", "n": n,
-                  "workload": "channel_cylinder-x (BASELINE configs[4]) EB cylinder, inflow / outflow / walls / periodic z, constant density",
+                  "workload": "channel_cylinder-x (BASELINE configs[4]) EB cylinder, inflow / outflow / walls / periodic z, " + ("variable density 4:1 across y" if VAR else "constant density"),
                   "ms_per_projection": ms, "ms_solve": mss, "ms_setup_and_update": ms - mss, "vcycles": st.iters, "nlevels": st.nlevels,
                   "bottom_iters": st.bottom_iters, "resid_over_bnorm": st.resnorm / max(st.rhsnorm, st.resnorm0), "launches": st.launches,
                   "cut_cells": int(geom.cut_mask().sum()), "covered_cells": int((geom.vfrac == 0).sum()), "geometry_s": t_geom,
