@@ -498,13 +498,16 @@ def north_star_block(ctx):
     n = (512, 512, 512)
     wl = workload(n, 1, 0, ctx.device)
     proj = make_projection(ctx, n, nranks=1)
+    # the two kernels first, timed alone after one warm-up solve (MEASURED_PEAKS' hbm_gbs is a burst figure as well); then the solves,
+    # which run into the power cap at this size (clocks sampled over both)
     sampler = ClockSampler(ctx.local)
     sampler.start()
-    ms, _, st, _ = timed_solves(ctx, proj, wl, 3, 1, n, "clone")
+    timed_solves(ctx, proj, wl, 1, 0, n, "clone")
     _, nn = proj.level_dims(0)
     nodes = nn[0] * nn[1] * nn[2]
     ms_sm = proj.time_op(0, npj.OP_SMOOTH, 2, reps=20) / 2.0
     ms_res = proj.time_op(0, npj.OP_RESIDUAL, 0, reps=20)
+    ms, _, st, _ = timed_solves(ctx, proj, wl, 3, 1, n, "clone")
     clocks = sampler.stop()
     peak, _ = peaks()
     gbs = lambda t: 32.0 * nodes / (t * 1e-3) / 1e9

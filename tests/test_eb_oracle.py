@@ -169,3 +169,40 @@ def test_odd_periodic_level_converges():
     r = eo.project(p, vel, 1.0, geom.vfrac, geom.intg, 1e-10, 1e-14)
     assert [L.n for L in r["mg"].lv] == [(12, 12, 12), (6, 6, 6), (3, 3, 3)] and r["mg"].lv[2].odd_periodic
     assert r["info"]["iters"] <= 12
+
+
+def test_uniform_flow_past_a_cylinder_converges_at_second_order():
+    """Projecting u = (1, 0, 0) in the fluid around a cylinder (periodic box) must give the potential flow around it: the natural boundary
+    condition of the fluid-integrated operator is no flux through the body.  No closed form in a periodic box, so: self-convergence of the
+    projected velocity under refinement by 2 (volume-weighted 2 x 2 averages of the finer solution) -- second order away from the
+    body (ratio ~ 4), between first and second order over all fluid cells"""
+    def solve(N):
+        n, h = (N, N, N // 8), 1.0 / N
+        geom = eg.cylinder(n, h, 0.1500001, (0.5, 0.5, 0.0), direction=2, small_vfrac=1e-3)
+        p = eo.Params(n, (h,) * 3, (0, 0, 0), (0, 0, 0))
+        vel = np.zeros((3, n[2] + 2, N + 2, N + 2))
+        vel[0, 1:-1, 1:-1, 1:-1] = (geom.vfrac > 0)
+        r = eo.project(p, vel, 1.0, geom.vfrac, geom.intg, 1e-12, 1e-15)
+        assert np.abs(r["vel"][2]).max() < 1e-10          # the problem is two-dimensional
+        return geom.vfrac[0], r["vel"][:2, 0]
+
+    def restrict(u, V):
+        parts = [(slice(None), slice(a, None, 2), slice(b, None, 2)) for a in (0, 1) for b in (0, 1)]
+        den = sum(V[s[1:]] for s in parts)
+        num = sum(u[s] * V[s[1:]] for s in parts)
+        return np.where(den > 0, num / np.where(den > 0, den, 1.0), 0.0)
+
+    sol = {N: solve(N) for N in (32, 64, 128)}
+    err = {}
+    for a, b in ((32, 64), (64, 128)):
+        Va, ua = sol[a]
+        ub = restrict(sol[b][1], sol[b][0])
+        x = (np.arange(a) + 0.5) / a
+        X, Y = np.meshgrid(x, x, indexing="xy")
+        far = (X - 0.5) ** 2 + (Y - 0.5) ** 2 > 0.2 ** 2
+        err[a] = (np.sqrt(np.mean((ub - ua)[:, far] ** 2)), np.sqrt(np.mean((ub - ua)[:, Va > 0] ** 2)))
+    assert err[32][0] / err[64][0] > 3.3 and err[64][0] < 3e-4
+    assert err[32][1] / err[64][1] > 2.2
+    # the flow is deflected around the body: faster than the free stream above / below it, slower in front of it
+    V, u = sol[128]
+    assert u[0, 64 + 26, 64] > 1.2 and u[0, 64, 64 - 26] < 0.8
