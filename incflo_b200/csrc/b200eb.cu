@@ -1190,6 +1190,56 @@ __global__ void __launch_bounds__(256) k_eb_permute(const EbLev L, const double*
     }
 }
 
+// ---- multi-box MultiFabs at the boundary (amr.max_grid_size < domain, e.g. test_3d/benchmark.channel_sphere: 16) ----
+struct EbMfFab {
+    double* p;
+    int lo[3];            // allocated box
+    int nx, ny, nz;
+    long long cs;
+};
+struct EDense {           // one box over the level with its extent (has())
+    double* p;
+    int lo[3], hi[3];
+    long long cs;
+    __device__ __forceinline__ bool has(int i, int j, int k) const { return i >= lo[0] && i <= hi[0] && j >= lo[1] && j <= hi[1] && k >= lo[2] && k <= hi[2]; }
+    __device__ __forceinline__ long long idx(int i, int j, int k) const
+    {
+        return (i - lo[0]) + (long long)(hi[0] - lo[0] + 1) * ((j - lo[1]) + (long long)(hi[1] - lo[1] + 1) * (k - lo[2]));
+    }
+};
+enum { EBMF_VALID = 0,      // the valid boxes only
+       EBMF_VALID_BC = 1 }; // gather: + ghost cells OUTSIDE the domain (the BC ghost layer of the velocity); scatter: every cell of the allocated box --
+                            // the dense value where there is one (valid cells, first ghost layer), 0 elsewhere (vel.setBndry(0))
+__global__ void __launch_bounds__(256) k_eb_mf_gather(const EbMfFab* __restrict__ tab, int ngrow, int ncomp, EDense dst, int mode, int dom0, int dom1, int dom2)
+{
+    const EbMfFab f = tab[blockIdx.y];
+    const long long total = (long long)f.nx * f.ny * f.nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int li = (int)(t % f.nx), lj = (int)((t / f.nx) % f.ny), lk = (int)(t / ((long long)f.nx * f.ny));
+        const int i = li + f.lo[0], j = lj + f.lo[1], k = lk + f.lo[2];
+        bool take = li >= ngrow && li < f.nx - ngrow && lj >= ngrow && lj < f.ny - ngrow && lk >= ngrow && lk < f.nz - ngrow;
+        if (!take && mode == EBMF_VALID_BC) take = i < 0 || i >= dom0 || j < 0 || j >= dom1 || k < 0 || k >= dom2;
+        if (!take || !dst.has(i, j, k)) continue;
+        const long long q = dst.idx(i, j, k);
+        for (int c = 0; c < ncomp; ++c) dst.p[c * dst.cs + q] = f.p[c * f.cs + t];
+    }
+}
+__global__ void __launch_bounds__(256) k_eb_mf_scatter(const EbMfFab* __restrict__ tab, int ngrow, int ncomp, EDense src, int mode)
+{
+    const EbMfFab f = tab[blockIdx.y];
+    const long long total = (long long)f.nx * f.ny * f.nz;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int li = (int)(t % f.nx), lj = (int)((t / f.nx) % f.ny), lk = (int)(t / ((long long)f.nx * f.ny));
+        const int i = li + f.lo[0], j = lj + f.lo[1], k = lk + f.lo[2];
+        const bool valid = li >= ngrow && li < f.nx - ngrow && lj >= ngrow && lj < f.ny - ngrow && lk >= ngrow && lk < f.nz - ngrow;
+        if (!valid && mode != EBMF_VALID_BC) continue;
+        const bool have = src.has(i, j, k);
+        if (!have && valid) continue;
+        const long long q = have ? src.idx(i, j, k) : 0;
+        for (int c = 0; c < ncomp; ++c) f.p[c * f.cs + t] = have ? src.p[c * src.cs + q] : 0.0;
+    }
+}
+
 struct EbLevel {
     EbLev g{};
     unsigned char* flag = nullptr;
@@ -1251,6 +1301,7 @@ struct b200eb {
     int small_nodes = 1000;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
     long long launches = 0, ncell = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[12];
+    struct Mf { double* dense = nullptr; size_t dense_doubles = 0; double* stage = nullptr; size_t stage_doubles = 0; EbMfFab* tab = nullptr; size_t tab_cap = 0; } mf[10];
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -1635,6 +1686,7 @@ void b200eb_destroy(b200eb_t* h)
     if (h->graph) cudaGraphDestroy(h->graph);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& s : h->stage) if (s.d) cudaFree(s.d);
+    for (auto& m : h->mf) { if (m.dense) cudaFree(m.dense); if (m.stage) cudaFree(m.stage); if (m.tab) cudaFree(m.tab); }
     if (h->hscal) cudaFreeHost(h->hscal);
     if (h->hinfo) cudaFreeHost(h->hinfo);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -1805,6 +1857,233 @@ int b200eb_apply_nodal_projection(b200eb_t* h, double* velocity, const b200np_fa
         ECK(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3])); st->ms_solve = ms;
         st->launches = h->launches;
         return st->status = status;
+    } catch (int e) { return st->status = e; }
+}
+
+}  // extern "C"
+
+namespace {
+struct EbMfView {
+    const b200np_mfab* m = nullptr;
+    int slot = 0, ncomp = 1;
+    bool staged = false;
+    std::vector<size_t> off;
+    double* dense = nullptr;
+    b200np_fab box{};        // the dense box
+};
+size_t ebmf_fab_doubles(const b200np_fab& b, int ncomp)
+{
+    return (size_t)(b.hi[0] - b.lo[0] + 1) * (b.hi[1] - b.lo[1] + 1) * (b.hi[2] - b.lo[2] + 1) * ncomp;
+}
+// the valid boxes (allocated box shrunk by ngrow) must lie inside [lo, hi] and, for cell-centred MultiFabs, tile it
+bool ebmf_ok(const b200np_mfab* m, const int lo[3], const int hi[3], int ncomp, bool tile, int min_grow = 0)
+{
+    if (!m || m->nfabs < 1 || m->ngrow < min_grow || m->ncomp < ncomp || !m->box || !m->data) return false;
+    long long vol = 0;
+    for (int f = 0; f < m->nfabs; ++f) {
+        if (!m->data[f]) return false;
+        long long v = 1;
+        for (int d = 0; d < 3; ++d) {
+            const int vlo = m->box[f].lo[d] + m->ngrow, vhi = m->box[f].hi[d] - m->ngrow;
+            if (vhi < vlo || vlo < lo[d] || vhi > hi[d]) return false;
+            v *= vhi - vlo + 1;
+        }
+        vol += v;
+    }
+    if (tile) {
+        long long want = 1;
+        for (int d = 0; d < 3; ++d) want *= hi[d] - lo[d] + 1;
+        if (vol != want) return false;
+    }
+    return true;
+}
+// fabs on the device (staged when they are host pointers) + a dense array over `box`
+void ebmf_map(b200eb* h, EbMfView& V, int slot, const b200np_mfab* m, int ncomp, const b200np_fab& box, bool copy_in, b200np_stats* st)
+{
+    V = EbMfView{};
+    if (!m) return;
+    V.m = m; V.slot = slot; V.ncomp = ncomp; V.box = box; V.box.ncomp = ncomp;
+    auto& S = h->mf[slot];
+    const int nf = m->nfabs;
+    V.staged = !eb_is_dev_ptr(m->data[0]);
+    V.off.assign(nf, 0);
+    size_t total = 0;
+    std::vector<EbMfFab> host(nf);
+    for (int f = 0; f < nf; ++f) {
+        const b200np_fab& b = m->box[f];
+        host[f].nx = b.hi[0] - b.lo[0] + 1; host[f].ny = b.hi[1] - b.lo[1] + 1; host[f].nz = b.hi[2] - b.lo[2] + 1;
+        host[f].cs = (long long)host[f].nx * host[f].ny * host[f].nz;
+        for (int q = 0; q < 3; ++q) host[f].lo[q] = b.lo[q];
+        V.off[f] = total;
+        total += ebmf_fab_doubles(b, m->ncomp);
+    }
+    if (V.staged) {
+        if (S.stage_doubles < total) { if (S.stage) ECK(cudaFree(S.stage)); ECK(cudaMalloc(&S.stage, total * sizeof(double))); S.stage_doubles = total; }
+        if (copy_in) {
+            for (int f = 0; f < nf; ++f)
+                ECK(cudaMemcpyAsync(S.stage + V.off[f], m->data[f], ebmf_fab_doubles(m->box[f], m->ncomp) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            if (st) st->h2d_bytes += (long long)(total * sizeof(double));
+        }
+    }
+    for (int f = 0; f < nf; ++f) host[f].p = V.staged ? S.stage + V.off[f] : m->data[f];
+    if (S.tab_cap < (size_t)nf) { if (S.tab) ECK(cudaFree(S.tab)); ECK(cudaMalloc(&S.tab, (size_t)nf * sizeof(EbMfFab))); S.tab_cap = nf; }
+    ECK(cudaMemcpyAsync(S.tab, host.data(), (size_t)nf * sizeof(EbMfFab), cudaMemcpyHostToDevice, h->stream));
+    ECK(cudaStreamSynchronize(h->stream));   // `host` goes out of scope
+    const size_t nd = ebmf_fab_doubles(box, ncomp);
+    if (S.dense_doubles < nd) { if (S.dense) ECK(cudaFree(S.dense)); ECK(cudaMalloc(&S.dense, nd * sizeof(double))); S.dense_doubles = nd; }
+    V.dense = S.dense;
+}
+EDense ebmf_dense(const EbMfView& V)
+{
+    EDense d{};
+    d.p = V.dense;
+    for (int q = 0; q < 3; ++q) { d.lo[q] = V.box.lo[q]; d.hi[q] = V.box.hi[q]; }
+    d.cs = (long long)(V.box.hi[0] - V.box.lo[0] + 1) * (V.box.hi[1] - V.box.lo[1] + 1) * (V.box.hi[2] - V.box.lo[2] + 1);
+    return d;
+}
+dim3 ebmf_grid(const b200np_mfab* m)
+{
+    long long mx = 1;
+    for (int f = 0; f < m->nfabs; ++f) mx = std::max<long long>(mx, (long long)ebmf_fab_doubles(m->box[f], 1));
+    return dim3((unsigned)std::min<long long>((mx + 255) / 256, 64), (unsigned)m->nfabs);
+}
+void ebmf_gather(b200eb* h, EbMfView& V, int mode)
+{
+    if (!V.m) return;
+    const int* n = h->geom.n_cell;
+    ELAUNCH(h, k_eb_mf_gather, ebmf_grid(V.m), 256, (const EbMfFab*)h->mf[V.slot].tab, V.m->ngrow, V.ncomp, ebmf_dense(V), mode, n[0], n[1], n[2]);
+}
+void ebmf_scatter(b200eb* h, EbMfView& V, int mode, b200np_stats* st)
+{
+    if (!V.m) return;
+    ELAUNCH(h, k_eb_mf_scatter, ebmf_grid(V.m), 256, (const EbMfFab*)h->mf[V.slot].tab, V.m->ngrow, V.ncomp, ebmf_dense(V), mode);
+    if (!V.staged) return;
+    size_t total = 0;
+    for (int f = 0; f < V.m->nfabs; ++f) {
+        const size_t nd = ebmf_fab_doubles(V.m->box[f], V.m->ncomp);
+        ECK(cudaMemcpyAsync(V.m->data[f], h->mf[V.slot].stage + V.off[f], nd * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        total += nd;
+    }
+    if (st) st->d2h_bytes += (long long)(total * sizeof(double));
+}
+void ebmf_boxes(const b200eb* h, b200np_fab& cells, b200np_fab& grown, b200np_fab& nodes)
+{
+    for (int d = 0; d < 3; ++d) {
+        cells.lo[d] = 0; cells.hi[d] = h->geom.n_cell[d] - 1;
+        grown.lo[d] = -1; grown.hi[d] = h->geom.n_cell[d];
+        nodes.lo[d] = 0; nodes.hi[d] = h->geom.n_cell[d];
+    }
+    cells.ncomp = 1; grown.ncomp = 3; nodes.ncomp = 1;
+}
+}  // namespace
+
+extern "C" {
+
+// b200eb_set_geometry over multi-box MultiFabs (getVolFrac(), the integral MultiFab)
+int b200eb_set_geometry_mf(b200eb_t* h, const b200np_mfab* vfrac, const b200np_mfab* intg)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    b200np_fab cells{}, grown{}, nodes{};
+    ebmf_boxes(h, cells, grown, nodes);
+    if (!ebmf_ok(vfrac, cells.lo, cells.hi, 1, true) || !ebmf_ok(intg, cells.lo, cells.hi, 18, true)) return B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        EbMfView Vv, Vi;
+        ebmf_map(h, Vv, 0, vfrac, 1, cells, true, nullptr);
+        ebmf_map(h, Vi, 1, intg, 18, cells, true, nullptr);
+        ebmf_gather(h, Vv, EBMF_VALID);
+        ebmf_gather(h, Vi, EBMF_VALID);
+        ECK(cudaStreamSynchronize(h->stream));
+        return b200eb_set_geometry(h, Vv.dense, &Vv.box, Vi.dense, &Vi.box);
+    } catch (int e) { return e; }
+}
+
+// b200eb_project over multi-box MultiFabs: bit-identical to the single-box call.  After the call every cell of vel's fabs that lies inside the
+// domain grown by one cell holds the projected velocity / the BC ghost value (interior ghost cells as after FillBoundary).
+int b200eb_project_mf(b200eb_t* h, const b200np_mfab* vel, const b200np_mfab* sigma, double const_sigma, const b200np_mfab* phi, const b200np_mfab* gphi,
+                      double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h || !h->have_geometry) return st->status = B200NP_ERR_BAD_ARG;
+    b200np_fab cells{}, grown{}, nodes{};
+    ebmf_boxes(h, cells, grown, nodes);
+    if (!ebmf_ok(vel, cells.lo, cells.hi, 3, true, 1)) return st->status = B200NP_ERR_BAD_ARG;
+    if (sigma && !ebmf_ok(sigma, cells.lo, cells.hi, 1, true)) return st->status = B200NP_ERR_BAD_ARG;
+    if (gphi && !ebmf_ok(gphi, cells.lo, cells.hi, 3, true)) return st->status = B200NP_ERR_BAD_ARG;
+    if (phi && !ebmf_ok(phi, nodes.lo, nodes.hi, 1, false)) return st->status = B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        b200np_stats outer{};
+        EbMfView Vv, Vs, Vp, Vg;
+        ebmf_map(h, Vv, 2, vel, 3, grown, true, &outer);
+        ebmf_map(h, Vs, 3, sigma, 1, cells, true, &outer);
+        ebmf_map(h, Vp, 4, phi, 1, nodes, false, &outer);
+        ebmf_map(h, Vg, 5, gphi, 3, cells, false, &outer);
+        ECK(cudaMemsetAsync(Vv.dense, 0, ebmf_fab_doubles(grown, 3) * sizeof(double), h->stream));
+        ebmf_gather(h, Vv, EBMF_VALID_BC);
+        ebmf_gather(h, Vs, EBMF_VALID);
+        ECK(cudaStreamSynchronize(h->stream));
+        const int rc = b200eb_project(h, Vv.dense, &Vv.box, sigma ? Vs.dense : nullptr, sigma ? &Vs.box : nullptr, const_sigma, phi ? Vp.dense : nullptr,
+                                      phi ? &Vp.box : nullptr, gphi ? Vg.dense : nullptr, gphi ? &Vg.box : nullptr, rtol, atol, st);
+        if (rc != B200NP_OK && rc != B200NP_ERR_NOT_CONVERGED && rc != B200NP_ERR_DIVERGED) return rc;
+        ebmf_scatter(h, Vv, EBMF_VALID_BC, &outer);
+        ebmf_scatter(h, Vp, EBMF_VALID, &outer);
+        ebmf_scatter(h, Vg, EBMF_VALID, &outer);
+        ECK(cudaStreamSynchronize(h->stream));
+        st->h2d_bytes += outer.h2d_bytes; st->d2h_bytes += outer.d2h_bytes;
+        return st->status = rc;
+    } catch (int e) { return st->status = e; }
+}
+
+// incflo::ApplyNodalProjection under AMREX_USE_EB over multi-box LevelData MultiFabs
+int b200eb_apply_nodal_projection_mf(b200eb_t* h, const b200np_mfab* velocity, const b200np_mfab* velocity_o, const b200np_mfab* density, double ro_0,
+                                     const b200np_mfab* gp, const b200np_mfab* p_nd, const b200np_mfab* inflow_vel, double scaling_factor, int incremental,
+                                     int proj_for_small_dt, double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!h || !h->have_geometry) return st->status = B200NP_ERR_BAD_ARG;
+    const bool use_old = incremental || proj_for_small_dt;
+    const bool set_inflow = !proj_for_small_dt && !incremental;
+    b200np_fab cells{}, grown{}, nodes{};
+    ebmf_boxes(h, cells, grown, nodes);
+    if (!ebmf_ok(velocity, cells.lo, cells.hi, 3, true, 1)) return st->status = B200NP_ERR_BAD_ARG;
+    if (use_old && !ebmf_ok(velocity_o, cells.lo, cells.hi, 3, true)) return st->status = B200NP_ERR_BAD_ARG;
+    if (density && !ebmf_ok(density, cells.lo, cells.hi, 1, true)) return st->status = B200NP_ERR_BAD_ARG;
+    if (!ebmf_ok(gp, cells.lo, cells.hi, 3, true) || !ebmf_ok(p_nd, nodes.lo, nodes.hi, 1, false)) return st->status = B200NP_ERR_BAD_ARG;
+    if (inflow_vel && set_inflow && !ebmf_ok(inflow_vel, cells.lo, cells.hi, 3, true, 1)) return st->status = B200NP_ERR_BAD_ARG;
+    try {
+        ECK(cudaSetDevice(h->device));
+        b200np_stats outer{};
+        EbMfView Vv, Vo, Vr, Vg, Vp, Vi;
+        b200np_fab c3 = cells; c3.ncomp = 3;
+        ebmf_map(h, Vv, 2, velocity, 3, grown, true, &outer);
+        ebmf_map(h, Vo, 3, use_old ? velocity_o : nullptr, 3, grown, true, &outer);
+        ebmf_map(h, Vr, 4, density, 1, cells, true, &outer);
+        ebmf_map(h, Vg, 5, gp, 3, c3, true, &outer);
+        ebmf_map(h, Vp, 6, p_nd, 1, nodes, incremental != 0, &outer);
+        ebmf_map(h, Vi, 7, (inflow_vel && set_inflow) ? inflow_vel : nullptr, 3, grown, true, &outer);
+        ECK(cudaMemsetAsync(Vv.dense, 0, ebmf_fab_doubles(grown, 3) * sizeof(double), h->stream));
+        ebmf_gather(h, Vv, EBMF_VALID);       // ghost cells are zeroed by the call itself (setBndry(0)); only the inflow layer comes from inflow_vel
+        if (Vo.m) { ECK(cudaMemsetAsync(Vo.dense, 0, ebmf_fab_doubles(grown, 3) * sizeof(double), h->stream)); ebmf_gather(h, Vo, EBMF_VALID); }
+        ebmf_gather(h, Vr, EBMF_VALID);
+        ebmf_gather(h, Vg, EBMF_VALID);
+        if (incremental) ebmf_gather(h, Vp, EBMF_VALID);
+        if (Vi.m) { ECK(cudaMemsetAsync(Vi.dense, 0, ebmf_fab_doubles(grown, 3) * sizeof(double), h->stream)); ebmf_gather(h, Vi, EBMF_VALID_BC); }
+        ECK(cudaStreamSynchronize(h->stream));
+        const int rc = b200eb_apply_nodal_projection(h, Vv.dense, &Vv.box, Vo.m ? Vo.dense : nullptr, density ? Vr.dense : nullptr, density ? &Vr.box : nullptr, ro_0,
+                                                     Vg.dense, &Vg.box, Vp.dense, &Vp.box, Vi.m ? Vi.dense : nullptr, scaling_factor, incremental, proj_for_small_dt,
+                                                     rtol, atol, st);
+        if (rc != B200NP_OK && rc != B200NP_ERR_NOT_CONVERGED && rc != B200NP_ERR_DIVERGED) return rc;
+        ebmf_scatter(h, Vv, EBMF_VALID_BC, &outer);
+        ebmf_scatter(h, Vg, EBMF_VALID, &outer);
+        ebmf_scatter(h, Vp, EBMF_VALID, &outer);
+        ECK(cudaStreamSynchronize(h->stream));
+        st->h2d_bytes += outer.h2d_bytes; st->d2h_bytes += outer.d2h_bytes;
+        return st->status = rc;
     } catch (int e) { return st->status = e; }
 }
 

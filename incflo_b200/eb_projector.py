@@ -109,6 +109,28 @@ class EBNodalProjector:
         self._chk(rc)
         return self.stats
 
+    # -- multi-box MultiFabs (nodal_projector.MultiFab: amr.max_grid_size < domain) --
+    def set_geometry_mf(self, vfrac, intg):
+        self._chk(self._L.b200eb_set_geometry_mf(self._h, vfrac.ref(), intg.ref()))
+
+    def project_mf(self, vel, sigma, rtol, atol, phi=None, gphi=None):
+        """vel / phi / gphi (and sigma unless it is a float): MultiFab"""
+        cs = float(sigma) if np.isscalar(sigma) else 0.0
+        ref = lambda m: m.ref() if m is not None else None
+        rc = self._L.b200eb_project_mf(self._h, vel.ref(), None if np.isscalar(sigma) else sigma.ref(), cs, ref(phi), ref(gphi), float(rtol), float(atol),
+                                       C.byref(self.stats))
+        self._chk(rc)
+        return self.stats
+
+    def apply_nodal_projection_mf(self, velocity, velocity_o, density, ro_0, gp, p_nd, scaling_factor, incremental, proj_for_small_dt, rtol, atol,
+                                  inflow_vel=None):
+        ref = lambda m: m.ref() if m is not None else None
+        rc = self._L.b200eb_apply_nodal_projection_mf(self._h, velocity.ref(), ref(velocity_o), ref(density), float(ro_0), gp.ref(), p_nd.ref(), ref(inflow_vel),
+                                                      float(scaling_factor), int(incremental), int(proj_for_small_dt), float(rtol), float(atol),
+                                                      C.byref(self.stats))
+        self._chk(rc)
+        return self.stats
+
     # -- per-kernel hooks used by the parity tests (host numpy arrays, natural node order) --
     def nlevels(self):
         return self._L.b200eb_nlevels(self._h)

@@ -327,6 +327,16 @@ int  b200eb_apply_nodal_projection(b200eb_t* h, double* velocity, const b200np_f
                                    const double* density, const b200np_fab* rho_box, double ro_0, double* gp, const b200np_fab* gp_box,
                                    double* p_nd, const b200np_fab* p_box, const double* inflow_vel, double scaling_factor,
                                    int incremental, int proj_for_small_dt, double rtol, double atol, b200np_stats* stats);
+/* The same over multi-box MultiFabs (b200np_mfab; amr.max_grid_size < domain, e.g. test_3d/benchmark.channel_sphere: 16): the fabs are gathered
+ * into one array per field, the single-box path runs, the results are scattered back -- bit-identical to the single-box calls.  After the
+ * call every cell of the velocity fabs inside the domain grown by one cell holds the new velocity / the BC ghost value, the cells beyond 0. */
+int  b200eb_set_geometry_mf(b200eb_t* h, const b200np_mfab* vfrac, const b200np_mfab* intg);
+int  b200eb_project_mf(b200eb_t* h, const b200np_mfab* vel, const b200np_mfab* sigma, double const_sigma, const b200np_mfab* phi,
+                       const b200np_mfab* gphi, double rtol, double atol, b200np_stats* stats);
+int  b200eb_apply_nodal_projection_mf(b200eb_t* h, const b200np_mfab* velocity, const b200np_mfab* velocity_o, const b200np_mfab* density,
+                                      double ro_0, const b200np_mfab* gp, const b200np_mfab* p_nd, const b200np_mfab* inflow_vel,
+                                      double scaling_factor, int incremental, int proj_for_small_dt, double rtol, double atol,
+                                      b200np_stats* stats);
 /* test hooks (host arrays, natural node order (nnz, nny, nnx), nn = n_cell in a periodic direction, n_cell + 1 otherwise):
  * build_stencils: MLNodeLaplacian::buildStencil for a sigma without projecting; level_stencil: the 13 forward entries
  * (offset t = (di+1) + 3(dj+1) + 9(dk+1), t = 14..26) + the diagonal of a level, (14, nnz, nny, nnx);

@@ -457,3 +457,70 @@ def test_odd_sizes_and_single_level(n):
     assert abs(st.iters - ref["info"]["iters"]) <= 1      # a BiCGStab-only "cycle" may stop one iteration apart in rounding
     assert rel(phi, ref["phi"]) < 1e-8 and rel(vel[:, 1:-1, 1:-1, 1:-1], ref["vel"]) < 1e-8
     pr.close()
+
+
+@pytest.mark.parametrize("device_ptrs", [False, True], ids=["host_ptrs", "device_ptrs"])
+@pytest.mark.parametrize("mode", ["project", "apply", "apply_incremental"])
+def test_multibox_equals_single_box(mode, device_ptrs):
+    """b200eb_*_mf: the MultiFabs of a deck with amr.max_grid_size < domain (test_3d/benchmark.channel_sphere: 16) against the single-box
+    calls -- bit for bit; velocity ghost cells: neighbours' values inside the domain, BC value in the first layer outside, 0 beyond"""
+    import torch
+    from incflo_b200 import eb_projector as ebp
+    from incflo_b200 import nodal_projector as npj
+    from oracle import eb_oracle as eo
+    g, p, _, _ = load("eb_channel_cylinder")
+    n = p.n
+    ng, mg = 2, 8
+    rng = np.random.default_rng(31)
+    fluid = g["vfrac"] > 0
+    shp = (3, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng)
+    inner = (slice(None),) + (slice(ng, -ng),) * 3
+    vel = rng.standard_normal(shp); vel[inner] *= fluid
+    velo = rng.standard_normal(shp); velo[inner] *= fluid
+    rho = np.ascontiguousarray(rng.uniform(1.0, 2.0, size=fluid.shape))
+    gp = np.ascontiguousarray(rng.standard_normal((3,) + fluid.shape) * fluid)
+    pn = np.ascontiguousarray(rng.standard_normal((n[2] + 1, n[1] + 1, n[0] + 1)))
+    inflow = np.zeros(shp)
+    y = (np.arange(-ng, n[1] + ng) + 0.5) / n[1]
+    inflow[0, :, :, ng - 1] = (6.0 * y * (1.0 - y))[None, :]
+    to = (lambda a: torch.from_numpy(a).cuda()) if device_ptrs else None
+    M = npj.MultiFab
+    # single box
+    p1 = make_projector(g, p)
+    # multi-box handle: geometry through the mf call as well
+    p2 = ebp.EBNodalProjector(n, p.dx, p.bclo, p.bchi, np.ones_like(g["vfrac"]), np.ascontiguousarray(g["intg"]))
+    intg_g = np.pad(g["intg"], ((0, 0), (1, 1), (1, 1), (1, 1)), constant_values=7.0e33)     # a ghost frame the library must not read
+    p2.set_geometry_mf(M.split(np.ascontiguousarray(g["vfrac"]), n, mg, 0, 1, to=to), M.split(np.ascontiguousarray(intg_g), n, mg, 1, 18, to=to))
+    if mode == "project":
+        # the velocity of project(): one ghost layer is input at non-periodic faces
+        v1 = vel.copy()
+        set_ghost = v1.copy(); set_ghost[inner] = 0
+        phi1 = np.zeros_like(pn); g1 = np.zeros_like(gp)
+        st1 = p1.project(v1, rho, 1e-11, 1e-14, phi=phi1, gphi=g1, ng=ng)
+        mv = M.split(vel, n, mg, ng, 3, to=to)
+        mphi = M.split(np.zeros_like(pn), n, mg, 0, 1, nodal=True, to=to)
+        mgph = M.split(np.zeros_like(gp), n, mg, 0, 3, to=to)
+        st2 = p2.project_mf(mv, M.split(rho, n, mg, 0, 1, to=to), 1e-11, 1e-14, phi=mphi, gphi=mgph)
+        assert st2.iters == st1.iters and st2.rhsnorm == st1.rhsnorm and st2.resnorm == st1.resnorm
+        assert np.array_equal(mv.assemble(n), v1[inner]) and np.array_equal(mphi.assemble(n)[0], phi1) and np.array_equal(mgph.assemble(n), g1)
+    else:
+        inc = mode == "apply_incremental"
+        v1, gp1, pn1 = vel.copy(), gp.copy(), pn.copy()
+        st1 = p1.apply_nodal_projection(v1, velo, rho, 1.0, gp1, pn1, 0.05, inc, False, 1e-11, 1e-14, inflow_vel=inflow, ng=ng)
+        mv = M.split(vel, n, mg, ng, 3, to=to)
+        mgp = M.split(gp, n, mg, 0, 3, to=to)
+        mp = M.split(pn, n, mg, 0, 1, nodal=True, to=to)
+        st2 = p2.apply_nodal_projection_mf(mv, M.split(velo, n, mg, ng, 3, to=to), M.split(rho, n, mg, 0, 1, to=to), 1.0, mgp, mp, 0.05, inc, False,
+                                           1e-11, 1e-14, inflow_vel=M.split(inflow, n, mg, ng, 3, to=to))
+        assert st2.iters == st1.iters and st2.rhsnorm == st1.rhsnorm
+        assert np.array_equal(mv.assemble(n), v1[inner]) and np.array_equal(mgp.assemble(n), gp1) and np.array_equal(mp.assemble(n)[0], pn1)
+        # ghost cells of the first box (corner x-lo / y-lo / z-lo): the single-box array's values where it has them in the first layer, 0 beyond
+        a = mv.arrays[0]
+        a = a.cpu().numpy() if device_ptrs else a
+        want = np.zeros_like(a)
+        want[:, ng - 1:, ng - 1:, ng - 1:] = v1[:, ng - 1:ng + mg + ng, ng - 1:ng + mg + ng, ng - 1:ng + mg + ng]
+        # periodic z: the ghost plane below z = 0 lies outside the (non-wrapped) index range of the dense array: FillBoundary is the caller's
+        want[:, :ng] = a[:, :ng]
+        assert np.array_equal(a, want)
+    assert (st2.h2d_bytes > 0) == (not device_ptrs)
+    p1.close(); p2.close()
