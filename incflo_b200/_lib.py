@@ -86,7 +86,7 @@ EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np
            "b200np_time_op", "b200np_composite_create", "b200np_composite_destroy", "b200np_composite_set_stream",
            "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection",
            "b200mac_create", "b200mac_destroy", "b200mac_nlevels", "b200mac_set_coeffs", "b200mac_project", "b200mac_level_op", "b200mac_level_dims",
-           "b200mac_set_coeffs_mf", "b200mac_project_mf",
+           "b200mac_set_coeffs_mf", "b200mac_project_mf", "b200mac_set_stream", "b200eb_set_stream",
            "b200eb_create", "b200eb_destroy", "b200eb_nlevels", "b200eb_set_geometry", "b200eb_set_eb_inflow_velocity", "b200eb_set_eb_flow",
            "b200eb_project", "b200eb_apply_nodal_projection", "b200eb_build_stencils", "b200eb_level_stencil", "b200eb_level_op", "b200eb_level_dims",
            "b200eb_compute_rhs", "b200eb_time_op", "b200eb_set_geometry_mf", "b200eb_project_mf", "b200eb_apply_nodal_projection_mf"]
@@ -173,6 +173,8 @@ def lib():
     L.b200eb_level_op.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp]
     L.b200eb_level_dims.argtypes = [vp, C.c_int, ip, ip]
     L.b200eb_compute_rhs.argtypes = [vp, dp, fb, dp]
+    L.b200eb_set_stream.argtypes = [vp, C.c_void_p]
+    L.b200mac_set_stream.argtypes = [vp, C.c_void_p]
     L.b200eb_set_geometry_mf.argtypes = [vp, mf, mf]
     L.b200eb_project_mf.argtypes = [vp, mf, mf, C.c_double, mf, mf, C.c_double, C.c_double, C.POINTER(Stats)]
     L.b200eb_apply_nodal_projection_mf.argtypes = [vp, mf, mf, mf, C.c_double, mf, mf, mf, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,

@@ -1284,7 +1284,7 @@ struct b200eb {
     b200np_geom geom{};
     b200np_opts opts{};
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     std::vector<EbLevel> lv;
     std::vector<void*> allocs;
     double *geo = nullptr, *ebf = nullptr, *sigma = nullptr;
@@ -1668,7 +1668,8 @@ int b200eb_create(b200eb_t** out, const b200np_geom* geom, const b200np_opts* op
         h->device = device;
         h->geom = *geom;
         if (opts) h->opts = *opts; else b200np_default_opts(&h->opts);
-        ECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        ECK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
         for (auto& e : h->ev) ECK(cudaEventCreate(&e));
         eb_build(h);
         ECK(cudaStreamSynchronize(h->stream));
@@ -1690,8 +1691,18 @@ void b200eb_destroy(b200eb_t* h)
     if (h->hscal) cudaFreeHost(h->hscal);
     if (h->hinfo) cudaFreeHost(h->hinfo);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+}
+
+// run on the caller's CUDA stream (e.g. amrex::Gpu::gpuStream()); NULL restores the handle's own non-blocking stream
+int b200eb_set_stream(b200eb_t* h, void* stream)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return B200NP_OK;
 }
 
 int b200eb_nlevels(const b200eb_t* h) { return h ? (int)h->lv.size() : 0; }

@@ -477,7 +477,7 @@ struct b200mac {
     b200np_geom geom{};
     b200np_opts opts{};
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     std::vector<MacLevel> lv;
     std::vector<void*> allocs;
     double *partial = nullptr, *dscal = nullptr, *work = nullptr, *snap = nullptr;
@@ -738,7 +738,8 @@ int b200mac_create(b200mac_t** out, const b200np_geom* geom, const b200np_opts* 
         h->geom = *geom;
         if (opts) h->opts = *opts;
         else { b200np_default_opts(&h->opts); h->opts.maxiter = 200; h->opts.bottom_maxiter = 200; }   // MLMG defaults (mac_proj.* keys)
-        MCK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        MCK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
         for (auto& e : h->ev) MCK(cudaEventCreate(&e));
         mac_build(h);
         MCK(cudaStreamSynchronize(h->stream));
@@ -760,8 +761,18 @@ void b200mac_destroy(b200mac_t* h)
     if (h->hscal) cudaFreeHost(h->hscal);
     if (h->hinfo) cudaFreeHost(h->hinfo);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+}
+
+// run on the caller's CUDA stream (e.g. amrex::Gpu::gpuStream()); NULL restores the handle's own non-blocking stream
+int b200mac_set_stream(b200mac_t* h, void* stream)
+{
+    if (!h) return B200NP_ERR_BAD_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return B200NP_OK;
 }
 
 int b200mac_nlevels(const b200mac_t* h) { return h ? (int)h->lv.size() : 0; }

@@ -252,6 +252,7 @@ typedef struct b200mac b200mac_t;
 int  b200mac_create(b200mac_t** out, const b200np_geom* geom, const b200np_opts* opts, int device);
 void b200mac_destroy(b200mac_t* h);
 int  b200mac_nlevels(const b200mac_t* h);
+int  b200mac_set_stream(b200mac_t* h, void* stream);   /* as b200np_set_stream */
 /* initProjector / updateCoeffs (bx, by, bz: face-centred dt / rho, boxes in face index space: x faces [0,nx] x [0,ny) x
  * [0,nz) ...) or, with all three NULL, initProjector(..., const_beta) / updateBeta(const_beta). */
 int  b200mac_set_coeffs(b200mac_t* h, const double* bx, const b200np_fab* bx_box, const double* by, const b200np_fab* by_box,
@@ -286,6 +287,7 @@ typedef struct b200eb b200eb_t;
 int  b200eb_create(b200eb_t** out, const b200np_geom* geom, const b200np_opts* opts, int device);
 void b200eb_destroy(b200eb_t* h);
 int  b200eb_nlevels(const b200eb_t* h);
+int  b200eb_set_stream(b200eb_t* h, void* stream);     /* as b200np_set_stream */
 /* The EB data the linear operator takes from the factory, per cell of the level (cell-centred boxes that cover the domain):
  *   vfrac  EBFArrayBoxFactory::getVolFrac()            1 comp
  *   intg   MLNodeLaplacian::m_integral (buildIntegral) 18 comps, integrals of x y z x2 y2 z2 xy xz yz x2y x2z xy2 y2z xz2 yz2 x2y2

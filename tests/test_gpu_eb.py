@@ -524,3 +524,35 @@ def test_multibox_equals_single_box(mode, device_ptrs):
         assert np.array_equal(a, want)
     assert (st2.h2d_bytes > 0) == (not device_ptrs)
     p1.close(); p2.close()
+
+
+def test_caller_stream_and_bad_multibox_arguments():
+    """b200eb_set_stream (the caller's stream, e.g. amrex::Gpu::gpuStream()) and the box checks of the multi-box calls"""
+    import ctypes as C
+    import torch
+    from incflo_b200 import nodal_projector as npj
+    from incflo_b200.nodal_projector import ProjectionError
+    g, p, sigma, _ = load("eb_channel_cylinder")
+    n = p.n
+    pr = make_projector(g, p)
+    v1 = torch.from_numpy(np.ascontiguousarray(g["vel"])).cuda()
+    st = pr.project(v1, sigma, 1e-11, 1e-14)
+    it = st.iters
+    s = torch.cuda.Stream()
+    assert pr._L.b200eb_set_stream(pr._h, C.c_void_p(s.cuda_stream)) == 0
+    with torch.cuda.stream(s):
+        v2 = torch.from_numpy(np.ascontiguousarray(g["vel"])).cuda()
+        st = pr.project(v2, sigma, 1e-11, 1e-14)
+    s.synchronize()
+    assert st.iters == it and torch.equal(v1, v2)
+    assert pr._L.b200eb_set_stream(pr._h, None) == 0
+    # boxes that do not tile the domain / a velocity without ghost cells
+    M = npj.MultiFab
+    vel = np.ascontiguousarray(g["vel"])
+    mv = M.split(vel, n, 8, 1, 3)
+    half = M(mv.boxes[:-1], mv.arrays[:-1], 1, 3)
+    with pytest.raises(ProjectionError):
+        pr.project_mf(half, sigma, 1e-11, 1e-14)
+    with pytest.raises(ProjectionError):
+        pr.project_mf(M.split(np.ascontiguousarray(vel[:, 1:-1, 1:-1, 1:-1]), n, 8, 0, 3), sigma, 1e-11, 1e-14)
+    pr.close()

@@ -212,3 +212,25 @@ def test_mac_multibox_equals_single_box(case, max_grid, ng, host):
         a = a.cpu().numpy() if hasattr(a, "cpu") else a
         assert np.all(a[0] == GARBAGE) and np.all(a[:, :, 0] == GARBAGE)
     p2.close()
+
+
+def test_mac_caller_stream():
+    """b200mac_set_stream: the projection on the caller's stream gives the same bits"""
+    import ctypes as C
+    import torch
+    mg, proj, rng = _make(CASES[1], True, seed=4)
+    name, n, dx, bclo, bchi = CASES[1]
+    u, v, w = rng.standard_normal((n[2], n[1], n[0] + 1)), rng.standard_normal((n[2], n[1] + 1, n[0])), rng.standard_normal((n[2] + 1, n[1], n[0]))
+    u[:, :, -1] = u[:, :, 0]; v[:, -1] = v[:, 0]
+    a = [torch.from_numpy(x.copy()).cuda() for x in (u, v, w)]
+    st = proj.project(a[0], a[1], a[2], 1e-11, 1e-14)
+    it = st.iters
+    s = torch.cuda.Stream()
+    assert proj._L.b200mac_set_stream(proj._h, C.c_void_p(s.cuda_stream)) == 0
+    with torch.cuda.stream(s):
+        b = [torch.from_numpy(x.copy()).cuda() for x in (u, v, w)]
+        st = proj.project(b[0], b[1], b[2], 1e-11, 1e-14)
+    s.synchronize()
+    assert st.iters == it and all(torch.equal(x, y) for x, y in zip(a, b))
+    assert proj._L.b200mac_set_stream(proj._h, None) == 0
+    proj.close()
