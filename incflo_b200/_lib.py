@@ -37,10 +37,21 @@ def build(force=False, verbose=False):
     cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
     nvcc = os.environ.get("NVCC", os.path.join(cuda_home, "bin", "nvcc"))
     ccbin = os.environ.get("B200NP_CCBIN", "/usr/bin/g++")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
-    subprocess.check_call(cmd + ["-ccbin", ccbin], env=env)
+    # one nvcc per translation unit, in parallel (the three files share no device symbols), then one link
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", ccbin]
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)], env=env))
+    rcs = [p.wait() for p in procs]
+    if any(rcs):
+        raise subprocess.CalledProcessError(max(rcs), "nvcc -c " + " ".join(SOURCES))
+    subprocess.check_call([nvcc, "-shared", "-ccbin", ccbin, "-o", SO] + objs, env=env)
     return SO
 
 
