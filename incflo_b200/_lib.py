@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
     rcs = [p.wait() for p in procs]
     if any(rcs):
         raise subprocess.CalledProcessError(max(rcs), "nvcc -c " + " ".join(SOURCES))
-    subprocess.check_call([nvcc, "-shared", "-ccbin", ccbin, "-o", SO] + objs, env=env)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", ccbin, "-o", SO] + objs, env=env)
     return SO
 
 

@@ -736,9 +736,11 @@ template <int BATCH, bool SIG>
 __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double* __restrict__ x, const double* __restrict__ rhs, double* __restrict__ out,
                                                      double* __restrict__ norm_partial)
 {
-    // block (64, 4) as in k_eb_gs; blockIdx.z = colour * H[2] + k/2.  norm_partial: one entry per block
+    // block (64, 4) as in k_eb_gs; blockIdx.z = 8 (k/2) + colour: the 8 colours of a pair of planes run next to each other in time, so
+    // the phi lines they all read come from L2 once (colour-major order, blockIdx.z = colour * H[2] + k/2, read 1.5 x more DRAM: ncu).
+    // norm_partial: one entry per block
     __shared__ double sh[34];
-    const int color = blockIdx.z / L.H[2], k2 = blockIdx.z - color * L.H[2];
+    const int color = blockIdx.z & 7, k2 = blockIdx.z >> 3;
     const int i2 = blockIdx.x * 64 + threadIdx.x, j2 = blockIdx.y * 4 + threadIdx.y;
     const int i = 2 * i2 + (color & 1), j = 2 * j2 + ((color >> 1) & 1), k = 2 * k2 + (color >> 2);
     double r = 0.0;

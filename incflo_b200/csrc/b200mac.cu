@@ -113,6 +113,13 @@ __device__ __forceinline__ double block_reduce(double v, double* sh)
 // A phi at one cell and the pieces the smoother needs
 __device__ __forceinline__ double adotx_cell(const MacLev& L, const double* __restrict__ phi, int i, int j, int k, double pc)
 {
+    if (i > 0 && i < L.n[0] - 1 && j > 0 && j < L.n[1] - 1 && k > 0 && k < L.n[2] - 1) {   // interior: no boundary logic, all loads up front
+        const long long c = cidx(L, i, j, k), sy = L.n[0], sz = (long long)L.n[0] * L.n[1];
+        const double xl = phi[c - 1], xh = phi[c + 1], yl = phi[c - sy], yh = phi[c + sy], zl = phi[c - sz], zh = phi[c + sz];
+        const long long cx = ((long long)k * L.n[1] + j) * (L.n[0] + 1) + i, cy = ((long long)k * (L.n[1] + 1) + j) * L.n[0] + i;
+        const double bxl = L.b[0][cx], bxh = L.b[0][cx + 1], byl = L.b[1][cy], byh = L.b[1][cy + sy], bzl = L.b[2][c], bzh = L.b[2][c + sz];
+        return -(L.dh[0] * (bxh * (xh - pc) - bxl * (pc - xl)) + L.dh[1] * (byh * (yh - pc) - byl * (pc - yl)) + L.dh[2] * (bzh * (zh - pc) - bzl * (pc - zl)));
+    }
     double y = 0.0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
