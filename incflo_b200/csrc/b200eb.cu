@@ -731,6 +731,56 @@ __global__ void __launch_bounds__(1024) k_eb_gs_small(const EbLev L, double* x, 
             __syncthreads();
         }
 }
+// The same with the level's vector resident in SHARED memory for the whole launch (loaded once, written back once): between the 8 x
+// nsweeps colour phases only __syncthreads, and the 20 / 26 neighbour reads of a node are LDS instead of global loads that the previous
+// phase's stores have just invalidated in L1 (a colour phase of k_eb_gs_small is one L2 round trip: 14 - 16 us per sweep on levels of
+// 54 and 340 nodes; 8 PDL launches per sweep cost 24 - 25 us on the levels of 2 376 and 17 680 nodes).  Flags, rhs, diagonal and the
+// stored rows are read-only and stay in L1.  Same operand order as offdiag_sum<true> / offdiag_sum_regular<true>: same bits.
+constexpr int EB_SMEM_MAX_NODES = 28000;   // 224 KB of the 227 KB a CTA may have
+__global__ void __launch_bounds__(1024) k_eb_gs_smem(const EbLev L, double* x, const double* __restrict__ rhs, int nsweeps)
+{
+    extern __shared__ __align__(16) double eb_xs[];
+    const int tid = threadIdx.x, nt = blockDim.x, nn = (int)L.nnode;
+    pdl_wait();
+    for (int t = tid; t < nn; t += nt) eb_xs[t] = x[t];
+    __syncthreads();
+    const double ce = __ldg(L.canon), cc = __ldg(L.canon + 1), cd = __ldg(L.canon + 2);
+    for (int s = 0; s < nsweeps; ++s)
+        for (int c = 0; c < 8; ++c) {
+            const int lo = c * L.CS, hi = lo + L.CS;
+            for (int p = lo + tid; p < hi; p += nt) {
+                int i, j, k;
+                if (!ndecode(L, p, i, j, k)) continue;
+                NbIdx q;
+                nb_index(L, i, j, k, q);
+                const double r = __ldg(rhs + p);
+                if (L.flag[p] == 1) {
+                    double se = 0.0, sc = 0.0;
+#pragma unroll
+                    for (int tt = 26; tt >= 0; --tt) {
+                        const int nz = (tt % 3 != 1) + ((tt / 3) % 3 != 1) + (tt / 9 != 1);
+                        if (nz == 2) se += eb_xs[q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]];
+                        if (nz == 3) sc += eb_xs[q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]];
+                    }
+                    eb_xs[p] = (r - (ce * se + cc * sc)) / cd;
+                    continue;
+                }
+                const double d = __ldg(L.st + 13 * L.nnode + p);
+                if (d == 0.0) { eb_xs[p] = 0.0; continue; }
+                double cf[27];
+#pragma unroll
+                for (int tt = 0; tt < 27; ++tt)
+                    if (tt != 13) cf[tt] = ld_early_nc(L.st + (long long)tt * L.nnode + p);
+                double ax = 0.0;
+#pragma unroll
+                for (int tt = 26; tt >= 0; --tt)
+                    if (tt != 13) ax += cf[tt] * eb_xs[q.X[tt % 3] + q.Y[(tt / 3) % 3] + q.Z[tt / 9]];
+                eb_xs[p] = (r - ax) / d;
+            }
+            __syncthreads();
+        }
+    for (int t = tid; t < nn; t += nt) x[t] = eb_xs[t];
+}
 // out = rhs - A x on the active nodes, 0 elsewhere; optional inf-norm partials
 template <int BATCH, bool SIG>
 __global__ void __launch_bounds__(256) k_eb_residual(const EbLev L, const double* __restrict__ x, const double* __restrict__ rhs, double* __restrict__ out,
@@ -1301,6 +1351,7 @@ struct b200eb {
     int use_pdl = 1;          // programmatic dependent launch between the V-cycle kernels (B200EB_PDL)
     int big_variant = 3;      // levels of >= batch_below nodes: 0 plain loads, 1 batched loads on the canonical rows, 3 speculative (B200EB_BIG_VARIANT)
     int small_nodes = 1000;   // levels up to this many nodes smooth in one CTA (B200EB_SMALL_NODES)
+    int smem_nodes = 3000;    // ... with the vector resident in shared memory (k_eb_gs_smem; B200EB_SMEM_NODES, at most EB_SMEM_MAX_NODES)
     long long launches = 0, ncell = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[12];
     struct Mf { double* dense = nullptr; size_t dense_doubles = 0; double* stage = nullptr; size_t stage_doubles = 0; EbMfFab* tab = nullptr; size_t tab_cap = 0; } mf[10];
@@ -1323,16 +1374,21 @@ int eb_blocks3(const EbLev& g, int ncolors) { const dim3 d = eb_grid3(g, ncolors
 
 // launch with the programmatic-stream-serialization attribute: ONLY for kernels that call pdl_wait() before touching data
 template <typename... KArgs, typename... Args>
-void eb_launch_pdl(b200eb* h, void (*kern)(KArgs...), dim3 grid, dim3 block, Args... args)
+void eb_launch_pdl_smem(b200eb* h, size_t smem, void (*kern)(KArgs...), dim3 grid, dim3 block, Args... args)
 {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = h->use_pdl ? 1 : 0;
     ECK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
     h->launches++;
+}
+template <typename... KArgs, typename... Args>
+void eb_launch_pdl(b200eb* h, void (*kern)(KArgs...), dim3 grid, dim3 block, Args... args)
+{
+    eb_launch_pdl_smem(h, 0, kern, grid, block, args...);
 }
 
 double* eb_alloc(b200eb* h, size_t doubles)
@@ -1381,6 +1437,9 @@ void eb_build(b200eb* h)
     h->canon = eb_alloc(h, 3 * h->lv.size());
     for (size_t l = 0; l < h->lv.size(); ++l) h->lv[l].g.canon = h->canon + 3 * l;
     if (const char* e = getenv("B200EB_SMALL_NODES")) h->small_nodes = atoi(e);
+    if (const char* e = getenv("B200EB_SMEM_NODES")) h->smem_nodes = atoi(e);
+    h->smem_nodes = std::min(h->smem_nodes, EB_SMEM_MAX_NODES);
+    ECK(cudaFuncSetAttribute(k_eb_gs_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMEM_MAX_NODES * (int)sizeof(double)));
     if (const char* e = getenv("B200EB_BATCH_BELOW")) h->batch_below = atoll(e);
     if (const char* e = getenv("B200EB_PDL")) h->use_pdl = atoi(e);
     if (const char* e = getenv("B200EB_BIG_VARIANT")) h->big_variant = atoi(e);
@@ -1467,6 +1526,10 @@ void eb_launch_residual(b200eb* h, EbLevel& L, const double* x, const double* rh
 void eb_smooth(b200eb* h, EbLevel& L, double* x, const double* rhs, int ncalls)
 {
     const int nsw = std::max(1, h->opts.smooth_num_sweeps);
+    if (L.g.nnode <= h->smem_nodes && !L.odd_periodic) {   // one CTA, the vector in shared memory
+        eb_launch_pdl_smem(h, (size_t)L.g.nnode * sizeof(double), k_eb_gs_smem, dim3(1), dim3(1024), L.g, x, rhs, ncalls * nsw);
+        return;
+    }
     if (L.g.nnode <= h->small_nodes) {
         eb_launch_pdl(h, k_eb_gs_small, dim3(1), dim3(1024), L.g, x, L.odd_periodic ? h->snap : (double*)nullptr, rhs, ncalls * nsw);
         return;
