@@ -95,7 +95,7 @@ EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np
            "b200np_apply_nodal_projection", "b200np_project_mf", "b200np_apply_nodal_projection_mf", "b200np_set_inflow_profile", "b200np_set_face_types", "b200np_check_overset_mask", "b200np_inout_flux", "b200np_strerror", "b200np_version", "b200np_nlevels",
            "b200np_level_dims", "b200np_halo_transport", "b200np_peer_map", "b200np_set_sigma", "b200np_level_set", "b200np_level_get", "b200np_level_op",
            "b200np_time_op", "b200np_composite_create", "b200np_composite_destroy", "b200np_composite_set_stream",
-           "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection",
+           "b200np_composite_level", "b200np_composite_project", "b200np_composite_apply_nodal_projection", "b200np_composite_apply_nodal_projection_mf",
            "b200mac_create", "b200mac_destroy", "b200mac_nlevels", "b200mac_set_coeffs", "b200mac_project", "b200mac_level_op", "b200mac_level_dims",
            "b200mac_set_coeffs_mf", "b200mac_project_mf", "b200mac_set_stream", "b200eb_set_stream",
            "b200eb_create", "b200eb_destroy", "b200eb_nlevels", "b200eb_set_geometry", "b200eb_set_eb_inflow_velocity", "b200eb_set_eb_flow",
@@ -159,6 +159,9 @@ def lib():
     p2, f2 = C.POINTER(C.c_void_p * 2), C.POINTER(fb * 2)
     L.b200np_composite_apply_nodal_projection.argtypes = [vp, p2, f2, p2, p2, f2, C.c_double, p2, f2, p2, f2, dp, C.c_double,
                                                           C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(Stats)]
+    m2 = C.POINTER(mf * 2)
+    L.b200np_composite_apply_nodal_projection_mf.argtypes = [vp, m2, m2, m2, C.c_double, m2, m2, mf, C.c_double, C.c_int, C.c_int,
+                                                             C.c_double, C.c_double, C.POINTER(Stats)]
     L.b200mac_create.argtypes = [C.POINTER(vp), C.POINTER(Geom), C.POINTER(Opts), C.c_int]
     L.b200mac_destroy.argtypes = [vp]
     L.b200mac_destroy.restype = None

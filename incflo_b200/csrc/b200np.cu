@@ -2271,6 +2271,108 @@ int b200np_composite_apply_nodal_projection(b200np_composite_t* C, double* const
     } catch (int e) { return st->status = e; }
 }
 
+// incflo::ApplyNodalProjection with finest_level = 1 over multi-box MultiFabs: both levels' fabs are gathered into one array per field
+// and level (level 1: the fine box in fine index space), the single-box composite path runs, the results are scattered back.
+int b200np_composite_apply_nodal_projection_mf(b200np_composite_t* C, const b200np_mfab* const velocity[2], const b200np_mfab* const velocity_o[2],
+                                               const b200np_mfab* const density[2], double ro_0, const b200np_mfab* const gp[2],
+                                               const b200np_mfab* const p_nd[2], const b200np_mfab* inflow_vel0, double scaling_factor,
+                                               int incremental, int proj_for_small_dt, double rtol, double atol, b200np_stats* stats)
+{
+    b200np_stats local{};
+    b200np_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof(*st));
+    if (!C || !velocity || !gp || !p_nd) return st->status = B200NP_ERR_BAD_ARG;
+    const int use_old = (incremental || proj_for_small_dt);
+    const bool var = density && (density[0] || density[1]);
+    if (var && (!density[0] || !density[1])) return st->status = B200NP_ERR_BAD_ARG;
+    if (use_old && (!velocity_o || !velocity_o[0] || !velocity_o[1])) return st->status = B200NP_ERR_BAD_ARG;
+    b200np* hh[2] = {C->h0, C->h1};
+    try {
+        CK(cudaSetDevice(hh[0]->device));
+        // per level: cells, cells grown by one, nodes -- level 0 over the domain, level 1 over the fine box (fine index space)
+        b200np_fab cells[2]{}, grown[2]{}, nodes[2]{};
+        mf_slab_boxes(hh[0], cells[0], grown[0], nodes[0]);
+        for (int d = 0; d < 3; ++d) {
+            cells[1].lo[d] = 2 * C->box.lo[d]; cells[1].hi[d] = 2 * C->box.hi[d] + 1;
+            grown[1].lo[d] = cells[1].lo[d] - 1; grown[1].hi[d] = cells[1].hi[d] + 1;
+            nodes[1].lo[d] = cells[1].lo[d]; nodes[1].hi[d] = cells[1].hi[d] + 1;
+        }
+        cells[1].ncomp = 1; grown[1].ncomp = 3; nodes[1].ncomp = 1;
+        const int set_inflow = (!proj_for_small_dt && !incremental);
+        for (int l = 0; l < 2; ++l) {
+            if (!mf_boxes_ok(velocity[l], cells[l].lo, cells[l].hi, 3, true) || velocity[l]->ngrow < 1) return st->status = B200NP_ERR_BAD_ARG;
+            if (use_old && !mf_boxes_ok(velocity_o[l], cells[l].lo, cells[l].hi, 3, true)) return st->status = B200NP_ERR_BAD_ARG;
+            if (var && !mf_boxes_ok(density[l], cells[l].lo, cells[l].hi, 1, true)) return st->status = B200NP_ERR_BAD_ARG;
+            if (!mf_boxes_ok(gp[l], cells[l].lo, cells[l].hi, 3, true) || !mf_boxes_ok(p_nd[l], nodes[l].lo, nodes[l].hi, 1, false)) return st->status = B200NP_ERR_BAD_ARG;
+        }
+        if (inflow_vel0 && set_inflow && (!mf_boxes_ok(inflow_vel0, cells[0].lo, cells[0].hi, 3, true) || inflow_vel0->ngrow < 1)) return st->status = B200NP_ERR_BAD_ARG;
+        mf_events(hh[0]);
+        b200np_stats outer{};
+        CK(cudaEventRecord(hh[0]->mf_ev[0], hh[0]->stream));
+        MfField Fv[2], Fo[2], Fr[2], Fg[2], Fp[2], Fi;
+        double *svel[2], *svelo[2], *srho[2], *sgp[2], *sp[2], *sin = nullptr;
+        b200np_fab gbox[2];
+        long long extra = 0;
+        for (int l = 0; l < 2; ++l) {
+            b200np* h = hh[l];
+            mf_map(h, 0, velocity[l], 3, true, &outer, Fv[l]);
+            mf_map(h, 1, use_old ? velocity_o[l] : nullptr, 3, true, &outer, Fo[l]);
+            mf_map(h, 2, var ? density[l] : nullptr, 1, true, &outer, Fr[l]);
+            mf_map(h, 3, gp[l], 3, true, &outer, Fg[l]);
+            mf_map(h, 4, p_nd[l], 1, incremental != 0, &outer, Fp[l]);
+            gbox[l] = cells[l]; gbox[l].ncomp = 3;
+            svel[l] = mf_slab(h, 0, grown[l]);
+            svelo[l] = Fo[l].mf ? mf_slab(h, 1, grown[l]) : nullptr;
+            srho[l] = Fr[l].mf ? mf_slab(h, 2, cells[l]) : nullptr;
+            sgp[l] = mf_slab(h, 3, gbox[l]);
+            sp[l] = mf_slab(h, 4, nodes[l]);
+            h->launches = 0;
+            CK(cudaMemsetAsync(svel[l], 0, fab_bytes(&grown[l]), h->stream));   // ghost cells: set by setBndry(0) / the inflow fill
+            mf_gather(h, Fv[l], 3, svel[l], grown[l], MF_VALID);
+            if (Fo[l].mf) { CK(cudaMemsetAsync(svelo[l], 0, fab_bytes(&grown[l]), h->stream)); mf_gather(h, Fo[l], 3, svelo[l], grown[l], MF_VALID); }
+            mf_gather(h, Fr[l], 1, srho[l], cells[l], MF_VALID);
+            mf_gather(h, Fg[l], 3, sgp[l], gbox[l], MF_VALID);
+            if (incremental) mf_gather(h, Fp[l], 1, sp[l], nodes[l], MF_VALID);
+            if (l == 0) {
+                mf_map(h, 5, (inflow_vel0 && set_inflow) ? inflow_vel0 : nullptr, 3, true, &outer, Fi);
+                if (Fi.mf) {
+                    sin = mf_slab(h, 5, grown[0]);
+                    CK(cudaMemsetAsync(sin, 0, fab_bytes(&grown[0]), h->stream));
+                    mf_gather(h, Fi, 3, sin, grown[0], MF_VALID_BC);
+                }
+            }
+            extra += h->launches;
+        }
+        double* const a_vel[2] = {svel[0], svel[1]};
+        const double* const a_velo[2] = {svelo[0], svelo[1]};
+        const double* const a_rho[2] = {srho[0], srho[1]};
+        double* const a_gp[2] = {sgp[0], sgp[1]};
+        double* const a_p[2] = {sp[0], sp[1]};
+        const b200np_fab* const b_vel[2] = {&grown[0], &grown[1]};
+        const b200np_fab* const b_rho[2] = {&cells[0], &cells[1]};
+        const b200np_fab* const b_gp[2] = {&gbox[0], &gbox[1]};
+        const b200np_fab* const b_p[2] = {&nodes[0], &nodes[1]};
+        int rc = b200np_composite_apply_nodal_projection(C, a_vel, b_vel, use_old ? a_velo : nullptr, var ? a_rho : nullptr, var ? b_rho : nullptr, ro_0,
+                                                         a_gp, b_gp, a_p, b_p, sin, scaling_factor, incremental, proj_for_small_dt, rtol, atol, st);
+        if (rc != B200NP_OK && rc != B200NP_ERR_NOT_CONVERGED && rc != B200NP_ERR_DIVERGED) return rc;
+        for (int l = 0; l < 2; ++l) {
+            b200np* h = hh[l];
+            h->launches = 0;
+            mf_scatter(h, Fv[l], 3, svel[l], grown[l], MF_VALID_BC);
+            mf_scatter(h, Fg[l], 3, sgp[l], gbox[l], MF_VALID);
+            mf_scatter(h, Fp[l], 1, sp[l], nodes[l], MF_VALID);
+            extra += h->launches;
+            mf_copy_back(h, 0, Fv[l], &outer); mf_copy_back(h, 3, Fg[l], &outer); mf_copy_back(h, 4, Fp[l], &outer);
+        }
+        CK(cudaEventRecord(hh[0]->mf_ev[1], hh[0]->stream));
+        CK(cudaEventSynchronize(hh[0]->mf_ev[1]));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, hh[0]->mf_ev[0], hh[0]->mf_ev[1])); st->ms_total = ms;
+        st->launches += extra; st->h2d_bytes += outer.h2d_bytes; st->d2h_bytes += outer.d2h_bytes;
+        return st->status = rc;
+    } catch (int e) { return st->status = e; }
+}
+
 // ---- test hooks ---------------------------------------------------------------------------
 static double* level_array(b200np* h, int lev, int which)
 {

@@ -272,19 +272,21 @@ class MultiFab:
         return C.byref(self.c)
 
     @staticmethod
-    def split(full, n_cell, max_grid, ngrow, ncomp, nodal=False, zlo=0, to=None):
+    def split(full, n_cell, max_grid, ngrow, ncomp, nodal=False, zlo=0, to=None, origin=(0, 0, 0)):
         """chop a single-box array (ncomp, nz+2ng(+1), ny+.., nx+..) over cells [0,n) x [0,n) x [zlo, zlo+nz) into boxes of
         at most max_grid cells per direction, each with its own ghost frame copied from `full` (zeros where `full` has
-        nothing); `to`: callable applied to each box array (e.g. lambda a: torch.from_numpy(a).cuda())"""
+        nothing); `to`: callable applied to each box array (e.g. lambda a: torch.from_numpy(a).cuda()); `origin`: index of
+        the array's first valid cell (a fine AMR level's box starts at 2 * fine_lo)"""
         nx, ny, nz = n_cell
+        ox, oy, oz = origin
         a4 = full.reshape((ncomp,) + tuple(full.shape)[-3:])
         boxes, arrs = [], []
         e = 1 if nodal else 0
         for k0 in range(0, nz, max_grid):
             for j0 in range(0, ny, max_grid):
                 for i0 in range(0, nx, max_grid):
-                    lo = (i0, j0, k0 + zlo)
-                    hi = (min(i0 + max_grid, nx) - 1, min(j0 + max_grid, ny) - 1, min(k0 + max_grid, nz) - 1 + zlo)
+                    lo = (i0 + ox, j0 + oy, k0 + zlo + oz)
+                    hi = (min(i0 + max_grid, nx) - 1 + ox, min(j0 + max_grid, ny) - 1 + oy, min(k0 + max_grid, nz) - 1 + zlo + oz)
                     sh = (ncomp, hi[2] - lo[2] + 1 + 2 * ngrow + e, hi[1] - lo[1] + 1 + 2 * ngrow + e, hi[0] - lo[0] + 1 + 2 * ngrow + e)
                     b = np.zeros(sh)
                     # the part of the grown box that `full` (cells [-ng, n+ng) around the same origin) holds
@@ -293,9 +295,11 @@ class MultiFab:
                     boxes.append((lo, hi)); arrs.append(np.ascontiguousarray(b) if to is None else to(np.ascontiguousarray(b)))
         return MultiFab(boxes, arrs, ngrow, ncomp, nodal)
 
-    def assemble(self, n_cell, zlo=0):
+    def assemble(self, n_cell, zlo=0, origin=(0, 0, 0)):
         """the valid regions put back together: (ncomp, nz(+1), ny(+1), nx(+1))"""
         nx, ny, nz = n_cell
+        ox, oy, oz = origin
+        zlo = zlo + oz
         e = 1 if self.nodal else 0
         out = np.zeros((self.ncomp, nz + e, ny + e, nx + e))
         g = self.ngrow
@@ -303,7 +307,7 @@ class MultiFab:
             a = a.detach().cpu().numpy() if hasattr(a, "detach") else a
             a = a.reshape((self.ncomp,) + tuple(a.shape)[-3:])
             v = a[:, g:a.shape[1] - g, g:a.shape[2] - g, g:a.shape[3] - g]
-            out[:, lo[2] - zlo:hi[2] - zlo + 1 + e, lo[1]:hi[1] + 1 + e, lo[0]:hi[0] + 1 + e] = v
+            out[:, lo[2] - zlo:hi[2] - zlo + 1 + e, lo[1] - oy:hi[1] - oy + 1 + e, lo[0] - ox:hi[0] - ox + 1 + e] = v
         return out
 
 
@@ -567,6 +571,29 @@ class CompositeProjection:
                                                              ref(pg), ref(bg), ref(pp), ref(bp), pi, float(scaling_factor),
                                                              int(incremental), int(proj_for_small_dt), float(mg_rtol),
                                                              float(mg_atol), C.byref(self.stats))
+        if rc != 0:
+            raise ProjectionError(rc)
+        return self.stats
+
+    def apply_nodal_projection_mf(self, velocity, gp, p_nd, density=None, ro_0=1.0, velocity_o=None, inflow_vel=None,
+                                  scaling_factor=1.0, incremental=False, proj_for_small_dt=False, mg_rtol=1e-11, mg_atol=1e-14):
+        """the same over multi-box MultiFabs: velocity, gp, p_nd, density, velocity_o are pairs (level 0, level 1) of class
+        MultiFab; the boxes of level 1 tile the fine box in fine index space (MultiFab.split(..., origin=2 * fine_lo))"""
+        mfp = C.POINTER(MFab)
+
+        def pair(ms):
+            if ms is None:
+                return None
+            a = (mfp * 2)()
+            for l in range(2):
+                a[l] = C.pointer(ms[l].c)
+            return a
+        keep = [pair(velocity), pair(velocity_o), pair(density), pair(gp), pair(p_nd)]
+        ref = lambda a: C.byref(a) if a is not None else None
+        rc = self._L.b200np_composite_apply_nodal_projection_mf(self._h, ref(keep[0]), ref(keep[1]), ref(keep[2]), float(ro_0), ref(keep[3]),
+                                                                ref(keep[4]), inflow_vel.ref() if inflow_vel is not None else None,
+                                                                float(scaling_factor), int(incremental), int(proj_for_small_dt),
+                                                                float(mg_rtol), float(mg_atol), C.byref(self.stats))
         if rc != 0:
             raise ProjectionError(rc)
         return self.stats

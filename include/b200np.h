@@ -238,6 +238,17 @@ int  b200np_composite_apply_nodal_projection(b200np_composite_t* c, double* cons
                                              const b200np_fab* const p_box[2], const double* inflow_vel0, double scaling_factor,
                                              int incremental, int proj_for_small_dt, double rtol, double atol, b200np_stats* stats);
 
+/* The same over multi-box MultiFabs (every deck chops both levels with amr.max_grid_size; e.g.
+ * test_no_eb_3d/benchmark.bouss_bubble_god:20): velocity[l], gp[l], p_nd[l], density[l], velocity_o[l] are the MultiFabs of
+ * incflo::LevelData on AMR level l as in b200np_apply_nodal_projection_mf.  The valid boxes of level 0 tile the domain, those of
+ * level 1 tile the fine box [2*fine_lo, 2*fine_hi+1] (fine index space) -- a refined region that is a union of several
+ * rectangles is still B200NP_ERR_UNSUPPORTED.  Results are bit-identical to the single-box call. */
+int  b200np_composite_apply_nodal_projection_mf(b200np_composite_t* c, const b200np_mfab* const velocity[2],
+                                                const b200np_mfab* const velocity_o[2], const b200np_mfab* const density[2],
+                                                double ro_0, const b200np_mfab* const gp[2], const b200np_mfab* const p_nd[2],
+                                                const b200np_mfab* inflow_vel0, double scaling_factor, int incremental,
+                                                int proj_for_small_dt, double rtol, double atol, b200np_stats* stats);
+
 /* ---- MAC projection: Hydro::MacProjector over amrex::MLMG / MLABecLaplacian --------------------------------------
  * Call sites: src/convection/incflo_compute_MAC_projected_velocities.cpp:69-129 (inv_rho on faces = dt / rho,
  * macproj->initProjector(lp_info, inv_rho) | initProjector(ba, dm, lp_info, dt / ro_0), setDomainBC(get_mac_projection_bc),

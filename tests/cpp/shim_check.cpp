@@ -172,6 +172,90 @@ static int multibox(int argc, char** argv)
     return 0;
 }
 
+// incflo::ApplyNodalProjection with finest_level = 1 through IncfloCompositeProjection: one box per level against both levels chopped
+// into boxes of mg cells (level 1 in fine index space) -- bit-identical
+static int composite_mf(int argc, char** argv)
+{
+    if (argc < 4) { std::printf("usage: shim_check composite_mf n max_grid\n"); return 2; }
+    abort_handler() = throwing_abort;
+    const int N = std::atoi(argv[2]), mg = std::atoi(argv[3]), ng = 2;
+    Geometry g{{N, N, N}, {1.0 / N, 1.0 / N, 1.0 / N}, {true, true, false}};
+    std::array<LinOpBCType, 3> lo{LinOpBCType::Periodic, LinOpBCType::Periodic, LinOpBCType::Neumann}, hi = lo;
+    const std::array<int, 3> flo{N / 4, N / 4, N / 4}, fhi{3 * N / 4 - 1, 3 * N / 4 - 1, 3 * N / 4 - 1};
+    const int nl[2][3] = {{N, N, N}, {N, N, N}};                 // cells per level (level 1: 2 * N / 2)
+    const int org[2][3] = {{0, 0, 0}, {2 * flo[0], 2 * flo[1], 2 * flo[2]}};
+    unsigned long long seed = 1234567891234567ull;
+    auto rnd = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return (double)(seed % 2000001ull) / 1.0e6 - 1.0; };
+    std::vector<double> vel[2], rho[2], gp[2], p[2];
+    for (int l = 0; l < 2; ++l) {
+        const int S = N + 2 * ng;
+        vel[l].resize((size_t)3 * S * S * S); rho[l].resize((size_t)S * S * S); gp[l].resize((size_t)3 * N * N * N); p[l].assign((size_t)(N + 1) * (N + 1) * (N + 1), 0.0);
+        for (auto& x : vel[l]) x = rnd();
+        for (auto& x : rho[l]) x = 1.0 + 0.5 * (rnd() + 1.0);
+        for (auto& x : gp[l]) x = 0.1 * rnd();
+    }
+    try {
+        IncfloCompositeProjection proj(g, lo, hi, flo, fhi);
+        // (a) one box per level
+        std::vector<double> v1[2] = {vel[0], vel[1]}, g1[2] = {gp[0], gp[1]}, p1[2] = {p[0], p[1]};
+        auto box = [&](double* d, int l, int ngr, int nc, bool nodal) {
+            const int vlo[3] = {org[l][0], org[l][1], org[l][2]}, vhi[3] = {org[l][0] + nl[l][0] - 1, org[l][1] + nl[l][1] - 1, org[l][2] + nl[l][2] - 1};
+            return Fab::make_box(d, vlo, vhi, ngr, nc, nodal);
+        };
+        std::array<Fab, 2> fv{box(v1[0].data(), 0, ng, 3, false), box(v1[1].data(), 1, ng, 3, false)};
+        std::array<Fab, 2> fr{box(rho[0].data(), 0, ng, 1, false), box(rho[1].data(), 1, ng, 1, false)};
+        std::array<Fab, 2> fg{box(g1[0].data(), 0, 0, 3, false), box(g1[1].data(), 1, 0, 3, false)};
+        std::array<Fab, 2> fp{box(p1[0].data(), 0, 0, 1, true), box(p1[1].data(), 1, 0, 1, true)};
+        proj.ApplyNodalProjection(&fr, 1.0, fv, nullptr, fg, fp, nullptr, 0.01, false);
+        const int it1 = proj.stats().iters;
+        // (b) boxes of mg^3 cells on both levels
+        std::vector<std::vector<double>> store;
+        auto chop = [&](const std::vector<double>& full, int l, int ncomp, int ngr, bool nodal) {
+            std::vector<Fab> fabs;
+            const int e = nodal ? 1 : 0, FS = N + 2 * ngr + e;
+            for (int k0 = 0; k0 < N; k0 += mg) for (int j0 = 0; j0 < N; j0 += mg) for (int i0 = 0; i0 < N; i0 += mg) {
+                const int vlo[3] = {org[l][0] + i0, org[l][1] + j0, org[l][2] + k0};
+                const int vhi[3] = {org[l][0] + std::min(i0 + mg, N) - 1, org[l][1] + std::min(j0 + mg, N) - 1, org[l][2] + std::min(k0 + mg, N) - 1};
+                const int bx = vhi[0] - vlo[0] + 1 + 2 * ngr + e, by = vhi[1] - vlo[1] + 1 + 2 * ngr + e, bz = vhi[2] - vlo[2] + 1 + 2 * ngr + e;
+                store.emplace_back((size_t)ncomp * bx * by * bz);
+                auto& b = store.back();
+                for (int c = 0; c < ncomp; ++c) for (int k = 0; k < bz; ++k) for (int j = 0; j < by; ++j) for (int i = 0; i < bx; ++i)
+                    b[(((size_t)c * bz + k) * by + j) * bx + i] = full[(((size_t)c * FS + (k0 + k)) * FS + (j0 + j)) * FS + (i0 + i)];
+                fabs.push_back(Fab::make_box(b.data(), vlo, vhi, ngr, ncomp, nodal));
+            }
+            return MultiFab(std::move(fabs), ngr, ncomp);
+        };
+        store.reserve(8 * (size_t)((N + mg - 1) / mg) * ((N + mg - 1) / mg) * ((N + mg - 1) / mg) + 8);   // Fab pointers stay valid
+        std::array<MultiFab, 2> mv{chop(vel[0], 0, 3, ng, false), chop(vel[1], 1, 3, ng, false)};
+        std::array<MultiFab, 2> mr{chop(rho[0], 0, 1, ng, false), chop(rho[1], 1, 1, ng, false)};
+        std::array<MultiFab, 2> mgp{chop(gp[0], 0, 3, 0, false), chop(gp[1], 1, 3, 0, false)};
+        std::array<MultiFab, 2> mp{chop(p[0], 0, 1, 0, true), chop(p[1], 1, 1, 0, true)};
+        proj.ApplyNodalProjection(&mr, 1.0, mv, nullptr, mgp, mp, nullptr, 0.01, false);
+        if (proj.stats().iters != it1) { std::printf("iterations differ: %d vs %d\n", proj.stats().iters, it1); return 5; }
+        size_t bad = 0;
+        const int S = N + 2 * ng;
+        for (int l = 0; l < 2; ++l) {
+            size_t f = 0;
+            for (int k0 = 0; k0 < N; k0 += mg) for (int j0 = 0; j0 < N; j0 += mg) for (int i0 = 0; i0 < N; i0 += mg, ++f) {
+                const Fab& a = mv[l].fabs[f];
+                const int bx = a.box.hi[0] - a.box.lo[0] + 1, by = a.box.hi[1] - a.box.lo[1] + 1, bz = a.box.hi[2] - a.box.lo[2] + 1;
+                for (int c = 0; c < 3; ++c) for (int k = ng; k < bz - ng; ++k) for (int j = ng; j < by - ng; ++j) for (int i = ng; i < bx - ng; ++i)
+                    if (a.p[(((size_t)c * bz + k) * by + j) * bx + i] != v1[l][(((size_t)c * S + (k0 + k)) * S + (j0 + j)) * S + (i0 + i)]) ++bad;
+                const Fab& q = mp[l].fabs[f];
+                const int qx = q.box.hi[0] - q.box.lo[0] + 1, qy = q.box.hi[1] - q.box.lo[1] + 1, qz = q.box.hi[2] - q.box.lo[2] + 1;
+                for (int k = 0; k < qz; ++k) for (int j = 0; j < qy; ++j) for (int i = 0; i < qx; ++i)
+                    if (q.p[((size_t)k * qy + j) * qx + i] != p1[l][((size_t)(k0 + k) * (N + 1) + (j0 + j)) * (N + 1) + (i0 + i)]) ++bad;
+            }
+        }
+        if (bad) { std::printf("%zu values differ between the multi-box and the single-box call\n", bad); return 6; }
+        std::printf("shim composite_mf OK: %zu + %zu boxes, %d iterations\n", mv[0].fabs.size(), mv[1].fabs.size(), it1);
+    } catch (const std::runtime_error& e) {
+        std::printf("amrex::Abort::%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 // the call sequence of incflo_apply_nodal_projection.cpp:181-219 with finest_level = 1
 static int composite(int argc, char** argv)
 {
@@ -350,6 +434,7 @@ int main(int argc, char** argv)
     if (argc >= 2 && !std::strcmp(argv[1], "mac")) return mac(argc, argv);
     if (argc >= 2 && !std::strcmp(argv[1], "host")) return host_checks();
     if (argc >= 2 && !std::strcmp(argv[1], "composite")) return composite(argc, argv);
+    if (argc >= 2 && !std::strcmp(argv[1], "composite_mf")) return composite_mf(argc, argv);
     if (argc >= 2 && !std::strcmp(argv[1], "multibox")) return multibox(argc, argv);
     if (argc < 15 || std::strcmp(argv[1], "project")) { std::printf("usage: see header comment\n"); return 2; }
     abort_handler() = throwing_abort;

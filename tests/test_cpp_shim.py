@@ -85,6 +85,15 @@ def test_shim_multibox_apply_equals_single_box(shim_exe):
 
 
 @pytest.mark.gpu
+def test_shim_composite_multibox_apply_equals_single_box(shim_exe):
+    """incflo::ApplyNodalProjection with finest_level = 1 through the C++ mirror (IncfloCompositeProjection): both AMR levels as
+    MultiFabs of 16^3 boxes against one box per level: bit-identical"""
+    out = subprocess.run([shim_exe, "composite_mf", "32", "16"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "shim composite_mf OK: 8 + 8 boxes" in out.stdout
+
+
+@pytest.mark.gpu
 def test_shim_two_level_project_matches_oracle(shim_exe, tmp_path, oracle):
     """Hydro::NodalProjector with two-element vectors (finest_level = 1) through the C++ mirror, against the
     composite oracle: periodic x/y, walls z, central box (bouss_bubble-like, BASELINE configs[3] scaled down)"""

@@ -126,6 +126,58 @@ def test_composite_apply_nodal_projection_variable_density(oracle):
     cp.close()
 
 
+@pytest.mark.parametrize("host", [True, False], ids=["host_ptrs", "device_ptrs"])
+@pytest.mark.parametrize("max_grid", [16, 12], ids=["grid16", "ragged12"])
+def test_composite_multibox_equals_single_box(max_grid, host):
+    """b200np_composite_apply_nodal_projection_mf: both AMR levels chopped into boxes of amr.max_grid_size cells (level 1 in fine index
+    space, its boxes tiling the fine box) must reproduce the single-box call bit for bit (velocity, gp, p_nd on both levels)"""
+    import torch
+    from incflo_b200 import nodal_projector as npj
+    N, ng = 32, 2
+    n0 = (N, N, N); dx0 = (1.0 / N,) * 3
+    bclo = bchi = (0, 0, 1)
+    clo, chi = (8, 4, 6), (23, 19, 25)
+    nf = tuple(2 * (h - l + 1) for l, h in zip(clo, chi))
+    org = tuple(2 * l for l in clo)
+    rng = np.random.default_rng(21)
+    vel, gp, p, rho = [], [], [], []
+    for n in (n0, nf):
+        v = np.zeros((3, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng)); v[:, ng:-ng, ng:-ng, ng:-ng] = rng.standard_normal((3,) + n[::-1])
+        vel.append(v)
+        gp.append(0.1 * rng.standard_normal((3,) + n[::-1]))
+        p.append(np.zeros((n[2] + 1, n[1] + 1, n[0] + 1)))
+        r = np.ones((n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng)); r[ng:-ng, ng:-ng, ng:-ng] = rng.uniform(1.0, 2.0, size=n[::-1])
+        rho.append(r)
+    dt = 0.3 / N
+    cp = npj.CompositeProjection(n0, dx0, bclo, bchi, clo, chi, opts=npj.nodal_proj_opts(tile=TILE))
+    svel = [v.copy() for v in vel]; sgp = [x.copy() for x in gp]; sp = [x.copy() for x in p]
+    st1 = cp.apply_nodal_projection(svel, (ng, ng), sgp, sp, density=rho, ngd=(ng, ng), scaling_factor=dt)
+    assert st1.status == 0
+    iters1 = st1.iters
+    to = None if host else (lambda a: torch.from_numpy(a).cuda())
+    origins = ((0, 0, 0), org)
+    mv = [npj.MultiFab.split(vel[l], (n0, nf)[l], max_grid, ng, 3, to=to, origin=origins[l]) for l in range(2)]
+    mg = [npj.MultiFab.split(gp[l], (n0, nf)[l], max_grid, 0, 3, to=to, origin=origins[l]) for l in range(2)]
+    mp = [npj.MultiFab.split(p[l][None], (n0, nf)[l], max_grid, 0, 1, nodal=True, to=to, origin=origins[l]) for l in range(2)]
+    mr = [npj.MultiFab.split(rho[l][None], (n0, nf)[l], max_grid, ng, 1, to=to, origin=origins[l]) for l in range(2)]
+    assert len(mv[1].boxes) > 1 and len(mv[0].boxes) > 1
+    st2 = cp.apply_nodal_projection_mf(mv, mg, mp, density=mr, scaling_factor=dt)
+    assert st2.status == 0 and st2.iters == iters1
+    if host:
+        assert st2.h2d_bytes > 0 and st2.d2h_bytes > 0
+    for l, n in enumerate((n0, nf)):
+        inner = (slice(None), slice(ng, ng + n[2]), slice(ng, ng + n[1]), slice(ng, ng + n[0]))
+        assert np.array_equal(mv[l].assemble(n, origin=origins[l]), svel[l][inner])
+        assert np.array_equal(mg[l].assemble(n, origin=origins[l]), sgp[l])
+        assert np.array_equal(mp[l].assemble(n, origin=origins[l])[0], sp[l])
+    # a level-1 MultiFab that does not tile the fine box is refused
+    bad = npj.MultiFab(mv[1].boxes[:-1], mv[1].arrays[:-1], ng, 3)
+    with pytest.raises(npj.ProjectionError) as e:
+        cp.apply_nodal_projection_mf([mv[0], bad], mg, mp, density=mr, scaling_factor=dt)
+    assert e.value.status == 4    # B200NP_ERR_BAD_ARG
+    cp.close()
+
+
 def test_composite_rejects_unsupported_boxes():
     from incflo_b200 import nodal_projector as npj
     with pytest.raises(npj.ProjectionError) as e:   # touches the domain face: B200NP_ERR_UNSUPPORTED
