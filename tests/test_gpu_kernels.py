@@ -157,23 +157,6 @@ def test_vcycle(var, oracle):
     _close(got, phi, 1e-8)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("B200NP_TEST_EXPERIMENTAL"),
-                    reason="k_interp_pipe (B200NP_INTERP=3): correct but slower than the default tile kernel (249 vs 168 us at 256^3); opt-in")
-@pytest.mark.parametrize("var", [False, True])
-@pytest.mark.parametrize("case", BC_CASES, ids=[c[0] for c in BC_CASES])
-def test_interpolation_pipelined_variant(case, var, oracle, monkeypatch):
-    """the persistent, software-pipelined interpolation kernel must give what the tile kernel gives"""
-    from incflo_b200.nodal_projector import A_COR, OP_INTERP
-    monkeypatch.setenv("B200NP_INTERP", "3")
-    mg, proj, rng = _setup(case, var, oracle)
-    for lev in range(mg.nlev - 1):
-        fine = _masked_random(mg, lev, rng)
-        crse = _masked_random(mg, lev + 1, rng)
-        proj.level_set(lev, A_COR, fine); proj.level_set(lev + 1, A_COR, crse)
-        proj.level_op(lev, OP_INTERP)
-        _close(proj.level_get(lev, A_COR), mg.interp_add(lev, fine.copy(), crse))
-
-
 # ---- the kernels that run at BENCHMARK size ------------------------------------------------------
 # b200np.cu routes a level with <= 148 smoother CTAs to the resident-chunk kernel (k_smooth_iso_res); every grid
 # above is that small.  B200NP_RES_CTAS=0 forces the ring-slot kernel k_smooth_iso (50 % of a 256^3 solve) onto the
