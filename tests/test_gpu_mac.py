@@ -234,3 +234,51 @@ def test_mac_caller_stream():
     assert st.iters == it and all(torch.equal(x, y) for x, y in zip(a, b))
     assert proj._L.b200mac_set_stream(proj._h, None) == 0
     proj.close()
+
+
+def test_mac_properties_at_bench_size():
+    """the bench configuration (256^3, rayleigh_taylor-like 4:1 density on the faces, periodic x / y + walls z) through properties that need no
+    oracle: convergence to rtol, the projected face velocity is discretely divergence-free, linearity in u, phi ~ 1 / beta at fixed u"""
+    import torch
+    from incflo_b200 import mac_projector as mp
+    N = 256
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    z = (torch.arange(N, device=dev, dtype=torch.float64) + 0.5) / N
+    rho = (1.0 + 1.5 * (1.0 + torch.tanh((z - 0.5) / 0.05)))[:, None, None].expand(N, N, N).contiguous()
+    dt = 0.01
+    bx = dt / (0.5 * (rho + torch.roll(rho, 1, 2))); bx = torch.cat([bx, bx[:, :, :1]], 2).contiguous()
+    by = dt / (0.5 * (rho + torch.roll(rho, 1, 1))); by = torch.cat([by, by[:, :1]], 1).contiguous()
+    rz = torch.cat([rho[:1], rho, rho[-1:]], 0)
+    bz = (dt / (0.5 * (rz[:-1] + rz[1:]))).contiguous()
+
+    def smooth(a):
+        for ax in range(3):
+            a = 0.5 * a + 0.25 * (torch.roll(a, 1, ax) + torch.roll(a, -1, ax))
+        return a
+    u0 = smooth(torch.randn((N, N, N + 1), device=dev, dtype=torch.float64, generator=g)); u0[:, :, -1] = u0[:, :, 0]
+    v0 = smooth(torch.randn((N, N + 1, N), device=dev, dtype=torch.float64, generator=g)); v0[:, -1] = v0[:, 0]
+    w0 = smooth(torch.randn((N + 1, N, N), device=dev, dtype=torch.float64, generator=g)); w0[0] = 0; w0[-1] = 0
+    proj = mp.MacProjector((N, N, N), (1.0 / N,) * 3, (0, 0, 1), (0, 0, 1))
+
+    def rel(a, b):
+        return float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b))
+
+    def run(scale_u=1.0, scale_b=1.0):
+        proj.updateCoeffs([scale_b * bx, scale_b * by, scale_b * bz])
+        u, v, w = scale_u * u0, scale_u * v0, scale_u * w0
+        phi = torch.zeros((N, N, N), device=dev, dtype=torch.float64)
+        st = proj.project(u, v, w, 1e-11, 1e-14, mac_phi=phi)
+        bnorm = max(st.rhsnorm, st.resnorm0)
+        assert st.status == 0 and st.resnorm <= 1e-11 * bnorm
+        div = (u[:, :, 1:] - u[:, :, :-1]) * N + (v[:, 1:] - v[:, :-1]) * N + (w[1:] - w[:-1]) * N
+        assert float((div - div.mean()).abs().max()) <= 2e-11 * bnorm
+        return u, v, w, phi - phi.mean(), st.iters
+
+    u1, v1, w1, p1, it1 = run()
+    assert it1 <= 12
+    u2, v2, w2, p2, _ = run(scale_u=-3.0)
+    assert rel(u2, -3.0 * u1) < 1e-9 and rel(w2, -3.0 * w1) < 1e-9 and rel(p2, -3.0 * p1) < 1e-9
+    u3, v3, w3, p3, _ = run(scale_b=4.0)
+    assert rel(u3, u1) < 1e-9 and rel(v3, v1) < 1e-9 and rel(4.0 * p3, p1) < 1e-9
+    proj.close()
