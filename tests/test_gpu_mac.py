@@ -265,9 +265,12 @@ def test_mac_properties_at_bench_size():
         return float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b))
 
     def run(scale_u=1.0, scale_b=1.0):
-        proj.updateCoeffs([scale_b * bx, scale_b * by, scale_b * bz])
+        cb = [scale_b * bx, scale_b * by, scale_b * bz]
+        torch.cuda.synchronize()
+        proj.updateCoeffs(cb)
         u, v, w = scale_u * u0, scale_u * v0, scale_u * w0
         phi = torch.zeros((N, N, N), device=dev, dtype=torch.float64)
+        torch.cuda.synchronize()   # the handle runs on its own stream: torch's fills must have landed
         st = proj.project(u, v, w, 1e-11, 1e-14, mac_phi=phi)
         bnorm = max(st.rhsnorm, st.resnorm0)
         assert st.status == 0 and st.resnorm <= 1e-11 * bnorm

@@ -220,6 +220,7 @@ def test_properties_at_baseline_size():
         v = (scale_u * vel).clone()
         gp = torch.zeros((3, N, N, N), dtype=torch.float64, device=dev)
         p = torch.zeros((N + 1,) * 3, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()   # the handle runs on its own stream (b200np_set_stream not used here): torch's fills must have landed
         st = proj.apply_nodal_projection(v, ng, gp, p, density=rho, ngd=ng, scaling_factor=dt * sigma_scale, mg_rtol=rtol, mg_atol=1e-14)
         assert st.status == 0 and st.resnorm <= max(1e-14, rtol * max(st.rhsnorm, st.resnorm0))
         return v[inner].clone(), p, gp, st.iters, st.rhsnorm
