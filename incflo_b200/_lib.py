@@ -105,6 +105,15 @@ EXPORTS = ["b200np_default_opts", "b200np_create", "b200np_create_dist", "b200np
 _lib = None
 
 
+def torch_sync():
+    """Device tensors handed to the library must be complete when the call is made: a handle runs on its own CUDA stream unless
+    *_set_stream gave it the caller's.  If torch is in use, wait for its current stream (a no-op when that stream is idle)."""
+    import sys
+    t = sys.modules.get("torch")
+    if t is not None and t.cuda.is_available() and t.cuda.is_initialized():
+        t.cuda.current_stream().synchronize()
+
+
 def lib():
     global _lib
     if _lib is not None:

@@ -88,6 +88,7 @@ class EBNodalProjector:
         pp, bp, _ = _ptr_box(phi, (0, 0, 0), 1)
         pg, bg, _ = _ptr_box(gphi, (0, 0, 0), 3)
         ref = lambda b: C.byref(b) if b is not None else None
+        _lib.torch_sync()
         rc = self._L.b200eb_project(self._h, pv, C.byref(bv), ps, ref(bs), cs, pp, ref(bp), pg, ref(bg), float(rtol), float(atol), C.byref(self.stats))
         self._chk(rc)
         return self.stats
@@ -103,6 +104,7 @@ class EBNodalProjector:
         pp, bp, _ = _ptr_box(p_nd, (0, 0, 0), 1)
         pi, _, _ = _ptr_box(inflow_vel, lo, 3)
         ref = lambda b: C.byref(b) if b is not None else None
+        _lib.torch_sync()
         rc = self._L.b200eb_apply_nodal_projection(self._h, pv, C.byref(bv), po, pr, ref(br), float(ro_0), pg, C.byref(bg), pp, C.byref(bp), pi,
                                                    float(scaling_factor), int(incremental), int(proj_for_small_dt), float(rtol), float(atol),
                                                    C.byref(self.stats))
@@ -117,6 +119,7 @@ class EBNodalProjector:
         """vel / phi / gphi (and sigma unless it is a float): MultiFab"""
         cs = float(sigma) if np.isscalar(sigma) else 0.0
         ref = lambda m: m.ref() if m is not None else None
+        _lib.torch_sync()
         rc = self._L.b200eb_project_mf(self._h, vel.ref(), None if np.isscalar(sigma) else sigma.ref(), cs, ref(phi), ref(gphi), float(rtol), float(atol),
                                        C.byref(self.stats))
         self._chk(rc)
@@ -125,6 +128,7 @@ class EBNodalProjector:
     def apply_nodal_projection_mf(self, velocity, velocity_o, density, ro_0, gp, p_nd, scaling_factor, incremental, proj_for_small_dt, rtol, atol,
                                   inflow_vel=None):
         ref = lambda m: m.ref() if m is not None else None
+        _lib.torch_sync()
         rc = self._L.b200eb_apply_nodal_projection_mf(self._h, velocity.ref(), ref(velocity_o), ref(density), float(ro_0), gp.ref(), p_nd.ref(), ref(inflow_vel),
                                                       float(scaling_factor), int(incremental), int(proj_for_small_dt), float(rtol), float(atol),
                                                       C.byref(self.stats))

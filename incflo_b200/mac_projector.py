@@ -108,9 +108,11 @@ class MacProjector:
     def updateCoeffs(self, beta):
         """beta: (bx, by, bz) face arrays dt / rho (initProjector / updateCoeffs), or a float (updateBeta)"""
         if np.isscalar(beta):
+            _lib.torch_sync()
             rc = self._L.b200mac_set_coeffs(self._h, None, None, None, None, None, None, float(beta))
         else:
             (px, bx), (py, by), (pz, bz) = (_ptr_box(a) for a in beta)
+            _lib.torch_sync()
             rc = self._L.b200mac_set_coeffs(self._h, px, C.byref(bx), py, C.byref(by), pz, C.byref(bz), 0.0)
         if rc != 0:
             raise ProjectionError(rc)
@@ -118,6 +120,7 @@ class MacProjector:
     def project(self, umac, vmac, wmac, rtol, atol, mac_phi=None, use_phi_as_guess=False):
         (pu, bu), (pv, bv), (pw, bw) = _ptr_box(umac), _ptr_box(vmac), _ptr_box(wmac)
         pp, bp = _ptr_box(mac_phi)
+        _lib.torch_sync()
         rc = self._L.b200mac_project(self._h, pu, C.byref(bu), pv, C.byref(bv), pw, C.byref(bw), pp, C.byref(bp) if bp is not None else None,
                                      int(use_phi_as_guess), float(rtol), float(atol), C.byref(self.stats))
         if rc != 0:
@@ -126,11 +129,13 @@ class MacProjector:
 
     def updateCoeffs_mf(self, bx, by, bz):
         """initProjector / updateCoeffs over multi-box face MultiFabs (FaceMultiFab)"""
+        _lib.torch_sync()
         rc = self._L.b200mac_set_coeffs_mf(self._h, bx.ref(), by.ref(), bz.ref())
         if rc != 0:
             raise ProjectionError(rc)
 
     def project_mf(self, umac, vmac, wmac, rtol, atol, mac_phi=None, use_phi_as_guess=False):
+        _lib.torch_sync()
         rc = self._L.b200mac_project_mf(self._h, umac.ref(), vmac.ref(), wmac.ref(), mac_phi.ref() if mac_phi is not None else None,
                                         int(use_phi_as_guess), float(rtol), float(atol), C.byref(self.stats))
         if rc != 0:

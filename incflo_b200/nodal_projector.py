@@ -145,6 +145,7 @@ class NodalProjector:
         ps, bs, _ = _ptr_box(self.sigma, (0, 0, 0), 1)
         pp, bp, _ = _ptr_box(self._phi, (0, 0, 0), 1)
         pg, bg, _ = _ptr_box(self._gphi, (0, 0, 0), 3)
+        _lib.torch_sync()
         rc = self._L.b200np_project(h, pv, C.byref(bv), ps, C.byref(bs) if bs is not None else None, self.const_sigma,
                                     pp, C.byref(bp), pg, C.byref(bg), float(rtol), float(atol), C.byref(self.stats))
         if rc != 0:
@@ -210,6 +211,7 @@ class NodalProjector:
 
     def set_sigma(self, sigma=None, const_sigma=1.0):
         ps, bs, _ = _ptr_box(sigma, (0, 0, 0), 1)
+        _lib.torch_sync()
         rc = self._L.b200np_set_sigma(self._handle(), ps, C.byref(bs) if bs is not None else None, float(const_sigma))
         if rc:
             raise ProjectionError(rc)
@@ -376,6 +378,7 @@ class IncfloProjection:
         pg, bg, _ = _ptr_box(gp, (0, 0, z), 3)
         pp, bp, _ = _ptr_box(p_nd, (0, 0, z), 1)
         pi, _, _ = _ptr_box(inflow_vel, (-ng, -ng, z - ng), 3)
+        _lib.torch_sync()
         rc = self._L.b200np_apply_nodal_projection(self._h, pv, C.byref(bv), po, pr, C.byref(br) if br is not None else None,
                                                    float(ro_0), pg, C.byref(bg), pp, C.byref(bp), pi,
                                                    float(scaling_factor), int(incremental), int(proj_for_small_dt),
@@ -388,6 +391,7 @@ class IncfloProjection:
                                   scaling_factor=1.0, incremental=False, proj_for_small_dt=False, mg_rtol=1e-11, mg_atol=1e-14):
         """incflo::ApplyNodalProjection over multi-box MultiFabs (class MultiFab)"""
         r = lambda m: m.ref() if m is not None else None
+        _lib.torch_sync()
         rc = self._L.b200np_apply_nodal_projection_mf(self._h, r(velocity), r(velocity_o), r(density), float(ro_0), r(gp), r(p_nd),
                                                       r(inflow_vel), float(scaling_factor), int(incremental), int(proj_for_small_dt),
                                                       float(mg_rtol), float(mg_atol), C.byref(self.stats))
@@ -398,6 +402,7 @@ class IncfloProjection:
     def project_mf(self, vel, sigma=None, const_sigma=1.0, phi=None, gphi=None, rtol=1e-11, atol=1e-14):
         """Hydro::NodalProjector::project + getPhi / getGradPhi over multi-box MultiFabs"""
         r = lambda m: m.ref() if m is not None else None
+        _lib.torch_sync()
         rc = self._L.b200np_project_mf(self._h, r(vel), r(sigma), float(const_sigma), r(phi), r(gphi), float(rtol), float(atol),
                                        C.byref(self.stats))
         if rc != 0:
@@ -533,6 +538,7 @@ class CompositeProjection:
         pg0, bg0, _ = _ptr_box(gphi0, (0, 0, 0), 3)
         pg1, bg1, _ = _ptr_box(gphi1, self._flo(0), 3)
         ref = lambda b: C.byref(b) if b is not None else None
+        _lib.torch_sync()
         rc = self._L.b200np_composite_project(self._h, pv0, ref(bv0), pv1, ref(bv1), ps0, ref(bs0), ps1, ref(bs1),
                                               float(const_sigma), pp0, ref(bp0), pp1, ref(bp1), pg0, ref(bg0), pg1, ref(bg1),
                                               float(rtol), float(atol), C.byref(self.stats))
@@ -567,6 +573,7 @@ class CompositeProjection:
         pp, bp, k5 = pair(p_nd, lo_0, 1)
         pi, _, _ = _ptr_box(inflow_vel, (-ng[0],) * 3, 3)
         ref = lambda a: C.byref(a) if a is not None else None
+        _lib.torch_sync()
         rc = self._L.b200np_composite_apply_nodal_projection(self._h, ref(pv), ref(bv), ref(po), ref(pr), ref(br), float(ro_0),
                                                              ref(pg), ref(bg), ref(pp), ref(bp), pi, float(scaling_factor),
                                                              int(incremental), int(proj_for_small_dt), float(mg_rtol),
@@ -590,6 +597,7 @@ class CompositeProjection:
             return a
         keep = [pair(velocity), pair(velocity_o), pair(density), pair(gp), pair(p_nd)]
         ref = lambda a: C.byref(a) if a is not None else None
+        _lib.torch_sync()
         rc = self._L.b200np_composite_apply_nodal_projection_mf(self._h, ref(keep[0]), ref(keep[1]), ref(keep[2]), float(ro_0), ref(keep[3]),
                                                                 ref(keep[4]), inflow_vel.ref() if inflow_vel is not None else None,
                                                                 float(scaling_factor), int(incremental), int(proj_for_small_dt),
