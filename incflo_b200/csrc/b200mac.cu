@@ -492,6 +492,7 @@ struct b200mac {
     double* hscal = nullptr;
     int* hinfo = nullptr;
     bool singular = true, have_coeffs = false;
+    bool top_direct = true;   // finest level of the V-cycle relaxes (sol, rhs) directly (B200MAC_TOP_DIRECT=0: MLMG's correction form)
     long long launches = 0;
     struct Stage { double* d = nullptr; size_t bytes = 0; } stage[8];
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -598,15 +599,21 @@ void mac_smooth(b200mac* h, MacLevel& L, double* phi, const double* rhs, int nca
         }
 }
 
+// One V-cycle.  top_direct (default): the finest level relaxes (sol, rhs) in place instead of (cor, res = rhs - A sol) from cor = 0 -- the
+// smoother is a stationary linear iteration, so both forms do the same arithmetic up to rounding, and the direct one needs no zeroed cor,
+// no sol += cor pass (24 B/cell) and no stored top-level residual (8 B/cell): the caller only takes the norm (as b200np.cu's V-cycle does).
 void mac_vcycle(b200mac* h)
 {
     const int nl = (int)h->lv.size();
     const int nu1 = h->opts.num_pre_smooth, nu2 = h->opts.num_post_smooth;
     for (int l = 0; l < nl - 1; ++l) {
         MacLevel &L = h->lv[l], &C = h->lv[l + 1];
-        MCK(cudaMemsetAsync(L.cor, 0, L.ncell * sizeof(double), h->stream));
-        mac_smooth(h, L, L.cor, L.res, nu1);
-        mac_launch_pdl(h, k_mac_residual, mac_grid3(L.g), dim3(64, 4), L.g, (const double*)L.cor, (const double*)L.res, L.rescor, (double*)nullptr);
+        const bool direct = l == 0 && h->top_direct;   // (nl > 1 here)
+        double* x = direct ? L.sol : L.cor;
+        const double* b = direct ? L.rhs : L.res;
+        if (!direct) MCK(cudaMemsetAsync(L.cor, 0, L.ncell * sizeof(double), h->stream));
+        mac_smooth(h, L, x, b, nu1);
+        mac_launch_pdl(h, k_mac_residual, mac_grid3(L.g), dim3(64, 4), L.g, (const double*)x, b, L.rescor, (double*)nullptr);
         mac_launch_pdl(h, k_mac_restrict, dim3(grid_for(C.ncell)), dim3(256), C.g, L.g.n[0], L.g.n[1], (const double*)L.rescor, C.res);
     }
     MacLevel& B = h->lv.back();
@@ -614,8 +621,11 @@ void mac_vcycle(b200mac* h)
             h->singular ? 1 : 0, h->dinfo);
     for (int l = nl - 2; l >= 0; --l) {
         MacLevel &L = h->lv[l], &C = h->lv[l + 1];
-        mac_launch_pdl(h, k_mac_interp_add, dim3(grid_for(L.ncell)), dim3(256), L.g, C.g.n[0], C.g.n[1], L.cor, (const double*)C.cor);
-        mac_smooth(h, L, L.cor, L.res, nu2);
+        const bool direct = l == 0 && h->top_direct;
+        double* x = direct ? L.sol : L.cor;
+        const double* b = direct ? L.rhs : L.res;
+        mac_launch_pdl(h, k_mac_interp_add, dim3(grid_for(L.ncell)), dim3(256), L.g, C.g.n[0], C.g.n[1], x, (const double*)C.cor);
+        mac_smooth(h, L, x, b, nu2);
     }
 }
 
@@ -665,7 +675,9 @@ int mac_solve(b200mac* h, double rtol, double atol, b200np_stats* st)
     const int nb_ = grid_for(L0.ncell);
     MLAUNCH(h, k_mac_absmax_partial, nb_, 256, (const double*)L0.rhs, L0.ncell, h->partial);
     st->rhsnorm = mac_read_norm(h, nb_);
-    MLAUNCH(h, k_mac_residual, mac_grid3(L0.g), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+    const bool direct = h->top_direct && h->lv.size() > 1;   // a single level: the bottom solve is the cycle, on (cor, res)
+    double* const top_res = direct ? (double*)nullptr : L0.res;   // direct form: only the norm of the top-level residual is needed
+    MLAUNCH(h, k_mac_residual, mac_grid3(L0.g), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, top_res, h->partial);
     st->resnorm0 = mac_read_norm(h, mac_blocks3(L0.g));
     const double maxnorm = std::max(st->rhsnorm, st->resnorm0);
     const double target = std::max(atol, std::max(rtol, 1e-16) * maxnorm);
@@ -676,8 +688,8 @@ int mac_solve(b200mac* h, double rtol, double atol, b200np_stats* st)
     bool converged = false;
     for (int it = 0; it < h->opts.maxiter; ++it) {
         mac_vcycle_run(h);
-        MLAUNCH(h, k_mac_axpy, nb_, 256, L0.sol, (const double*)L0.cor, L0.ncell);
-        MLAUNCH(h, k_mac_residual, mac_grid3(L0.g), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, L0.res, h->partial);
+        if (!direct) MLAUNCH(h, k_mac_axpy, nb_, 256, L0.sol, (const double*)L0.cor, L0.ncell);
+        MLAUNCH(h, k_mac_residual, mac_grid3(L0.g), dim3(64, 4), L0.g, (const double*)L0.sol, (const double*)L0.rhs, top_res, h->partial);
         st->resnorm = mac_read_norm(h, mac_blocks3(L0.g));
         st->iters = it + 1;
         if (it + 1 < 128) st->resnorm_hist[it + 1] = st->resnorm;
@@ -748,6 +760,7 @@ int b200mac_create(b200mac_t** out, const b200np_geom* geom, const b200np_opts* 
         MCK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
         for (auto& e : h->ev) MCK(cudaEventCreate(&e));
+        if (const char* e = getenv("B200MAC_TOP_DIRECT")) h->top_direct = atoi(e) != 0;
         mac_build(h);
         MCK(cudaStreamSynchronize(h->stream));
     } catch (int e) { b200mac_destroy(h); return e; }

@@ -285,3 +285,32 @@ def test_mac_properties_at_bench_size():
     u3, v3, w3, p3, _ = run(scale_b=4.0)
     assert rel(u3, u1) < 1e-9 and rel(v3, v1) < 1e-9 and rel(4.0 * p3, p1) < 1e-9
     proj.close()
+
+
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[4]], ids=["rt_walls_z", "channel_inflow_outflow", "odd_periodic_bottom"])
+def test_mac_top_level_forms_agree(case, monkeypatch):
+    """the V-cycle's finest level in direct form (default: relax (sol, rhs) in place, no sol += cor, norm-only top residual) against MLMG's
+    correction form (B200MAC_TOP_DIRECT=0): same iteration count, same phi and velocities to the solver tolerance, both equal to the oracle"""
+    name, n, dx, bclo, bchi = case
+    out = []
+    for form in ("1", "0"):
+        monkeypatch.setenv("B200MAC_TOP_DIRECT", form)
+        mg, proj, rng = _make(case, True, seed=7)
+        u, v, w = rng.standard_normal((n[2], n[1], n[0] + 1)), rng.standard_normal((n[2], n[1] + 1, n[0])), rng.standard_normal((n[2] + 1, n[1], n[0]))
+        vel = [u, v, w]
+        for d, ax in ((0, 2), (1, 1), (2, 0)):
+            sl = lambda s: tuple(s if a == ax else slice(None) for a in range(3))
+            if bclo[d] == 0:
+                vel[d][sl(n[d])] = vel[d][sl(0)]
+        if form == "1":
+            ou, ov, ow = u.copy(), v.copy(), w.copy()
+            ref = mo.project(mg.p, ou, ov, ow, mg.lv[0].b, 1e-11, 1e-14)
+        phi = np.zeros((n[2], n[1], n[0]))
+        st = proj.project(u, v, w, 1e-11, 1e-14, mac_phi=phi)
+        assert st.status == 0 and abs(st.iters - ref["stats"]["iters"]) <= 1
+        out.append((u, v, w, phi - phi.mean(), st.iters))
+        proj.close()
+    assert out[0][4] == out[1][4]
+    for a, b in zip(out[0][:4], out[1][:4]):
+        assert rel(a, b) < 1e-9
+    assert rel(out[0][0], ou) < 1e-9 and rel(out[0][2], ow) < 1e-9 and rel(out[0][3], ref["phi"] - ref["phi"].mean()) < 1e-9

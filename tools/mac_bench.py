@@ -52,8 +52,10 @@ for s in range(K + 2):
     if s >= 2:
         times.append(st.ms_total)
 ms = sum(times) / len(times)
-# algorithmic bytes per cell and V-cycle: 8 half-sweeps x 40 + residual 48 + restriction 9 + interpolation 17 + (top) sol += cor 24 + residual 48
-per_cell = (8 * 40 + 48 + 9 + 17) * 8.0 / 7.0 + 24 + 48
+# algorithmic bytes per cell and V-cycle: 8 half-sweeps x 40 + residual 48 + restriction 9 + interpolation 17 on every level, + the top-level residual
+# norm (40: nothing stored, no sol += cor in the direct form; B200MAC_TOP_DIRECT=0 adds 24 + 8)
+direct = os.environ.get("B200MAC_TOP_DIRECT", "1") != "0"
+per_cell = (8 * 40 + 48 + 9 + 17) * 8.0 / 7.0 + (40 if direct else 24 + 48)
 total = per_cell * N ** 3 * st.iters + (24 + 8 + 48 + 8 + 3 * 24) * N ** 3
 print(json.dumps({"metric": "mac_projection_Mcell_updates_per_s", "value": N ** 3 / ms / 1e3, "unit": "Mcell-updates/s", "n": N,
                   "ms_per_projection": ms, "ms_solve": st.ms_solve, "vcycles": st.iters, "resid_over_bnorm": st.resnorm / max(st.rhsnorm, st.resnorm0),
