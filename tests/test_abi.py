@@ -139,3 +139,29 @@ def test_eb_argument_checks_need_no_gpu():
         assert L.b200eb_create(C.byref(h), C.byref(g), None, 0) == 5   # B200NP_ERR_CUDA: no CPU fallback
     assert L.b200eb_project(None, None, None, None, None, 1.0, None, None, None, None, 1e-11, 1e-14, None) == 4
     assert L.b200eb_nlevels(None) == 0
+
+
+def test_multifab_split_and_assemble_round_trip_with_an_origin():
+    """host logic of the multi-box mirror: chopping a single-box array into boxes (own ghost frames, optional index origin as a fine AMR
+    level has it) and putting the valid regions back together is the identity; the b200np_mfab view carries the allocated boxes"""
+    import numpy as np
+    from incflo_b200 import nodal_projector as npj
+    rng = np.random.default_rng(5)
+    n, ng, org = (10, 6, 8), 2, (16, 8, 12)
+    full = rng.standard_normal((3, n[2] + 2 * ng, n[1] + 2 * ng, n[0] + 2 * ng))
+    m = npj.MultiFab.split(full, n, 4, ng, 3, origin=org)
+    assert len(m.boxes) == 3 * 2 * 2 and m.c.nfabs == 12 and m.c.ngrow == ng and m.c.ncomp == 3
+    assert m.boxes[0] == ((16, 8, 12), (19, 11, 15))
+    assert m.boxes[-1] == ((24, 12, 16), (25, 13, 19))           # ragged last boxes: 2 x 2 x 4 cells
+    b0 = m.c.box[0]
+    assert [b0.lo[d] for d in range(3)] == [14, 6, 10] and [b0.hi[d] for d in range(3)] == [21, 13, 17]   # valid box grown by ngrow
+    assert np.array_equal(m.assemble(n, origin=org), full[:, ng:-ng, ng:-ng, ng:-ng])
+    # interior ghost cells of a box hold the neighbour's valid values
+    lo, hi = m.boxes[1]
+    a = m.arrays[1]
+    assert np.array_equal(a[:, ng:-ng, ng:-ng, 0:ng], full[:, ng:ng + 4, ng:ng + 4, ng + 4 - ng:ng + 4])
+    pn = rng.standard_normal((1, n[2] + 1, n[1] + 1, n[0] + 1))
+    mn = npj.MultiFab.split(pn, n, 4, 0, 1, nodal=True, origin=org)
+    assert np.array_equal(mn.assemble(n, origin=org), pn)
+    q = mn.c.box[0]
+    assert [q.hi[d] - q.lo[d] + 1 for d in range(3)] == [5, 5, 5]   # nodal: one more node than cells per direction
